@@ -1,0 +1,193 @@
+/* stil_head.h — C ABI of the B200-native STiL semi-supervised head (libstil_head.so).
+ *
+ * The reference (kgutjahr/STiL-TTA) is pure Python/PyTorch and has NO FFI for this path: the head
+ * sits behind two nn.Module objects and inline tensor code.  The entry points
+ * below are what a binding for that path binds; each cites the reference interface it replaces.
+ * INTEGRATION.md shows the ctypes stub and the three-line change in the reference trainers.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE address unless stated; matrices are row-major with an explicit
+ *     leading dimension `ld*` counted in elements; sizes are int64_t; no torch types anywhere.
+ *   - `dtype` is a stil_dtype_t.  Embeddings/logits may be STIL_F32 or STIL_BF16 (bf16 values are
+ *     consumed exactly; all arithmetic accumulates in fp32).  Embedding rows must be 16-byte
+ *     aligned (dim % 8 == 0 for bf16, % 4 for f32, base pointers 16-B aligned).
+ *   - every function returns 0 (STIL_OK) or a negative stil_status_t, never throws, never aborts,
+ *     never synchronises the device; stil_last_error() gives the message (thread-local).
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are CUDA-graph
+ *     capturable.  The library allocates no device memory: scratch comes from the caller through
+ *     `workspace` (size from the matching *_workspace_bytes query; 256-B aligned).
+ *   - kernels exist for sm_100a only; there is no CPU or generic-GPU fallback.
+ */
+#ifndef STIL_HEAD_H_
+#define STIL_HEAD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STIL_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#if defined(__GNUC__)
+#define STIL_API __attribute__((visibility("default")))
+#else
+#define STIL_API
+#endif
+
+typedef enum { STIL_F32 = 0, STIL_BF16 = 1 } stil_dtype_t;
+
+typedef enum {
+    STIL_OK = 0,
+    STIL_E_SHAPE = -1, /* size out of the supported range */
+    STIL_E_DTYPE = -2,
+    STIL_E_ALIGN = -3, /* pointer / leading dimension alignment */
+    STIL_E_ARCH = -4,  /* device is not sm_100 */
+    STIL_E_CUDA = -5,  /* a CUDA runtime/driver call failed */
+    STIL_E_ARG = -6,   /* null pointer, bad scalar (e.g. lambda_0 outside [0,1]) */
+    STIL_E_WORKSPACE = -7
+} stil_status_t;
+
+STIL_API int stil_version(void);
+STIL_API const char* stil_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), STIL_E_ARCH otherwise. */
+STIL_API int stil_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1 — DCC cross-modal InfoNCE.  Replaces CLIPLoss.forward, utils/clip_loss.py:27-40.
+ *   a_loc, b_loc : this rank's rows [m, dim]     (out0 / out1 of the reference)
+ *   a_all, b_all : all ranks' rows  [n, dim]     (== a_loc / b_loc and n == m when not distributed)
+ *   row_offset   : global index of local row 0   (0 when not distributed)
+ * fwd writes lse_row[m] (log-sum-exp over all n columns of the local rows of a·bT/T), lse_col[m]
+ * (same for the local rows of b·aT/T, i.e. the local COLUMNS of the logits) and
+ *   loss_sum[0] = sum_local (lambda0*(lse_row_i - d_i) + (1-lambda0)*(lse_col_i - d_i)) / n
+ * which IS the reference loss when n == m, and sums to it over ranks otherwise.
+ * `logits` (optional, may be NULL) receives the local rows of the [n-column] logits in fp32
+ * (the reference returns them for validation top-k, STiLModel.py:437-438).
+ * bwd needs the LSE vectors of ALL n rows/columns (all-gathered by the caller when distributed),
+ * a device scalar grad_loss (NULL = 1.0) and writes d_a, d_b [m, dim] in `grad_dtype`.
+ * Returns STIL_E_ARG if lambda0 is outside [0,1] (reference raises ValueError, clip_loss.py:22-23). */
+STIL_API int64_t stil_infonce_workspace_bytes(int64_t m, int64_t n, int64_t dim, int dtype);
+STIL_API int stil_infonce_fwd(const void* a_loc, const void* b_loc, const void* a_all, const void* b_all, int dtype,
+                     int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset, float temperature,
+                     float lambda0, float* loss_sum, float* lse_row, float* lse_col, float* logits,
+                     int64_t ld_logits, void* workspace, int64_t workspace_bytes, void* stream);
+STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* a_all, const void* b_all, int dtype,
+                     int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset, float temperature,
+                     float lambda0, const float* lse_row_all, const float* lse_col_all, const float* grad_loss,
+                     void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3 (first half) — raw prototype similarities out[r,k] = feat[r,:]·prototypes[k,:] in fp32.
+ * Replaces `feat_m_ue @ prototypes.t()`, STiLModel.py:293 (also :350).  prototypes is fp32 [k, dim]. */
+STIL_API int64_t stil_proto_logits_workspace_bytes(int64_t rows, int64_t k, int64_t dim, int dtype);
+STIL_API int stil_proto_logits(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const float* prototypes,
+                      int64_t k, float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2 + a3 — CGPL consensus pseudo-labels and PGLS smoothing/threshold for the unlabelled rows.
+ * Replaces the inline block STiLModel.py:262-298 (sharpen_predictions :195-196 with T=1).
+ *   y_m,y_i,y_t      teacher logits [rows, k] (logit_dtype, leading dim ld_y)
+ *   teacher_logits   fp32 [rows, k] from stil_proto_logits (divided by `temperature` here, :294)
+ * Outputs (any may be NULL except pseudo_label/max_idx/mask1):
+ *   pseudo_label [rows,k] f32 (:295), prediction [rows,k] f32 (:296), max_prob f32, max_idx i64 (:297),
+ *   mask1 u8 (:298), case1/case2_i/case2_t/case3 u8 (:264-267), top1 i64 [3, rows] (:263, order m,i,t),
+ *   cls i32 [rows] (= max_idx) and conf u8 (= mask1 when `past_start_epoch`, else 0 — the gate of
+ *   :317-320 zeroes `prediction`, whose max is then 0 with argmax 0) for the prototype kernels.
+ * Index/mask outputs follow torch semantics: first index among equal maxima, >= on fp32. */
+STIL_API int stil_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
+                   const float* teacher_logits, int64_t ld_t, int64_t rows, int64_t k, float temperature,
+                   float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
+                   float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
+                   uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
+                   int32_t* cls, uint8_t* conf, void* stream);
+
+/* Row max / argmax / threshold of a dense soft label: (max_prob, max_id) = label.max(1); conf = max>=th.
+ * Replaces utils/prototype_loss.py:31-32 and STiLModel.py:204-205. */
+STIL_API int stil_label_argmax(const float* label, int64_t ld, int64_t rows, int64_t k, float threshold, int32_t* cls,
+                      uint8_t* conf, float* max_prob, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4 — PGLS prototype loss.  Replaces PrototypeLoss.forward, utils/prototype_loss.py:24-40, with the
+ * label already reduced to (cls, conf) by stil_label_argmax / stil_cgpl_pgls.
+ *   loss[0] = -(1/rows) * sum_i conf_i * log(softmax(feat·protoT/T)[i, cls_i] + 1e-7)
+ * fwd also writes lse[rows] and the backward coefficient w[rows] = conf_i/rows * p/(p+1e-7). */
+STIL_API int64_t stil_proto_ce_workspace_bytes(int64_t rows, int64_t k, int64_t dim, int dtype);
+STIL_API int stil_proto_ce_fwd(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const float* prototypes,
+                      int64_t k, const int32_t* cls, const uint8_t* conf, float temperature, float* loss,
+                      float* lse, float* w, void* workspace, int64_t workspace_bytes, void* stream);
+STIL_API int stil_proto_ce_bwd(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const float* prototypes,
+                      int64_t k, const int32_t* cls, const float* lse, const float* w, float temperature,
+                      const float* grad_loss, void* d_feat, int grad_dtype, int64_t ld_grad, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5 — prototype bank partial sums.  Replaces cal_prototypes_separate (STiLModel.py:216-226, which
+ * calls cal_prototypes :199-214 on rows [:b_l] and [b_l:]) and, when psum/pcount are given, the
+ * accumulate of :380-381.  class_sum [k, dim] f32, class_count [k] f32 (fractional: labelled rows
+ * weigh 1/repeat_ratio).  Pass b_l = 0, repeat_ratio = 1 for plain cal_prototypes.  Deterministic
+ * (rows are added in index order; no atomics). */
+STIL_API int stil_proto_accumulate(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const int32_t* cls,
+                          const uint8_t* conf, int64_t b_l, float repeat_ratio, int64_t k, float* class_sum,
+                          float* class_count, float* psum, float* pcount, void* stream);
+/* prototypes_sum += class_sum; prototypes_count_sum += class_count  (STiLModel.py:380-381), for the
+ * distributed path where the partials are all-reduced between the two calls (:377-379). */
+STIL_API int stil_proto_add(const float* class_sum, const float* class_count, int64_t k, int64_t dim, float* psum,
+                   float* pcount, void* stream);
+/* Epoch end: prototypes = psum / pcount; psum = pcount = 0; *empty_classes = #{k: pcount_k < 1}
+ * (device int; the reference asserts it is 0 on the host, STiLModel.py:408-415). */
+STIL_API int stil_proto_finalize(float* prototypes, float* psum, float* pcount, int64_t k, int64_t dim,
+                        int32_t* empty_classes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * f-1 — masked soft-target CE of the three student heads on the unlabelled rows, forward and
+ * gradient in one pass.  Replaces STiLModel.py:301-303.
+ *   losses[3]  = (loss_m_u, loss_i_u, loss_t_u), each a mean over `rows`
+ *   d_y_*      = d(loss_*)/d(y_*) * grad_scale   (NULL to skip), leading dim ld_g, fp32 */
+STIL_API int64_t stil_masked_softce_workspace_bytes(int64_t rows);
+STIL_API int stil_masked_softce(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
+                       const float* pseudo_label, int64_t ld_pl, const uint8_t* mask1, const uint8_t* case1,
+                       const uint8_t* case2_i, const uint8_t* case2_t, const uint8_t* case3,
+                       const uint8_t* mask_random, int64_t rows, int64_t k, float* losses, float* d_y_m,
+                       float* d_y_i, float* d_y_t, int64_t ld_g, float grad_scale, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole per-batch head in one call (what STiLModel.training_step lines 262-303, 317-322, 339,
+ * 374-381 do), with launches batched across the sub-problems.  Used by bench.py and STiLHead.step. */
+typedef struct stil_head_step_args {
+    /* sizes */
+    int64_t batch, b_l, k, dim;
+    int embed_dtype, logit_dtype, grad_dtype;
+    /* hyper-parameters (configs/config_dvm_STiL.yaml) */
+    float temperature, lambda0, th1, rate_pseudo, repeat_ratio;
+    int past_start_epoch;
+    /* inputs */
+    const void *feat_i, *feat_t, *feat_m, *feat_m_e; /* [batch, dim], ld = dim */
+    const void *y_m_ue, *y_i_ue, *y_t_ue;             /* teacher logits [b_u, k] */
+    const void *y_m, *y_i, *y_t;                      /* student logits [batch, k] (may be NULL: skip f-1) */
+    const int64_t* y_l;                               /* [b_l] */
+    const float* prototypes;                          /* [k, dim] */
+    const uint8_t* mask_random;                       /* [b_u] */
+    /* outputs */
+    float* losses;                                    /* [5]: itc, pt, m_u, i_u, t_u */
+    void *d_feat_i, *d_feat_t, *d_feat_m;             /* [batch, dim] grad_dtype */
+    float *d_y_m, *d_y_i, *d_y_t;                     /* [batch, k] f32 (rows < b_l are zero) */
+    float* pseudo_label;                              /* [b_u, k] */
+    float* max_prob; int64_t* max_idx; uint8_t *mask1, *case1, *case2_i, *case2_t, *case3;
+    float *class_sum, *class_count;                   /* [k, dim], [k] */
+    float *prototypes_sum, *prototypes_count_sum;     /* accumulated in place when non-NULL */
+    float rate_uce_scale;                             /* grad_scale of the f-1 gradients */
+    void* workspace; int64_t workspace_bytes; void* stream;
+} stil_head_step_args;
+STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int64_t k, int64_t dim, int embed_dtype);
+STIL_API int stil_head_step(const stil_head_step_args* args);
+/* number of kernel launches one stil_head_step enqueues for these args (for bench.py's gpu_launches) */
+STIL_API int stil_head_step_launches(const stil_head_step_args* args);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STIL_HEAD_H_ */

@@ -1,0 +1,23 @@
+"""stil_tta_b200 — B200-native (sm_100a) implementation of the STiL per-batch semi-supervised head.
+
+Drop-ins for the reference's hot path (kgutjahr/STiL-TTA): ``CLIPLoss`` (utils/clip_loss.py),
+``PrototypeLoss`` (utils/prototype_loss.py), ``cal_prototypes`` / ``cal_prototypes_separate`` and the
+inline CGPL/PGLS block of ``models/Disentangle/STiLModel.py`` (``cgpl_pgls``), over a C-ABI CUDA
+extension (include/stil_head.h).  Importing this package does not need a GPU; calling an op does,
+and fails loudly when ``_C/libstil_head.so`` is missing (no CPU fallback).
+"""
+from .synth import HeadConfig, cardiac_config, dvm_config, make_batch  # noqa: F401
+
+_LAZY = {
+    "CLIPLoss": "losses", "PrototypeLoss": "losses", "masked_soft_ce": "losses", "label_argmax": "losses",
+    "cgpl_pgls": "pseudo_label", "prototype_logits": "pseudo_label", "PseudoLabels": "pseudo_label",
+    "cal_prototypes": "prototypes", "cal_prototypes_separate": "prototypes", "PrototypeBank": "prototypes",
+    "STiLHead": "head", "GlobalBatch": "distributed", "all_reduce_prototype_partials": "distributed",
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+        return getattr(importlib.import_module(f".{_LAZY[name]}", __name__), name)
+    raise AttributeError(name)

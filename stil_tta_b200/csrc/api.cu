@@ -1,0 +1,863 @@
+// extern "C" entry points of libstil_head.so (see include/stil_head.h).  Host-side composition only:
+// plans the caller-provided workspace, builds TMA descriptors and job tables, enqueues kernels.
+#include <cstdarg>
+#include <cstring>
+
+#include "internal.h"
+
+namespace stil {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+namespace {
+
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+int check_embed(const void* p, int dtype, int64_t rows, int64_t dim, int64_t ld, const char* what) {
+    STIL_REQUIRE(dtype == STIL_F32 || dtype == STIL_BF16, STIL_E_DTYPE, "%s: dtype %d not in {f32, bf16}", what, dtype);
+    STIL_REQUIRE(rows >= 0 && rows < (1LL << 30) && dim >= 1 && dim <= 16384, STIL_E_SHAPE,
+                 "%s: unsupported shape [%lld, %lld]", what, (long long)rows, (long long)dim);
+    STIL_REQUIRE(p != nullptr || rows == 0, STIL_E_ARG, "%s: null pointer", what);
+    const int per16 = dtype == STIL_BF16 ? 8 : 4;
+    STIL_REQUIRE(dim % per16 == 0 && ld % per16 == 0 && ld >= dim, STIL_E_ALIGN,
+                 "%s: dim %lld / ld %lld must be multiples of %d elements (16-byte rows)", what, (long long)dim,
+                 (long long)ld, per16);
+    STIL_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, STIL_E_ALIGN, "%s: pointer not 16-byte aligned", what);
+    return STIL_OK;
+}
+
+// A matrix presented to the tensor cores: bf16 inputs are used in place (1 segment), fp32 inputs are
+// carried as `nseg` bf16 segments written by the prep kernel.
+struct Operand {
+    const __nv_bfloat16* base;  // [rows, nseg, dim]
+    int nseg;
+    int64_t row_stride, seg_stride;
+};
+
+inline int64_t pad8(int64_t n) { return round_up(n, 8); }
+
+// segment pairs (x_seg, y_seg) for an (nx, ny)-segment product, most significant first
+int seg_pairs(int nx, int ny, int* xs, int* ys) {
+    int n = 0;
+    auto add = [&](int a, int b) { xs[n] = a; ys[n] = b; ++n; };
+    add(0, 0);
+    if (ny > 1) add(0, 1);
+    if (nx > 1) add(1, 0);
+    if (nx == 1 && ny > 2) add(0, 2);
+    if (ny == 1 && nx > 2) add(2, 0);
+    return n;
+}
+
+int fill_gemm_common(GemmJob& J, const Operand& X, int64_t xrow0, int64_t M, const Operand& Y, int64_t N, int64_t D) {
+    std::memset(&J, 0, sizeof(J));
+    int rc = make_operand_map(&J.tmx, X.base + xrow0 * X.row_stride, D, M, X.nseg, X.row_stride, X.seg_stride);
+    if (rc) return rc;
+    rc = make_operand_map(&J.tmy, Y.base, D, N, Y.nseg, Y.row_stride, Y.seg_stride);
+    if (rc) return rc;
+    J.M = (int)M; J.N = (int)N; J.D = (int)D;
+    J.npair = seg_pairs(X.nseg, Y.nseg, J.xseg, J.yseg);
+    J.alpha = 1.f;
+    return STIL_OK;
+}
+
+// ------------------------------------------------------------------------------------------ InfoNCE plan
+struct InfoncePlan {
+    int nseg;
+    __nv_bfloat16 *a_op, *b_op, *a_t, *b_t;   // [n, nseg, dim], [dim, nseg, ldt]
+    int64_t ldt;
+    float *ra, *rb;                             // inverse norms [n]
+    float *pmax[2], *psum[2];                   // [tiles_n, m]
+    float* block_partials;
+    unsigned int* ticket;
+    __nv_bfloat16* gop[2];                      // [m, 2, ldg]
+    int64_t ldg;
+    float* g[2];                                // [m, dim]
+    int64_t bytes;
+};
+
+InfoncePlan plan_infonce(void* ws, int64_t ws_bytes, int64_t m, int64_t n, int64_t dim, int dtype, bool bwd) {
+    InfoncePlan P;
+    Workspace W(ws, ws_bytes);
+    P.nseg = dtype == STIL_BF16 ? 1 : 2;
+    P.ldt = pad8(n);
+    P.ldg = pad8(n);
+    P.ticket = W.take<unsigned int>(64);
+    P.ra = W.take<float>(n);
+    P.rb = W.take<float>(n);
+    P.a_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(n * P.nseg * dim);
+    P.b_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(n * P.nseg * dim);
+    const int64_t tiles_n = ceil_div(n, kTileN);
+    for (int s = 0; s < 2; ++s) {
+        P.pmax[s] = W.take<float>(tiles_n * m);
+        P.psum[s] = W.take<float>(tiles_n * m);
+    }
+    P.block_partials = W.take<float>(2 * finish_blocks((int)(3 * m)) + 8);  // 3m rows: the fused step adds the prototype rows
+    // backward-only regions (the forward never touches them, the query always counts them)
+    P.a_t = W.take<__nv_bfloat16>(dim * P.nseg * P.ldt);
+    P.b_t = W.take<__nv_bfloat16>(dim * P.nseg * P.ldt);
+    for (int s = 0; s < 2; ++s) {
+        P.gop[s] = W.take<__nv_bfloat16>(m * 2 * P.ldg);
+        P.g[s] = W.take<float>(m * dim);
+    }
+    (void)bwd;
+    P.bytes = W.off;
+    return P;
+}
+
+Operand rowmajor_operand(const void* x, int dtype, int64_t dim, int64_t ld, const __nv_bfloat16* op, int nseg) {
+    Operand O;
+    if (dtype == STIL_BF16) {
+        O.base = static_cast<const __nv_bfloat16*>(x);
+        O.nseg = 1;
+        O.row_stride = ld;
+        O.seg_stride = dim;  // unused (single segment) but must be 16-byte granular
+    } else {
+        O.base = op;
+        O.nseg = nseg;
+        O.row_stride = (int64_t)nseg * dim;
+        O.seg_stride = dim;
+    }
+    return O;
+}
+Operand transposed_operand(const __nv_bfloat16* op_t, int nseg, int64_t ldt) {
+    Operand O;
+    O.base = op_t;
+    O.nseg = nseg;
+    O.row_stride = (int64_t)nseg * ldt;
+    O.seg_stride = ldt;
+    return O;
+}
+Operand grad_operand(const __nv_bfloat16* gop, int64_t ldg) {
+    Operand O;
+    O.base = gop;
+    O.nseg = 2;
+    O.row_stride = 2 * ldg;
+    O.seg_stride = ldg;
+    return O;
+}
+
+// ------------------------------------------------------------------------------------------ proto plan
+struct ProtoPlan {
+    int feat_nseg, proto_nseg;
+    __nv_bfloat16 *feat_op, *proto_op, *proto_t;
+    int64_t ldt;       // pad8(k)
+    float *pmax, *psum;
+    float* block_partials;
+    unsigned int* ticket;
+    __nv_bfloat16* gop;
+    int64_t ldg;
+    float* g;
+    int64_t bytes;
+};
+
+ProtoPlan plan_proto(void* ws, int64_t ws_bytes, int64_t rows, int64_t k, int64_t dim, int dtype) {
+    ProtoPlan P;
+    Workspace W(ws, ws_bytes);
+    P.feat_nseg = dtype == STIL_BF16 ? 1 : 2;
+    P.proto_nseg = dtype == STIL_BF16 ? 3 : 2;
+    P.ldt = pad8(k);
+    P.ldg = pad8(k);
+    P.ticket = W.take<unsigned int>(64);
+    P.feat_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(rows * P.feat_nseg * dim);
+    P.proto_op = W.take<__nv_bfloat16>(k * P.proto_nseg * dim);
+    P.proto_t = W.take<__nv_bfloat16>(dim * 2 * P.ldt);
+    const int64_t tiles_n = ceil_div(k, kTileN);
+    P.pmax = W.take<float>(tiles_n * rows);
+    P.psum = W.take<float>(tiles_n * rows);
+    P.block_partials = W.take<float>(2 * finish_blocks((int)rows) + 8);
+    P.gop = W.take<__nv_bfloat16>(rows * 2 * P.ldg);
+    P.g = W.take<float>(rows * dim);
+    P.bytes = W.off;
+    return P;
+}
+
+PrepJob prep_job(const void* x, int dtype, int64_t rows, int64_t dim, int64_t ld, int nseg, __nv_bfloat16* op,
+                 __nv_bfloat16* op_t, int64_t ld_t, int nseg_t, float* inv_norm) {
+    PrepJob j;
+    std::memset(&j, 0, sizeof(j));
+    j.x = x; j.dtype = dtype; j.rows = (int)rows; j.dim = (int)dim; j.ld = ld;
+    j.nseg = nseg; j.op = op; j.op_t = op_t; j.ld_t = ld_t; j.nseg_t = nseg_t; j.inv_norm = inv_norm;
+    return j;
+}
+
+int infonce_args_check(const void* a_all, const void* b_all, int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld,
+                       int64_t row_offset, float temperature, float lambda0) {
+    int rc = check_embed(a_all, dtype, n, dim, ld, "infonce a");
+    if (rc) return rc;
+    rc = check_embed(b_all, dtype, n, dim, ld, "infonce b");
+    if (rc) return rc;
+    STIL_REQUIRE(lambda0 >= 0.f && lambda0 <= 1.f, STIL_E_ARG, "lambda_0 must be a float between 0 and 1.");
+    STIL_REQUIRE(temperature > 0.f, STIL_E_ARG, "temperature must be positive");
+    STIL_REQUIRE(m >= 0 && row_offset >= 0 && row_offset + m <= n, STIL_E_SHAPE,
+                 "local rows [%lld, %lld) outside the %lld global rows", (long long)row_offset,
+                 (long long)(row_offset + m), (long long)n);
+    return STIL_OK;
+}
+
+// jobs shared by the op-level entry points and stil_head_step --------------------------------------
+int infonce_stats_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const Operand& B, int64_t m, int64_t n,
+                       int64_t dim, int64_t off, float inv_t, float* logits, int64_t ld_logits) {
+    for (int s = 0; s < 2; ++s) {
+        const Operand& X = s == 0 ? A : B;
+        const Operand& Y = s == 0 ? B : A;
+        int rc = fill_gemm_common(J2[s], X, off, m, Y, n, dim);
+        if (rc) return rc;
+        J2[s].mode = GEMM_STATS;
+        J2[s].alpha = inv_t;
+        J2[s].sx = (s == 0 ? P.ra : P.rb) + off;
+        J2[s].sy = s == 0 ? P.rb : P.ra;
+        J2[s].part_max = P.pmax[s];
+        J2[s].part_sum = P.psum[s];
+        if (s == 0 && logits) {
+            J2[s].out = logits;
+            J2[s].ld_out = ld_logits;
+        }
+    }
+    return STIL_OK;
+}
+
+void infonce_finish_jobs(FinishJob* F2, const InfoncePlan& P, const void* a_all, const void* b_all, int dtype,
+                         int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t off, float inv_t, float lambda0,
+                         float* lse_row, float* lse_col, int loss_slot) {
+    const int esz = dtype == STIL_BF16 ? 2 : 4;
+    for (int s = 0; s < 2; ++s) {
+        FinishJob& F = F2[s];
+        std::memset(&F, 0, sizeof(F));
+        F.kind = 0;
+        F.M = (int)m;
+        F.tiles_n = (int)ceil_div(n, kTileN);
+        F.part_max = P.pmax[s];
+        F.part_sum = P.psum[s];
+        F.lse = s == 0 ? lse_row : lse_col;
+        const char* xa = static_cast<const char*>(s == 0 ? a_all : b_all);
+        F.x = xa + off * ld * esz;
+        F.x_dtype = dtype; F.ldx = ld;
+        F.y = s == 0 ? b_all : a_all;
+        F.y_dtype = dtype; F.ldy = ld;
+        F.y_offset = (int)off;
+        F.dim = (int)dim;
+        F.sx = (s == 0 ? P.ra : P.rb) + off;
+        F.sy = s == 0 ? P.rb : P.ra;
+        F.alpha = inv_t;
+        F.coef = (s == 0 ? lambda0 : 1.f - lambda0) / (float)n;
+        F.loss_slot = loss_slot;
+    }
+}
+
+int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const Operand& B, int64_t m, int64_t n,
+                      int64_t dim, int64_t off, float inv_t, float lambda0, const float* lse_row_all,
+                      const float* lse_col_all, const float* grad_loss) {
+    for (int s = 0; s < 2; ++s) {
+        const Operand& X = s == 0 ? A : B;
+        const Operand& Y = s == 0 ? B : A;
+        int rc = fill_gemm_common(J2[s], X, off, m, Y, n, dim);
+        if (rc) return rc;
+        GemmJob& J = J2[s];
+        J.mode = GEMM_GRAD;
+        J.alpha = inv_t;
+        J.sx = (s == 0 ? P.ra : P.rb) + off;
+        J.sy = s == 0 ? P.rb : P.ra;
+        J.lse_x = (s == 0 ? lse_row_all : lse_col_all) + off;
+        J.lse_y = s == 0 ? lse_col_all : lse_row_all;
+        J.u_scalar = (s == 0 ? lambda0 : 1.f - lambda0) / (float)n;
+        J.v_scalar = (s == 0 ? 1.f - lambda0 : lambda0) / (float)n;
+        J.d_scalar = 1.f / (float)n;
+        J.tgt_offset = (int)off;
+        J.gscale = grad_loss;
+        J.gop = P.gop[s];
+        J.ld_g = P.ldg;
+    }
+    return STIL_OK;
+}
+
+int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, int64_t m, int64_t n, int64_t dim) {
+    for (int s = 0; s < 2; ++s) {
+        // d(x̂_i) = sum_j G'_ij y_j : X = G' [m, (hi,lo), n], Y = yᵀ [dim, nseg, n]
+        const Operand X = grad_operand(P.gop[s], P.ldg);
+        const Operand Y = transposed_operand(s == 0 ? P.b_t : P.a_t, P.nseg, P.ldt);
+        int rc = fill_gemm_common(J2[s], X, 0, m, Y, dim, n);
+        if (rc) return rc;
+        J2[s].mode = GEMM_STORE;
+        J2[s].out = P.g[s];
+        J2[s].ld_out = dim;
+    }
+    return STIL_OK;
+}
+
+}  // namespace
+}  // namespace stil
+
+using namespace stil;
+
+extern "C" {
+
+STIL_API int stil_version(void) { return STIL_VERSION; }
+STIL_API const char* stil_last_error(void) { return stil::last_error(); }
+
+STIL_API int stil_check_device(void) {
+    int dev = 0;
+    STIL_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    STIL_CUDA(cudaGetDeviceProperties(&p, dev));
+    STIL_REQUIRE(p.major == 10, STIL_E_ARCH, "device %d is sm_%d%d; libstil_head is built for sm_100a only", dev, p.major,
+                 p.minor);
+    return STIL_OK;
+}
+
+// =============================================================================================== a1
+STIL_API int64_t stil_infonce_workspace_bytes(int64_t m, int64_t n, int64_t dim, int dtype) {
+    return plan_infonce(nullptr, 0, m, n, dim, dtype, true).bytes;
+}
+
+STIL_API int stil_infonce_fwd(const void* a_loc, const void* b_loc, const void* a_all, const void* b_all, int dtype,
+                     int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset, float temperature,
+                     float lambda0, float* loss_sum, float* lse_row, float* lse_col, float* logits,
+                     int64_t ld_logits, void* workspace, int64_t workspace_bytes, void* stream) {
+    (void)a_loc; (void)b_loc;
+    int rc = infonce_args_check(a_all, b_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0);
+    if (rc) return rc;
+    STIL_REQUIRE(loss_sum && lse_row && lse_col, STIL_E_ARG, "infonce_fwd: null output");
+    InfoncePlan P = plan_infonce(workspace, workspace_bytes, m, n, dim, dtype, false);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "infonce workspace too small: need %lld bytes",
+                 (long long)P.bytes);
+    const float inv_t = 1.0f / temperature;
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    PL.zero_words = P.ticket; PL.n_zero = 8;
+    prep_add(PL, prep_job(a_all, dtype, n, dim, ld, P.nseg, P.a_op, nullptr, 0, 0, P.ra));
+    prep_add(PL, prep_job(b_all, dtype, n, dim, ld, P.nseg, P.b_op, nullptr, 0, 0, P.rb));
+    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    if (m == 0) {
+        STIL_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(float), S(stream)));
+        return STIL_OK;
+    }
+    const Operand A = rowmajor_operand(a_all, dtype, dim, ld, P.a_op, P.nseg);
+    const Operand B = rowmajor_operand(b_all, dtype, dim, ld, P.b_op, P.nseg);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = infonce_stats_jobs(GL.job, P, A, B, m, n, dim, row_offset, inv_t, logits, ld_logits))) return rc;
+    GL.njobs = 2;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    FinishLaunch FL;
+    std::memset(&FL, 0, sizeof(FL));
+    infonce_finish_jobs(FL.job, P, a_all, b_all, dtype, m, n, dim, ld, row_offset, inv_t, lambda0, lse_row, lse_col, 0);
+    FL.job[0].row_begin = 0;
+    FL.job[1].row_begin = (int)m;
+    FL.njobs = 2;
+    FL.total_rows = (int)(2 * m);
+    FL.block_partials = P.block_partials;
+    FL.ticket = P.ticket;
+    FL.out_loss = loss_sum;  // slot 0 only
+    return launch_finish(FL, S(stream));
+}
+
+STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* a_all, const void* b_all, int dtype,
+                     int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset, float temperature,
+                     float lambda0, const float* lse_row_all, const float* lse_col_all, const float* grad_loss,
+                     void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    (void)a_loc; (void)b_loc;
+    int rc = infonce_args_check(a_all, b_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0);
+    if (rc) return rc;
+    STIL_REQUIRE(lse_row_all && lse_col_all && d_a && d_b, STIL_E_ARG, "infonce_bwd: null pointer");
+    STIL_REQUIRE(grad_dtype == STIL_F32 || grad_dtype == STIL_BF16, STIL_E_DTYPE, "bad grad dtype");
+    InfoncePlan P = plan_infonce(workspace, workspace_bytes, m, n, dim, dtype, true);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "infonce workspace too small: need %lld bytes",
+                 (long long)P.bytes);
+    if (m == 0) return STIL_OK;
+    const float inv_t = 1.0f / temperature;
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    prep_add(PL, prep_job(a_all, dtype, n, dim, ld, P.nseg, P.a_op, P.a_t, P.ldt, P.nseg, P.ra));
+    prep_add(PL, prep_job(b_all, dtype, n, dim, ld, P.nseg, P.b_op, P.b_t, P.ldt, P.nseg, P.rb));
+    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    const Operand A = rowmajor_operand(a_all, dtype, dim, ld, P.a_op, P.nseg);
+    const Operand B = rowmajor_operand(b_all, dtype, dim, ld, P.b_op, P.nseg);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = infonce_grad_jobs(GL.job, P, A, B, m, n, dim, row_offset, inv_t, lambda0, lse_row_all, lse_col_all,
+                                grad_loss)))
+        return rc;
+    GL.njobs = 2;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = infonce_store_jobs(GL.job, P, m, n, dim))) return rc;
+    GL.njobs = 2;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    GradFinishLaunch GF;
+    std::memset(&GF, 0, sizeof(GF));
+    const int esz = dtype == STIL_BF16 ? 2 : 4;
+    for (int s = 0; s < 2; ++s) {
+        GradFinishJob& j = GF.job[s];
+        j.g = P.g[s];
+        j.x = static_cast<const char*>(s == 0 ? a_all : b_all) + row_offset * ld * esz;
+        j.x_dtype = dtype; j.ldx = ld;
+        j.sx = (s == 0 ? P.ra : P.rb) + row_offset;
+        j.dx = s == 0 ? d_a : d_b;
+        j.dx_dtype = grad_dtype; j.ld_dx = ld_grad;
+        j.rows = (int)m; j.dim = (int)dim;
+        j.row_begin = (int)(s * m);
+    }
+    GF.njobs = 2;
+    GF.total_rows = (int)(2 * m);
+    return launch_grad_finish(GF, S(stream));
+}
+
+// =============================================================================================== a3 logits
+STIL_API int64_t stil_proto_logits_workspace_bytes(int64_t rows, int64_t k, int64_t dim, int dtype) {
+    return plan_proto(nullptr, 0, rows, k, dim, dtype).bytes;
+}
+
+STIL_API int stil_proto_logits(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const float* prototypes,
+                      int64_t k, float* out, int64_t ld_out, void* workspace, int64_t workspace_bytes,
+                      void* stream) {
+    int rc = check_embed(feat, dtype, rows, dim, ld, "proto_logits feat");
+    if (rc) return rc;
+    if ((rc = check_embed(prototypes, STIL_F32, k, dim, dim, "prototypes"))) return rc;
+    STIL_REQUIRE(out && ld_out >= k, STIL_E_ARG, "proto_logits: bad output");
+    ProtoPlan P = plan_proto(workspace, workspace_bytes, rows, k, dim, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "proto workspace too small: need %lld bytes",
+                 (long long)P.bytes);
+    if (rows == 0 || k == 0) return STIL_OK;
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    if (dtype != STIL_BF16) prep_add(PL, prep_job(feat, dtype, rows, dim, ld, P.feat_nseg, P.feat_op, nullptr, 0, 0, nullptr));
+    prep_add(PL, prep_job(prototypes, STIL_F32, k, dim, dim, P.proto_nseg, P.proto_op, nullptr, 0, 0, nullptr));
+    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    const Operand X = rowmajor_operand(feat, dtype, dim, ld, P.feat_op, P.feat_nseg);
+    const Operand Y = rowmajor_operand(nullptr, STIL_F32, dim, dim, P.proto_op, P.proto_nseg);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = fill_gemm_common(GL.job[0], X, 0, rows, Y, k, dim))) return rc;
+    GL.job[0].mode = GEMM_STORE;
+    GL.job[0].out = out;
+    GL.job[0].ld_out = ld_out;
+    GL.njobs = 1;
+    gemm_job_tiles(GL);
+    return launch_gemm(GL, S(stream));
+}
+
+// =============================================================================================== a2+a3
+STIL_API int stil_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
+                   const float* teacher_logits, int64_t ld_t, int64_t rows, int64_t k, float temperature,
+                   float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
+                   float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
+                   uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
+                   int32_t* cls, uint8_t* conf, void* stream) {
+    STIL_REQUIRE(logit_dtype == STIL_F32 || logit_dtype == STIL_BF16, STIL_E_DTYPE, "cgpl_pgls: bad logit dtype");
+    STIL_REQUIRE(rows == 0 || (y_m && y_i && y_t && teacher_logits && pseudo_label && max_idx && mask1), STIL_E_ARG,
+                 "cgpl_pgls: null pointer");
+    STIL_REQUIRE(ld_y >= k && ld_t >= k && ld_pl >= k && (!prediction || ld_pred >= k), STIL_E_SHAPE,
+                 "cgpl_pgls: leading dimension smaller than k");
+    return launch_cgpl_pgls(y_m, y_i, y_t, logit_dtype, ld_y, teacher_logits, ld_t, rows, k, temperature, rate_pseudo,
+                            th1, past_start_epoch, pseudo_label, ld_pl, prediction, ld_pred, max_prob, max_idx, mask1,
+                            case1, case2_i, case2_t, case3, top1, cls, conf, S(stream));
+}
+
+STIL_API int stil_label_argmax(const float* label, int64_t ld, int64_t rows, int64_t k, float threshold, int32_t* cls,
+                      uint8_t* conf, float* max_prob, void* stream) {
+    STIL_REQUIRE(rows == 0 || (label && cls && conf), STIL_E_ARG, "label_argmax: null pointer");
+    STIL_REQUIRE(ld >= k, STIL_E_SHAPE, "label_argmax: ld < k");
+    return launch_label_argmax(label, ld, rows, k, threshold, cls, conf, max_prob, S(stream));
+}
+
+// =============================================================================================== a4
+STIL_API int64_t stil_proto_ce_workspace_bytes(int64_t rows, int64_t k, int64_t dim, int dtype) {
+    return plan_proto(nullptr, 0, rows, k, dim, dtype).bytes;
+}
+
+namespace {
+int proto_stats_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                    int64_t k, float inv_t) {
+    const Operand X = rowmajor_operand(feat, dtype, dim, ld, P.feat_op, P.feat_nseg);
+    const Operand Y = rowmajor_operand(nullptr, STIL_F32, dim, dim, P.proto_op, P.proto_nseg);
+    int rc = fill_gemm_common(J, X, 0, rows, Y, k, dim);
+    if (rc) return rc;
+    J.mode = GEMM_STATS;
+    J.alpha = inv_t;
+    J.part_max = P.pmax;
+    J.part_sum = P.psum;
+    return STIL_OK;
+}
+void proto_finish_job(FinishJob& F, const ProtoPlan& P, const void* feat, int dtype, int64_t rows, int64_t dim,
+                      int64_t ld, const float* prototypes, int64_t k, const int32_t* cls, const uint8_t* conf,
+                      float inv_t, float* lse, float* w, int loss_slot) {
+    std::memset(&F, 0, sizeof(F));
+    F.kind = 1;
+    F.M = (int)rows;
+    F.tiles_n = (int)ceil_div(k, kTileN);
+    F.part_max = P.pmax; F.part_sum = P.psum;
+    F.lse = lse;
+    F.x = feat; F.x_dtype = dtype; F.ldx = ld;
+    F.y = prototypes; F.y_dtype = STIL_F32; F.ldy = dim;
+    F.dim = (int)dim;
+    F.alpha = inv_t;
+    F.coef = 1.f / (float)rows;   // .mean() over ALL rows (utils/prototype_loss.py:39)
+    F.cls = cls; F.conf = conf; F.w = w;
+    F.loss_slot = loss_slot;
+}
+int proto_grad_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                   int64_t k, float inv_t, const int32_t* cls, const float* lse, const float* w,
+                   const float* grad_loss) {
+    const Operand X = rowmajor_operand(feat, dtype, dim, ld, P.feat_op, P.feat_nseg);
+    const Operand Y = rowmajor_operand(nullptr, STIL_F32, dim, dim, P.proto_op, P.proto_nseg);
+    int rc = fill_gemm_common(J, X, 0, rows, Y, k, dim);
+    if (rc) return rc;
+    J.mode = GEMM_GRAD;
+    J.alpha = inv_t;
+    J.lse_x = lse;
+    J.u_vec = w;
+    J.tgt_vec = cls;
+    J.gscale = grad_loss;
+    J.gop = P.gop;
+    J.ld_g = P.ldg;
+    return STIL_OK;
+}
+int proto_store_job(GemmJob& J, const ProtoPlan& P, int64_t rows, int64_t dim, int64_t k, float* out, int64_t ld_out) {
+    const Operand X = grad_operand(P.gop, P.ldg);
+    const Operand Y = transposed_operand(P.proto_t, 2, P.ldt);
+    int rc = fill_gemm_common(J, X, 0, rows, Y, dim, k);
+    if (rc) return rc;
+    J.mode = GEMM_STORE;
+    J.out = out;
+    J.ld_out = ld_out;
+    return STIL_OK;
+}
+}  // namespace
+
+STIL_API int stil_proto_ce_fwd(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const float* prototypes,
+                      int64_t k, const int32_t* cls, const uint8_t* conf, float temperature, float* loss,
+                      float* lse, float* w, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_embed(feat, dtype, rows, dim, ld, "proto_ce feat");
+    if (rc) return rc;
+    if ((rc = check_embed(prototypes, STIL_F32, k, dim, dim, "prototypes"))) return rc;
+    STIL_REQUIRE(loss && (rows == 0 || (cls && conf && lse && w)), STIL_E_ARG, "proto_ce_fwd: null pointer");
+    STIL_REQUIRE(temperature > 0.f && k >= 1, STIL_E_ARG, "proto_ce_fwd: bad temperature / k");
+    ProtoPlan P = plan_proto(workspace, workspace_bytes, rows, k, dim, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "proto workspace too small: need %lld bytes",
+                 (long long)P.bytes);
+    if (rows == 0) {
+        STIL_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), S(stream)));
+        return STIL_OK;
+    }
+    const float inv_t = 1.0f / temperature;
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    PL.zero_words = P.ticket; PL.n_zero = 8;
+    if (dtype != STIL_BF16) prep_add(PL, prep_job(feat, dtype, rows, dim, ld, P.feat_nseg, P.feat_op, nullptr, 0, 0, nullptr));
+    prep_add(PL, prep_job(prototypes, STIL_F32, k, dim, dim, P.proto_nseg, P.proto_op, nullptr, 0, 0, nullptr));
+    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = proto_stats_job(GL.job[0], P, feat, dtype, rows, dim, ld, k, inv_t))) return rc;
+    GL.njobs = 1;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    FinishLaunch FL;
+    std::memset(&FL, 0, sizeof(FL));
+    proto_finish_job(FL.job[0], P, feat, dtype, rows, dim, ld, prototypes, k, cls, conf, inv_t, lse, w, 0);
+    FL.njobs = 1;
+    FL.total_rows = (int)rows;
+    FL.block_partials = P.block_partials;
+    FL.ticket = P.ticket;
+    FL.out_loss = loss;
+    return launch_finish(FL, S(stream));
+}
+
+STIL_API int stil_proto_ce_bwd(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const float* prototypes,
+                      int64_t k, const int32_t* cls, const float* lse, const float* w, float temperature,
+                      const float* grad_loss, void* d_feat, int grad_dtype, int64_t ld_grad, void* workspace,
+                      int64_t workspace_bytes, void* stream) {
+    int rc = check_embed(feat, dtype, rows, dim, ld, "proto_ce feat");
+    if (rc) return rc;
+    if ((rc = check_embed(prototypes, STIL_F32, k, dim, dim, "prototypes"))) return rc;
+    STIL_REQUIRE(rows == 0 || (cls && lse && w && d_feat), STIL_E_ARG, "proto_ce_bwd: null pointer");
+    STIL_REQUIRE(grad_dtype == STIL_F32 || grad_dtype == STIL_BF16, STIL_E_DTYPE, "bad grad dtype");
+    ProtoPlan P = plan_proto(workspace, workspace_bytes, rows, k, dim, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "proto workspace too small: need %lld bytes",
+                 (long long)P.bytes);
+    if (rows == 0) return STIL_OK;
+    const float inv_t = 1.0f / temperature;
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    if (dtype != STIL_BF16) prep_add(PL, prep_job(feat, dtype, rows, dim, ld, P.feat_nseg, P.feat_op, nullptr, 0, 0, nullptr));
+    prep_add(PL, prep_job(prototypes, STIL_F32, k, dim, dim, P.proto_nseg, P.proto_op, P.proto_t, P.ldt, 2, nullptr));
+    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = proto_grad_job(GL.job[0], P, feat, dtype, rows, dim, ld, k, inv_t, cls, lse, w, grad_loss))) return rc;
+    GL.njobs = 1;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    const bool direct = grad_dtype == STIL_F32 && ld_grad % 4 == 0;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = proto_store_job(GL.job[0], P, rows, dim, k, direct ? static_cast<float*>(d_feat) : P.g,
+                              direct ? ld_grad : dim)))
+        return rc;
+    GL.njobs = 1;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    if (!direct) {
+        GradFinishLaunch GF;
+        std::memset(&GF, 0, sizeof(GF));
+        GradFinishJob& j = GF.job[0];
+        j.g = P.g; j.dx = d_feat; j.dx_dtype = grad_dtype; j.ld_dx = ld_grad;
+        j.rows = (int)rows; j.dim = (int)dim;
+        GF.njobs = 1;
+        GF.total_rows = (int)rows;
+        return launch_grad_finish(GF, S(stream));
+    }
+    return STIL_OK;
+}
+
+// =============================================================================================== a5
+STIL_API int stil_proto_accumulate(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const int32_t* cls,
+                          const uint8_t* conf, int64_t b_l, float repeat_ratio, int64_t k, float* class_sum,
+                          float* class_count, float* psum, float* pcount, void* stream) {
+    STIL_REQUIRE(dtype == STIL_F32 || dtype == STIL_BF16, STIL_E_DTYPE, "proto_accumulate: bad dtype");
+    STIL_REQUIRE(class_sum && class_count && (rows == 0 || (feat && cls && conf)), STIL_E_ARG, "proto_accumulate: null pointer");
+    STIL_REQUIRE(b_l >= 0 && b_l <= rows && repeat_ratio > 0.f, STIL_E_ARG, "proto_accumulate: bad b_l / repeat_ratio");
+    STIL_REQUIRE((psum == nullptr) == (pcount == nullptr), STIL_E_ARG, "proto_accumulate: psum/pcount must come together");
+    return launch_proto_accumulate(feat, dtype, rows, dim, ld, cls, conf, b_l, repeat_ratio, k, class_sum, class_count,
+                                   psum, pcount, S(stream));
+}
+
+STIL_API int stil_proto_add(const float* class_sum, const float* class_count, int64_t k, int64_t dim, float* psum,
+                   float* pcount, void* stream) {
+    STIL_REQUIRE(class_sum && class_count && psum && pcount, STIL_E_ARG, "proto_add: null pointer");
+    return launch_proto_add(class_sum, class_count, k, dim, psum, pcount, S(stream));
+}
+
+STIL_API int stil_proto_finalize(float* prototypes, float* psum, float* pcount, int64_t k, int64_t dim,
+                        int32_t* empty_classes, void* stream) {
+    STIL_REQUIRE(prototypes && psum && pcount && empty_classes, STIL_E_ARG, "proto_finalize: null pointer");
+    return launch_proto_finalize(prototypes, psum, pcount, k, dim, empty_classes, S(stream));
+}
+
+// =============================================================================================== f-1
+STIL_API int64_t stil_masked_softce_workspace_bytes(int64_t rows) {
+    Workspace W(nullptr, 0);
+    W.take<unsigned int>(64);
+    W.take<float>(3 * masked_softce_blocks(rows, 0) + 8);
+    return W.off;
+}
+
+STIL_API int stil_masked_softce(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
+                       const float* pseudo_label, int64_t ld_pl, const uint8_t* mask1, const uint8_t* case1,
+                       const uint8_t* case2_i, const uint8_t* case2_t, const uint8_t* case3,
+                       const uint8_t* mask_random, int64_t rows, int64_t k, float* losses, float* d_y_m,
+                       float* d_y_i, float* d_y_t, int64_t ld_g, float grad_scale, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+    STIL_REQUIRE(logit_dtype == STIL_F32 || logit_dtype == STIL_BF16, STIL_E_DTYPE, "masked_softce: bad logit dtype");
+    STIL_REQUIRE(losses && (rows == 0 || (y_m && y_i && y_t && pseudo_label && mask1 && case1 && case2_i && case2_t &&
+                                          case3 && mask_random)),
+                 STIL_E_ARG, "masked_softce: null pointer");
+    STIL_REQUIRE(workspace && workspace_bytes >= stil_masked_softce_workspace_bytes(rows), STIL_E_WORKSPACE,
+                 "masked_softce workspace too small");
+    Workspace W(workspace, workspace_bytes);
+    unsigned int* ticket = W.take<unsigned int>(64);
+    float* partials = W.take<float>(3 * masked_softce_blocks(rows, 0) + 8);
+    STIL_CUDA(cudaMemsetAsync(ticket, 0, 16, S(stream)));
+    return launch_masked_softce(y_m, y_i, y_t, logit_dtype, ld_y, pseudo_label, ld_pl, mask1, case1, case2_i, case2_t,
+                                case3, mask_random, rows, k, losses, d_y_m, d_y_i, d_y_t, ld_g, grad_scale, partials,
+                                ticket, S(stream));
+}
+
+// =============================================================================================== whole step
+namespace {
+struct StepPlan {
+    InfoncePlan nce;
+    ProtoPlan pt;        // student feat_m x prototypes
+    __nv_bfloat16* teach_op;   // teacher feat_m_e operand (fp32 input only)
+    float* teacher_logits;     // [b_u, ldk]
+    int64_t ldk;
+    int32_t* cls;              // [batch]
+    uint8_t* conf;             // [batch]
+    float *lse_row, *lse_col, *lse_pt, *w_pt;
+    float* ce_partials;
+    unsigned int* ce_ticket;
+    int64_t bytes;
+};
+
+StepPlan plan_step(void* ws, int64_t ws_bytes, int64_t batch, int64_t b_l, int64_t k, int64_t dim, int dtype) {
+    StepPlan P;
+    const int64_t b_u = batch - b_l;
+    // sub-plans are laid out back to back inside the same workspace
+    InfoncePlan n0 = plan_infonce(nullptr, 0, batch, batch, dim, dtype, true);
+    ProtoPlan p0 = plan_proto(nullptr, 0, batch, k, dim, dtype);
+    char* base = static_cast<char*>(ws);
+    P.nce = plan_infonce(base, base ? n0.bytes : 0, batch, batch, dim, dtype, true);
+    P.pt = plan_proto(base ? base + n0.bytes : nullptr, base ? p0.bytes : 0, batch, k, dim, dtype);
+    Workspace W(base ? base + n0.bytes + p0.bytes : nullptr, ws_bytes - n0.bytes - p0.bytes);
+    P.ldk = round_up(k, 4);
+    P.teach_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(b_u * 2 * dim);
+    P.teacher_logits = W.take<float>(b_u * P.ldk);
+    P.cls = W.take<int32_t>(batch);
+    P.conf = W.take<uint8_t>(batch);
+    P.lse_row = W.take<float>(batch);
+    P.lse_col = W.take<float>(batch);
+    P.lse_pt = W.take<float>(batch);
+    P.w_pt = W.take<float>(batch);
+    P.ce_ticket = P.nce.ticket ? P.nce.ticket + 16 : nullptr;
+    P.ce_partials = W.take<float>(3 * masked_softce_blocks(b_u, k) + 8);
+    P.bytes = n0.bytes + p0.bytes + W.off;
+    return P;
+}
+}  // namespace
+
+STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int64_t k, int64_t dim, int embed_dtype) {
+    return plan_step(nullptr, 0, batch, b_l, k, dim, embed_dtype).bytes;
+}
+
+STIL_API int stil_head_step_launches(const stil_head_step_args* a) {
+    if (!a) return 0;
+    // prep, gemm(stats+teacher), labelled cls, cgpl_pgls, finish, gemm(grad), gemm(store), grad_finish, proto_accumulate
+    int n = 9;
+    if (a->b_l == 0) n -= 1;
+    if (a->batch == a->b_l) n -= 1;
+    if (a->y_m) n += 1;  // masked soft CE
+    return n;
+}
+
+STIL_API int stil_head_step(const stil_head_step_args* a) {
+    STIL_REQUIRE(a != nullptr, STIL_E_ARG, "head_step: null args");
+    const int64_t B = a->batch, B_l = a->b_l, B_u = a->batch - a->b_l, K = a->k, D = a->dim;
+    const int dt = a->embed_dtype;
+    cudaStream_t st = S(a->stream);
+    STIL_REQUIRE(B >= 1 && B_l >= 0 && B_l <= B && K >= 1, STIL_E_SHAPE, "head_step: bad sizes");
+    int rc;
+    if ((rc = check_embed(a->feat_i, dt, B, D, D, "feat_i"))) return rc;
+    if ((rc = check_embed(a->feat_t, dt, B, D, D, "feat_t"))) return rc;
+    if ((rc = check_embed(a->feat_m, dt, B, D, D, "feat_m"))) return rc;
+    if ((rc = check_embed(a->feat_m_e, dt, B, D, D, "feat_m_e"))) return rc;
+    if ((rc = check_embed(a->prototypes, STIL_F32, K, D, D, "prototypes"))) return rc;
+    STIL_REQUIRE(a->lambda0 >= 0.f && a->lambda0 <= 1.f, STIL_E_ARG, "lambda_0 must be a float between 0 and 1.");
+    STIL_REQUIRE(a->temperature > 0.f && a->repeat_ratio > 0.f, STIL_E_ARG, "head_step: bad temperature / repeat_ratio");
+    STIL_REQUIRE(a->losses && a->d_feat_i && a->d_feat_t && a->d_feat_m && a->pseudo_label && a->max_idx && a->mask1 &&
+                     a->case1 && a->case2_i && a->case2_t && a->case3 && a->class_sum && a->class_count && a->y_l &&
+                     a->y_m_ue && a->y_i_ue && a->y_t_ue,
+                 STIL_E_ARG, "head_step: null pointer");
+    StepPlan P = plan_step(a->workspace, a->workspace_bytes, B, B_l, K, D, dt);
+    STIL_REQUIRE(a->workspace && P.bytes <= a->workspace_bytes, STIL_E_WORKSPACE, "head_step workspace too small: need %lld",
+                 (long long)P.bytes);
+    const float inv_t = 1.0f / a->temperature;
+    const int esz = dt == STIL_BF16 ? 2 : 4;
+    const void* feat_m_ue = static_cast<const char*>(a->feat_m_e) + B_l * D * esz;
+
+    // 1. operand preparation (all matrices, one launch)
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    PL.zero_words = P.nce.ticket; PL.n_zero = 32;   // [0] finish ticket, [16] masked-CE ticket
+    prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, P.nce.a_t, P.nce.ldt, P.nce.nseg, P.nce.ra));
+    prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, P.nce.b_t, P.nce.ldt, P.nce.nseg, P.nce.rb));
+    if (dt != STIL_BF16) {
+        prep_add(PL, prep_job(a->feat_m, dt, B, D, D, P.pt.feat_nseg, P.pt.feat_op, nullptr, 0, 0, nullptr));
+        prep_add(PL, prep_job(feat_m_ue, dt, B_u, D, D, 2, P.teach_op, nullptr, 0, 0, nullptr));
+    }
+    prep_add(PL, prep_job(a->prototypes, STIL_F32, K, D, D, P.pt.proto_nseg, P.pt.proto_op, P.pt.proto_t, P.pt.ldt, 2, nullptr));
+    if ((rc = launch_prep(PL, st))) return rc;
+
+    // 2. forward GEMMs: InfoNCE both sides (stats), prototype CE (stats), teacher prototype logits (store)
+    const Operand A = rowmajor_operand(a->feat_i, dt, D, D, P.nce.a_op, P.nce.nseg);
+    const Operand Bm = rowmajor_operand(a->feat_t, dt, D, D, P.nce.b_op, P.nce.nseg);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = infonce_stats_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, nullptr, 0))) return rc;
+    if ((rc = proto_stats_job(GL.job[2], P.pt, a->feat_m, dt, B, D, D, K, inv_t))) return rc;
+    GL.njobs = 3;
+    if (B_u > 0) {
+        const Operand X = rowmajor_operand(feat_m_ue, dt, D, D, P.teach_op, 2);
+        const Operand Y = rowmajor_operand(nullptr, STIL_F32, D, D, P.pt.proto_op, P.pt.proto_nseg);
+        if ((rc = fill_gemm_common(GL.job[3], X, 0, B_u, Y, K, D))) return rc;
+        GL.job[3].mode = GEMM_STORE;
+        GL.job[3].out = P.teacher_logits;
+        GL.job[3].ld_out = P.ldk;
+        GL.njobs = 4;
+    }
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, st))) return rc;
+
+    // 3. CGPL + PGLS on the unlabelled rows; (cls, conf) of every row for the prototype kernels
+    if ((rc = launch_labelled_cls(a->y_l, B_l, a->th1, P.cls, P.conf, st))) return rc;
+    if ((rc = launch_cgpl_pgls(a->y_m_ue, a->y_i_ue, a->y_t_ue, a->logit_dtype, K, P.teacher_logits, P.ldk, B_u, K,
+                               a->temperature, a->rate_pseudo, a->th1, a->past_start_epoch, a->pseudo_label, K, nullptr,
+                               0, a->max_prob, a->max_idx, a->mask1, a->case1, a->case2_i, a->case2_t, a->case3,
+                               nullptr, P.cls + B_l, P.conf + B_l, st)))
+        return rc;
+
+    // 4. merge statistics -> LSEs, losses, backward coefficients
+    FinishLaunch FL;
+    std::memset(&FL, 0, sizeof(FL));
+    infonce_finish_jobs(FL.job, P.nce, a->feat_i, a->feat_t, dt, B, B, D, D, 0, inv_t, a->lambda0, P.lse_row, P.lse_col, 0);
+    proto_finish_job(FL.job[2], P.pt, a->feat_m, dt, B, D, D, a->prototypes, K, P.cls, P.conf, inv_t, P.lse_pt, P.w_pt, 1);
+    FL.job[0].row_begin = 0;
+    FL.job[1].row_begin = (int)B;
+    FL.job[2].row_begin = (int)(2 * B);
+    FL.njobs = 3;
+    FL.total_rows = (int)(3 * B);
+    FL.block_partials = P.nce.block_partials;   // sized for 2B rows; 3B rows need more -> use proto's too
+    FL.ticket = P.nce.ticket;
+    FL.out_loss = a->losses;                     // [0] = itc, [1] = pt
+    if ((rc = launch_finish(FL, st))) return rc;
+
+    // 5. backward: G tiles (bf16 hi/lo) then dX = G · Y
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = infonce_grad_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, a->lambda0, P.lse_row, P.lse_col, nullptr))) return rc;
+    if ((rc = proto_grad_job(GL.job[2], P.pt, a->feat_m, dt, B, D, D, K, inv_t, P.cls, P.lse_pt, P.w_pt, nullptr))) return rc;
+    GL.njobs = 3;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, st))) return rc;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = infonce_store_jobs(GL.job, P.nce, B, B, D))) return rc;
+    if ((rc = proto_store_job(GL.job[2], P.pt, B, D, K, P.pt.g, D))) return rc;
+    GL.njobs = 3;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, st))) return rc;
+    GradFinishLaunch GF;
+    std::memset(&GF, 0, sizeof(GF));
+    for (int s = 0; s < 3; ++s) {
+        GradFinishJob& j = GF.job[s];
+        j.g = s == 0 ? P.nce.g[0] : s == 1 ? P.nce.g[1] : P.pt.g;
+        j.x = s == 0 ? a->feat_i : s == 1 ? a->feat_t : a->feat_m;
+        j.x_dtype = dt; j.ldx = D;
+        j.sx = s == 0 ? P.nce.ra : s == 1 ? P.nce.rb : nullptr;
+        j.dx = s == 0 ? a->d_feat_i : s == 1 ? a->d_feat_t : a->d_feat_m;
+        j.dx_dtype = a->grad_dtype; j.ld_dx = D;
+        j.rows = (int)B; j.dim = (int)D;
+        j.row_begin = (int)(s * B);
+    }
+    GF.njobs = 3;
+    GF.total_rows = (int)(3 * B);
+    if ((rc = launch_grad_finish(GF, st))) return rc;
+
+    // 6. prototype partial sums (+ in-place accumulate), teacher features (STiLModel.py:376)
+    if ((rc = launch_proto_accumulate(a->feat_m_e, dt, B, D, D, P.cls, P.conf, B_l, a->repeat_ratio, K, a->class_sum,
+                                      a->class_count, a->prototypes_sum, a->prototypes_count_sum, st)))
+        return rc;
+
+    // 7. masked soft-target CE of the student heads (f-1)
+    if (a->y_m) {
+        STIL_REQUIRE(a->y_i && a->y_t && a->mask_random, STIL_E_ARG, "head_step: student logits need y_i, y_t, mask_random");
+        const int lsz = a->logit_dtype == STIL_BF16 ? 2 : 4;
+        auto urow = [&](const void* p) { return static_cast<const char*>(p) + B_l * K * lsz; };
+        auto grow = [&](float* p) { return p ? p + B_l * K : nullptr; };
+        if ((rc = launch_masked_softce(urow(a->y_m), urow(a->y_i), urow(a->y_t), a->logit_dtype, K, a->pseudo_label, K,
+                                       a->mask1, a->case1, a->case2_i, a->case2_t, a->case3, a->mask_random, B_u, K,
+                                       a->losses + 2, grow(a->d_y_m), grow(a->d_y_i), grow(a->d_y_t), K,
+                                       a->rate_uce_scale, P.ce_partials, P.ce_ticket, st)))
+            return rc;
+    }
+    return STIL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// Shared host/device helpers for the STiL head kernels (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/stil_head.h"
+
+namespace stil {
+
+// ---- thread-local error message behind stil_last_error()
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define STIL_REQUIRE(cond, code, ...)      \
+    do {                                   \
+        if (!(cond)) {                     \
+            ::stil::set_error(__VA_ARGS__); \
+            return (code);                 \
+        }                                  \
+    } while (0)
+
+#define STIL_CUDA(expr)                                                                        \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::stil::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return STIL_E_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define STIL_LAUNCH_CHECK() STIL_CUDA(cudaGetLastError())
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- bump allocator over a caller-provided workspace (the extension allocates nothing)
+struct Workspace {
+    char* base;
+    int64_t size, off;
+    Workspace(void* p, int64_t n) : base(static_cast<char*>(p)), size(n), off(0) {}
+    template <class T>
+    T* take(int64_t count) {
+        int64_t bytes = round_up(count * (int64_t)sizeof(T), 256);
+        char* p = base ? base + off : nullptr;
+        off += bytes;
+        return reinterpret_cast<T*>(p);
+    }
+    bool ok() const { return base == nullptr || off <= size; }
+};
+
+#ifdef __CUDACC__
+// ---- device helpers
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int W>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int W>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float ld_as_float(const void* p, int dtype, int64_t i) {
+    return dtype == STIL_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i])
+                              : static_cast<const float*>(p)[i];
+}
+__device__ __forceinline__ void st_from_float(void* p, int dtype, int64_t i, float v) {
+    if (dtype == STIL_BF16)
+        static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+    else
+        static_cast<float*>(p)[i] = v;
+}
+
+// Deterministic grid-wide scalar sum: every block stores its partial, the last block to take a
+// ticket adds them in index order.  `ticket` must be zero on entry and is reset for the next launch.
+__device__ __forceinline__ void ticket_sum(float block_value, float* partials, unsigned int* ticket, float* out,
+                                           float scale) {
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = block_value;
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        float s = 0.f;
+        for (unsigned int b = 0; b < gridDim.x; ++b) s += reinterpret_cast<volatile float*>(partials)[b];
+        *out = s * scale;
+        *ticket = 0u;
+    }
+}
+
+// Sum `v` over the block (blockDim.x multiple of 32, <= 1024); result valid in thread 0.
+__device__ __forceinline__ float block_sum(float v) {
+    __shared__ float red[32];
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float s = 0.f;
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        s = l < nw ? red[l] : 0.f;
+        s = warp_sum(s);
+    }
+    return s;
+}
+#endif  // __CUDACC__
+
+}  // namespace stil

@@ -1,0 +1,313 @@
+// Similarity GEMM with fused softmax-statistics / gradient epilogues on tcgen05 (sm_100a).
+//
+//   L[i,j] = alpha * sx[i] * sy[j] * sum_{(p,q) in pairs} <X[i,p,:], Y[j,q,:]>
+//
+// One CTA per 128x128 tile.  Warp 0 streams 128x64 bf16 operand boxes with TMA (128-byte swizzle)
+// through a 3-stage mbarrier ring, warp 1 issues tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32 in
+// TMEM), warps 2-5 drain the accumulator with tcgen05.ld (thread = row) and run one of three
+// epilogues (see GemmMode in internal.h).  Used for: the InfoNCE logits of utils/clip_loss.py:33 and
+// their row/column log-sum-exp (:36-37), the prototype logits of utils/prototype_loss.py:26 and
+// STiLModel.py:293, and both GEMMs of their backward passes.
+#include <cstdarg>
+#include <mutex>
+
+#include "internal.h"
+#include "tc05.cuh"
+
+namespace stil {
+
+namespace {
+
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+constexpr int kStageBytes = (kTileM + kTileN) * kTileK * 2;  // 32 KiB
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2048 /*scales*/ + 256 /*barriers*/;
+constexpr uint32_t kTmemCols = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_constant__ GemmLaunch L) {
+    extern __shared__ uint8_t smem_raw[];
+    // carve: [stages x (A 16K | B 16K)] 1024-aligned, then scales, then barriers
+    const uint32_t raw = tc05::smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* tiles = smem_raw + pad;
+    float* col_scale = reinterpret_cast<float*>(tiles + kStages * kStageBytes);  // [128]
+    float* col_lse = col_scale + kTileN;                                          // [128]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(col_lse + kTileN + 128);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- which job / tile
+    int jid = 0;
+#pragma unroll
+    for (int j = 1; j < kMaxGemmJobs; ++j)
+        if (j < L.njobs && (int)blockIdx.x >= L.job[j].tile_begin) jid = j;
+    const GemmJob& J = L.job[jid];
+    const int t = blockIdx.x - J.tile_begin;
+    const int tm = t / J.tiles_n, tn = t % J.tiles_n;
+    const int m0 = tm * kTileM, n0 = tn * kTileN;
+    const int kper = (J.D + kTileK - 1) / kTileK;
+    const int nkb = J.npair * kper;
+
+    if (warp == 0 && lane == 0) {
+        tc05::tma_prefetch_desc(&J.tmx);
+        tc05::tma_prefetch_desc(&J.tmy);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) {
+                tc05::mbar_init(&full_bar[s], 1);
+                tc05::mbar_init(&empty_bar[s], 1);
+            }
+            tc05::mbar_init(tmem_full_bar, 1);
+            tc05::fence_mbar_init();
+        }
+        __syncwarp();
+        tc05::tmem_alloc(tmem_slot, kTmemCols);
+        tc05::tmem_relinquish();
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                tc05::mbar_wait(&empty_bar[s], ph ^ 1);
+                const int p = kb / kper, kk = kb - p * kper;
+                uint8_t* a_dst = tiles + s * kStageBytes;
+                uint8_t* b_dst = a_dst + kTileM * kTileK * 2;
+                tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                tc05::tma_load_3d(a_dst, &J.tmx, &full_bar[s], kk * kTileK, m0, J.xseg[p]);
+                tc05::tma_load_3d(b_dst, &J.tmy, &full_bar[s], kk * kTileK, n0, J.yseg[p]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, kTileN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (kb / kStages) & 1;
+                tc05::mbar_wait(&full_bar[s], ph);
+                tc05::fence_after_sync();
+                const uint32_t a_addr = tc05::smem_u32(tiles + s * kStageBytes);
+                const uint32_t b_addr = a_addr + kTileM * kTileK * 2;
+                const uint64_t a_desc = tc05::make_kmajor_sw128_desc(a_addr);
+                const uint64_t b_desc = tc05::make_kmajor_sw128_desc(b_addr);
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k) {
+                    // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (>>4) start-address field
+                    tc05::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                }
+                tc05::mma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+            }
+            tc05::mma_commit(tmem_full_bar);
+        }
+    } else {
+        // ===================== epilogue (4 warps, thread = accumulator row) =====================
+        const int e = threadIdx.x - 64;  // 0..127
+        const int q = warp & 3;          // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < J.M;
+        const int ncols = min(kTileN, J.N - n0);
+        {
+            const int col = n0 + e;
+            float cs = 0.f, cl = 0.f;
+            if (col < J.N) {
+                cs = J.alpha * (J.sy ? J.sy[col] : 1.f);
+                if (J.mode == GEMM_GRAD && J.lse_y) cl = J.lse_y[col];
+            }
+            col_scale[e] = cs;
+            col_lse[e] = cl;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue-only named barrier
+
+        const float rs = (row_ok && J.sx) ? J.sx[row] : 1.f;
+        float lse_x = 0.f, u = 0.f, d = 0.f, gs = 1.f;
+        int tgt = -1;
+        if (J.mode == GEMM_GRAD && row_ok) {
+            lse_x = J.lse_x[row];
+            u = J.u_vec ? J.u_vec[row] : J.u_scalar;
+            d = J.u_vec ? u : J.d_scalar;
+            tgt = J.tgt_vec ? J.tgt_vec[row] : row + J.tgt_offset;
+            gs = J.gscale ? *J.gscale : 1.f;
+        }
+        const float v = (J.mode == GEMM_GRAD && J.lse_y) ? J.v_scalar : 0.f;
+
+        tc05::mbar_wait(tmem_full_bar, 0);
+        tc05::fence_after_sync();
+
+        float run_max = -INFINITY, run_sum = 0.f;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < kTileN / 32; ++c) {
+            if (c * 32 >= ncols) break;  // warp-uniform
+            uint32_t acc[32];
+            tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
+            tc05::tmem_ld_wait();
+            const int nv = min(32, ncols - c * 32);
+            float l[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) l[j] = __uint_as_float(acc[j]) * rs * col_scale[c * 32 + j];
+
+            if (J.mode == GEMM_STATS) {
+                float cmax = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) cmax = fmaxf(cmax, l[j]);
+                const float new_max = fmaxf(run_max, cmax);
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) s += fast_exp2((l[j] - new_max) * kLog2e);
+                run_sum = run_sum * fast_exp2((run_max - new_max) * kLog2e) + s;
+                run_max = new_max;
+            }
+            if ((J.mode == GEMM_STATS || J.mode == GEMM_STORE) && J.out && row_ok) {
+                float* dst = J.out + (long long)row * J.ld_out + n0 + c * 32;
+                if (nv == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(l[j], l[j + 1], l[j + 2], l[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nv) dst[j] = l[j];
+                }
+            }
+            if (J.mode == GEMM_GRAD && row_ok) {
+                __nv_bfloat16* hi_dst = J.gop + (long long)row * 2 * J.ld_g + n0 + c * 32;
+                __nv_bfloat16* lo_dst = hi_dst + J.ld_g;
+                uint32_t hi_pk[16], lo_pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float g2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int jj = j + h;
+                        float g = u * fast_exp2((l[jj] - lse_x) * kLog2e);
+                        if (v != 0.f) g += v * fast_exp2((l[jj] - col_lse[c * 32 + jj]) * kLog2e);
+                        if (n0 + c * 32 + jj == tgt) g -= d;
+                        g2[h] = g * col_scale[c * 32 + jj] * gs;
+                    }
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(g2[0]), h1 = __float2bfloat16_rn(g2[1]);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(g2[0] - __bfloat162float(h0));
+                    const __nv_bfloat16 l1 = __float2bfloat16_rn(g2[1] - __bfloat162float(h1));
+                    hi_pk[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lo_pk[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                if (nv == 32 && ((reinterpret_cast<uintptr_t>(hi_dst) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(lo_dst) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        *reinterpret_cast<uint4*>(hi_dst + 2 * j) = make_uint4(hi_pk[j], hi_pk[j + 1], hi_pk[j + 2], hi_pk[j + 3]);
+                        *reinterpret_cast<uint4*>(lo_dst + 2 * j) = make_uint4(lo_pk[j], lo_pk[j + 1], lo_pk[j + 2], lo_pk[j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nv) {
+                            const uint32_t hp = hi_pk[j / 2], lp = lo_pk[j / 2];
+                            hi_dst[j] = __ushort_as_bfloat16((unsigned short)((j & 1) ? (hp >> 16) : (hp & 0xffff)));
+                            lo_dst[j] = __ushort_as_bfloat16((unsigned short)((j & 1) ? (lp >> 16) : (lp & 0xffff)));
+                        }
+                }
+            }
+        }
+        if (J.mode == GEMM_STATS && row_ok) {
+            J.part_max[(long long)tn * J.M + row] = run_max;
+            J.part_sum[(long long)tn * J.M + row] = run_sum;
+        }
+    }
+
+    // ---- teardown: all TMEM reads done before dealloc
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc05::fence_after_sync();
+        tc05::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+}  // namespace
+
+int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t rows, int64_t nseg,
+                     int64_t row_stride, int64_t seg_stride) {
+    EncodeTiledFn enc = get_encode_fn();
+    STIL_REQUIRE(enc != nullptr, STIL_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    STIL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, STIL_E_ALIGN, "operand base %p not 16-byte aligned", base);
+    STIL_REQUIRE((row_stride * 2) % 16 == 0 && (seg_stride * 2) % 16 == 0, STIL_E_ALIGN,
+                 "operand strides (%lld, %lld elements) must be multiples of 8 bf16", (long long)row_stride,
+                 (long long)seg_stride);
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nseg};
+    cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)seg_stride * 2};
+    cuuint32_t box[3] = {kTileK, kTileM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    STIL_REQUIRE(r == CUDA_SUCCESS, STIL_E_CUDA,
+                 "cuTensorMapEncodeTiled failed (%d) for [%lld x %lld x %lld], strides %lld/%lld", (int)r,
+                 (long long)inner, (long long)rows, (long long)nseg, (long long)row_stride, (long long)seg_stride);
+    return STIL_OK;
+}
+
+void gemm_job_tiles(GemmLaunch& L) {
+    int begin = 0;
+    for (int j = 0; j < L.njobs; ++j) {
+        GemmJob& J = L.job[j];
+        J.tiles_m = (int)ceil_div(J.M, kTileM);
+        J.tiles_n = (int)ceil_div(J.N, kTileN);
+        J.tile_begin = begin;
+        begin += J.tiles_m * J.tiles_n;
+    }
+    L.total_tiles = begin;
+}
+
+int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
+    STIL_REQUIRE(L.njobs >= 1 && L.njobs <= kMaxGemmJobs, STIL_E_ARG, "gemm launch with %d jobs", L.njobs);
+    if (L.total_tiles == 0) return STIL_OK;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(gemm_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    });
+    STIL_CUDA(attr_err);
+    gemm_tc05_kernel<<<L.total_tiles, kThreads, kSmemBytes, stream>>>(L);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+}  // namespace stil

@@ -1,0 +1,175 @@
+// Internal launcher interfaces shared by the translation units of libstil_head.so.
+#pragma once
+#include "common.cuh"
+
+namespace stil {
+
+// --------------------------------------------------------------------------- tcgen05 GEMM (gemm_tc05.cu)
+// One kernel computes 128x128 tiles of  L = alpha * diag(sx) * (X · Yᵀ) * diag(sy)  on tcgen05 with the
+// accumulator in TMEM, for up to kMaxGemmJobs independent problems per launch.  X and Y are bf16
+// "operand tensors" [rows, nseg, D]: an fp32 matrix is carried as a sum of bf16 segments (hi, lo, lolo)
+// and the product is accumulated over the listed (xseg, yseg) pairs in fp32 — fp32-accurate results
+// from bf16 tensor-core passes.
+enum GemmMode : int {
+    GEMM_STATS = 0,  // per-row online (max, sum-exp) partial per column tile  [+ optional fp32 store]
+    GEMM_STORE = 1,  // fp32 store of L
+    GEMM_GRAD = 2    // G = u_i e^{L-lse_x[i]} + v e^{L-lse_y[j]} - d_i [j == tgt_i], times cs_j, as bf16 hi/lo
+};
+constexpr int kMaxGemmJobs = 4;
+constexpr int kMaxSegPairs = 4;
+constexpr int kTileM = 128, kTileN = 128, kTileK = 64;
+
+struct alignas(64) GemmJob {
+    CUtensorMap tmx, tmy;  // 3-D maps (D, rows, nseg), box 64 x 128 x 1, 128-B swizzle
+    int M, N, D;           // X rows, Y rows, per-segment contraction length
+    int npair;
+    int xseg[kMaxSegPairs], yseg[kMaxSegPairs];
+    int mode;
+    int tiles_m, tiles_n, tile_begin;
+    float alpha;
+    const float* sx;  // [M] row scale or nullptr
+    const float* sy;  // [N] column scale or nullptr
+    // STATS
+    float* part_max;  // [tiles_n, M]
+    float* part_sum;
+    // STORE / STATS(optional)
+    float* out;
+    long long ld_out;
+    // GRAD
+    const float* lse_x;      // [M]
+    const float* lse_y;      // [N] or nullptr (v ignored)
+    const float* u_vec;      // [M] or nullptr -> u_scalar, d_scalar
+    float u_scalar, v_scalar, d_scalar;
+    const int* tgt_vec;      // [M] or nullptr -> tgt = row + tgt_offset
+    int tgt_offset;
+    const float* gscale;     // device scalar or nullptr (1.0)
+    __nv_bfloat16* gop;      // [M, 2, ld_g]
+    long long ld_g;
+};
+
+struct GemmLaunch {
+    GemmJob job[kMaxGemmJobs];
+    int njobs;
+    int total_tiles;
+};
+
+// Build the operand tensor map.  `base` bf16, logical [rows, nseg, inner]; strides in elements.
+int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t rows, int64_t nseg,
+                     int64_t row_stride, int64_t seg_stride);
+void gemm_job_tiles(GemmLaunch& L);  // fills tiles_m/tiles_n/tile_begin/total_tiles
+int launch_gemm(const GemmLaunch& L, cudaStream_t stream);
+
+// --------------------------------------------------------------------------- row kernels (row_kernels.cu)
+// Operand preparation: for every row of x (f32 or bf16) write the bf16 segments (hi[,lo[,lolo]]) into
+// op [rows, nseg, dim] and/or the transposed operand op_t [dim, nseg, ld_t] (only first `nseg_t` segments),
+// and the inverse L2 norm 1/max(||x||, eps) (F.normalize semantics, clip_loss.py:29-30).
+struct PrepJob {
+    const void* x;
+    int dtype;
+    int rows, dim;
+    long long ld;
+    int nseg;
+    __nv_bfloat16* op;       // nullable
+    __nv_bfloat16* op_t;     // nullable
+    long long ld_t;
+    int nseg_t;
+    float* inv_norm;         // nullable
+    int block_begin;
+};
+constexpr int kMaxPrepJobs = 8;
+struct PrepLaunch {
+    PrepJob job[kMaxPrepJobs];
+    int njobs;
+    int total_blocks;
+    unsigned int* zero_words;  // words zeroed by block 0 (reduction tickets), n_zero <= 256
+    int n_zero;
+};
+void prep_add(PrepLaunch& L, const PrepJob& j);
+int launch_prep(const PrepLaunch& L, cudaStream_t stream);
+
+// Merge the per-column-tile (max, sum) partials of GEMM_STATS into row LSEs and loss terms.
+struct FinishJob {
+    int kind;  // 0 = InfoNCE side, 1 = prototype CE
+    int M;     // rows
+    int tiles_n;
+    const float* part_max;
+    const float* part_sum;
+    float* lse;  // [M] out
+    // kind 0: diag term d_i = alpha*sx_i*sy_{i+off}*<x_i, y_{i+off}>, rowterm = coef*(lse_i - d_i)
+    // kind 1: z = alpha*<x_i, proto_{cls_i}>, p = e^{z-lse}, rowterm = -conf_i*log(p+1e-7)*coef, w_i = conf_i*coef*p/(p+1e-7)
+    const void* x;
+    int x_dtype;
+    long long ldx;
+    const void* y;
+    int y_dtype;
+    long long ldy;
+    int y_offset;
+    int dim;
+    const float* sx;
+    const float* sy;
+    float alpha, coef;
+    const int* cls;
+    const unsigned char* conf;
+    float* w;
+    int loss_slot;  // which of out_loss[] this job adds into
+    int row_begin;
+};
+constexpr int kMaxFinishJobs = 4;
+struct FinishLaunch {
+    FinishJob job[kMaxFinishJobs];
+    int njobs;
+    int total_rows;
+    float* block_partials;   // [blocks * 2]
+    unsigned int* ticket;    // zeroed once by the caller's workspace init, self-resetting
+    float* out_loss;         // [2]
+};
+int launch_finish(const FinishLaunch& L, cudaStream_t stream);
+int64_t finish_blocks(int total_rows);
+
+// dx = sx*(g - xh*(xh·g)) with xh = sx*x  (backward of F.normalize) or dx = g when sx == nullptr.
+struct GradFinishJob {
+    const float* g;  // [rows, dim] f32
+    const void* x;
+    int x_dtype;
+    long long ldx;
+    const float* sx;
+    void* dx;
+    int dx_dtype;
+    long long ld_dx;
+    int rows, dim;
+    int row_begin;
+};
+struct GradFinishLaunch {
+    GradFinishJob job[4];
+    int njobs;
+    int total_rows;
+};
+int launch_grad_finish(const GradFinishLaunch& L, cudaStream_t stream);
+
+int launch_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
+                     const float* teacher_logits, int64_t ld_t, int64_t rows, int64_t k, float temperature,
+                     float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
+                     float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
+                     uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
+                     int32_t* cls, uint8_t* conf, cudaStream_t stream);
+int launch_label_argmax(const float* label, int64_t ld, int64_t rows, int64_t k, float threshold, int32_t* cls,
+                        uint8_t* conf, float* max_prob, cudaStream_t stream);
+// cls/conf of the labelled rows: cls = y_l, conf = (1 >= th) (a one-hot row has max 1, STiLModel.py:321)
+int launch_labelled_cls(const int64_t* y_l, int64_t b_l, float th, int32_t* cls, uint8_t* conf, cudaStream_t stream);
+int launch_proto_accumulate(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const int32_t* cls,
+                            const uint8_t* conf, int64_t b_l, float repeat_ratio, int64_t k, float* class_sum,
+                            float* class_count, float* psum, float* pcount, cudaStream_t stream);
+int launch_proto_add(const float* class_sum, const float* class_count, int64_t k, int64_t dim, float* psum,
+                     float* pcount, cudaStream_t stream);
+int launch_proto_finalize(float* prototypes, float* psum, float* pcount, int64_t k, int64_t dim,
+                          int32_t* empty_classes, cudaStream_t stream);
+int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
+                         const float* pseudo_label, int64_t ld_pl, const uint8_t* mask1, const uint8_t* case1,
+                         const uint8_t* case2_i, const uint8_t* case2_t, const uint8_t* case3,
+                         const uint8_t* mask_random, int64_t rows, int64_t k, float* losses, float* d_y_m,
+                         float* d_y_i, float* d_y_t, int64_t ld_g, float grad_scale, float* block_partials,
+                         unsigned int* ticket, cudaStream_t stream);
+int64_t masked_softce_blocks(int64_t rows, int64_t k);
+int launch_zero_u32(unsigned int* p, int n, cudaStream_t stream);
+
+}  // namespace stil

@@ -1,0 +1,827 @@
+// Row-wise (HBM-bound) kernels of the STiL head: operand preparation, CGPL+PGLS pseudo-labelling,
+// soft-label argmax, statistics merge / loss terms, normalise-backward, masked soft-target CE and the
+// segmented per-class prototype sums.  Warp-shuffle reductions, vectorised coalesced row access.
+#include "internal.h"
+
+namespace stil {
+
+namespace {
+
+constexpr int kRowBlock = 256;  // 8 warps
+
+// =====================================================================================
+// Operand preparation
+// =====================================================================================
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& l, __nv_bfloat16& ll) {
+    h = __float2bfloat16_rn(x);
+    float r = x - __bfloat162float(h);
+    l = __float2bfloat16_rn(r);
+    r -= __bfloat162float(l);
+    ll = __float2bfloat16_rn(r);
+}
+
+constexpr int kPrepRows = 32;
+constexpr int kPrepChunk = 256;
+
+__global__ void __launch_bounds__(kRowBlock) prep_kernel(const __grid_constant__ PrepLaunch L) {
+    __shared__ float tile[kPrepRows][kPrepChunk + 1];
+    // reduction tickets of the later kernels of this op start from zero (workspace content is arbitrary)
+    if (blockIdx.x == 0 && (int)threadIdx.x < L.n_zero) L.zero_words[threadIdx.x] = 0u;
+    int jid = 0;
+#pragma unroll
+    for (int j = 1; j < kMaxPrepJobs; ++j)
+        if (j < L.njobs && (int)blockIdx.x >= L.job[j].block_begin) jid = j;
+    const PrepJob& J = L.job[jid];
+    const int r0 = (blockIdx.x - J.block_begin) * kPrepRows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // phase A: norms + row-major segments, one warp per row (4 rows per warp)
+    for (int rr = warp; rr < kPrepRows; rr += kRowBlock / 32) {
+        const int r = r0 + rr;
+        if (r >= J.rows) break;
+        float ss = 0.f;
+        for (int d = lane; d < J.dim; d += 32) {
+            const float x = ld_as_float(J.x, J.dtype, (long long)r * J.ld + d);
+            ss += x * x;
+            if (J.op) {
+                __nv_bfloat16 h, l, ll;
+                split3(x, h, l, ll);
+                __nv_bfloat16* o = J.op + ((long long)r * J.nseg) * J.dim + d;
+                o[0] = h;
+                if (J.nseg > 1) o[J.dim] = l;
+                if (J.nseg > 2) o[2 * J.dim] = ll;
+            }
+        }
+        if (J.inv_norm) {
+            ss = warp_sum(ss);
+            if (lane == 0) J.inv_norm[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+        }
+    }
+    // phase B: transposed segments op_t[d, s, r] through a shared tile (coalesced along r)
+    if (J.op_t) {
+        for (int c0 = 0; c0 < J.dim; c0 += kPrepChunk) {
+            const int cw = min(kPrepChunk, J.dim - c0);
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < kPrepRows * cw; idx += kRowBlock) {
+                const int rr = idx / cw, cc = idx - rr * cw;
+                const int r = r0 + rr;
+                tile[rr][cc] = r < J.rows ? ld_as_float(J.x, J.dtype, (long long)r * J.ld + c0 + cc) : 0.f;
+            }
+            __syncthreads();
+            const int r = r0 + lane;
+            if (r < J.rows) {
+                for (int cc = warp; cc < cw; cc += kRowBlock / 32) {
+                    __nv_bfloat16 h, l, ll;
+                    split3(tile[lane][cc], h, l, ll);
+                    __nv_bfloat16* o = J.op_t + ((long long)(c0 + cc) * J.nseg_t) * J.ld_t + r;
+                    o[0] = h;
+                    if (J.nseg_t > 1) o[J.ld_t] = l;
+                    if (J.nseg_t > 2) o[2 * J.ld_t] = ll;
+                }
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// CGPL + PGLS (STiLModel.py:262-298), LPR lanes per row, NV float2 items per lane
+// =====================================================================================
+struct CgplArgs {
+    const void *y_m, *y_i, *y_t;
+    int logit_dtype;
+    long long ld_y;
+    const float* tl;
+    long long ld_t;
+    int rows, k;
+    float temperature, rate_pseudo, one_minus_rate, th1;
+    int past_start;
+    float* pseudo_label;
+    long long ld_pl;
+    float* prediction;
+    long long ld_pred;
+    float* max_prob;
+    long long* max_idx;
+    unsigned char *mask1, *case1, *case2_i, *case2_t, *case3;
+    long long* top1;
+    int* cls;
+    unsigned char* conf;
+    int vec_y, vec_t, vec_pl, vec_pred;  // 8-byte (f32) / 4-byte (bf16) pair access allowed
+};
+
+template <int LPR, int NV>
+__device__ __forceinline__ void load_row(const void* base, int dtype, long long ld, int row, int k, int sub, int vec,
+                                         float (&a)[2 * NV]) {
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+        const int e0 = 2 * (sub + LPR * it);
+        float x0 = -INFINITY, x1 = -INFINITY;
+        if (e0 + 1 < k && vec) {
+            if (dtype == STIL_BF16) {
+                const __nv_bfloat162 p =
+                    *reinterpret_cast<const __nv_bfloat162*>(static_cast<const __nv_bfloat16*>(base) + (long long)row * ld + e0);
+                x0 = __bfloat162float(p.x);
+                x1 = __bfloat162float(p.y);
+            } else {
+                const float2 p = *reinterpret_cast<const float2*>(static_cast<const float*>(base) + (long long)row * ld + e0);
+                x0 = p.x;
+                x1 = p.y;
+            }
+        } else {
+            if (e0 < k) x0 = ld_as_float(base, dtype, (long long)row * ld + e0);
+            if (e0 + 1 < k) x1 = ld_as_float(base, dtype, (long long)row * ld + e0 + 1);
+        }
+        a[2 * it] = x0;
+        a[2 * it + 1] = x1;
+    }
+}
+
+template <int LPR, int NV>
+__device__ __forceinline__ void store_row(float* base, long long ld, int row, int k, int sub, int vec,
+                                          const float (&a)[2 * NV]) {
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+        const int e0 = 2 * (sub + LPR * it);
+        if (e0 + 1 < k && vec) {
+            *reinterpret_cast<float2*>(base + (long long)row * ld + e0) = make_float2(a[2 * it], a[2 * it + 1]);
+        } else {
+            if (e0 < k) base[(long long)row * ld + e0] = a[2 * it];
+            if (e0 + 1 < k) base[(long long)row * ld + e0 + 1] = a[2 * it + 1];
+        }
+    }
+}
+
+// in: logits a (−inf padded). out: e = exp(a − max) in place; returns the row sum (all lanes of the group).
+template <int LPR, int NV>
+__device__ __forceinline__ float softmax_exp(float (&a)[2 * NV]) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 2 * NV; ++j) m = fmaxf(m, a[j]);
+    m = group_max<LPR>(m);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2 * NV; ++j) {
+        a[j] = expf(a[j] - m);
+        s += a[j];
+    }
+    return group_sum<LPR>(s);
+}
+
+// first-index argmax across the LPR lanes of a row group
+template <int LPR>
+__device__ __forceinline__ void group_argmax(float& v, int& idx) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) {
+            v = ov;
+            idx = oi;
+        }
+    }
+}
+
+// argmax_k softmax(a)_k with torch's first-index rule, without dividing every element: e_max = exp(0) = 1
+// exactly, and fl(e/s) can only tie with fl(1/s) for e within a few ulp of 1, so only those are divided.
+template <int LPR, int NV>
+__device__ __forceinline__ int argmax_of_softmax(float (&e)[2 * NV], float s, int sub, int k) {
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int idx = 2 * (sub + LPR * it) + h;
+            const float ev = e[2 * it + h];
+            if (idx < k && ev >= 0.9999f) {
+                const float p = __fdiv_rn(ev, s);
+                if (p > bv) {  // ascending idx within a lane: strict > keeps the first
+                    bv = p;
+                    bi = idx;
+                }
+            }
+        }
+    }
+    group_argmax<LPR>(bv, bi);
+    return bi;
+}
+
+template <int LPR, int NV>
+__global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) {
+    constexpr int RPW = 32 / LPR;
+    const int warp_global = blockIdx.x * (kRowBlock / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR;
+    const int row = warp_global * RPW + lane / LPR;
+    // rows beyond the end keep running with a clamped index so that the full-warp shuffles stay converged
+    const bool row_ok = row < A.rows;
+    const int r = row_ok ? row : A.rows - 1;
+    const int k = A.k;
+
+    float ym[2 * NV], yi[2 * NV], yt[2 * NV];
+    load_row<LPR, NV>(A.y_m, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, ym);
+    load_row<LPR, NV>(A.y_i, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, yi);
+    load_row<LPR, NV>(A.y_t, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, yt);
+
+    // ---- :262-263  top-1 of the three softmaxes
+    float pm[2 * NV];  // becomes softmax(y_m) = `prediction` (:279) and the case-3 pseudo label (:273)
+#pragma unroll
+    for (int j = 0; j < 2 * NV; ++j) pm[j] = ym[j];
+    const float sm = softmax_exp<LPR, NV>(pm);
+    int top_m;
+    {
+        float bv = -1.f;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int it = 0; it < NV; ++it)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int idx = 2 * (sub + LPR * it) + h;
+                pm[2 * it + h] = __fdiv_rn(pm[2 * it + h], sm);
+                if (idx < k && pm[2 * it + h] > bv) {
+                    bv = pm[2 * it + h];
+                    bi = idx;
+                }
+            }
+        group_argmax<LPR>(bv, bi);
+        top_m = bi;
+    }
+    int top_i, top_t;
+    {
+        float w[2 * NV];
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j) w[j] = yi[j];
+        float s = softmax_exp<LPR, NV>(w);
+        top_i = argmax_of_softmax<LPR, NV>(w, s, sub, k);
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j) w[j] = yt[j];
+        s = softmax_exp<LPR, NV>(w);
+        top_t = argmax_of_softmax<LPR, NV>(w, s, sub, k);
+    }
+    // ---- :264-267 agreement cases
+    const bool mi = top_m == top_i, mt = top_m == top_t;
+    const bool c1 = mi && mt, c2i = mi && !mt, c2t = mt && !mi;
+    const bool c3 = !(c1 || c2i || c2t);
+
+    // ---- :270-274 case-selected softmax of the averaged logits (eager rounding: no FMA contraction)
+    float pl[2 * NV];
+    if (c3) {
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j) pl[j] = pm[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j) {
+            float a;
+            if (c1)
+                a = __fdiv_rn(__fadd_rn(__fadd_rn(ym[j], yi[j]), yt[j]), 3.0f);
+            else if (c2i)
+                a = __fmul_rn(__fadd_rn(ym[j], yi[j]), 0.5f);
+            else
+                a = __fmul_rn(__fadd_rn(ym[j], yt[j]), 0.5f);
+            pl[j] = a;
+        }
+        const float s = softmax_exp<LPR, NV>(pl);
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j) pl[j] = __fdiv_rn(pl[j], s);
+    }
+    // ---- :293-294 teacher prototype probabilities
+    float tp[2 * NV];
+    load_row<LPR, NV>(A.tl, STIL_F32, A.ld_t, r, k, sub, A.vec_t, tp);
+#pragma unroll
+    for (int j = 0; j < 2 * NV; ++j) tp[j] = __fdiv_rn(tp[j], A.temperature);
+    {
+        const float s = softmax_exp<LPR, NV>(tp);
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j) tp[j] = __fdiv_rn(tp[j], s);
+    }
+    // ---- :295-298 smoothing mix, max/argmax, threshold
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int it = 0; it < NV; ++it)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 2 * it + h;
+            const int idx = 2 * (sub + LPR * it) + h;
+            const float t = __fmul_rn(A.one_minus_rate, tp[j]);
+            pl[j] = __fadd_rn(__fmul_rn(A.rate_pseudo, pl[j]), t);
+            pm[j] = __fadd_rn(__fmul_rn(A.rate_pseudo, pm[j]), t);
+            if (idx < k && pm[j] > bv) {
+                bv = pm[j];
+                bi = idx;
+            }
+        }
+    group_argmax<LPR>(bv, bi);
+    const bool m1 = bv >= A.th1;
+
+    if (!row_ok) return;
+    store_row<LPR, NV>(A.pseudo_label, A.ld_pl, row, k, sub, A.vec_pl, pl);
+    if (A.prediction) store_row<LPR, NV>(A.prediction, A.ld_pred, row, k, sub, A.vec_pred, pm);
+    if (sub == 0) {
+        if (A.max_prob) A.max_prob[row] = bv;
+        A.max_idx[row] = bi;
+        A.mask1[row] = m1;
+        if (A.case1) A.case1[row] = c1;
+        if (A.case2_i) A.case2_i[row] = c2i;
+        if (A.case2_t) A.case2_t[row] = c2t;
+        if (A.case3) A.case3[row] = c3;
+        if (A.top1) {
+            A.top1[row] = top_m;
+            A.top1[A.rows + row] = top_i;
+            A.top1[2LL * A.rows + row] = top_t;
+        }
+        if (A.cls) A.cls[row] = A.past_start ? bi : 0;
+        if (A.conf) A.conf[row] = A.past_start ? (unsigned char)m1 : (unsigned char)(0.0f >= A.th1);
+    }
+}
+
+// =====================================================================================
+// label.max(1) with threshold (utils/prototype_loss.py:31-32, STiLModel.py:204-205)
+// =====================================================================================
+__global__ void __launch_bounds__(kRowBlock) label_argmax_kernel(const float* __restrict__ label, long long ld,
+                                                                 int rows, int k, float th, int* cls,
+                                                                 unsigned char* conf, float* max_prob) {
+    const int row = blockIdx.x * (kRowBlock / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    bool has_nan = false;
+    for (int j = lane; j < k; j += 32) {
+        const float x = label[(long long)row * ld + j];
+        if (x != x && !has_nan) {  // torch.max propagates the first NaN
+            has_nan = true;
+            bv = x;
+            bi = j;
+        }
+        if (!has_nan && (x > bv || bi == 0x7fffffff)) {
+            bv = x;
+            bi = j;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const bool onan = ov != ov, mnan = bv != bv;
+        bool take;
+        if (onan || mnan)
+            take = onan && (!mnan || oi < bi);
+        else
+            take = ov > bv || (ov == bv && oi < bi);
+        if (take) {
+            bv = ov;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        cls[row] = bi;
+        conf[row] = bv >= th;
+        if (max_prob) max_prob[row] = bv;
+    }
+}
+
+__global__ void labelled_cls_kernel(const long long* y_l, int b_l, float th, int* cls, unsigned char* conf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b_l) {
+        cls[i] = (int)y_l[i];
+        conf[i] = 1.0f >= th;
+    }
+}
+
+// =====================================================================================
+// merge GEMM_STATS partials -> LSE, diagonal / picked logit, loss terms (deterministic reduction)
+// =====================================================================================
+__global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant__ FinishLaunch L) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grow = blockIdx.x * (kRowBlock / 32) + warp;
+    float term[2] = {0.f, 0.f};
+    if (grow < L.total_rows) {
+        int jid = 0;
+#pragma unroll
+        for (int j = 1; j < kMaxFinishJobs; ++j)
+            if (j < L.njobs && grow >= L.job[j].row_begin) jid = j;
+        const FinishJob& J = L.job[jid];
+        const int i = grow - J.row_begin;
+        // merge (max, sum) partials over column tiles
+        float m = -INFINITY;
+        for (int t = lane; t < J.tiles_n; t += 32) m = fmaxf(m, J.part_max[(long long)t * J.M + i]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int t = lane; t < J.tiles_n; t += 32)
+            s += J.part_sum[(long long)t * J.M + i] * expf(J.part_max[(long long)t * J.M + i] - m);
+        s = warp_sum(s);
+        const float lse = m + logf(s);
+        // dot product with the partner row
+        const long long yrow = J.kind == 0 ? (long long)(i + J.y_offset) : (long long)J.cls[i];
+        float dot = 0.f;
+        for (int d = lane; d < J.dim; d += 32)
+            dot += ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d) * ld_as_float(J.y, J.y_dtype, yrow * J.ldy + d);
+        dot = warp_sum(dot);
+        float z = dot * J.alpha;
+        if (J.sx) z *= J.sx[i];
+        if (J.sy) z *= J.sy[i + J.y_offset];
+        if (lane == 0) {
+            J.lse[i] = lse;
+            if (J.kind == 0) {
+                term[J.loss_slot] = J.coef * (lse - z);
+            } else {
+                const float p = expf(z - lse);
+                const float c = J.conf[i] ? 1.f : 0.f;
+                term[J.loss_slot] = -c * logf(p + 1e-7f) * J.coef;   // utils/prototype_loss.py:28,37-39
+                J.w[i] = c * J.coef * p / (p + 1e-7f);
+            }
+        }
+    }
+    // block partial (two slots), then the last block adds the partials in order
+    __shared__ float sred[2][kRowBlock / 32];
+    __shared__ bool is_last;
+    if (lane == 0) {
+        sred[0][warp] = term[0];
+        sred[1][warp] = term[1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < kRowBlock / 32; ++w) {
+            a += sred[0][w];
+            b += sred[1][w];
+        }
+        L.block_partials[2 * blockIdx.x] = a;
+        L.block_partials[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        is_last = atomicAdd(L.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 2) {
+        __threadfence();
+        float sum = 0.f;
+        const volatile float* bp = L.block_partials;
+        for (unsigned int b = 0; b < gridDim.x; ++b) sum += bp[2 * b + threadIdx.x];
+        bool used = false;
+        for (int j = 0; j < L.njobs; ++j) used |= L.job[j].loss_slot == (int)threadIdx.x;
+        if (used) L.out_loss[threadIdx.x] = sum;
+        if (threadIdx.x == 0) *L.ticket = 0u;
+    }
+}
+
+// =====================================================================================
+// backward of F.normalize (or plain cast) on the GEMM2 output
+// =====================================================================================
+__global__ void __launch_bounds__(kRowBlock) grad_finish_kernel(const __grid_constant__ GradFinishLaunch L) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grow = blockIdx.x * (kRowBlock / 32) + warp;
+    if (grow >= L.total_rows) return;
+    int jid = 0;
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+        if (j < L.njobs && grow >= L.job[j].row_begin) jid = j;
+    const GradFinishJob& J = L.job[jid];
+    const int i = grow - J.row_begin;
+    const float* g = J.g + (long long)i * J.dim;
+    if (J.sx) {
+        const float sx = J.sx[i];
+        float dot = 0.f;
+        for (int d = lane; d < J.dim; d += 32) dot += sx * ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d) * g[d];
+        dot = warp_sum(dot);
+        for (int d = lane; d < J.dim; d += 32) {
+            const float xh = sx * ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d);
+            st_from_float(J.dx, J.dx_dtype, (long long)i * J.ld_dx + d, sx * (g[d] - xh * dot));
+        }
+    } else {
+        for (int d = lane; d < J.dim; d += 32) st_from_float(J.dx, J.dx_dtype, (long long)i * J.ld_dx + d, g[d]);
+    }
+}
+
+// =====================================================================================
+// segmented per-class sums (STiLModel.py:199-226, 380-381): one warp per class, rows in index order
+// =====================================================================================
+__global__ void __launch_bounds__(kRowBlock) proto_accumulate_kernel(const void* __restrict__ feat, int dtype, int rows,
+                                                                     int dim, long long ld,
+                                                                     const int* __restrict__ cls,
+                                                                     const unsigned char* __restrict__ conf, int b_l,
+                                                                     float repeat_ratio, int k, float* class_sum,
+                                                                     float* class_count, float* psum, float* pcount) {
+    const int c = blockIdx.x * (kRowBlock / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= k) return;
+    for (int d0 = 0; d0 < dim; d0 += 128) {
+        float al[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
+        float nl = 0.f, nu = 0.f;
+        for (int r0 = 0; r0 < rows; r0 += 32) {
+            const int r = r0 + lane;
+            const bool hit = r < rows && conf[r] && cls[r] == c;
+            unsigned int ballot = __ballot_sync(0xffffffffu, hit);
+            while (ballot) {
+                const int b = __ffs(ballot) - 1;
+                ballot &= ballot - 1;
+                const int rr = r0 + b;
+                float* acc = rr < b_l ? al : au;
+                if (rr < b_l) nl += 1.f; else nu += 1.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int d = d0 + lane * 4 + j;
+                    if (d < dim) acc[j] += ld_as_float(feat, dtype, (long long)rr * ld + d);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = d0 + lane * 4 + j;
+            if (d < dim) {
+                const float v = __fadd_rn(__fdiv_rn(al[j], repeat_ratio), au[j]);   // :224
+                class_sum[(long long)c * dim + d] = v;
+                if (psum) psum[(long long)c * dim + d] += v;                         // :380
+            }
+        }
+        if (d0 == 0 && lane == 0) {
+            const float v = __fadd_rn(__fdiv_rn(nl, repeat_ratio), nu);             // :225
+            class_count[c] = v;
+            if (pcount) pcount[c] += v;                                              // :381
+        }
+    }
+}
+
+__global__ void proto_add_kernel(const float* class_sum, const float* class_count, int k, int dim, float* psum,
+                                 float* pcount) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (long long)k * dim) psum[i] += class_sum[i];
+    if (i < k) pcount[i] += class_count[i];
+}
+
+__global__ void proto_finalize_kernel(float* prototypes, float* psum, float* pcount, int dim, int* empty) {
+    const int c = blockIdx.x;
+    const float cnt = pcount[c];
+    __syncthreads();
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+        prototypes[(long long)c * dim + d] = psum[(long long)c * dim + d] / cnt;   // STiLModel.py:413
+        psum[(long long)c * dim + d] = 0.f;                                         // :414
+    }
+    if (threadIdx.x == 0) {
+        pcount[c] = 0.f;                                                            // :415
+        if (cnt < 1.f) atomicAdd(empty, 1);                                         // :411-412 (assert -> flag)
+    }
+}
+
+// =====================================================================================
+// masked soft-target CE, forward + gradient (STiLModel.py:301-303)
+// =====================================================================================
+struct SoftCeArgs {
+    const void* y[3];
+    int logit_dtype;
+    long long ld_y;
+    const float* pl;
+    long long ld_pl;
+    const unsigned char *mask1, *case1, *case2_i, *case2_t, *case3, *mask_random;
+    int rows, k;
+    float* dy[3];
+    long long ld_g;
+    float grad_scale;
+    float* block_partials;  // [blocks*3]
+    unsigned int* ticket;
+    float* losses;          // [3]
+};
+
+__global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeArgs A) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (kRowBlock / 32) + warp;
+    float lossv[3] = {0.f, 0.f, 0.f};
+    if (row < A.rows) {
+        const float m1 = A.mask1[row] ? 1.f : 0.f;
+        const float c1 = A.case1[row] ? 1.f : 0.f, c2i = A.case2_i[row] ? 1.f : 0.f;
+        const float c2t = A.case2_t[row] ? 1.f : 0.f, c3 = A.case3[row] ? 1.f : 0.f;
+        const float mr = A.mask_random[row] ? 1.f : 0.f;
+        const float wgt[3] = {m1 * c1, m1 * (c1 + c2t + c3 * mr), m1 * (c1 + c2i + c3 * (1.f - mr))};
+        const float* pl = A.pl + (long long)row * A.ld_pl;
+        float spl = 0.f;
+        for (int j = lane; j < A.k; j += 32) spl += pl[j];
+        spl = warp_sum(spl);
+        const float inv_rows = 1.0f / (float)A.rows;
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            float* dy = A.dy[h] ? A.dy[h] + (long long)row * A.ld_g : nullptr;
+            if (wgt[h] == 0.f) {
+                if (dy)
+                    for (int j = lane; j < A.k; j += 32) dy[j] = 0.f;
+                continue;  // warp-uniform
+            }
+            const long long off = (long long)row * A.ld_y;
+            float m = -INFINITY;
+            for (int j = lane; j < A.k; j += 32) m = fmaxf(m, ld_as_float(A.y[h], A.logit_dtype, off + j));
+            m = warp_max(m);
+            float s = 0.f, py = 0.f;
+            for (int j = lane; j < A.k; j += 32) {
+                const float y = ld_as_float(A.y[h], A.logit_dtype, off + j);
+                s += expf(y - m);
+                py += pl[j] * y;
+            }
+            s = warp_sum(s);
+            py = warp_sum(py);
+            const float lse = m + logf(s);
+            lossv[h] = (lse * spl - py) * wgt[h];   // -sum_k pl_k log_softmax(y)_k, times the row weight
+            if (dy) {
+                const float gs = A.grad_scale * wgt[h] * inv_rows;
+                for (int j = lane; j < A.k; j += 32) {
+                    const float y = ld_as_float(A.y[h], A.logit_dtype, off + j);
+                    dy[j] = gs * (expf(y - lse) * spl - pl[j]);
+                }
+            }
+        }
+    }
+    __shared__ float sred[3][kRowBlock / 32];
+    __shared__ bool is_last;
+    if (lane == 0)
+        for (int h = 0; h < 3; ++h) sred[h][warp] = lossv[h];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int h = 0; h < 3; ++h) {
+            float a = 0.f;
+            for (int w = 0; w < kRowBlock / 32; ++w) a += sred[h][w];
+            A.block_partials[3 * blockIdx.x + h] = a;
+        }
+        __threadfence();
+        is_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 3) {
+        __threadfence();
+        float sum = 0.f;
+        const volatile float* bp = A.block_partials;
+        for (unsigned int b = 0; b < gridDim.x; ++b) sum += bp[3 * b + threadIdx.x];
+        A.losses[threadIdx.x] = sum / (float)A.rows;   // .mean() over B_u
+        if (threadIdx.x == 0) *A.ticket = 0u;
+    }
+}
+
+__global__ void zero_u32_kernel(unsigned int* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0u;
+}
+
+template <int LPR, int NV>
+int launch_cgpl_t(const CgplArgs& A, cudaStream_t stream) {
+    const int rows_per_block = (kRowBlock / 32) * (32 / LPR);
+    const int blocks = (int)ceil_div(A.rows, rows_per_block);
+    cgpl_pgls_kernel<LPR, NV><<<blocks, kRowBlock, 0, stream>>>(A);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------- launchers
+void prep_add(PrepLaunch& L, const PrepJob& j) {
+    PrepJob& d = L.job[L.njobs];
+    d = j;
+    d.block_begin = L.total_blocks;
+    L.total_blocks += (int)ceil_div(j.rows, kPrepRows);
+    L.njobs++;
+}
+
+int launch_prep(const PrepLaunch& L, cudaStream_t stream) {
+    if (L.total_blocks == 0) {
+        if (L.n_zero > 0) return launch_zero_u32(L.zero_words, L.n_zero, stream);
+        return STIL_OK;
+    }
+    prep_kernel<<<L.total_blocks, kRowBlock, 0, stream>>>(L);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int launch_zero_u32(unsigned int* p, int n, cudaStream_t stream) {
+    zero_u32_kernel<<<(int)ceil_div(n, 128), 128, 0, stream>>>(p, n);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int64_t finish_blocks(int total_rows) { return ceil_div(total_rows, kRowBlock / 32); }
+
+int launch_finish(const FinishLaunch& L, cudaStream_t stream) {
+    if (L.total_rows == 0) return STIL_OK;
+    finish_kernel<<<(int)finish_blocks(L.total_rows), kRowBlock, 0, stream>>>(L);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int launch_grad_finish(const GradFinishLaunch& L, cudaStream_t stream) {
+    if (L.total_rows == 0) return STIL_OK;
+    grad_finish_kernel<<<(int)ceil_div(L.total_rows, kRowBlock / 32), kRowBlock, 0, stream>>>(L);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int launch_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
+                     const float* teacher_logits, int64_t ld_t, int64_t rows, int64_t k, float temperature,
+                     float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
+                     float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
+                     uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
+                     int32_t* cls, uint8_t* conf, cudaStream_t stream) {
+    STIL_REQUIRE(k >= 1 && k <= 1024, STIL_E_SHAPE, "cgpl_pgls supports 1 <= k <= 1024 classes (got %lld)", (long long)k);
+    STIL_REQUIRE(rows >= 0 && rows < (1LL << 31), STIL_E_SHAPE, "rows out of range");
+    if (rows == 0) return STIL_OK;
+    CgplArgs A;
+    A.y_m = y_m; A.y_i = y_i; A.y_t = y_t;
+    A.logit_dtype = logit_dtype; A.ld_y = ld_y;
+    A.tl = teacher_logits; A.ld_t = ld_t;
+    A.rows = (int)rows; A.k = (int)k;
+    A.temperature = temperature;
+    A.rate_pseudo = rate_pseudo;
+    // `1 - rate_pseudo` is formed in Python double and then rounded to fp32 (STiLModel.py:295)
+    A.one_minus_rate = (float)(1.0 - (double)rate_pseudo);
+    A.th1 = th1;
+    A.past_start = past_start_epoch;
+    A.pseudo_label = pseudo_label; A.ld_pl = ld_pl;
+    A.prediction = prediction; A.ld_pred = ld_pred;
+    A.max_prob = max_prob; A.max_idx = reinterpret_cast<long long*>(max_idx);
+    A.mask1 = mask1; A.case1 = case1; A.case2_i = case2_i; A.case2_t = case2_t; A.case3 = case3;
+    A.top1 = reinterpret_cast<long long*>(top1);
+    A.cls = cls; A.conf = conf;
+    const int esz = logit_dtype == STIL_BF16 ? 2 : 4;
+    auto al = [](const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+    A.vec_y = (ld_y % 2 == 0) && al(y_m, 2 * esz) && al(y_i, 2 * esz) && al(y_t, 2 * esz);
+    A.vec_t = (ld_t % 2 == 0) && al(teacher_logits, 8);
+    A.vec_pl = (ld_pl % 2 == 0) && al(pseudo_label, 8);
+    A.vec_pred = prediction ? ((ld_pred % 2 == 0) && al(prediction, 8)) : 0;
+    if (k <= 2) return launch_cgpl_t<1, 1>(A, stream);
+    if (k <= 16) return launch_cgpl_t<4, 2>(A, stream);
+    if (k <= 64) return launch_cgpl_t<8, 4>(A, stream);
+    if (k <= 128) return launch_cgpl_t<32, 2>(A, stream);
+    if (k <= 320) return launch_cgpl_t<32, 5>(A, stream);
+    if (k <= 512) return launch_cgpl_t<32, 8>(A, stream);
+    return launch_cgpl_t<32, 16>(A, stream);
+}
+
+int launch_label_argmax(const float* label, int64_t ld, int64_t rows, int64_t k, float threshold, int32_t* cls,
+                        uint8_t* conf, float* max_prob, cudaStream_t stream) {
+    if (rows == 0) return STIL_OK;
+    STIL_REQUIRE(k >= 1, STIL_E_SHAPE, "label_argmax needs k >= 1");
+    label_argmax_kernel<<<(int)ceil_div(rows, kRowBlock / 32), kRowBlock, 0, stream>>>(label, ld, (int)rows, (int)k,
+                                                                                      threshold, cls, conf, max_prob);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int launch_labelled_cls(const int64_t* y_l, int64_t b_l, float th, int32_t* cls, uint8_t* conf, cudaStream_t stream) {
+    if (b_l == 0) return STIL_OK;
+    labelled_cls_kernel<<<(int)ceil_div(b_l, 128), 128, 0, stream>>>(reinterpret_cast<const long long*>(y_l), (int)b_l,
+                                                                     th, cls, conf);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int launch_proto_accumulate(const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld, const int32_t* cls,
+                            const uint8_t* conf, int64_t b_l, float repeat_ratio, int64_t k, float* class_sum,
+                            float* class_count, float* psum, float* pcount, cudaStream_t stream) {
+    if (k == 0) return STIL_OK;
+    proto_accumulate_kernel<<<(int)ceil_div(k, kRowBlock / 32), kRowBlock, 0, stream>>>(
+        feat, dtype, (int)rows, (int)dim, ld, cls, conf, (int)b_l, repeat_ratio, (int)k, class_sum, class_count, psum,
+        pcount);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int launch_proto_add(const float* class_sum, const float* class_count, int64_t k, int64_t dim, float* psum,
+                     float* pcount, cudaStream_t stream) {
+    if (k == 0) return STIL_OK;
+    proto_add_kernel<<<(int)ceil_div(k * dim, 256), 256, 0, stream>>>(class_sum, class_count, (int)k, (int)dim, psum,
+                                                                       pcount);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int launch_proto_finalize(float* prototypes, float* psum, float* pcount, int64_t k, int64_t dim,
+                          int32_t* empty_classes, cudaStream_t stream) {
+    STIL_CUDA(cudaMemsetAsync(empty_classes, 0, sizeof(int32_t), stream));
+    if (k == 0) return STIL_OK;
+    proto_finalize_kernel<<<(int)k, 128, 0, stream>>>(prototypes, psum, pcount, (int)dim, empty_classes);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int64_t masked_softce_blocks(int64_t rows, int64_t) { return ceil_div(rows, kRowBlock / 32); }
+
+int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
+                         const float* pseudo_label, int64_t ld_pl, const uint8_t* mask1, const uint8_t* case1,
+                         const uint8_t* case2_i, const uint8_t* case2_t, const uint8_t* case3,
+                         const uint8_t* mask_random, int64_t rows, int64_t k, float* losses, float* d_y_m,
+                         float* d_y_i, float* d_y_t, int64_t ld_g, float grad_scale, float* block_partials,
+                         unsigned int* ticket, cudaStream_t stream) {
+    if (rows == 0) {
+        STIL_CUDA(cudaMemsetAsync(losses, 0, 3 * sizeof(float), stream));
+        return STIL_OK;
+    }
+    SoftCeArgs A;
+    A.y[0] = y_m; A.y[1] = y_i; A.y[2] = y_t;
+    A.logit_dtype = logit_dtype; A.ld_y = ld_y;
+    A.pl = pseudo_label; A.ld_pl = ld_pl;
+    A.mask1 = mask1; A.case1 = case1; A.case2_i = case2_i; A.case2_t = case2_t; A.case3 = case3;
+    A.mask_random = mask_random;
+    A.rows = (int)rows; A.k = (int)k;
+    A.dy[0] = d_y_m; A.dy[1] = d_y_i; A.dy[2] = d_y_t;
+    A.ld_g = ld_g; A.grad_scale = grad_scale;
+    A.block_partials = block_partials; A.ticket = ticket; A.losses = losses;
+    masked_softce_kernel<<<(int)masked_softce_blocks(rows, k), kRowBlock, 0, stream>>>(A);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+}  // namespace stil

@@ -1,0 +1,160 @@
+"""``STiLHead`` — the whole per-batch semi-supervised head as one enqueued step.
+
+One call of :meth:`STiLHead.run` does what ``STiLModel.training_step`` does between the encoders and
+``loss.backward()`` (``models/Disentangle/STiLModel.py:262-303, 317-322, 339, 374-381``): CGPL, PGLS,
+the ITC (InfoNCE) and PT (prototype) losses with their gradients w.r.t. the embeddings, the masked
+soft-target CE of the three student heads with its gradients, and the prototype partial sums added into
+the running buffers — ~10 kernel launches through ``stil_head_step`` (include/stil_head.h), captured in
+a CUDA graph.  All buffers are static (allocated once), so a replay has no host-side work.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import HeadStepArgs, check
+from .synth import HeadConfig
+
+_IN_EMBED = ("feat_i", "feat_t", "feat_m", "feat_m_e")
+_IN_TEACHER = ("y_m_ue", "y_i_ue", "y_t_ue")
+_IN_STUDENT = ("y_m", "y_i", "y_t")
+
+
+class STiLHead:
+    def __init__(self, cfg: HeadConfig, device="cuda", student_ce: bool = True, use_graph: bool = True,
+                 rate_uce: float = 1.0, logit_dtype: torch.dtype = torch.float32) -> None:
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("STiLHead runs on a CUDA device (sm_100a) only")
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        _lib.ensure_device(self.dev)
+        self.student_ce, self.use_graph, self.rate_uce = student_ce, use_graph, rate_uce
+        B, B_l, B_u, K, P = cfg.batch, cfg.b_l, cfg.b_u, cfg.num_classes, cfg.proj_dim
+        edt = torch.bfloat16 if cfg.embed_dtype == "bf16" else torch.float32
+        dev = self.dev
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)
+        self.inp: Dict[str, torch.Tensor] = {k: z(B, P, dtype=edt) for k in _IN_EMBED}
+        self.inp.update({k: z(B_u, K, dtype=logit_dtype) for k in _IN_TEACHER})
+        if student_ce:
+            self.inp.update({k: z(B, K, dtype=logit_dtype) for k in _IN_STUDENT})
+        self.inp["y_l"] = z(B_l, dtype=torch.int64)
+        self.inp["mask_random"] = z(B_u, dtype=torch.bool)
+        # state buffers carry the reference names (STiLModel.py:94-96)
+        self.prototypes = z(K, P)
+        self.prototypes_sum = z(K, P)
+        self.prototypes_count_sum = z(K, 1)
+        self.out: Dict[str, torch.Tensor] = {
+            "losses": z(5),                      # itc, pt, m_u, i_u, t_u
+            "d_feat_i": z(B, P, dtype=edt), "d_feat_t": z(B, P, dtype=edt), "d_feat_m": z(B, P, dtype=edt),
+            "pseudo_label": z(B_u, K), "max_prob": z(B_u), "max_idx": z(B_u, dtype=torch.int64),
+            "mask1": z(B_u, dtype=torch.bool), "case1": z(B_u, dtype=torch.bool), "case2_i": z(B_u, dtype=torch.bool),
+            "case2_t": z(B_u, dtype=torch.bool), "case3": z(B_u, dtype=torch.bool),
+            "class_sum": z(K, P), "class_count": z(K, 1),
+        }
+        if student_ce:
+            self.out.update({"d_y_m": z(B, K), "d_y_i": z(B, K), "d_y_t": z(B, K)})
+        lib = _lib.load()
+        code = _lib.STIL_BF16 if edt == torch.bfloat16 else _lib.STIL_F32
+        self._ws = torch.empty(lib.stil_head_step_workspace_bytes(B, B_l, K, P, code), dtype=torch.uint8, device=dev)
+        self._args = self._make_args(code, _lib.STIL_BF16 if logit_dtype == torch.bfloat16 else _lib.STIL_F32)
+        self.launches_per_step = lib.stil_head_step_launches(C.byref(self._args))
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._pinned: Optional[Dict[str, torch.Tensor]] = None
+        self._losses_host = torch.zeros(5, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.inp.values())
+        self.d2h_bytes = self._losses_host.numel() * 4
+
+    # ------------------------------------------------------------------------------------------
+    def _make_args(self, embed_code: int, logit_code: int) -> HeadStepArgs:
+        c, i, o = self.cfg, self.inp, self.out
+        p = lambda t: t.data_ptr()
+        a = HeadStepArgs()
+        a.batch, a.b_l, a.k, a.dim = c.batch, c.b_l, c.num_classes, c.proj_dim
+        a.embed_dtype, a.logit_dtype, a.grad_dtype = embed_code, logit_code, embed_code
+        a.temperature, a.lambda0, a.th1 = c.temperature, c.lambda_0, c.th1
+        a.rate_pseudo, a.repeat_ratio = c.rate_pseudo, c.repeat_ratio
+        a.past_start_epoch = int(c.past_start_epoch)
+        for k in _IN_EMBED + _IN_TEACHER:
+            setattr(a, k, p(i[k]))
+        if self.student_ce:
+            for k in _IN_STUDENT:
+                setattr(a, k, p(i[k]))
+            a.d_y_m, a.d_y_i, a.d_y_t = p(o["d_y_m"]), p(o["d_y_i"]), p(o["d_y_t"])
+        a.y_l, a.prototypes, a.mask_random = p(i["y_l"]), p(self.prototypes), p(i["mask_random"])
+        a.losses = p(o["losses"])
+        a.d_feat_i, a.d_feat_t, a.d_feat_m = p(o["d_feat_i"]), p(o["d_feat_t"]), p(o["d_feat_m"])
+        a.pseudo_label, a.max_prob, a.max_idx = p(o["pseudo_label"]), p(o["max_prob"]), p(o["max_idx"])
+        for k in ("mask1", "case1", "case2_i", "case2_t", "case3", "class_sum", "class_count"):
+            setattr(a, k, p(o[k]))
+        a.prototypes_sum, a.prototypes_count_sum = p(self.prototypes_sum), p(self.prototypes_count_sum)
+        a.rate_uce_scale = self.rate_uce
+        a.workspace, a.workspace_bytes = p(self._ws), self._ws.numel()
+        return a
+
+    def load(self, batch: Dict[str, torch.Tensor]) -> None:
+        """Copy one batch (CPU or CUDA tensors, keys as in synth.make_batch) into the static input buffers."""
+        for k, dst in self.inp.items():
+            dst.copy_(batch[k].to(dst.dtype) if batch[k].dtype != dst.dtype else batch[k], non_blocking=True)
+        if "prototypes" in batch:
+            self.prototypes.copy_(batch["prototypes"], non_blocking=True)
+
+    def _enqueue(self) -> None:
+        self._args.stream = torch.cuda.current_stream(self.dev).cuda_stream
+        check(_lib.load().stil_head_step(C.byref(self._args)))
+
+    def capture(self) -> None:
+        """Warm up once, then record the step into a CUDA graph (kernel params are baked in)."""
+        with torch.cuda.device(self.dev):
+            s = torch.cuda.Stream(self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                self._enqueue()
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self._graph = g
+
+    def run(self) -> None:
+        """Enqueue one head step on the current stream (graph replay when captured)."""
+        with torch.cuda.device(self.dev):
+            if self.use_graph:
+                if self._graph is None:
+                    self.capture()
+                self._graph.replay()
+            else:
+                self._enqueue()
+
+    # ------------------------------------------------------------------------------------------ end to end
+    def pin(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Stage a host batch in pinned memory (done once per batch by a data loader, outside the step)."""
+        pinned = {}
+        for k, dst in self.inp.items():
+            pinned[k] = batch[k].to(dst.dtype).contiguous().pin_memory()
+        return pinned
+
+    def step_host(self, pinned: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """One end-to-end step from HOST buffers: H2D of every input, the head, D2H of the five losses.
+        Returns the pinned host tensor of losses (valid after the stream synchronises)."""
+        with torch.cuda.device(self.dev):
+            for k, dst in self.inp.items():
+                dst.copy_(pinned[k], non_blocking=True)
+            self.run()
+            self._losses_host.copy_(self.out["losses"], non_blocking=True)
+        return self._losses_host
+
+    def finalize_prototypes(self) -> torch.Tensor:
+        """Epoch end (STiLModel.py:408-415)."""
+        empty = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        k, d = self.prototypes.shape
+        with torch.cuda.device(self.dev):
+            check(_lib.load().stil_proto_finalize(self.prototypes.data_ptr(), self.prototypes_sum.data_ptr(),
+                                                  self.prototypes_count_sum.data_ptr(), k, d, empty.data_ptr(),
+                                                  torch.cuda.current_stream(self.dev).cuda_stream))
+        return empty
