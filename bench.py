@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — STiL head-step throughput on B200 (BASELINE.json metric), with roofline and CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C2|C3]
+
+One "step" = one pass of the whole per-batch head (CGPL, PGLS, InfoNCE fwd+bwd, prototype loss fwd+bwd,
+masked soft-target CE fwd+bwd, prototype partial sums) over one synthetic DVM-shaped batch (C2: B=512 = 64
+labelled + 448 unlabelled, K=286, P=128, bf16 embeddings).  `value` = samples/s with inputs resident in HBM
+(CUDA-graph replay), `e2e` = the same through STiLHead.step_host with pinned HOST buffers (H2D of every
+input and D2H of the losses inside the timed region).  Timed steps rotate over enough distinct batches that
+the touched working set exceeds the 126 MB L2.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+import torch  # noqa: E402
+
+METRIC = "stil_head_step_samples_per_sec"
+UNIT = "samples/s"
+L2_BYTES = 126 * 2 ** 20
+
+
+def peaks():
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def get_cfg(name: str):
+    from stil_tta_b200 import synth
+    return synth.CONFIGS[name]()
+
+
+def workload_name(cfg, name):
+    return (f"{name} {cfg.name} head step B={cfg.batch} ({cfg.b_l}l+{cfg.b_u}u) K={cfg.num_classes} "
+            f"P={cfg.proj_dim} {cfg.embed_dtype} embeddings")
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_steps(cfg, steps: int, warmup: int, budget_s: float = 30.0):
+    """The reference head on the host cores: the oracle port (torch CPU, fp32, fwd+bwd), every op of
+    STiLModel.training_step lines 262-303, 317-322, 339, 374-381.  Returns (ms_per_step, steps_done, threads)."""
+    from oracle import stil_head_oracle as O
+    from stil_tta_b200 import synth
+    ncpu = len(os.sched_getaffinity(0))
+    batches = [synth.make_batch(cfg, seed=100 + i) for i in range(4)]
+    state = {"prototypes_sum": torch.zeros(cfg.num_classes, cfg.proj_dim),
+             "prototypes_count_sum": torch.zeros(cfg.num_classes, 1)}
+    # give the reference its best thread count (oversubscribed intra-op threads can be slower than one)
+    best = (float("inf"), 1)
+    for n in sorted({1, 2, 4, 8, 16, 32, ncpu}):
+        if n > ncpu:
+            continue
+        torch.set_num_threads(n)
+        O.head_step(batches[0], cfg, state=state)
+        t0 = time.perf_counter()
+        for i in range(3):
+            O.head_step(batches[i % 4], cfg, state=state)
+        best = min(best, ((time.perf_counter() - t0) / 3, n))
+    n = best[1]
+    torch.set_num_threads(n)
+    for i in range(warmup):
+        O.head_step(batches[i % 4], cfg, state=state)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        O.head_step(batches[i % 4], cfg, state=state)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dt / done * 1e3, done, n
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = get_cfg(args.config)
+    ms, done, n = cpu_reference_steps(cfg, args.steps, args.warmup, budget_s=120.0)
+    value = cfg.batch / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, args.config), "l2": "n/a (host)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n, "kind": "port",
+                         "sample": f"{done} head steps (fwd+bwd) of the oracle port of STiLModel.training_step's head, "
+                                   f"torch {torch.__version__} CPU fp32, best of 1..{len(os.sched_getaffinity(0))} threads = {n}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def timed_region(fn_step, steps, warmup, dist_on, dev):
+    """warm-up, barrier+sync, K steps between CUDA events on the current stream, barrier+sync; ms total."""
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn_step(i)
+    torch.cuda.synchronize(dev)
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn_step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if dist_on:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms
+
+
+def kernel_rooflines(cfg, dev, pk, reps=20, nbuf=48):
+    """Average launch duration of the row kernels, measured live with CUDA events around a CUDA graph of
+    `reps` back-to-back launches on rotating buffers (so the working set exceeds L2)."""
+    import stil_tta_b200 as S
+    from stil_tta_b200 import _lib
+    from stil_tta_b200._lib import ptr
+    lib = _lib.load()
+    B_u, K = cfg.b_u, cfg.num_classes
+    g = torch.Generator(device="cpu").manual_seed(1)
+    res = {}
+    # ---- cgpl_pgls: reads 3 logit rows + teacher logits (f32), writes pseudo_label + per-row outputs
+    ys = [[torch.randn(B_u, K, generator=g).to(dev) * 3 for _ in range(3)] for _ in range(nbuf)]
+    tl = [torch.randn(B_u, K, generator=g).to(dev) for _ in range(nbuf)]
+    pl = [torch.empty(B_u, K, device=dev) for _ in range(nbuf)]
+    mp = torch.empty(B_u, device=dev); mi = torch.empty(B_u, dtype=torch.int64, device=dev)
+    fl = [torch.empty(B_u, dtype=torch.bool, device=dev) for _ in range(5)]
+    cls = torch.empty(B_u, dtype=torch.int32, device=dev); conf = torch.empty(B_u, dtype=torch.bool, device=dev)
+
+    def launch_cgpl(i):
+        j = i % nbuf
+        _lib.check(lib.stil_cgpl_pgls(ptr(ys[j][0]), ptr(ys[j][1]), ptr(ys[j][2]), 0, K, ptr(tl[j]), K, B_u, K,
+                                      cfg.temperature, cfg.rate_pseudo, cfg.th1, 1, ptr(pl[j]), K, None, 0, ptr(mp),
+                                      ptr(mi), ptr(fl[0]), ptr(fl[1]), ptr(fl[2]), ptr(fl[3]), ptr(fl[4]), None,
+                                      ptr(cls), ptr(conf), _lib.stream_ptr(dev)))
+
+    def time_graph(launch):
+        s = torch.cuda.Stream(dev)
+        with torch.cuda.stream(s):
+            for i in range(3):
+                launch(i)
+        torch.cuda.synchronize(dev)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for i in range(reps):
+                launch(i)
+        gr.replay()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / (5 * reps) * 1e-3   # seconds per launch
+
+    t = time_graph(launch_cgpl)
+    bytes_alg = 4 * B_u * K * 4 + B_u * K * 4 + B_u * (4 + 8 + 5 + 4 + 1)
+    res["cgpl_pgls_kernel"] = {"bound": "hbm", "seconds": t, "alg_bytes": bytes_alg,
+                               "achieved": bytes_alg / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s"}
+    return res
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    import stil_tta_b200 as S
+    from stil_tta_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the STiL head has no CPU fallback (use --impl reference "
+                         "for the host-CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_on = world > 1
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = get_cfg(args.config)
+    pk = peaks()
+
+    # enough distinct batches that inputs+outputs+scratch touched between two uses of a buffer exceed L2
+    probe = S.STiLHead(cfg, device=dev)
+    per_head = probe.h2d_bytes + sum(t.numel() * t.element_size() for t in probe.out.values()) + probe._ws.numel()
+    nbuf = max(4, int(1.25 * L2_BYTES / per_head) + 1)
+    heads = [probe] + [S.STiLHead(cfg, device=dev) for _ in range(nbuf - 1)]
+    host_batches = [synth.make_batch(cfg, seed=2022 + i, rank=rank) for i in range(min(nbuf, 8))]
+    for i, h in enumerate(heads):
+        h.load(host_batches[i % len(host_batches)])
+        h.capture()
+    pinned = [heads[0].pin(b) for b in host_batches]
+    torch.cuda.synchronize(dev)
+
+    def step_resident(i):
+        heads[i % nbuf].run()
+
+    def step_e2e(i):
+        heads[i % nbuf].step_host(pinned[i % len(pinned)])
+
+    with ClockSampler(local) as cs:
+        ms = timed_region(step_resident, args.steps, args.warmup, dist_on, dev)
+    clocks = cs.summary()
+    ms_e2e = timed_region(step_e2e, args.steps, args.warmup, dist_on, dev)
+    ms_step, ms_step_e2e = ms / args.steps, ms_e2e / args.steps
+    value = cfg.batch * world / (ms_step * 1e-3)
+    e2e = cfg.batch * world / (ms_step_e2e * 1e-3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 operands / f32 accumulate" if cfg.embed_dtype == "bf16" else "f32 (3xbf16 split) / f32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": workload_name(cfg, args.config), "per_gpu_batch": cfg.batch,
+                   "l2": f"inputs larger than L2: {nbuf} rotating batches x {per_head / 2**20:.1f} MiB touched per step",
+                   "parallelism": f"dp{world}", "cuda_graph": True},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": heads[0].h2d_bytes,
+                "d2h_bytes_per_step": heads[0].d2h_bytes},
+        "gpu_launches": heads[0].launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+    if rank == 0:
+        rl = kernel_rooflines(cfg, dev, pk)
+        top = rl["cgpl_pgls_kernel"]
+        line["roofline"] = {"kernel": "cgpl_pgls_kernel", "bound": top["bound"], "achieved": top["achieved"],
+                            "peak": top["peak"], "unit": top["unit"], "frac": top["achieved"] / top["peak"],
+                            "traffic": None, "peak_source": pk["src"], "us_per_launch": top["seconds"] * 1e6}
+        if world == 1 and not args.no_cpu_baseline:
+            ms_cpu, done, n = cpu_reference_steps(cfg, 400, 3, budget_s=15.0)
+            line["cpu_baseline"] = {"value": cfg.batch / (ms_cpu * 1e-3), "unit": UNIT, "cores": n, "kind": "port",
+                                    "sample": f"{done} head steps (fwd+bwd) of the oracle port on the host, "
+                                              f"{ms_cpu:.2f} ms/step, best thread count of 1..{len(os.sched_getaffinity(0))} = {n}"}
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

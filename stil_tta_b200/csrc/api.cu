@@ -43,33 +43,34 @@ struct Operand {
 
 inline int64_t pad8(int64_t n) { return round_up(n, 8); }
 
-// segment pairs (x_seg, y_seg) for an (nx, ny)-segment product, most significant first
-int seg_pairs(int nx, int ny, int* xs, int* ys) {
+// segment pairs (x_seg, y_seg) with x_seg + y_seg <= order, most significant first.  Segment s carries
+// ~2^-9s of the value, so order 2 keeps every product above ~2^-26 (fp32-accurate), order 1 above 2^-17.
+int seg_pairs(int nx, int ny, int order, int* xs, int* ys) {
     int n = 0;
-    auto add = [&](int a, int b) { xs[n] = a; ys[n] = b; ++n; };
-    add(0, 0);
-    if (ny > 1) add(0, 1);
-    if (nx > 1) add(1, 0);
-    if (nx == 1 && ny > 2) add(0, 2);
-    if (ny == 1 && nx > 2) add(2, 0);
+    for (int o = 0; o <= order; ++o)
+        for (int a = 0; a <= o; ++a) {
+            const int b = o - a;
+            if (a < nx && b < ny && n < kMaxSegPairs) { xs[n] = a; ys[n] = b; ++n; }
+        }
     return n;
 }
 
-int fill_gemm_common(GemmJob& J, const Operand& X, int64_t xrow0, int64_t M, const Operand& Y, int64_t N, int64_t D) {
+int fill_gemm_common(GemmJob& J, const Operand& X, int64_t xrow0, int64_t M, const Operand& Y, int64_t N, int64_t D,
+                     int order = 2) {
     std::memset(&J, 0, sizeof(J));
     int rc = make_operand_map(&J.tmx, X.base + xrow0 * X.row_stride, D, M, X.nseg, X.row_stride, X.seg_stride);
     if (rc) return rc;
     rc = make_operand_map(&J.tmy, Y.base, D, N, Y.nseg, Y.row_stride, Y.seg_stride);
     if (rc) return rc;
     J.M = (int)M; J.N = (int)N; J.D = (int)D;
-    J.npair = seg_pairs(X.nseg, Y.nseg, J.xseg, J.yseg);
+    J.npair = seg_pairs(X.nseg, Y.nseg, order, J.xseg, J.yseg);
     J.alpha = 1.f;
     return STIL_OK;
 }
 
 // ------------------------------------------------------------------------------------------ InfoNCE plan
 struct InfoncePlan {
-    int nseg;
+    int nseg, nseg_t;
     __nv_bfloat16 *a_op, *b_op, *a_t, *b_t;   // [n, nseg, dim], [dim, nseg, ldt]
     int64_t ldt;
     float *ra, *rb;                             // inverse norms [n]
@@ -85,7 +86,7 @@ struct InfoncePlan {
 InfoncePlan plan_infonce(void* ws, int64_t ws_bytes, int64_t m, int64_t n, int64_t dim, int dtype, bool bwd) {
     InfoncePlan P;
     Workspace W(ws, ws_bytes);
-    P.nseg = dtype == STIL_BF16 ? 1 : 2;
+    P.nseg = dtype == STIL_BF16 ? 1 : 3;
     P.ldt = pad8(n);
     P.ldg = pad8(n);
     P.ticket = W.take<unsigned int>(64);
@@ -100,8 +101,9 @@ InfoncePlan plan_infonce(void* ws, int64_t ws_bytes, int64_t m, int64_t n, int64
     }
     P.block_partials = W.take<float>(2 * finish_blocks((int)(3 * m)) + 8);  // 3m rows: the fused step adds the prototype rows
     // backward-only regions (the forward never touches them, the query always counts them)
-    P.a_t = W.take<__nv_bfloat16>(dim * P.nseg * P.ldt);
-    P.b_t = W.take<__nv_bfloat16>(dim * P.nseg * P.ldt);
+    P.nseg_t = P.nseg > 2 ? 2 : P.nseg;
+    P.a_t = W.take<__nv_bfloat16>(dim * P.nseg_t * P.ldt);
+    P.b_t = W.take<__nv_bfloat16>(dim * P.nseg_t * P.ldt);
     for (int s = 0; s < 2; ++s) {
         P.gop[s] = W.take<__nv_bfloat16>(m * 2 * P.ldg);
         P.g[s] = W.take<float>(m * dim);
@@ -160,8 +162,8 @@ struct ProtoPlan {
 ProtoPlan plan_proto(void* ws, int64_t ws_bytes, int64_t rows, int64_t k, int64_t dim, int dtype) {
     ProtoPlan P;
     Workspace W(ws, ws_bytes);
-    P.feat_nseg = dtype == STIL_BF16 ? 1 : 2;
-    P.proto_nseg = dtype == STIL_BF16 ? 3 : 2;
+    P.feat_nseg = dtype == STIL_BF16 ? 1 : 3;
+    P.proto_nseg = 3;
     P.ldt = pad8(k);
     P.ldg = pad8(k);
     P.ticket = W.take<unsigned int>(64);
@@ -281,8 +283,8 @@ int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, int64_t m, int64_t n, 
     for (int s = 0; s < 2; ++s) {
         // d(x̂_i) = sum_j G'_ij y_j : X = G' [m, (hi,lo), n], Y = yᵀ [dim, nseg, n]
         const Operand X = grad_operand(P.gop[s], P.ldg);
-        const Operand Y = transposed_operand(s == 0 ? P.b_t : P.a_t, P.nseg, P.ldt);
-        int rc = fill_gemm_common(J2[s], X, 0, m, Y, dim, n);
+        const Operand Y = transposed_operand(s == 0 ? P.b_t : P.a_t, P.nseg_t, P.ldt);
+        int rc = fill_gemm_common(J2[s], X, 0, m, Y, dim, n, 1);
         if (rc) return rc;
         J2[s].mode = GEMM_STORE;
         J2[s].out = P.g[s];
@@ -376,8 +378,8 @@ STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* 
     const float inv_t = 1.0f / temperature;
     PrepLaunch PL;
     std::memset(&PL, 0, sizeof(PL));
-    prep_add(PL, prep_job(a_all, dtype, n, dim, ld, P.nseg, P.a_op, P.a_t, P.ldt, P.nseg, P.ra));
-    prep_add(PL, prep_job(b_all, dtype, n, dim, ld, P.nseg, P.b_op, P.b_t, P.ldt, P.nseg, P.rb));
+    prep_add(PL, prep_job(a_all, dtype, n, dim, ld, P.nseg, P.a_op, P.a_t, P.ldt, P.nseg_t, P.ra));
+    prep_add(PL, prep_job(b_all, dtype, n, dim, ld, P.nseg, P.b_op, P.b_t, P.ldt, P.nseg_t, P.rb));
     if ((rc = launch_prep(PL, S(stream)))) return rc;
     const Operand A = rowmajor_operand(a_all, dtype, dim, ld, P.a_op, P.nseg);
     const Operand B = rowmajor_operand(b_all, dtype, dim, ld, P.b_op, P.nseg);
@@ -526,7 +528,7 @@ int proto_grad_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, 
 int proto_store_job(GemmJob& J, const ProtoPlan& P, int64_t rows, int64_t dim, int64_t k, float* out, int64_t ld_out) {
     const Operand X = grad_operand(P.gop, P.ldg);
     const Operand Y = transposed_operand(P.proto_t, 2, P.ldt);
-    int rc = fill_gemm_common(J, X, 0, rows, Y, dim, k);
+    int rc = fill_gemm_common(J, X, 0, rows, Y, dim, k, 1);
     if (rc) return rc;
     J.mode = GEMM_STORE;
     J.out = out;
@@ -700,7 +702,7 @@ StepPlan plan_step(void* ws, int64_t ws_bytes, int64_t batch, int64_t b_l, int64
     P.pt = plan_proto(base ? base + n0.bytes : nullptr, base ? p0.bytes : 0, batch, k, dim, dtype);
     Workspace W(base ? base + n0.bytes + p0.bytes : nullptr, ws_bytes - n0.bytes - p0.bytes);
     P.ldk = round_up(k, 4);
-    P.teach_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(b_u * 2 * dim);
+    P.teach_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(b_u * 3 * dim);
     P.teacher_logits = W.take<float>(b_u * P.ldk);
     P.cls = W.take<int32_t>(batch);
     P.conf = W.take<uint8_t>(batch);
@@ -758,11 +760,11 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     PrepLaunch PL;
     std::memset(&PL, 0, sizeof(PL));
     PL.zero_words = P.nce.ticket; PL.n_zero = 32;   // [0] finish ticket, [16] masked-CE ticket
-    prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, P.nce.a_t, P.nce.ldt, P.nce.nseg, P.nce.ra));
-    prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, P.nce.b_t, P.nce.ldt, P.nce.nseg, P.nce.rb));
+    prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, P.nce.a_t, P.nce.ldt, P.nce.nseg_t, P.nce.ra));
+    prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, P.nce.b_t, P.nce.ldt, P.nce.nseg_t, P.nce.rb));
     if (dt != STIL_BF16) {
         prep_add(PL, prep_job(a->feat_m, dt, B, D, D, P.pt.feat_nseg, P.pt.feat_op, nullptr, 0, 0, nullptr));
-        prep_add(PL, prep_job(feat_m_ue, dt, B_u, D, D, 2, P.teach_op, nullptr, 0, 0, nullptr));
+        prep_add(PL, prep_job(feat_m_ue, dt, B_u, D, D, 3, P.teach_op, nullptr, 0, 0, nullptr));
     }
     prep_add(PL, prep_job(a->prototypes, STIL_F32, K, D, D, P.pt.proto_nseg, P.pt.proto_op, P.pt.proto_t, P.pt.ldt, 2, nullptr));
     if ((rc = launch_prep(PL, st))) return rc;
@@ -776,7 +778,7 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     if ((rc = proto_stats_job(GL.job[2], P.pt, a->feat_m, dt, B, D, D, K, inv_t))) return rc;
     GL.njobs = 3;
     if (B_u > 0) {
-        const Operand X = rowmajor_operand(feat_m_ue, dt, D, D, P.teach_op, 2);
+        const Operand X = rowmajor_operand(feat_m_ue, dt, D, D, P.teach_op, 3);
         const Operand Y = rowmajor_operand(nullptr, STIL_F32, D, D, P.pt.proto_op, P.pt.proto_nseg);
         if ((rc = fill_gemm_common(GL.job[3], X, 0, B_u, Y, K, D))) return rc;
         GL.job[3].mode = GEMM_STORE;

@@ -16,7 +16,7 @@ enum GemmMode : int {
     GEMM_GRAD = 2    // G = u_i e^{L-lse_x[i]} + v e^{L-lse_y[j]} - d_i [j == tgt_i], times cs_j, as bf16 hi/lo
 };
 constexpr int kMaxGemmJobs = 4;
-constexpr int kMaxSegPairs = 4;
+constexpr int kMaxSegPairs = 6;
 constexpr int kTileM = 128, kTileN = 128, kTileK = 64;
 
 struct alignas(64) GemmJob {

@@ -110,11 +110,15 @@ class STiLHead:
     def capture(self) -> None:
         """Warm up once, then record the step into a CUDA graph (kernel params are baked in)."""
         with torch.cuda.device(self.dev):
+            # the warm-up run must not leave a trace in the running accumulators (STiLModel.py:380-381)
+            keep = (self.prototypes_sum.clone(), self.prototypes_count_sum.clone())
             s = torch.cuda.Stream(self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
                 self._enqueue()
             torch.cuda.current_stream(self.dev).wait_stream(s)
+            self.prototypes_sum.copy_(keep[0])
+            self.prototypes_count_sum.copy_(keep[1])
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

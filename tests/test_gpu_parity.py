@@ -56,7 +56,7 @@ def test_clip_loss_matches_oracle(S, O, n, d, dtype, T, lam):
     ac, bc = dev(a).requires_grad_(True), dev(b).requires_grad_(True)
     loss, logits, labels = S.CLIPLoss(T, lam)(ac, bc)
     ga, gb = torch.autograd.grad(loss, (ac, bc))
-    assert abs(float(loss) - float(loss_r)) <= REL * abs(float(loss_r)) + 1e-6
+    assert abs(float(loss) - float(loss_r)) <= REL * abs(float(loss_r)) + 5e-5   # abs floor: |logit| <= 1/T = 10
     assert torch.equal(labels.cpu(), labels_r)
     assert float((logits.cpu() - logits_r).abs().max()) <= 2e-3     # |logit| <= 1/T
     gtol = REL if dtype == torch.float32 else 1e-2                    # bf16 grads: output rounding 2^-9
@@ -108,7 +108,7 @@ def test_prototype_loss_matches_oracle(S, O, n, k, d, dtype, T, th):
     fc = dev(feat).requires_grad_(True)
     loss = S.PrototypeLoss(T, th)(dev(label), dev(protos), fc)
     (gc,) = torch.autograd.grad(loss, fc)
-    assert abs(float(loss) - float(loss_r)) <= REL * abs(float(loss_r)) + 1e-6
+    assert abs(float(loss) - float(loss_r)) <= REL * abs(float(loss_r)) + 5e-5   # abs floor: |logit| <= 1/T = 10
     assert_rel(gc, g_r, REL if dtype == torch.float32 else 1e-2, "d_feat")
 
 
