@@ -181,6 +181,9 @@ typedef struct stil_head_step_args {
     float *prototypes_sum, *prototypes_count_sum;     /* accumulated in place when non-NULL */
     float rate_uce_scale;                             /* grad_scale of the f-1 gradients */
     void* workspace; int64_t workspace_bytes; void* stream;
+    /* optional instrumentation (bench.py): cudaEvent_t[n_timing_events] recorded on `stream` before each
+     * main-chain launch and after the last one; leave NULL/0 otherwise (and always during graph capture) */
+    void** timing_events; int n_timing_events;
 } stil_head_step_args;
 STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int64_t k, int64_t dim, int embed_dtype);
 STIL_API int stil_head_step(const stil_head_step_args* args);

@@ -2,6 +2,7 @@
 // plans the caller-provided workspace, builds TMA descriptors and job tables, enqueues kernels.
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 
 #include "internal.h"
 
@@ -68,11 +69,25 @@ int fill_gemm_common(GemmJob& J, const Operand& X, int64_t xrow0, int64_t M, con
     return STIL_OK;
 }
 
+// dX[M, ncols] = G[M, (hi,lo), n] · Y[n, ncols]: X = G (K-major), Y read in place as an MN-major operand
+int fill_gemm_store_mn(GemmJob& J, const Operand& G, int64_t M, const Operand& Y, int64_t n, int64_t ncols) {
+    std::memset(&J, 0, sizeof(J));
+    int rc = make_operand_map(&J.tmx, G.base, n, M, G.nseg, G.row_stride, G.seg_stride, 128);
+    if (rc) return rc;
+    rc = make_operand_map(&J.tmy, Y.base, ncols, n, Y.nseg, Y.row_stride, Y.seg_stride, 64);
+    if (rc) return rc;
+    J.M = (int)M; J.N = (int)ncols; J.D = (int)n;
+    J.npair = seg_pairs(G.nseg, Y.nseg, 1, J.xseg, J.yseg);
+    J.alpha = 1.f;
+    J.mode = GEMM_STORE;
+    J.y_mn_major = 1;
+    return STIL_OK;
+}
+
 // ------------------------------------------------------------------------------------------ InfoNCE plan
 struct InfoncePlan {
-    int nseg, nseg_t;
-    __nv_bfloat16 *a_op, *b_op, *a_t, *b_t;   // [n, nseg, dim], [dim, nseg, ldt]
-    int64_t ldt;
+    int nseg;
+    __nv_bfloat16 *a_op, *b_op;                 // [n, nseg, dim] (fp32 inputs only)
     float *ra, *rb;                             // inverse norms [n]
     float *pmax[2], *psum[2];                   // [tiles_n, m]
     float* block_partials;
@@ -87,7 +102,6 @@ InfoncePlan plan_infonce(void* ws, int64_t ws_bytes, int64_t m, int64_t n, int64
     InfoncePlan P;
     Workspace W(ws, ws_bytes);
     P.nseg = dtype == STIL_BF16 ? 1 : 3;
-    P.ldt = pad8(n);
     P.ldg = pad8(n);
     P.ticket = W.take<unsigned int>(64);
     P.ra = W.take<float>(n);
@@ -101,9 +115,6 @@ InfoncePlan plan_infonce(void* ws, int64_t ws_bytes, int64_t m, int64_t n, int64
     }
     P.block_partials = W.take<float>(2 * finish_blocks((int)(3 * m)) + 8);  // 3m rows: the fused step adds the prototype rows
     // backward-only regions (the forward never touches them, the query always counts them)
-    P.nseg_t = P.nseg > 2 ? 2 : P.nseg;
-    P.a_t = W.take<__nv_bfloat16>(dim * P.nseg_t * P.ldt);
-    P.b_t = W.take<__nv_bfloat16>(dim * P.nseg_t * P.ldt);
     for (int s = 0; s < 2; ++s) {
         P.gop[s] = W.take<__nv_bfloat16>(m * 2 * P.ldg);
         P.g[s] = W.take<float>(m * dim);
@@ -128,14 +139,6 @@ Operand rowmajor_operand(const void* x, int dtype, int64_t dim, int64_t ld, cons
     }
     return O;
 }
-Operand transposed_operand(const __nv_bfloat16* op_t, int nseg, int64_t ldt) {
-    Operand O;
-    O.base = op_t;
-    O.nseg = nseg;
-    O.row_stride = (int64_t)nseg * ldt;
-    O.seg_stride = ldt;
-    return O;
-}
 Operand grad_operand(const __nv_bfloat16* gop, int64_t ldg) {
     Operand O;
     O.base = gop;
@@ -148,8 +151,7 @@ Operand grad_operand(const __nv_bfloat16* gop, int64_t ldg) {
 // ------------------------------------------------------------------------------------------ proto plan
 struct ProtoPlan {
     int feat_nseg, proto_nseg;
-    __nv_bfloat16 *feat_op, *proto_op, *proto_t;
-    int64_t ldt;       // pad8(k)
+    __nv_bfloat16 *feat_op, *proto_op;
     float *pmax, *psum;
     float* block_partials;
     unsigned int* ticket;
@@ -164,12 +166,10 @@ ProtoPlan plan_proto(void* ws, int64_t ws_bytes, int64_t rows, int64_t k, int64_
     Workspace W(ws, ws_bytes);
     P.feat_nseg = dtype == STIL_BF16 ? 1 : 3;
     P.proto_nseg = 3;
-    P.ldt = pad8(k);
     P.ldg = pad8(k);
     P.ticket = W.take<unsigned int>(64);
     P.feat_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(rows * P.feat_nseg * dim);
     P.proto_op = W.take<__nv_bfloat16>(k * P.proto_nseg * dim);
-    P.proto_t = W.take<__nv_bfloat16>(dim * 2 * P.ldt);
     const int64_t tiles_n = ceil_div(k, kTileN);
     P.pmax = W.take<float>(tiles_n * rows);
     P.psum = W.take<float>(tiles_n * rows);
@@ -266,8 +266,16 @@ int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const
         J.alpha = inv_t;
         J.sx = (s == 0 ? P.ra : P.rb) + off;
         J.sy = s == 0 ? P.rb : P.ra;
-        J.lse_x = (s == 0 ? lse_row_all : lse_col_all) + off;
-        J.lse_y = s == 0 ? lse_col_all : lse_row_all;
+        if (lse_row_all) {
+            J.lse_x = (s == 0 ? lse_row_all : lse_col_all) + off;
+            J.lse_y = s == 0 ? lse_col_all : lse_row_all;
+        } else {
+            // single-process step: merge the GEMM_STATS partials in the kernel (rows: this side, columns: the
+            // other side's rows) instead of waiting for the finish kernel
+            J.px_max = P.pmax[s]; J.px_sum = P.psum[s];
+            J.py_max = P.pmax[1 - s]; J.py_sum = P.psum[1 - s];
+            J.px_tiles = J.py_tiles = (int)ceil_div(n, kTileN);
+        }
         J.u_scalar = (s == 0 ? lambda0 : 1.f - lambda0) / (float)n;
         J.v_scalar = (s == 0 ? 1.f - lambda0 : lambda0) / (float)n;
         J.d_scalar = 1.f / (float)n;
@@ -279,17 +287,75 @@ int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const
     return STIL_OK;
 }
 
-int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, int64_t m, int64_t n, int64_t dim) {
+// d(x̂_i) = sum_j G'_ij y_j, then the backward of F.normalize in the epilogue when one tile spans `dim`
+int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const Operand& B, const void* a_all,
+                       const void* b_all, int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t off,
+                       void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, bool* fused) {
+    const int esz = dtype == STIL_BF16 ? 2 : 4;
+    *fused = dim <= kTileN;
     for (int s = 0; s < 2; ++s) {
-        // d(x̂_i) = sum_j G'_ij y_j : X = G' [m, (hi,lo), n], Y = yᵀ [dim, nseg, n]
         const Operand X = grad_operand(P.gop[s], P.ldg);
-        const Operand Y = transposed_operand(s == 0 ? P.b_t : P.a_t, P.nseg_t, P.ldt);
-        int rc = fill_gemm_common(J2[s], X, 0, m, Y, dim, n, 1);
+        const Operand& Y = s == 0 ? B : A;
+        int rc = fill_gemm_store_mn(J2[s], X, m, Y, n, dim);
         if (rc) return rc;
-        J2[s].mode = GEMM_STORE;
-        J2[s].out = P.g[s];
-        J2[s].ld_out = dim;
+        if (*fused) {
+            J2[s].fin_dx = s == 0 ? d_a : d_b;
+            J2[s].fin_dx_dtype = grad_dtype;
+            J2[s].fin_ld_dx = ld_grad;
+            J2[s].fin_x = static_cast<const char*>(s == 0 ? a_all : b_all) + off * ld * esz;
+            J2[s].fin_x_dtype = dtype;
+            J2[s].fin_ldx = ld;
+            J2[s].fin_sx = (s == 0 ? P.ra : P.rb) + off;
+        } else {
+            J2[s].out = P.g[s];
+            J2[s].ld_out = dim;
+        }
     }
+    return STIL_OK;
+}
+
+void infonce_gradfinish_jobs(GradFinishJob* G2, const InfoncePlan& P, const void* a_all, const void* b_all, int dtype,
+                             int64_t m, int64_t dim, int64_t ld, int64_t off, void* d_a, void* d_b, int grad_dtype,
+                             int64_t ld_grad) {
+    const int esz = dtype == STIL_BF16 ? 2 : 4;
+    for (int s = 0; s < 2; ++s) {
+        GradFinishJob& j = G2[s];
+        std::memset(&j, 0, sizeof(j));
+        j.g = P.g[s];
+        j.x = static_cast<const char*>(s == 0 ? a_all : b_all) + off * ld * esz;
+        j.x_dtype = dtype; j.ldx = ld;
+        j.sx = (s == 0 ? P.ra : P.rb) + off;
+        j.dx = s == 0 ? d_a : d_b;
+        j.dx_dtype = grad_dtype; j.ld_dx = ld_grad;
+        j.rows = (int)m; j.dim = (int)dim;
+        j.row_begin = (int)(s * m);
+    }
+}
+
+// side streams for the independent branches of the step (fork/join with events; capturable)
+struct SideStreams {
+    cudaStream_t s[3];
+    cudaEvent_t fork, join[3];
+    bool ready;
+};
+SideStreams g_side[64];
+std::mutex g_side_mutex;
+
+int get_side_streams(SideStreams** out) {
+    int dev = 0;
+    STIL_CUDA(cudaGetDevice(&dev));
+    STIL_REQUIRE(dev >= 0 && dev < 64, STIL_E_ARG, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    SideStreams& S = g_side[dev];
+    if (!S.ready) {
+        for (int i = 0; i < 3; ++i) {
+            STIL_CUDA(cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking));
+            STIL_CUDA(cudaEventCreateWithFlags(&S.join[i], cudaEventDisableTiming));
+        }
+        STIL_CUDA(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
+        S.ready = true;
+    }
+    *out = &S;
     return STIL_OK;
 }
 
@@ -378,8 +444,8 @@ STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* 
     const float inv_t = 1.0f / temperature;
     PrepLaunch PL;
     std::memset(&PL, 0, sizeof(PL));
-    prep_add(PL, prep_job(a_all, dtype, n, dim, ld, P.nseg, P.a_op, P.a_t, P.ldt, P.nseg_t, P.ra));
-    prep_add(PL, prep_job(b_all, dtype, n, dim, ld, P.nseg, P.b_op, P.b_t, P.ldt, P.nseg_t, P.rb));
+    prep_add(PL, prep_job(a_all, dtype, n, dim, ld, P.nseg, P.a_op, nullptr, 0, 0, P.ra));
+    prep_add(PL, prep_job(b_all, dtype, n, dim, ld, P.nseg, P.b_op, nullptr, 0, 0, P.rb));
     if ((rc = launch_prep(PL, S(stream)))) return rc;
     const Operand A = rowmajor_operand(a_all, dtype, dim, ld, P.a_op, P.nseg);
     const Operand B = rowmajor_operand(b_all, dtype, dim, ld, P.b_op, P.nseg);
@@ -392,24 +458,17 @@ STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* 
     gemm_job_tiles(GL);
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
     std::memset(&GL, 0, sizeof(GL));
-    if ((rc = infonce_store_jobs(GL.job, P, m, n, dim))) return rc;
+    bool fused = false;
+    if ((rc = infonce_store_jobs(GL.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
+                                 ld_grad, &fused)))
+        return rc;
     GL.njobs = 2;
     gemm_job_tiles(GL);
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    if (fused) return STIL_OK;
     GradFinishLaunch GF;
     std::memset(&GF, 0, sizeof(GF));
-    const int esz = dtype == STIL_BF16 ? 2 : 4;
-    for (int s = 0; s < 2; ++s) {
-        GradFinishJob& j = GF.job[s];
-        j.g = P.g[s];
-        j.x = static_cast<const char*>(s == 0 ? a_all : b_all) + row_offset * ld * esz;
-        j.x_dtype = dtype; j.ldx = ld;
-        j.sx = (s == 0 ? P.ra : P.rb) + row_offset;
-        j.dx = s == 0 ? d_a : d_b;
-        j.dx_dtype = grad_dtype; j.ld_dx = ld_grad;
-        j.rows = (int)m; j.dim = (int)dim;
-        j.row_begin = (int)(s * m);
-    }
+    infonce_gradfinish_jobs(GF.job, P, a_all, b_all, dtype, m, dim, ld, row_offset, d_a, d_b, grad_dtype, ld_grad);
     GF.njobs = 2;
     GF.total_rows = (int)(2 * m);
     return launch_grad_finish(GF, S(stream));
@@ -463,7 +522,7 @@ STIL_API int stil_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, i
                  "cgpl_pgls: leading dimension smaller than k");
     return launch_cgpl_pgls(y_m, y_i, y_t, logit_dtype, ld_y, teacher_logits, ld_t, rows, k, temperature, rate_pseudo,
                             th1, past_start_epoch, pseudo_label, ld_pl, prediction, ld_pred, max_prob, max_idx, mask1,
-                            case1, case2_i, case2_t, case3, top1, cls, conf, S(stream));
+                            case1, case2_i, case2_t, case3, top1, cls, conf, nullptr, 0, nullptr, nullptr, S(stream));
 }
 
 STIL_API int stil_label_argmax(const float* label, int64_t ld, int64_t rows, int64_t k, float threshold, int32_t* cls,
@@ -510,29 +569,47 @@ void proto_finish_job(FinishJob& F, const ProtoPlan& P, const void* feat, int dt
 }
 int proto_grad_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld,
                    int64_t k, float inv_t, const int32_t* cls, const float* lse, const float* w,
-                   const float* grad_loss) {
+                   const float* grad_loss, const float* prototypes, const uint8_t* conf) {
     const Operand X = rowmajor_operand(feat, dtype, dim, ld, P.feat_op, P.feat_nseg);
     const Operand Y = rowmajor_operand(nullptr, STIL_F32, dim, dim, P.proto_op, P.proto_nseg);
     int rc = fill_gemm_common(J, X, 0, rows, Y, k, dim);
     if (rc) return rc;
     J.mode = GEMM_GRAD;
     J.alpha = inv_t;
-    J.lse_x = lse;
-    J.u_vec = w;
     J.tgt_vec = cls;
     J.gscale = grad_loss;
     J.gop = P.gop;
     J.ld_g = P.ldg;
+    if (lse) {
+        J.lse_x = lse;
+        J.u_vec = w;
+    } else {
+        // fused: LSE from the GEMM_STATS partials, coefficient from the picked logit, both in the kernel
+        J.px_max = P.pmax; J.px_sum = P.psum;
+        J.px_tiles = (int)ceil_div(k, kTileN);
+        J.w_x = feat; J.w_x_dtype = dtype; J.w_ldx = ld;
+        J.w_y = prototypes; J.w_ldy = dim;
+        J.w_conf = conf;
+        J.w_coef = 1.f / (float)rows;
+    }
     return STIL_OK;
 }
-int proto_store_job(GemmJob& J, const ProtoPlan& P, int64_t rows, int64_t dim, int64_t k, float* out, int64_t ld_out) {
+// d_feat = G · prototypes (prototypes read in place, MN-major); cast to grad_dtype in the epilogue when possible
+int proto_store_job(GemmJob& J, const ProtoPlan& P, int64_t rows, int64_t dim, int64_t k, void* d_feat, int grad_dtype,
+                    int64_t ld_grad, bool* fused) {
     const Operand X = grad_operand(P.gop, P.ldg);
-    const Operand Y = transposed_operand(P.proto_t, 2, P.ldt);
-    int rc = fill_gemm_common(J, X, 0, rows, Y, dim, k, 1);
+    const Operand Y = rowmajor_operand(nullptr, STIL_F32, dim, dim, P.proto_op, P.proto_nseg);
+    int rc = fill_gemm_store_mn(J, X, rows, Y, k, dim);
     if (rc) return rc;
-    J.mode = GEMM_STORE;
-    J.out = out;
-    J.ld_out = ld_out;
+    *fused = dim <= kTileN;
+    if (*fused) {
+        J.fin_dx = d_feat;
+        J.fin_dx_dtype = grad_dtype;
+        J.fin_ld_dx = ld_grad;
+    } else {
+        J.out = P.g;
+        J.ld_out = dim;
+    }
     return STIL_OK;
 }
 }  // namespace
@@ -593,23 +670,23 @@ STIL_API int stil_proto_ce_bwd(const void* feat, int dtype, int64_t rows, int64_
     PrepLaunch PL;
     std::memset(&PL, 0, sizeof(PL));
     if (dtype != STIL_BF16) prep_add(PL, prep_job(feat, dtype, rows, dim, ld, P.feat_nseg, P.feat_op, nullptr, 0, 0, nullptr));
-    prep_add(PL, prep_job(prototypes, STIL_F32, k, dim, dim, P.proto_nseg, P.proto_op, P.proto_t, P.ldt, 2, nullptr));
+    prep_add(PL, prep_job(prototypes, STIL_F32, k, dim, dim, P.proto_nseg, P.proto_op, nullptr, 0, 0, nullptr));
     if ((rc = launch_prep(PL, S(stream)))) return rc;
     GemmLaunch GL;
     std::memset(&GL, 0, sizeof(GL));
-    if ((rc = proto_grad_job(GL.job[0], P, feat, dtype, rows, dim, ld, k, inv_t, cls, lse, w, grad_loss))) return rc;
-    GL.njobs = 1;
-    gemm_job_tiles(GL);
-    if ((rc = launch_gemm(GL, S(stream)))) return rc;
-    const bool direct = grad_dtype == STIL_F32 && ld_grad % 4 == 0;
-    std::memset(&GL, 0, sizeof(GL));
-    if ((rc = proto_store_job(GL.job[0], P, rows, dim, k, direct ? static_cast<float*>(d_feat) : P.g,
-                              direct ? ld_grad : dim)))
+    if ((rc = proto_grad_job(GL.job[0], P, feat, dtype, rows, dim, ld, k, inv_t, cls, lse, w, grad_loss, prototypes,
+                             nullptr)))
         return rc;
     GL.njobs = 1;
     gemm_job_tiles(GL);
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
-    if (!direct) {
+    std::memset(&GL, 0, sizeof(GL));
+    bool fused = false;
+    if ((rc = proto_store_job(GL.job[0], P, rows, dim, k, d_feat, grad_dtype, ld_grad, &fused))) return rc;
+    GL.njobs = 1;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    if (!fused) {
         GradFinishLaunch GF;
         std::memset(&GF, 0, sizeof(GF));
         GradFinishJob& j = GF.job[0];
@@ -723,11 +800,11 @@ STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int6
 
 STIL_API int stil_head_step_launches(const stil_head_step_args* a) {
     if (!a) return 0;
-    // prep, gemm(stats+teacher), labelled cls, cgpl_pgls, finish, gemm(grad), gemm(store), grad_finish, proto_accumulate
-    int n = 9;
-    if (a->b_l == 0) n -= 1;
-    if (a->batch == a->b_l) n -= 1;
-    if (a->y_m) n += 1;  // masked soft CE
+    // main chain: prep, gemm(stats+teacher), cgpl_pgls, gemm(grad), gemm(dX) [+ grad_finish when dim > 128]
+    // side branches: finish (losses), proto_accumulate, masked soft CE
+    int n = 7;
+    if (a->dim > kTileN) n += 1;
+    if (a->y_m) n += 1;
     return n;
 }
 
@@ -749,24 +826,34 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
                      a->case1 && a->case2_i && a->case2_t && a->case3 && a->class_sum && a->class_count && a->y_l &&
                      a->y_m_ue && a->y_i_ue && a->y_t_ue,
                  STIL_E_ARG, "head_step: null pointer");
+    STIL_REQUIRE(a->grad_dtype == STIL_F32 || a->grad_dtype == STIL_BF16, STIL_E_DTYPE, "head_step: bad grad dtype");
     StepPlan P = plan_step(a->workspace, a->workspace_bytes, B, B_l, K, D, dt);
     STIL_REQUIRE(a->workspace && P.bytes <= a->workspace_bytes, STIL_E_WORKSPACE, "head_step workspace too small: need %lld",
                  (long long)P.bytes);
+    SideStreams* SS = nullptr;
+    if ((rc = get_side_streams(&SS))) return rc;
     const float inv_t = 1.0f / a->temperature;
     const int esz = dt == STIL_BF16 ? 2 : 4;
     const void* feat_m_ue = static_cast<const char*>(a->feat_m_e) + B_l * D * esz;
+    cudaEvent_t* tev = reinterpret_cast<cudaEvent_t*>(a->timing_events);   // optional: bench instrumentation
+    int tev_i = 0;
+    auto mark = [&]() -> int {
+        if (tev && tev_i < a->n_timing_events) STIL_CUDA(cudaEventRecord(tev[tev_i++], st));
+        return STIL_OK;
+    };
 
-    // 1. operand preparation (all matrices, one launch)
+    // 1. operand preparation (all matrices, one launch): inverse norms, fp32 -> bf16 segment split
     PrepLaunch PL;
     std::memset(&PL, 0, sizeof(PL));
     PL.zero_words = P.nce.ticket; PL.n_zero = 32;   // [0] finish ticket, [16] masked-CE ticket
-    prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, P.nce.a_t, P.nce.ldt, P.nce.nseg_t, P.nce.ra));
-    prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, P.nce.b_t, P.nce.ldt, P.nce.nseg_t, P.nce.rb));
+    prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, nullptr, 0, 0, P.nce.ra));
+    prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, nullptr, 0, 0, P.nce.rb));
     if (dt != STIL_BF16) {
         prep_add(PL, prep_job(a->feat_m, dt, B, D, D, P.pt.feat_nseg, P.pt.feat_op, nullptr, 0, 0, nullptr));
         prep_add(PL, prep_job(feat_m_ue, dt, B_u, D, D, 3, P.teach_op, nullptr, 0, 0, nullptr));
     }
-    prep_add(PL, prep_job(a->prototypes, STIL_F32, K, D, D, P.pt.proto_nseg, P.pt.proto_op, P.pt.proto_t, P.pt.ldt, 2, nullptr));
+    prep_add(PL, prep_job(a->prototypes, STIL_F32, K, D, D, P.pt.proto_nseg, P.pt.proto_op, nullptr, 0, 0, nullptr));
+    if ((rc = mark())) return rc;
     if ((rc = launch_prep(PL, st))) return rc;
 
     // 2. forward GEMMs: InfoNCE both sides (stats), prototype CE (stats), teacher prototype logits (store)
@@ -787,67 +874,44 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         GL.njobs = 4;
     }
     gemm_job_tiles(GL);
+    if ((rc = mark())) return rc;
     if ((rc = launch_gemm(GL, st))) return rc;
 
     // 3. CGPL + PGLS on the unlabelled rows; (cls, conf) of every row for the prototype kernels
-    if ((rc = launch_labelled_cls(a->y_l, B_l, a->th1, P.cls, P.conf, st))) return rc;
+    if ((rc = mark())) return rc;
     if ((rc = launch_cgpl_pgls(a->y_m_ue, a->y_i_ue, a->y_t_ue, a->logit_dtype, K, P.teacher_logits, P.ldk, B_u, K,
                                a->temperature, a->rate_pseudo, a->th1, a->past_start_epoch, a->pseudo_label, K, nullptr,
                                0, a->max_prob, a->max_idx, a->mask1, a->case1, a->case2_i, a->case2_t, a->case3,
-                               nullptr, P.cls + B_l, P.conf + B_l, st)))
+                               nullptr, P.cls + B_l, P.conf + B_l, a->y_l, B_l, P.cls, P.conf, st)))
         return rc;
 
-    // 4. merge statistics -> LSEs, losses, backward coefficients
-    FinishLaunch FL;
-    std::memset(&FL, 0, sizeof(FL));
-    infonce_finish_jobs(FL.job, P.nce, a->feat_i, a->feat_t, dt, B, B, D, D, 0, inv_t, a->lambda0, P.lse_row, P.lse_col, 0);
-    proto_finish_job(FL.job[2], P.pt, a->feat_m, dt, B, D, D, a->prototypes, K, P.cls, P.conf, inv_t, P.lse_pt, P.w_pt, 1);
-    FL.job[0].row_begin = 0;
-    FL.job[1].row_begin = (int)B;
-    FL.job[2].row_begin = (int)(2 * B);
-    FL.njobs = 3;
-    FL.total_rows = (int)(3 * B);
-    FL.block_partials = P.nce.block_partials;   // sized for 2B rows; 3B rows need more -> use proto's too
-    FL.ticket = P.nce.ticket;
-    FL.out_loss = a->losses;                     // [0] = itc, [1] = pt
-    if ((rc = launch_finish(FL, st))) return rc;
+    // ---- fork: three independent branches run beside the backward GEMM chain
+    STIL_CUDA(cudaEventRecord(SS->fork, st));
+    for (int i = 0; i < 3; ++i) STIL_CUDA(cudaStreamWaitEvent(SS->s[i], SS->fork, 0));
 
-    // 5. backward: G tiles (bf16 hi/lo) then dX = G · Y
-    std::memset(&GL, 0, sizeof(GL));
-    if ((rc = infonce_grad_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, a->lambda0, P.lse_row, P.lse_col, nullptr))) return rc;
-    if ((rc = proto_grad_job(GL.job[2], P.pt, a->feat_m, dt, B, D, D, K, inv_t, P.cls, P.lse_pt, P.w_pt, nullptr))) return rc;
-    GL.njobs = 3;
-    gemm_job_tiles(GL);
-    if ((rc = launch_gemm(GL, st))) return rc;
-    std::memset(&GL, 0, sizeof(GL));
-    if ((rc = infonce_store_jobs(GL.job, P.nce, B, B, D))) return rc;
-    if ((rc = proto_store_job(GL.job[2], P.pt, B, D, K, P.pt.g, D))) return rc;
-    GL.njobs = 3;
-    gemm_job_tiles(GL);
-    if ((rc = launch_gemm(GL, st))) return rc;
-    GradFinishLaunch GF;
-    std::memset(&GF, 0, sizeof(GF));
-    for (int s = 0; s < 3; ++s) {
-        GradFinishJob& j = GF.job[s];
-        j.g = s == 0 ? P.nce.g[0] : s == 1 ? P.nce.g[1] : P.pt.g;
-        j.x = s == 0 ? a->feat_i : s == 1 ? a->feat_t : a->feat_m;
-        j.x_dtype = dt; j.ldx = D;
-        j.sx = s == 0 ? P.nce.ra : s == 1 ? P.nce.rb : nullptr;
-        j.dx = s == 0 ? a->d_feat_i : s == 1 ? a->d_feat_t : a->d_feat_m;
-        j.dx_dtype = a->grad_dtype; j.ld_dx = D;
-        j.rows = (int)B; j.dim = (int)D;
-        j.row_begin = (int)(s * B);
+    // side 0: merge statistics -> losses (and LSE vectors)
+    {
+        FinishLaunch FL;
+        std::memset(&FL, 0, sizeof(FL));
+        infonce_finish_jobs(FL.job, P.nce, a->feat_i, a->feat_t, dt, B, B, D, D, 0, inv_t, a->lambda0, P.lse_row,
+                            P.lse_col, 0);
+        proto_finish_job(FL.job[2], P.pt, a->feat_m, dt, B, D, D, a->prototypes, K, P.cls, P.conf, inv_t, P.lse_pt,
+                         P.w_pt, 1);
+        FL.job[0].row_begin = 0;
+        FL.job[1].row_begin = (int)B;
+        FL.job[2].row_begin = (int)(2 * B);
+        FL.njobs = 3;
+        FL.total_rows = (int)(3 * B);
+        FL.block_partials = P.nce.block_partials;
+        FL.ticket = P.nce.ticket;
+        FL.out_loss = a->losses;   // [0] = itc, [1] = pt
+        if ((rc = launch_finish(FL, SS->s[0]))) return rc;
     }
-    GF.njobs = 3;
-    GF.total_rows = (int)(3 * B);
-    if ((rc = launch_grad_finish(GF, st))) return rc;
-
-    // 6. prototype partial sums (+ in-place accumulate), teacher features (STiLModel.py:376)
+    // side 1: prototype partial sums (+ in-place accumulate) from the teacher features (STiLModel.py:376-381)
     if ((rc = launch_proto_accumulate(a->feat_m_e, dt, B, D, D, P.cls, P.conf, B_l, a->repeat_ratio, K, a->class_sum,
-                                      a->class_count, a->prototypes_sum, a->prototypes_count_sum, st)))
+                                      a->class_count, a->prototypes_sum, a->prototypes_count_sum, SS->s[1])))
         return rc;
-
-    // 7. masked soft-target CE of the student heads (f-1)
+    // side 2: masked soft-target CE of the student heads (f-1)
     if (a->y_m) {
         STIL_REQUIRE(a->y_i && a->y_t && a->mask_random, STIL_E_ARG, "head_step: student logits need y_i, y_t, mask_random");
         const int lsz = a->logit_dtype == STIL_BF16 ? 2 : 4;
@@ -856,8 +920,50 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         if ((rc = launch_masked_softce(urow(a->y_m), urow(a->y_i), urow(a->y_t), a->logit_dtype, K, a->pseudo_label, K,
                                        a->mask1, a->case1, a->case2_i, a->case2_t, a->case3, a->mask_random, B_u, K,
                                        a->losses + 2, grow(a->d_y_m), grow(a->d_y_i), grow(a->d_y_t), K,
-                                       a->rate_uce_scale, P.ce_partials, P.ce_ticket, st)))
+                                       a->rate_uce_scale, P.ce_partials, P.ce_ticket, SS->s[2])))
             return rc;
+    }
+
+    // 4. backward on the main stream: G tiles (bf16 hi/lo; statistics merged in-kernel) ...
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = infonce_grad_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, a->lambda0, nullptr, nullptr, nullptr))) return rc;
+    if ((rc = proto_grad_job(GL.job[2], P.pt, a->feat_m, dt, B, D, D, K, inv_t, P.cls, nullptr, nullptr, nullptr,
+                             a->prototypes, P.conf)))
+        return rc;
+    GL.njobs = 3;
+    gemm_job_tiles(GL);
+    if ((rc = mark())) return rc;
+    if ((rc = launch_gemm(GL, st))) return rc;
+    // 5. ... then dX = G · Y with the normalise-backward / cast in the epilogue
+    std::memset(&GL, 0, sizeof(GL));
+    bool fused = false, fused_pt = false;
+    if ((rc = infonce_store_jobs(GL.job, P.nce, A, Bm, a->feat_i, a->feat_t, dt, B, B, D, D, 0, a->d_feat_i, a->d_feat_t,
+                                 a->grad_dtype, D, &fused)))
+        return rc;
+    if ((rc = proto_store_job(GL.job[2], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
+    GL.njobs = 3;
+    gemm_job_tiles(GL);
+    if ((rc = mark())) return rc;
+    if ((rc = launch_gemm(GL, st))) return rc;
+    if (!fused) {
+        GradFinishLaunch GF;
+        std::memset(&GF, 0, sizeof(GF));
+        infonce_gradfinish_jobs(GF.job, P.nce, a->feat_i, a->feat_t, dt, B, D, D, 0, a->d_feat_i, a->d_feat_t,
+                                a->grad_dtype, D);
+        GradFinishJob& j = GF.job[2];
+        j.g = P.pt.g; j.dx = a->d_feat_m; j.dx_dtype = a->grad_dtype; j.ld_dx = D;
+        j.rows = (int)B; j.dim = (int)D; j.row_begin = (int)(2 * B);
+        GF.njobs = 3;
+        GF.total_rows = (int)(3 * B);
+        if ((rc = mark())) return rc;
+        if ((rc = launch_grad_finish(GF, st))) return rc;
+    }
+    if ((rc = mark())) return rc;
+
+    // ---- join
+    for (int i = 0; i < 3; ++i) {
+        STIL_CUDA(cudaEventRecord(SS->join[i], SS->s[i]));
+        STIL_CUDA(cudaStreamWaitEvent(st, SS->join[i], 0));
     }
     return STIL_OK;
 }

@@ -7,7 +7,9 @@
 // TMEM), warps 2-5 drain the accumulator with tcgen05.ld (thread = row) and run one of three
 // epilogues (see GemmMode in internal.h).  Used for: the InfoNCE logits of utils/clip_loss.py:33 and
 // their row/column log-sum-exp (:36-37), the prototype logits of utils/prototype_loss.py:26 and
-// STiLModel.py:293, and both GEMMs of their backward passes.
+// STiLModel.py:293, and both GEMMs of their backward passes (G = dLoss/dLogits is formed on chip from a
+// recomputed tile and written as bf16 hi/lo; dX = G·Y reads Y in place as an MN-major operand and applies
+// the backward of F.normalize in its epilogue).
 #include <cstdarg>
 #include <mutex>
 
@@ -29,6 +31,81 @@ __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// log-sum-exp of one row/column from its per-tile (max, sum) partials laid out [tiles, stride]
+__device__ __forceinline__ float merge_partials(const float* pmax, const float* psum, int tiles, long long stride,
+                                                int idx) {
+    float m = -INFINITY;
+    for (int t = 0; t < tiles; ++t) m = fmaxf(m, pmax[t * stride + idx]);
+    float s = 0.f;
+    for (int t = 0; t < tiles; ++t) s += psum[t * stride + idx] * expf(pmax[t * stride + idx] - m);
+    return m + logf(s);
+}
+
+__device__ __forceinline__ void load32_as_float(const void* base, int dtype, long long off, int nv, float (&x)[32]) {
+    if (dtype == STIL_BF16) {
+        const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(base) + off;
+        if (nv == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const uint4 v = *reinterpret_cast<const uint4*>(p + j);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    x[j + 2 * h] = __uint_as_float(w[h] << 16);
+                    x[j + 2 * h + 1] = __uint_as_float(w[h] & 0xffff0000u);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = j < nv ? __bfloat162float(p[j]) : 0.f;
+        }
+    } else {
+        const float* p = static_cast<const float*>(base) + off;
+        if (nv == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(p + j);
+                x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = j < nv ? p[j] : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ void store32_from_float(void* base, int dtype, long long off, int nv, const float (&x)[32]) {
+    if (dtype == STIL_BF16) {
+        __nv_bfloat16* p = static_cast<__nv_bfloat16*>(base) + off;
+        if (nv == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint32_t w[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const __nv_bfloat162 b = __floats2bfloat162_rn(x[j + 2 * h], x[j + 2 * h + 1]);
+                    w[h] = *reinterpret_cast<const uint32_t*>(&b);
+                }
+                *reinterpret_cast<uint4*>(p + j) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nv) p[j] = __float2bfloat16_rn(x[j]);
+        }
+    } else {
+        float* p = static_cast<float*>(base) + off;
+        if (nv == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nv) p[j] = x[j];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_constant__ GemmLaunch L) {
@@ -93,13 +170,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 uint8_t* b_dst = a_dst + kTileM * kTileK * 2;
                 tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
                 tc05::tma_load_3d(a_dst, &J.tmx, &full_bar[s], kk * kTileK, m0, J.xseg[p]);
-                tc05::tma_load_3d(b_dst, &J.tmy, &full_bar[s], kk * kTileK, n0, J.yseg[p]);
+                if (!J.y_mn_major) {
+                    tc05::tma_load_3d(b_dst, &J.tmy, &full_bar[s], kk * kTileK, n0, J.yseg[p]);
+                } else {
+                    // Y tile [64 contraction rows x 128 N] as two 64x64 boxes (N chunks 8 KiB apart)
+                    tc05::tma_load_3d(b_dst, &J.tmy, &full_bar[s], n0, kk * kTileK, J.yseg[p]);
+                    tc05::tma_load_3d(b_dst + 64 * kTileK * 2, &J.tmy, &full_bar[s], n0 + 64, kk * kTileK, J.yseg[p]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, kTileN);
+            const bool mn = J.y_mn_major != 0;
+            const uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, kTileN) | (mn ? (1u << 16) : 0u);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
@@ -108,12 +192,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 const uint32_t a_addr = tc05::smem_u32(tiles + s * kStageBytes);
                 const uint32_t b_addr = a_addr + kTileM * kTileK * 2;
                 const uint64_t a_desc = tc05::make_kmajor_sw128_desc(a_addr);
-                const uint64_t b_desc = tc05::make_kmajor_sw128_desc(b_addr);
+                const uint64_t b_desc = mn ? tc05::make_mnmajor_sw128_desc(b_addr, 64 * kTileK * 2)
+                                           : tc05::make_kmajor_sw128_desc(b_addr);
+                // K-major: 16 bf16 = 32 B inside the swizzle atom (+2 in the >>4 address field);
+                // MN-major: 16 contraction rows = 2 KiB (+128)
+                const uint32_t b_step = mn ? 128u : 2u;
 #pragma unroll
-                for (int k = 0; k < kTileK / 16; ++k) {
-                    // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (>>4) start-address field
-                    tc05::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                }
+                for (int k = 0; k < kTileK / 16; ++k)
+                    tc05::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + b_step * k, idesc, (kb | k) ? 1u : 0u);
                 tc05::mma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
             }
             tc05::mma_commit(tmem_full_bar);
@@ -125,12 +211,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < J.M;
         const int ncols = min(kTileN, J.N - n0);
+        const int mode = J.mode;
         {
             const int col = n0 + e;
             float cs = 0.f, cl = 0.f;
             if (col < J.N) {
                 cs = J.alpha * (J.sy ? J.sy[col] : 1.f);
-                if (J.mode == GEMM_GRAD && J.lse_y) cl = J.lse_y[col];
+                if (mode == GEMM_GRAD) {
+                    if (J.lse_y) cl = J.lse_y[col];
+                    else if (J.py_max) cl = merge_partials(J.py_max, J.py_sum, J.py_tiles, J.N, col);
+                }
             }
             col_scale[e] = cs;
             col_lse[e] = cl;
@@ -140,20 +230,58 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
         const float rs = (row_ok && J.sx) ? J.sx[row] : 1.f;
         float lse_x = 0.f, u = 0.f, d = 0.f, gs = 1.f;
         int tgt = -1;
-        if (J.mode == GEMM_GRAD && row_ok) {
-            lse_x = J.lse_x[row];
-            u = J.u_vec ? J.u_vec[row] : J.u_scalar;
-            d = J.u_vec ? u : J.d_scalar;
+        if (mode == GEMM_GRAD && row_ok) {
+            lse_x = J.lse_x ? J.lse_x[row] : merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
             tgt = J.tgt_vec ? J.tgt_vec[row] : row + J.tgt_offset;
+            if (J.w_x) {
+                // prototype CE coefficient from the picked logit (utils/prototype_loss.py:28,37-39)
+                float dot = 0.f;
+                for (int d0 = 0; d0 < J.D; d0 += 32) {
+                    float xv[32], yv[32];
+                    const int nv = min(32, J.D - d0);
+                    load32_as_float(J.w_x, J.w_x_dtype, (long long)row * J.w_ldx + d0, nv, xv);
+                    load32_as_float(J.w_y, STIL_F32, (long long)tgt * J.w_ldy + d0, nv, yv);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dot += xv[j] * yv[j];
+                }
+                const float p = expf(dot * J.alpha - lse_x);
+                u = (J.w_conf[row] ? J.w_coef : 0.f) * p / (p + 1e-7f);
+                d = u;
+            } else {
+                u = J.u_vec ? J.u_vec[row] : J.u_scalar;
+                d = J.u_vec ? u : J.d_scalar;
+            }
             gs = J.gscale ? *J.gscale : 1.f;
         }
-        const float v = (J.mode == GEMM_GRAD && J.lse_y) ? J.v_scalar : 0.f;
+        const float v = (mode == GEMM_GRAD && (J.lse_y || J.py_max)) ? J.v_scalar : 0.f;
+        const bool fused_fin = mode == GEMM_STORE && J.fin_dx != nullptr;
+        const float fsx = (fused_fin && row_ok && J.fin_sx) ? J.fin_sx[row] : 0.f;
 
         tc05::mbar_wait(tmem_full_bar, 0);
         tc05::fence_after_sync();
 
         float run_max = -INFINITY, run_sum = 0.f;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+        float fin_dot = 0.f;
+        if (fused_fin && J.fin_sx) {
+            // pass 1 of the normalise-backward: <xh, g> over the whole row (tile spans all of N)
+#pragma unroll 1
+            for (int c = 0; c < kTileN / 32; ++c) {
+                if (c * 32 >= ncols) break;
+                uint32_t acc[32];
+                tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
+                tc05::tmem_ld_wait();
+                if (row_ok) {
+                    float xv[32];
+                    const int nv = min(32, ncols - c * 32);
+                    load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + n0 + c * 32, nv, xv);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) fin_dot += fsx * xv[j] * (__uint_as_float(acc[j]) * rs * col_scale[c * 32 + j]);
+                }
+            }
+        }
+
 #pragma unroll 1
         for (int c = 0; c < kTileN / 32; ++c) {
             if (c * 32 >= ncols) break;  // warp-uniform
@@ -165,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 32; ++j) l[j] = __uint_as_float(acc[j]) * rs * col_scale[c * 32 + j];
 
-            if (J.mode == GEMM_STATS) {
+            if (mode == GEMM_STATS) {
                 float cmax = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -178,19 +306,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 run_sum = run_sum * fast_exp2((run_max - new_max) * kLog2e) + s;
                 run_max = new_max;
             }
-            if ((J.mode == GEMM_STATS || J.mode == GEMM_STORE) && J.out && row_ok) {
-                float* dst = J.out + (long long)row * J.ld_out + n0 + c * 32;
-                if (nv == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            if (fused_fin) {
+                if (row_ok) {
+                    if (J.fin_sx) {
+                        float xv[32];
+                        load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + n0 + c * 32, nv, xv);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(l[j], l[j + 1], l[j + 2], l[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nv) dst[j] = l[j];
+                        for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xv[j] * fin_dot);
+                    }
+                    store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + n0 + c * 32, nv, l);
                 }
+            } else if ((mode == GEMM_STATS || mode == GEMM_STORE) && J.out && row_ok) {
+                store32_from_float(J.out, STIL_F32, (long long)row * J.ld_out + n0 + c * 32, nv, l);
             }
-            if (J.mode == GEMM_GRAD && row_ok) {
+            if (mode == GEMM_GRAD && row_ok) {
                 __nv_bfloat16* hi_dst = J.gop + (long long)row * 2 * J.ld_g + n0 + c * 32;
                 __nv_bfloat16* lo_dst = hi_dst + J.ld_g;
                 uint32_t hi_pk[16], lo_pk[16];
@@ -229,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 }
             }
         }
-        if (J.mode == GEMM_STATS && row_ok) {
+        if (mode == GEMM_STATS && row_ok) {
             J.part_max[(long long)tn * J.M + row] = run_max;
             J.part_sum[(long long)tn * J.M + row] = run_sum;
         }
@@ -264,7 +393,7 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t rows, int64_t nseg,
-                     int64_t row_stride, int64_t seg_stride) {
+                     int64_t row_stride, int64_t seg_stride, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     STIL_REQUIRE(enc != nullptr, STIL_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     STIL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, STIL_E_ALIGN, "operand base %p not 16-byte aligned", base);
@@ -273,7 +402,7 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t r
                  (long long)seg_stride);
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nseg};
     cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)seg_stride * 2};
-    cuuint32_t box[3] = {kTileK, kTileM, 1};
+    cuuint32_t box[3] = {kTileK, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

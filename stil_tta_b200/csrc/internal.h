@@ -45,6 +45,29 @@ struct alignas(64) GemmJob {
     const float* gscale;     // device scalar or nullptr (1.0)
     __nv_bfloat16* gop;      // [M, 2, ld_g]
     long long ld_g;
+    // GRAD with the statistics merge fused in (used when lse_x == nullptr): per-column-tile (max, sum)
+    // partials of GEMM_STATS for this job's rows (px_*) and, for the symmetric InfoNCE, columns (py_*)
+    const float *px_max, *px_sum, *py_max, *py_sum;
+    int px_tiles, py_tiles;
+    // GRAD for the prototype CE: u_i = d_i = conf_i*w_coef*p/(p+1e-7), p = exp(alpha*<x_i, proto[tgt_i]> - lse_i)
+    const void* w_x;         // raw feat rows (nullptr -> u/d as above)
+    int w_x_dtype;
+    long long w_ldx;
+    const float* w_y;        // raw fp32 prototypes
+    long long w_ldy;
+    const unsigned char* w_conf;
+    float w_coef;
+    // STORE with Y given MN-major ([contraction rows, N contiguous]) — the backward's dX = G · Y
+    int y_mn_major;
+    // STORE with the normalise-backward / cast fused in (needs tiles_n == 1):
+    //   dx = fin_sx ? sx*(g - xh*(xh·g)), xh = sx*x : g      written in fin_dx_dtype
+    void* fin_dx;            // nullptr -> plain fp32 store to `out`
+    int fin_dx_dtype;
+    long long fin_ld_dx;
+    const void* fin_x;
+    int fin_x_dtype;
+    long long fin_ldx;
+    const float* fin_sx;
 };
 
 struct GemmLaunch {
@@ -55,7 +78,7 @@ struct GemmLaunch {
 
 // Build the operand tensor map.  `base` bf16, logical [rows, nseg, inner]; strides in elements.
 int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t rows, int64_t nseg,
-                     int64_t row_stride, int64_t seg_stride);
+                     int64_t row_stride, int64_t seg_stride, int box_rows = 128);
 void gemm_job_tiles(GemmLaunch& L);  // fills tiles_m/tiles_n/tile_begin/total_tiles
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream);
 
@@ -151,7 +174,8 @@ int launch_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logi
                      float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
                      float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
                      uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
-                     int32_t* cls, uint8_t* conf, cudaStream_t stream);
+                     int32_t* cls, uint8_t* conf, const int64_t* y_l, int64_t b_l, int32_t* cls_l, uint8_t* conf_l,
+                     cudaStream_t stream);
 int launch_label_argmax(const float* label, int64_t ld, int64_t rows, int64_t k, float threshold, int32_t* cls,
                         uint8_t* conf, float* max_prob, cudaStream_t stream);
 // cls/conf of the labelled rows: cls = y_l, conf = (1 >= th) (a one-hot row has max 1, STiLModel.py:321)

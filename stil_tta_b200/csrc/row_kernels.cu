@@ -106,6 +106,11 @@ struct CgplArgs {
     int* cls;
     unsigned char* conf;
     int vec_y, vec_t, vec_pl, vec_pred;  // 8-byte (f32) / 4-byte (bf16) pair access allowed
+    // labelled rows ride along: cls = y_l, conf = (1 >= th1)  (one-hot rows of pseudo_label_all, STiLModel.py:321)
+    const long long* y_l;
+    int b_l;
+    int* cls_l;
+    unsigned char* conf_l;
 };
 
 template <int LPR, int NV>
@@ -208,6 +213,10 @@ __device__ __forceinline__ int argmax_of_softmax(float (&e)[2 * NV], float s, in
 template <int LPR, int NV>
 __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) {
     constexpr int RPW = 32 / LPR;
+    for (int i = blockIdx.x * kRowBlock + threadIdx.x; i < A.b_l; i += gridDim.x * kRowBlock) {
+        A.cls_l[i] = (int)A.y_l[i];
+        A.conf_l[i] = 1.0f >= A.th1;
+    }
     const int warp_global = blockIdx.x * (kRowBlock / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
@@ -669,6 +678,7 @@ int launch_cgpl_t(const CgplArgs& A, cudaStream_t stream) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------- launchers
+int launch_labelled_cls(const int64_t* y_l, int64_t b_l, float th, int32_t* cls, uint8_t* conf, cudaStream_t stream);
 void prep_add(PrepLaunch& L, const PrepJob& j) {
     PrepJob& d = L.job[L.njobs];
     d = j;
@@ -714,11 +724,13 @@ int launch_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logi
                      float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
                      float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
                      uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
-                     int32_t* cls, uint8_t* conf, cudaStream_t stream) {
+                     int32_t* cls, uint8_t* conf, const int64_t* y_l, int64_t b_l, int32_t* cls_l, uint8_t* conf_l,
+                     cudaStream_t stream) {
     STIL_REQUIRE(k >= 1 && k <= 1024, STIL_E_SHAPE, "cgpl_pgls supports 1 <= k <= 1024 classes (got %lld)", (long long)k);
     STIL_REQUIRE(rows >= 0 && rows < (1LL << 31), STIL_E_SHAPE, "rows out of range");
-    if (rows == 0) return STIL_OK;
+    if (rows == 0) return launch_labelled_cls(y_l, y_l ? b_l : 0, th1, cls_l, conf_l, stream);
     CgplArgs A;
+    A.y_l = reinterpret_cast<const long long*>(y_l); A.b_l = y_l ? (int)b_l : 0; A.cls_l = cls_l; A.conf_l = conf_l;
     A.y_m = y_m; A.y_i = y_i; A.y_t = y_t;
     A.logit_dtype = logit_dtype; A.ld_y = ld_y;
     A.tl = teacher_logits; A.ld_t = ld_t;

@@ -125,6 +125,29 @@ class STiLHead:
                 self._enqueue()
             self._graph = g
 
+    def timed_run(self, names=False):
+        """One un-captured step with a CUDA event before every main-chain launch and after the last one;
+        returns the per-launch durations in milliseconds (bench.py's live kernel timing)."""
+        labels = ["prep_kernel", "gemm_tc05_kernel[stats+teacher]", "cgpl_pgls_kernel", "gemm_tc05_kernel[grad]",
+                  "gemm_tc05_kernel[dX]"] + (["grad_finish_kernel"] if self.cfg.proj_dim > 128 else [])
+        n = len(labels) + 1
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream(self.dev)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+            for e in evs:
+                e.record(st)            # materialise the cudaEvent_t handles
+            arr = (C.c_void_p * n)(*[e.cuda_event for e in evs])
+            self._args.timing_events = C.cast(arr, C.c_void_p)
+            self._args.n_timing_events = n
+            try:
+                self._enqueue()
+            finally:
+                self._args.timing_events = None
+                self._args.n_timing_events = 0
+            torch.cuda.synchronize(self.dev)
+            ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(n - 1)]
+        return list(zip(labels, ms)) if names else ms
+
     def run(self) -> None:
         """Enqueue one head step on the current stream (graph replay when captured)."""
         with torch.cuda.device(self.dev):
