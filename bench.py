@@ -256,14 +256,17 @@ def run_gpu_arm(args):
     pk = peaks()
 
     # enough distinct batches that inputs+outputs+scratch touched between two uses of a buffer exceed L2
-    probe = S.STiLHead(cfg, device=dev)
+    Head = (lambda c, device: S.DistributedSTiLHead(c, device=device)) if dist_on else \
+           (lambda c, device: S.STiLHead(c, device=device))
+    probe = Head(cfg, device=dev)
     per_head = probe.h2d_bytes + sum(t.numel() * t.element_size() for t in probe.out.values()) + probe._ws.numel()
     nbuf = max(4, int(1.25 * L2_BYTES / per_head) + 1)
-    heads = [probe] + [S.STiLHead(cfg, device=dev) for _ in range(nbuf - 1)]
+    heads = [probe] + [Head(cfg, device=dev) for _ in range(nbuf - 1)]
     host_batches = [synth.make_batch(cfg, seed=2022 + i, rank=rank) for i in range(min(nbuf, 8))]
     for i, h in enumerate(heads):
         h.load(host_batches[i % len(host_batches)])
-        h.capture()
+        if not dist_on:
+            h.capture()
     pinned = [heads[0].pin(b) for b in host_batches]
     torch.cuda.synchronize(dev)
 
@@ -274,9 +277,10 @@ def run_gpu_arm(args):
         heads[i % nbuf].step_host(pinned[i % len(pinned)])
 
     with ClockSampler(local) as cs:
+        time.sleep(0.3)                      # let nvidia-smi start polling before the load begins
         ms = timed_region(step_resident, args.steps, args.warmup, dist_on, dev)
+        ms_e2e = timed_region(step_e2e, args.steps, args.warmup, dist_on, dev)
     clocks = cs.summary()
-    ms_e2e = timed_region(step_e2e, args.steps, args.warmup, dist_on, dev)
     ms_step, ms_step_e2e = ms / args.steps, ms_e2e / args.steps
     value = cfg.batch * world / (ms_step * 1e-3)
     e2e = cfg.batch * world / (ms_step_e2e * 1e-3)
@@ -288,18 +292,48 @@ def run_gpu_arm(args):
         "data": "synthetic",
         "config": {"workload": workload_name(cfg, args.config), "per_gpu_batch": cfg.batch,
                    "l2": f"inputs larger than L2: {nbuf} rotating batches x {per_head / 2**20:.1f} MiB touched per step",
-                   "parallelism": f"dp{world}", "cuda_graph": True},
+                   "parallelism": f"dp{world}", "cuda_graph": not dist_on},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": heads[0].h2d_bytes,
                 "d2h_bytes_per_step": heads[0].d2h_bytes},
         "gpu_launches": heads[0].launches_per_step * args.steps,
         "clocks": clocks,
     }
-    if rank == 0:
+    # live per-launch durations of the main-chain kernels: CUDA events recorded on the launching stream around
+    # every launch of an un-captured step (stil_head_step's instrumentation hook), rotating over the batches
+    per = {}
+    reps = 0 if dist_on else max(20, min(args.steps, 100))
+    for i in range((3 + reps) if reps else 0):
+        tr = heads[i % nbuf].timed_run(names=True)
+        if i >= 3:
+            for name, ms1 in tr:
+                per.setdefault(name, []).append(ms1)
+    kern = {k: sum(v) / len(v) * 1e3 for k, v in per.items()}      # us per launch
+    if rank == 0 and dist_on:
+        line["config"]["cuda_graph"] = False
+        line["config"]["collectives"] = ("NCCL: 2x all_gather(embeddings) overlapped with the row-local step, "
+                                         "all_gather(LSE), 1 packed all_reduce(loss, class_sum, class_count)")
+        line["config"]["infonce"] = f"global batch {cfg.batch * world} (all-gathered)"
+        print(json.dumps(line), flush=True)
+    if rank == 0 and not dist_on:
+        B, B_u, K, P = cfg.batch, cfg.b_u, cfg.num_classes, cfg.proj_dim
+        gemm_us = [v for k, v in kern.items() if k.startswith("gemm_tc05_kernel")]
+        # algorithmic GEMM flops of one head step: a1 6*B^2*P, a3 2*B_u*K*P, a4 4*B*K*P — no
+        # recompute, no padding, no split-precision passes — spread over the kernel's launches per step
+        flops_step = 6.0 * B * B * P + 2.0 * B_u * K * P + 4.0 * B * K * P
+        n_l = len(gemm_us)
+        t_avg = sum(gemm_us) / n_l * 1e-6
+        ach = flops_step / n_l / t_avg / 1e12
+        line["roofline"] = {"kernel": "gemm_tc05_kernel", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"],
+                            "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+                            "peak_source": pk["src"] + " bf16 sustained", "launches_per_step": n_l,
+                            "us_per_launch": t_avg * 1e6, "alg_flops_per_launch": flops_step / n_l,
+                            "share_of_main_chain": sum(gemm_us) / sum(kern.values())}
         rl = kernel_rooflines(cfg, dev, pk)
         top = rl["cgpl_pgls_kernel"]
-        line["roofline"] = {"kernel": "cgpl_pgls_kernel", "bound": top["bound"], "achieved": top["achieved"],
-                            "peak": top["peak"], "unit": top["unit"], "frac": top["achieved"] / top["peak"],
-                            "traffic": None, "peak_source": pk["src"], "us_per_launch": top["seconds"] * 1e6}
+        line["roofline_hbm_kernel"] = {"kernel": "cgpl_pgls_kernel", "bound": "hbm", "achieved": top["achieved"],
+                                       "peak": top["peak"], "unit": "GB/s", "frac": top["achieved"] / top["peak"],
+                                       "us_per_launch": top["seconds"] * 1e6, "alg_bytes_per_launch": top["alg_bytes"]}
+        line["kernel_us"] = {k: round(v, 2) for k, v in kern.items()}
         if world == 1 and not args.no_cpu_baseline:
             ms_cpu, done, n = cpu_reference_steps(cfg, 400, 3, budget_s=15.0)
             line["cpu_baseline"] = {"value": cfg.batch / (ms_cpu * 1e-3), "unit": UNIT, "cores": n, "kind": "port",
@@ -314,8 +348,8 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")

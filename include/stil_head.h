@@ -184,6 +184,9 @@ typedef struct stil_head_step_args {
     /* optional instrumentation (bench.py): cudaEvent_t[n_timing_events] recorded on `stream` before each
      * main-chain launch and after the last one; leave NULL/0 otherwise (and always during graph capture) */
     void** timing_events; int n_timing_events;
+    /* 1: leave the InfoNCE (losses[0], d_feat_i, d_feat_t) to the caller — the data-parallel path computes it on
+     * the all-gathered global batch with stil_infonce_fwd/bwd while this call does everything row-local */
+    int skip_infonce;
 } stil_head_step_args;
 STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int64_t k, int64_t dim, int embed_dtype);
 STIL_API int stil_head_step(const stil_head_step_args* args);

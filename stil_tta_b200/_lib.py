@@ -43,7 +43,7 @@ class HeadStepArgs(C.Structure):
         ("prototypes_sum", vp), ("prototypes_count_sum", vp),
         ("rate_uce_scale", f32),
         ("workspace", vp), ("workspace_bytes", i64), ("stream", vp),
-        ("timing_events", vp), ("n_timing_events", i32),
+        ("timing_events", vp), ("n_timing_events", i32), ("skip_infonce", i32),
     ]
 
 

@@ -846,8 +846,11 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     PrepLaunch PL;
     std::memset(&PL, 0, sizeof(PL));
     PL.zero_words = P.nce.ticket; PL.n_zero = 32;   // [0] finish ticket, [16] masked-CE ticket
-    prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, nullptr, 0, 0, P.nce.ra));
-    prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, nullptr, 0, 0, P.nce.rb));
+    const bool nce = !a->skip_infonce;
+    if (nce) {
+        prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, nullptr, 0, 0, P.nce.ra));
+        prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, nullptr, 0, 0, P.nce.rb));
+    }
     if (dt != STIL_BF16) {
         prep_add(PL, prep_job(a->feat_m, dt, B, D, D, P.pt.feat_nseg, P.pt.feat_op, nullptr, 0, 0, nullptr));
         prep_add(PL, prep_job(feat_m_ue, dt, B_u, D, D, 3, P.teach_op, nullptr, 0, 0, nullptr));
@@ -861,18 +864,22 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     const Operand Bm = rowmajor_operand(a->feat_t, dt, D, D, P.nce.b_op, P.nce.nseg);
     GemmLaunch GL;
     std::memset(&GL, 0, sizeof(GL));
-    if ((rc = infonce_stats_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, nullptr, 0))) return rc;
-    if ((rc = proto_stats_job(GL.job[2], P.pt, a->feat_m, dt, B, D, D, K, inv_t))) return rc;
-    GL.njobs = 3;
+    int nj = 0;
+    if (nce) {
+        if ((rc = infonce_stats_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, nullptr, 0))) return rc;
+        nj = 2;
+    }
+    if ((rc = proto_stats_job(GL.job[nj++], P.pt, a->feat_m, dt, B, D, D, K, inv_t))) return rc;
     if (B_u > 0) {
         const Operand X = rowmajor_operand(feat_m_ue, dt, D, D, P.teach_op, 3);
         const Operand Y = rowmajor_operand(nullptr, STIL_F32, D, D, P.pt.proto_op, P.pt.proto_nseg);
-        if ((rc = fill_gemm_common(GL.job[3], X, 0, B_u, Y, K, D))) return rc;
-        GL.job[3].mode = GEMM_STORE;
-        GL.job[3].out = P.teacher_logits;
-        GL.job[3].ld_out = P.ldk;
-        GL.njobs = 4;
+        if ((rc = fill_gemm_common(GL.job[nj], X, 0, B_u, Y, K, D))) return rc;
+        GL.job[nj].mode = GEMM_STORE;
+        GL.job[nj].out = P.teacher_logits;
+        GL.job[nj].ld_out = P.ldk;
+        ++nj;
     }
+    GL.njobs = nj;
     gemm_job_tiles(GL);
     if ((rc = mark())) return rc;
     if ((rc = launch_gemm(GL, st))) return rc;
@@ -885,23 +892,76 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
                                nullptr, P.cls + B_l, P.conf + B_l, a->y_l, B_l, P.cls, P.conf, st)))
         return rc;
 
-    // ---- fork: three independent branches run beside the backward GEMM chain
+    // ---- fork point: three independent branches run beside the backward GEMM chain (enqueued below)
     STIL_CUDA(cudaEventRecord(SS->fork, st));
     for (int i = 0; i < 3; ++i) STIL_CUDA(cudaStreamWaitEvent(SS->s[i], SS->fork, 0));
 
+    // 4. backward on the main stream: G tiles (bf16 hi/lo; statistics merged in-kernel) ...
+    std::memset(&GL, 0, sizeof(GL));
+    nj = 0;
+    if (nce) {
+        if ((rc = infonce_grad_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, a->lambda0, nullptr, nullptr, nullptr))) return rc;
+        nj = 2;
+    }
+    if ((rc = proto_grad_job(GL.job[nj++], P.pt, a->feat_m, dt, B, D, D, K, inv_t, P.cls, nullptr, nullptr, nullptr,
+                             a->prototypes, P.conf)))
+        return rc;
+    GL.njobs = nj;
+    gemm_job_tiles(GL);
+    if ((rc = mark())) return rc;
+    if ((rc = launch_gemm(GL, st))) return rc;
+    // 5. ... then dX = G · Y with the normalise-backward / cast in the epilogue
+    std::memset(&GL, 0, sizeof(GL));
+    bool fused = false, fused_pt = false;
+    nj = 0;
+    if (nce) {
+        if ((rc = infonce_store_jobs(GL.job, P.nce, A, Bm, a->feat_i, a->feat_t, dt, B, B, D, D, 0, a->d_feat_i,
+                                     a->d_feat_t, a->grad_dtype, D, &fused)))
+            return rc;
+        nj = 2;
+    }
+    if ((rc = proto_store_job(GL.job[nj++], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
+    GL.njobs = nj;
+    gemm_job_tiles(GL);
+    if ((rc = mark())) return rc;
+    if ((rc = launch_gemm(GL, st))) return rc;
+    if (!fused_pt) {
+        GradFinishLaunch GF;
+        std::memset(&GF, 0, sizeof(GF));
+        int gj = 0;
+        if (nce) {
+            infonce_gradfinish_jobs(GF.job, P.nce, a->feat_i, a->feat_t, dt, B, D, D, 0, a->d_feat_i, a->d_feat_t,
+                                    a->grad_dtype, D);
+            gj = 2;
+        }
+        GradFinishJob& j = GF.job[gj];
+        j.g = P.pt.g; j.dx = a->d_feat_m; j.dx_dtype = a->grad_dtype; j.ld_dx = D;
+        j.rows = (int)B; j.dim = (int)D; j.row_begin = (int)(gj * B);
+        GF.njobs = gj + 1;
+        GF.total_rows = (int)((gj + 1) * B);
+        if ((rc = mark())) return rc;
+        if ((rc = launch_grad_finish(GF, st))) return rc;
+    }
+    if ((rc = mark())) return rc;
+
+    // ---- side branches (enqueued after the critical path; they only depend on the fork event)
     // side 0: merge statistics -> losses (and LSE vectors)
     {
         FinishLaunch FL;
         std::memset(&FL, 0, sizeof(FL));
-        infonce_finish_jobs(FL.job, P.nce, a->feat_i, a->feat_t, dt, B, B, D, D, 0, inv_t, a->lambda0, P.lse_row,
-                            P.lse_col, 0);
-        proto_finish_job(FL.job[2], P.pt, a->feat_m, dt, B, D, D, a->prototypes, K, P.cls, P.conf, inv_t, P.lse_pt,
+        int fj = 0;
+        if (nce) {
+            infonce_finish_jobs(FL.job, P.nce, a->feat_i, a->feat_t, dt, B, B, D, D, 0, inv_t, a->lambda0, P.lse_row,
+                                P.lse_col, 0);
+            FL.job[0].row_begin = 0;
+            FL.job[1].row_begin = (int)B;
+            fj = 2;
+        }
+        proto_finish_job(FL.job[fj], P.pt, a->feat_m, dt, B, D, D, a->prototypes, K, P.cls, P.conf, inv_t, P.lse_pt,
                          P.w_pt, 1);
-        FL.job[0].row_begin = 0;
-        FL.job[1].row_begin = (int)B;
-        FL.job[2].row_begin = (int)(2 * B);
-        FL.njobs = 3;
-        FL.total_rows = (int)(3 * B);
+        FL.job[fj].row_begin = (int)(fj * B);
+        FL.njobs = fj + 1;
+        FL.total_rows = (int)((fj + 1) * B);
         FL.block_partials = P.nce.block_partials;
         FL.ticket = P.nce.ticket;
         FL.out_loss = a->losses;   // [0] = itc, [1] = pt
@@ -923,42 +983,6 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
                                        a->rate_uce_scale, P.ce_partials, P.ce_ticket, SS->s[2])))
             return rc;
     }
-
-    // 4. backward on the main stream: G tiles (bf16 hi/lo; statistics merged in-kernel) ...
-    std::memset(&GL, 0, sizeof(GL));
-    if ((rc = infonce_grad_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, a->lambda0, nullptr, nullptr, nullptr))) return rc;
-    if ((rc = proto_grad_job(GL.job[2], P.pt, a->feat_m, dt, B, D, D, K, inv_t, P.cls, nullptr, nullptr, nullptr,
-                             a->prototypes, P.conf)))
-        return rc;
-    GL.njobs = 3;
-    gemm_job_tiles(GL);
-    if ((rc = mark())) return rc;
-    if ((rc = launch_gemm(GL, st))) return rc;
-    // 5. ... then dX = G · Y with the normalise-backward / cast in the epilogue
-    std::memset(&GL, 0, sizeof(GL));
-    bool fused = false, fused_pt = false;
-    if ((rc = infonce_store_jobs(GL.job, P.nce, A, Bm, a->feat_i, a->feat_t, dt, B, B, D, D, 0, a->d_feat_i, a->d_feat_t,
-                                 a->grad_dtype, D, &fused)))
-        return rc;
-    if ((rc = proto_store_job(GL.job[2], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
-    GL.njobs = 3;
-    gemm_job_tiles(GL);
-    if ((rc = mark())) return rc;
-    if ((rc = launch_gemm(GL, st))) return rc;
-    if (!fused) {
-        GradFinishLaunch GF;
-        std::memset(&GF, 0, sizeof(GF));
-        infonce_gradfinish_jobs(GF.job, P.nce, a->feat_i, a->feat_t, dt, B, D, D, 0, a->d_feat_i, a->d_feat_t,
-                                a->grad_dtype, D);
-        GradFinishJob& j = GF.job[2];
-        j.g = P.pt.g; j.dx = a->d_feat_m; j.dx_dtype = a->grad_dtype; j.ld_dx = D;
-        j.rows = (int)B; j.dim = (int)D; j.row_begin = (int)(2 * B);
-        GF.njobs = 3;
-        GF.total_rows = (int)(3 * B);
-        if ((rc = mark())) return rc;
-        if ((rc = launch_grad_finish(GF, st))) return rc;
-    }
-    if ((rc = mark())) return rc;
 
     // ---- join
     for (int i = 0; i < 3; ++i) {

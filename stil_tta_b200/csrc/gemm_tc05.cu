@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: next kernel may begin its prologue
 
     // ---- which job / tile
     int jid = 0;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     __syncthreads();
     tc05::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: predecessor's results are visible from here on
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -434,8 +436,7 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
         attr_err = cudaFuncSetAttribute(gemm_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     });
     STIL_CUDA(attr_err);
-    gemm_tc05_kernel<<<L.total_tiles, kThreads, kSmemBytes, stream>>>(L);
-    STIL_LAUNCH_CHECK();
+    STIL_CUDA(launch_pdl(gemm_tc05_kernel, dim3(L.total_tiles), dim3(kThreads), kSmemBytes, stream, L));
     return STIL_OK;
 }
 

@@ -20,11 +20,16 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16&
     ll = __float2bfloat16_rn(r);
 }
 
-constexpr int kPrepRows = 32;
-constexpr int kPrepChunk = 256;
+constexpr int kPrepRows = kRowBlock / 32;  // one warp per row
+
+// Programmatic dependent launch (no-ops unless the launch carries the attribute): let the next kernel of the
+// chain start its prologue now, and wait for the previous one's results before touching global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kRowBlock) prep_kernel(const __grid_constant__ PrepLaunch L) {
-    __shared__ float tile[kPrepRows][kPrepChunk + 1];
+    pdl_launch_dependents();
+    pdl_wait();
     // reduction tickets of the later kernels of this op start from zero (workspace content is arbitrary)
     if (blockIdx.x == 0 && (int)threadIdx.x < L.n_zero) L.zero_words[threadIdx.x] = 0u;
     int jid = 0;
@@ -32,14 +37,40 @@ __global__ void __launch_bounds__(kRowBlock) prep_kernel(const __grid_constant__
     for (int j = 1; j < kMaxPrepJobs; ++j)
         if (j < L.njobs && (int)blockIdx.x >= L.job[j].block_begin) jid = j;
     const PrepJob& J = L.job[jid];
-    const int r0 = (blockIdx.x - J.block_begin) * kPrepRows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // phase A: norms + row-major segments, one warp per row (4 rows per warp)
-    for (int rr = warp; rr < kPrepRows; rr += kRowBlock / 32) {
-        const int r = r0 + rr;
-        if (r >= J.rows) break;
-        float ss = 0.f;
+    const int r = (blockIdx.x - J.block_begin) * kPrepRows + warp;
+    if (r >= J.rows) return;
+    float ss = 0.f;
+    const bool vec = (J.dim % 128 == 0) && (J.ld % 4 == 0) &&
+                     (reinterpret_cast<uintptr_t>(J.x) % (J.dtype == STIL_BF16 ? 8 : 16) == 0);
+    if (vec) {
+        // each lane owns 4 consecutive elements of every 128-element slab
+        for (int d0 = lane * 4; d0 < J.dim; d0 += 128) {
+            float x[4];
+            if (J.dtype == STIL_BF16) {
+                const uint2 v = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(J.x) + (long long)r * J.ld + d0);
+                x[0] = __uint_as_float(v.x << 16); x[1] = __uint_as_float(v.x & 0xffff0000u);
+                x[2] = __uint_as_float(v.y << 16); x[3] = __uint_as_float(v.y & 0xffff0000u);
+            } else {
+                const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(J.x) + (long long)r * J.ld + d0);
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            }
+            ss += x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+            if (J.op) {
+                __nv_bfloat16 h[4], l[4], ll[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split3(x[j], h[j], l[j], ll[j]);
+                __nv_bfloat16* o = J.op + ((long long)r * J.nseg) * J.dim + d0;
+                auto pack = [](const __nv_bfloat16 (&q)[4]) {
+                    return make_uint2((uint32_t)__bfloat16_as_ushort(q[0]) | ((uint32_t)__bfloat16_as_ushort(q[1]) << 16),
+                                      (uint32_t)__bfloat16_as_ushort(q[2]) | ((uint32_t)__bfloat16_as_ushort(q[3]) << 16));
+                };
+                *reinterpret_cast<uint2*>(o) = pack(h);
+                if (J.nseg > 1) *reinterpret_cast<uint2*>(o + J.dim) = pack(l);
+                if (J.nseg > 2) *reinterpret_cast<uint2*>(o + 2 * J.dim) = pack(ll);
+            }
+        }
+    } else {
         for (int d = lane; d < J.dim; d += 32) {
             const float x = ld_as_float(J.x, J.dtype, (long long)r * J.ld + d);
             ss += x * x;
@@ -52,34 +83,10 @@ __global__ void __launch_bounds__(kRowBlock) prep_kernel(const __grid_constant__
                 if (J.nseg > 2) o[2 * J.dim] = ll;
             }
         }
-        if (J.inv_norm) {
-            ss = warp_sum(ss);
-            if (lane == 0) J.inv_norm[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
-        }
     }
-    // phase B: transposed segments op_t[d, s, r] through a shared tile (coalesced along r)
-    if (J.op_t) {
-        for (int c0 = 0; c0 < J.dim; c0 += kPrepChunk) {
-            const int cw = min(kPrepChunk, J.dim - c0);
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < kPrepRows * cw; idx += kRowBlock) {
-                const int rr = idx / cw, cc = idx - rr * cw;
-                const int r = r0 + rr;
-                tile[rr][cc] = r < J.rows ? ld_as_float(J.x, J.dtype, (long long)r * J.ld + c0 + cc) : 0.f;
-            }
-            __syncthreads();
-            const int r = r0 + lane;
-            if (r < J.rows) {
-                for (int cc = warp; cc < cw; cc += kRowBlock / 32) {
-                    __nv_bfloat16 h, l, ll;
-                    split3(tile[lane][cc], h, l, ll);
-                    __nv_bfloat16* o = J.op_t + ((long long)(c0 + cc) * J.nseg_t) * J.ld_t + r;
-                    o[0] = h;
-                    if (J.nseg_t > 1) o[J.ld_t] = l;
-                    if (J.nseg_t > 2) o[2 * J.ld_t] = ll;
-                }
-            }
-        }
+    if (J.inv_norm) {
+        ss = warp_sum(ss);
+        if (lane == 0) J.inv_norm[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (clip_loss.py:29-30)
     }
 }
 
@@ -213,6 +220,8 @@ __device__ __forceinline__ int argmax_of_softmax(float (&e)[2 * NV], float s, in
 template <int LPR, int NV>
 __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) {
     constexpr int RPW = 32 / LPR;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = blockIdx.x * kRowBlock + threadIdx.x; i < A.b_l; i += gridDim.x * kRowBlock) {
         A.cls_l[i] = (int)A.y_l[i];
         A.conf_l[i] = 1.0f >= A.th1;
@@ -226,10 +235,11 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
     const int r = row_ok ? row : A.rows - 1;
     const int k = A.k;
 
-    float ym[2 * NV], yi[2 * NV], yt[2 * NV];
+    float ym[2 * NV], yi[2 * NV], yt[2 * NV], tp[2 * NV];
     load_row<LPR, NV>(A.y_m, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, ym);
     load_row<LPR, NV>(A.y_i, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, yi);
     load_row<LPR, NV>(A.y_t, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, yt);
+    load_row<LPR, NV>(A.tl, STIL_F32, A.ld_t, r, k, sub, A.vec_t, tp);   // all four rows in flight together
 
     // ---- :262-263  top-1 of the three softmaxes
     float pm[2 * NV];  // becomes softmax(y_m) = `prediction` (:279) and the case-3 pseudo label (:273)
@@ -293,8 +303,6 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
         for (int j = 0; j < 2 * NV; ++j) pl[j] = __fdiv_rn(pl[j], s);
     }
     // ---- :293-294 teacher prototype probabilities
-    float tp[2 * NV];
-    load_row<LPR, NV>(A.tl, STIL_F32, A.ld_t, r, k, sub, A.vec_t, tp);
 #pragma unroll
     for (int j = 0; j < 2 * NV; ++j) tp[j] = __fdiv_rn(tp[j], A.temperature);
     {
@@ -461,14 +469,16 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
         is_last = atomicAdd(L.ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last && threadIdx.x < 2) {
+    if (is_last && warp < 2) {
+        // warp `w` reduces slot `w`: lane-strided partial sums in block order, then a fixed shuffle tree
         __threadfence();
         float sum = 0.f;
         const volatile float* bp = L.block_partials;
-        for (unsigned int b = 0; b < gridDim.x; ++b) sum += bp[2 * b + threadIdx.x];
+        for (unsigned int b = lane; b < gridDim.x; b += 32) sum += bp[2 * b + warp];
+        sum = warp_sum(sum);
         bool used = false;
-        for (int j = 0; j < L.njobs; ++j) used |= L.job[j].loss_slot == (int)threadIdx.x;
-        if (used) L.out_loss[threadIdx.x] = sum;
+        for (int j = 0; j < L.njobs; ++j) used |= L.job[j].loss_slot == warp;
+        if (used && lane == 0) L.out_loss[warp] = sum;
         if (threadIdx.x == 0) *L.ticket = 0u;
     }
 }
@@ -504,42 +514,85 @@ __global__ void __launch_bounds__(kRowBlock) grad_finish_kernel(const __grid_con
 // =====================================================================================
 // segmented per-class sums (STiLModel.py:199-226, 380-381): one warp per class, rows in index order
 // =====================================================================================
+constexpr int kAccChunk = 2048;   // rows of (cls, conf) codes staged in shared memory per pass
+
+__device__ __forceinline__ void load4_as_float(const void* feat, int dtype, long long off, int d, int dim, bool vec,
+                                               float (&x)[4]) {
+    if (vec) {
+        if (dtype == STIL_BF16) {
+            const uint2 v = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(feat) + off + d);
+            x[0] = __uint_as_float(v.x << 16); x[1] = __uint_as_float(v.x & 0xffff0000u);
+            x[2] = __uint_as_float(v.y << 16); x[3] = __uint_as_float(v.y & 0xffff0000u);
+        } else {
+            const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(feat) + off + d);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = (d + j < dim) ? ld_as_float(feat, dtype, off + d + j) : 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(kRowBlock) proto_accumulate_kernel(const void* __restrict__ feat, int dtype, int rows,
                                                                      int dim, long long ld,
                                                                      const int* __restrict__ cls,
                                                                      const unsigned char* __restrict__ conf, int b_l,
                                                                      float repeat_ratio, int k, float* class_sum,
                                                                      float* class_count, float* psum, float* pcount) {
+    __shared__ int codes[kAccChunk];   // class of a confident row, -1 otherwise
     const int c = blockIdx.x * (kRowBlock / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (c >= k) return;
+    const bool vec = (dim % 4 == 0) && (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(feat) % 16 == 0);
     for (int d0 = 0; d0 < dim; d0 += 128) {
         float al[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
         float nl = 0.f, nu = 0.f;
-        for (int r0 = 0; r0 < rows; r0 += 32) {
-            const int r = r0 + lane;
-            const bool hit = r < rows && conf[r] && cls[r] == c;
-            unsigned int ballot = __ballot_sync(0xffffffffu, hit);
-            while (ballot) {
-                const int b = __ffs(ballot) - 1;
-                ballot &= ballot - 1;
-                const int rr = r0 + b;
-                float* acc = rr < b_l ? al : au;
-                if (rr < b_l) nl += 1.f; else nu += 1.f;
+        const int d = d0 + lane * 4;
+        for (int base = 0; base < rows; base += kAccChunk) {
+            const int nrow = min(kAccChunk, rows - base);
+            __syncthreads();
+            for (int i = threadIdx.x; i < nrow; i += kRowBlock) codes[i] = conf[base + i] ? cls[base + i] : -1;
+            __syncthreads();
+            if (c >= k) continue;
+            for (int r0 = 0; r0 < nrow; r0 += 32) {
+                const bool hit = (r0 + lane < nrow) && codes[r0 + lane] == c;
+                unsigned int ballot = __ballot_sync(0xffffffffu, hit);
+                while (ballot) {
+                    // up to four matching rows in flight, added in ascending row order (deterministic)
+                    int idx[4];
+                    int n = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int d = d0 + lane * 4 + j;
-                    if (d < dim) acc[j] += ld_as_float(feat, dtype, (long long)rr * ld + d);
+                    for (int j = 0; j < 4; ++j)
+                        if (ballot) {
+                            idx[j] = base + r0 + __ffs(ballot) - 1;
+                            ballot &= ballot - 1;
+                            n = j + 1;
+                        }
+                    float x[4][4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < n && d < dim) load4_as_float(feat, dtype, (long long)idx[j] * ld, d, dim, vec, x[j]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < n) {
+                            const bool lab = idx[j] < b_l;
+                            if (lab) nl += 1.f; else nu += 1.f;
+                            if (d < dim) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    if (lab) al[q] += x[j][q]; else au[q] += x[j][q];
+                                }
+                            }
+                        }
                 }
             }
         }
+        if (c >= k) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int d = d0 + lane * 4 + j;
-            if (d < dim) {
+            if (d + j < dim) {
                 const float v = __fadd_rn(__fdiv_rn(al[j], repeat_ratio), au[j]);   // :224
-                class_sum[(long long)c * dim + d] = v;
-                if (psum) psum[(long long)c * dim + d] += v;                         // :380
+                class_sum[(long long)c * dim + d + j] = v;
+                if (psum) psum[(long long)c * dim + d + j] += v;                     // :380
             }
         }
         if (d0 == 0 && lane == 0) {
@@ -588,52 +641,62 @@ struct SoftCeArgs {
     float* block_partials;  // [blocks*3]
     unsigned int* ticket;
     float* losses;          // [3]
+    int vec_y, vec_pl, vec_g;
 };
 
+template <int NV>
 __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeArgs A) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (kRowBlock / 32) + warp;
     float lossv[3] = {0.f, 0.f, 0.f};
     if (row < A.rows) {
+        const int k = A.k;
+        // all four rows of this sample in flight together
+        float pl[2 * NV], y[3][2 * NV];
+        load_row<32, NV>(A.pl, STIL_F32, A.ld_pl, row, k, lane, A.vec_pl, pl);
+#pragma unroll
+        for (int h = 0; h < 3; ++h) load_row<32, NV>(A.y[h], A.logit_dtype, A.ld_y, row, k, lane, A.vec_y, y[h]);
         const float m1 = A.mask1[row] ? 1.f : 0.f;
         const float c1 = A.case1[row] ? 1.f : 0.f, c2i = A.case2_i[row] ? 1.f : 0.f;
         const float c2t = A.case2_t[row] ? 1.f : 0.f, c3 = A.case3[row] ? 1.f : 0.f;
         const float mr = A.mask_random[row] ? 1.f : 0.f;
         const float wgt[3] = {m1 * c1, m1 * (c1 + c2t + c3 * mr), m1 * (c1 + c2i + c3 * (1.f - mr))};
-        const float* pl = A.pl + (long long)row * A.ld_pl;
         float spl = 0.f;
-        for (int j = lane; j < A.k; j += 32) spl += pl[j];
+#pragma unroll
+        for (int it = 0; it < NV; ++it)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (2 * (lane + 32 * it) + h >= k) pl[2 * it + h] = 0.f;   // padding was -inf
+                spl += pl[2 * it + h];
+            }
         spl = warp_sum(spl);
         const float inv_rows = 1.0f / (float)A.rows;
 #pragma unroll
         for (int h = 0; h < 3; ++h) {
-            float* dy = A.dy[h] ? A.dy[h] + (long long)row * A.ld_g : nullptr;
-            if (wgt[h] == 0.f) {
-                if (dy)
-                    for (int j = lane; j < A.k; j += 32) dy[j] = 0.f;
-                continue;  // warp-uniform
-            }
-            const long long off = (long long)row * A.ld_y;
-            float m = -INFINITY;
-            for (int j = lane; j < A.k; j += 32) m = fmaxf(m, ld_as_float(A.y[h], A.logit_dtype, off + j));
-            m = warp_max(m);
-            float s = 0.f, py = 0.f;
-            for (int j = lane; j < A.k; j += 32) {
-                const float y = ld_as_float(A.y[h], A.logit_dtype, off + j);
-                s += expf(y - m);
-                py += pl[j] * y;
-            }
-            s = warp_sum(s);
-            py = warp_sum(py);
-            const float lse = m + logf(s);
-            lossv[h] = (lse * spl - py) * wgt[h];   // -sum_k pl_k log_softmax(y)_k, times the row weight
-            if (dy) {
-                const float gs = A.grad_scale * wgt[h] * inv_rows;
-                for (int j = lane; j < A.k; j += 32) {
-                    const float y = ld_as_float(A.y[h], A.logit_dtype, off + j);
-                    dy[j] = gs * (expf(y - lse) * spl - pl[j]);
+            float dy[2 * NV];
+            if (wgt[h] != 0.f) {   // warp-uniform
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 2 * NV; ++j) m = fmaxf(m, y[h][j]);
+                m = warp_max(m);
+                float s = 0.f, py = 0.f;
+#pragma unroll
+                for (int j = 0; j < 2 * NV; ++j) {
+                    s += expf(y[h][j] - m);                       // exp(-inf) = 0 for the padding
+                    if (pl[j] != 0.f) py += pl[j] * y[h][j];
                 }
+                s = warp_sum(s);
+                py = warp_sum(py);
+                const float lse = m + logf(s);
+                lossv[h] = (lse * spl - py) * wgt[h];             // -sum_k pl_k log_softmax(y)_k, times the row weight
+                const float gs = A.grad_scale * wgt[h] * inv_rows;
+#pragma unroll
+                for (int j = 0; j < 2 * NV; ++j) dy[j] = gs * (expf(y[h][j] - lse) * spl - pl[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2 * NV; ++j) dy[j] = 0.f;
             }
+            if (A.dy[h]) store_row<32, NV>(A.dy[h], A.ld_g, row, k, lane, A.vec_g, dy);
         }
     }
     __shared__ float sred[3][kRowBlock / 32];
@@ -651,12 +714,13 @@ __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeAr
         is_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last && threadIdx.x < 3) {
+    if (is_last && warp < 3) {
         __threadfence();
         float sum = 0.f;
         const volatile float* bp = A.block_partials;
-        for (unsigned int b = 0; b < gridDim.x; ++b) sum += bp[3 * b + threadIdx.x];
-        A.losses[threadIdx.x] = sum / (float)A.rows;   // .mean() over B_u
+        for (unsigned int b = lane; b < gridDim.x; b += 32) sum += bp[3 * b + warp];
+        sum = warp_sum(sum);
+        if (lane == 0) A.losses[warp] = sum / (float)A.rows;   // .mean() over B_u
         if (threadIdx.x == 0) *A.ticket = 0u;
     }
 }
@@ -670,8 +734,7 @@ template <int LPR, int NV>
 int launch_cgpl_t(const CgplArgs& A, cudaStream_t stream) {
     const int rows_per_block = (kRowBlock / 32) * (32 / LPR);
     const int blocks = (int)ceil_div(A.rows, rows_per_block);
-    cgpl_pgls_kernel<LPR, NV><<<blocks, kRowBlock, 0, stream>>>(A);
-    STIL_LAUNCH_CHECK();
+    STIL_CUDA(launch_pdl(cgpl_pgls_kernel<LPR, NV>, dim3(blocks), dim3(kRowBlock), 0, stream, A));
     return STIL_OK;
 }
 
@@ -692,8 +755,7 @@ int launch_prep(const PrepLaunch& L, cudaStream_t stream) {
         if (L.n_zero > 0) return launch_zero_u32(L.zero_words, L.n_zero, stream);
         return STIL_OK;
     }
-    prep_kernel<<<L.total_blocks, kRowBlock, 0, stream>>>(L);
-    STIL_LAUNCH_CHECK();
+    STIL_CUDA(launch_pdl(prep_kernel, dim3(L.total_blocks), dim3(kRowBlock), 0, stream, L));
     return STIL_OK;
 }
 
@@ -831,7 +893,17 @@ int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int 
     A.dy[0] = d_y_m; A.dy[1] = d_y_i; A.dy[2] = d_y_t;
     A.ld_g = ld_g; A.grad_scale = grad_scale;
     A.block_partials = block_partials; A.ticket = ticket; A.losses = losses;
-    masked_softce_kernel<<<(int)masked_softce_blocks(rows, k), kRowBlock, 0, stream>>>(A);
+    STIL_REQUIRE(k >= 1 && k <= 1024, STIL_E_SHAPE, "masked_softce supports 1 <= k <= 1024 classes (got %lld)", (long long)k);
+    const int esz = logit_dtype == STIL_BF16 ? 2 : 4;
+    auto al = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+    A.vec_y = (ld_y % 2 == 0) && al(y_m, 2 * esz) && al(y_i, 2 * esz) && al(y_t, 2 * esz);
+    A.vec_pl = (ld_pl % 2 == 0) && al(pseudo_label, 8);
+    A.vec_g = (ld_g % 2 == 0) && al(d_y_m, 8) && al(d_y_i, 8) && al(d_y_t, 8);
+    const int blocks = (int)masked_softce_blocks(rows, k);
+    if (k <= 64) masked_softce_kernel<1><<<blocks, kRowBlock, 0, stream>>>(A);
+    else if (k <= 320) masked_softce_kernel<5><<<blocks, kRowBlock, 0, stream>>>(A);
+    else if (k <= 512) masked_softce_kernel<8><<<blocks, kRowBlock, 0, stream>>>(A);
+    else masked_softce_kernel<16><<<blocks, kRowBlock, 0, stream>>>(A);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }

@@ -140,6 +140,9 @@ class STiLHead:
             self._args.timing_events = C.cast(arr, C.c_void_p)
             self._args.n_timing_events = n
             try:
+                # keep the GPU busy while the host enqueues the whole step, so the event intervals are GPU-side
+                # durations rather than host launch gaps
+                torch.cuda._sleep(400_000)
                 self._enqueue()
             finally:
                 self._args.timing_events = None
@@ -185,3 +188,74 @@ class STiLHead:
                                                   self.prototypes_count_sum.data_ptr(), k, d, empty.data_ptr(),
                                                   torch.cuda.current_stream(self.dev).cuda_stream))
         return empty
+
+
+class DistributedSTiLHead(STiLHead):
+    """Data-parallel head over one node (one process per GPU, ``torch.distributed`` / NCCL over NVLink).
+
+    Everything row-local runs in ``stil_head_step`` with ``skip_infonce``; the two coupled pieces follow
+    SURVEY §8e: (i) InfoNCE on the GLOBAL batch — both embeddings all-gathered, local rows scored against all
+    columns, only the two LSE vectors gathered again for the backward (oracle: reference ``CLIPLoss`` on the
+    concatenated batch); (ii) prototype partial sums all-reduced before they are accumulated
+    (``STiLModel.py:377-379``) — packed with the InfoNCE loss partial into ONE all-reduce.
+    ``losses[0]`` is the global InfoNCE loss (same on every rank); ``d_feat_i/t`` are its gradients w.r.t. the
+    local rows.
+    """
+
+    def __init__(self, cfg: HeadConfig, device="cuda", group=None, **kw) -> None:
+        kw["use_graph"] = False          # NCCL collectives are issued between the kernels
+        super().__init__(cfg, device=device, **kw)
+        import torch.distributed as dist
+        from .distributed import GlobalBatch
+        self.dist, self.group, self.gb = dist, group, GlobalBatch(group)
+        self.world, self.rank = self.gb.world_size, self.gb.rank
+        B, K, P = cfg.batch, cfg.num_classes, cfg.proj_dim
+        n = B * self.world
+        dev, edt = self.dev, self.inp["feat_i"].dtype
+        self._a_all = torch.empty(n, P, dtype=edt, device=dev)
+        self._b_all = torch.empty(n, P, dtype=edt, device=dev)
+        self._lse_loc = torch.empty(2, B, dtype=torch.float32, device=dev)
+        self._lse_all = torch.empty(self.world, 2, B, dtype=torch.float32, device=dev)
+        self._lse_cat = torch.empty(2, n, dtype=torch.float32, device=dev)
+        # [loss partial | class_sum | class_count] reduced with one collective
+        self._packed = torch.zeros(1 + K * P + K, dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        code = _lib.dtype_code(self.inp["feat_i"])
+        self._nce_ws = torch.empty(lib.stil_infonce_workspace_bytes(B, n, P, code), dtype=torch.uint8, device=dev)
+        a = self._args
+        a.skip_infonce = 1
+        a.class_sum = self._packed[1:1 + K * P].data_ptr()
+        a.class_count = self._packed[1 + K * P:].data_ptr()
+        a.prototypes_sum, a.prototypes_count_sum = None, None
+        self.out["class_sum"] = self._packed[1:1 + K * P].view(K, P)
+        self.out["class_count"] = self._packed[1 + K * P:].view(K, 1)
+        self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 4 + 3 + 1   # + infonce fwd/bwd + add
+
+    def run(self) -> None:
+        cfg, dist, lib = self.cfg, self.dist, _lib.load()
+        B, K, P, W = cfg.batch, cfg.num_classes, cfg.proj_dim, self.world
+        n, off = B * W, B * self.rank
+        code = _lib.dtype_code(self.inp["feat_i"])
+        p = lambda t: t.data_ptr()
+        with torch.cuda.device(self.dev):
+            # the gathers fly while the row-local part of the step runs
+            h1 = dist.all_gather_into_tensor(self._a_all, self.inp["feat_i"], group=self.group, async_op=True)
+            h2 = dist.all_gather_into_tensor(self._b_all, self.inp["feat_t"], group=self.group, async_op=True)
+            self._enqueue()
+            h1.wait(); h2.wait()
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            check(lib.stil_infonce_fwd(p(self.inp["feat_i"]), p(self.inp["feat_t"]), p(self._a_all), p(self._b_all), code,
+                                       B, n, P, P, off, cfg.temperature, cfg.lambda_0, p(self._packed),
+                                       p(self._lse_loc[0]), p(self._lse_loc[1]), None, 0, p(self._nce_ws),
+                                       self._nce_ws.numel(), st))
+            dist.all_gather_into_tensor(self._lse_all, self._lse_loc, group=self.group)
+            dist.all_reduce(self._packed, op=dist.ReduceOp.SUM, group=self.group)
+            self._lse_cat.view(2, W, B).copy_(self._lse_all.transpose(0, 1))
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            check(lib.stil_infonce_bwd(p(self.inp["feat_i"]), p(self.inp["feat_t"]), p(self._a_all), p(self._b_all), code,
+                                       B, n, P, P, off, cfg.temperature, cfg.lambda_0, p(self._lse_cat[0]),
+                                       p(self._lse_cat[1]), None, p(self.out["d_feat_i"]), p(self.out["d_feat_t"]),
+                                       _lib.dtype_code(self.out["d_feat_i"]), P, p(self._nce_ws), self._nce_ws.numel(), st))
+            check(lib.stil_proto_add(p(self.out["class_sum"]), p(self.out["class_count"]), K, P, p(self.prototypes_sum),
+                                     p(self.prototypes_count_sum), st))
+            self.out["losses"][0:1].copy_(self._packed[0:1], non_blocking=True)
