@@ -42,7 +42,9 @@ struct Operand {
     int64_t row_stride, seg_stride;
 };
 
-inline int64_t pad8(int64_t n) { return round_up(n, 8); }
+inline int64_t pad32(int64_t n) { return round_up(n, 32); }
+// GEMM_STATS writes one (max, sum) partial per 64-column half tile
+inline int64_t stat_slots(int64_t n) { return 2 * ceil_div(n, kTileN); }
 
 // segment pairs (x_seg, y_seg) with x_seg + y_seg <= order, most significant first.  Segment s carries
 // ~2^-9s of the value, so order 2 keeps every product above ~2^-26 (fp32-accurate), order 1 above 2^-17.
@@ -102,16 +104,15 @@ InfoncePlan plan_infonce(void* ws, int64_t ws_bytes, int64_t m, int64_t n, int64
     InfoncePlan P;
     Workspace W(ws, ws_bytes);
     P.nseg = dtype == STIL_BF16 ? 1 : 3;
-    P.ldg = pad8(n);
+    P.ldg = pad32(n);
     P.ticket = W.take<unsigned int>(64);
     P.ra = W.take<float>(n);
     P.rb = W.take<float>(n);
     P.a_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(n * P.nseg * dim);
     P.b_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(n * P.nseg * dim);
-    const int64_t tiles_n = ceil_div(n, kTileN);
     for (int s = 0; s < 2; ++s) {
-        P.pmax[s] = W.take<float>(tiles_n * m);
-        P.psum[s] = W.take<float>(tiles_n * m);
+        P.pmax[s] = W.take<float>(stat_slots(n) * m);
+        P.psum[s] = W.take<float>(stat_slots(n) * m);
     }
     P.block_partials = W.take<float>(2 * finish_blocks((int)(3 * m)) + 8);  // 3m rows: the fused step adds the prototype rows
     // backward-only regions (the forward never touches them, the query always counts them)
@@ -166,13 +167,12 @@ ProtoPlan plan_proto(void* ws, int64_t ws_bytes, int64_t rows, int64_t k, int64_
     Workspace W(ws, ws_bytes);
     P.feat_nseg = dtype == STIL_BF16 ? 1 : 3;
     P.proto_nseg = 3;
-    P.ldg = pad8(k);
+    P.ldg = pad32(k);
     P.ticket = W.take<unsigned int>(64);
     P.feat_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(rows * P.feat_nseg * dim);
     P.proto_op = W.take<__nv_bfloat16>(k * P.proto_nseg * dim);
-    const int64_t tiles_n = ceil_div(k, kTileN);
-    P.pmax = W.take<float>(tiles_n * rows);
-    P.psum = W.take<float>(tiles_n * rows);
+    P.pmax = W.take<float>(stat_slots(k) * rows);
+    P.psum = W.take<float>(stat_slots(k) * rows);
     P.block_partials = W.take<float>(2 * finish_blocks((int)rows) + 8);
     P.gop = W.take<__nv_bfloat16>(rows * 2 * P.ldg);
     P.g = W.take<float>(rows * dim);
@@ -234,7 +234,7 @@ void infonce_finish_jobs(FinishJob* F2, const InfoncePlan& P, const void* a_all,
         std::memset(&F, 0, sizeof(F));
         F.kind = 0;
         F.M = (int)m;
-        F.tiles_n = (int)ceil_div(n, kTileN);
+        F.tiles_n = (int)stat_slots(n);
         F.part_max = P.pmax[s];
         F.part_sum = P.psum[s];
         F.lse = s == 0 ? lse_row : lse_col;
@@ -274,7 +274,7 @@ int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const
             // other side's rows) instead of waiting for the finish kernel
             J.px_max = P.pmax[s]; J.px_sum = P.psum[s];
             J.py_max = P.pmax[1 - s]; J.py_sum = P.psum[1 - s];
-            J.px_tiles = J.py_tiles = (int)ceil_div(n, kTileN);
+            J.px_tiles = J.py_tiles = (int)stat_slots(n);
         }
         J.u_scalar = (s == 0 ? lambda0 : 1.f - lambda0) / (float)n;
         J.v_scalar = (s == 0 ? 1.f - lambda0 : lambda0) / (float)n;
@@ -556,7 +556,7 @@ void proto_finish_job(FinishJob& F, const ProtoPlan& P, const void* feat, int dt
     std::memset(&F, 0, sizeof(F));
     F.kind = 1;
     F.M = (int)rows;
-    F.tiles_n = (int)ceil_div(k, kTileN);
+    F.tiles_n = (int)stat_slots(k);
     F.part_max = P.pmax; F.part_sum = P.psum;
     F.lse = lse;
     F.x = feat; F.x_dtype = dtype; F.ldx = ld;
@@ -586,7 +586,7 @@ int proto_grad_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, 
     } else {
         // fused: LSE from the GEMM_STATS partials, coefficient from the picked logit, both in the kernel
         J.px_max = P.pmax; J.px_sum = P.psum;
-        J.px_tiles = (int)ceil_div(k, kTileN);
+        J.px_tiles = (int)stat_slots(k);
         J.w_x = feat; J.w_x_dtype = dtype; J.w_ldx = ld;
         J.w_y = prototypes; J.w_ldy = dim;
         J.w_conf = conf;
@@ -759,6 +759,7 @@ struct StepPlan {
     ProtoPlan pt;        // student feat_m x prototypes
     __nv_bfloat16* teach_op;   // teacher feat_m_e operand (fp32 input only)
     float* teacher_logits;     // [b_u, ldk]
+    float *teach_pmax, *teach_psum;
     int64_t ldk;
     int32_t* cls;              // [batch]
     uint8_t* conf;             // [batch]
@@ -781,6 +782,8 @@ StepPlan plan_step(void* ws, int64_t ws_bytes, int64_t batch, int64_t b_l, int64
     P.ldk = round_up(k, 4);
     P.teach_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(b_u * 3 * dim);
     P.teacher_logits = W.take<float>(b_u * P.ldk);
+    P.teach_pmax = W.take<float>(stat_slots(k) * b_u);
+    P.teach_psum = W.take<float>(stat_slots(k) * b_u);
     P.cls = W.take<int32_t>(batch);
     P.conf = W.take<uint8_t>(batch);
     P.lse_row = W.take<float>(batch);
@@ -874,7 +877,9 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         const Operand X = rowmajor_operand(feat_m_ue, dt, D, D, P.teach_op, 3);
         const Operand Y = rowmajor_operand(nullptr, STIL_F32, D, D, P.pt.proto_op, P.pt.proto_nseg);
         if ((rc = fill_gemm_common(GL.job[nj], X, 0, B_u, Y, K, D))) return rc;
-        GL.job[nj].mode = GEMM_STORE;
+        GL.job[nj].mode = GEMM_STATS;            // same launch as the statistics jobs; its partials are unused
+        GL.job[nj].part_max = P.teach_pmax;
+        GL.job[nj].part_sum = P.teach_psum;
         GL.job[nj].out = P.teacher_logits;
         GL.job[nj].ld_out = P.ldk;
         ++nj;

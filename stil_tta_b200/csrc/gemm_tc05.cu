@@ -20,10 +20,10 @@ namespace stil {
 
 namespace {
 
-constexpr int kStages = 3;
-constexpr int kThreads = 192;
+constexpr int kStages = 6;
+constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kStageBytes = (kTileM + kTileN) * kTileK * 2;  // 32 KiB
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2048 /*scales*/ + 256 /*barriers*/;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2048 /*scales, dot partials*/ + 256 /*barriers*/;
 constexpr uint32_t kTmemCols = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -108,6 +108,16 @@ __device__ __forceinline__ void store32_from_float(void* base, int dtype, long l
     }
 }
 
+// Slow-path helpers for a partial / unaligned 32-column chunk: compact loops over single TMEM columns so that
+// the unrolled fast paths stay small (code size is what bounds these short kernels' start-up).
+__device__ __forceinline__ float tmem_ld_col(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    tc05::tmem_ld_wait();
+    return __uint_as_float(v);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_constant__ GemmLaunch L) {
     extern __shared__ uint8_t smem_raw[];
     // carve: [stages x (A 16K | B 16K)] 1024-aligned, then scales, then barriers
@@ -116,7 +126,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     uint8_t* tiles = smem_raw + pad;
     float* col_scale = reinterpret_cast<float*>(tiles + kStages * kStageBytes);  // [128]
     float* col_lse = col_scale + kTileN;                                          // [128]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(col_lse + kTileN + 128);
+    float* dot_part = col_lse + kTileN;                                           // [2][128]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(dot_part + 2 * kTileM);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -163,6 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            const bool mn = MODE == GEMM_STORE && J.y_mn_major != 0;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
@@ -172,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 uint8_t* b_dst = a_dst + kTileM * kTileK * 2;
                 tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
                 tc05::tma_load_3d(a_dst, &J.tmx, &full_bar[s], kk * kTileK, m0, J.xseg[p]);
-                if (!J.y_mn_major) {
+                if (!mn) {
                     tc05::tma_load_3d(b_dst, &J.tmy, &full_bar[s], kk * kTileK, n0, J.yseg[p]);
                 } else {
                     // Y tile [64 contraction rows x 128 N] as two 64x64 boxes (N chunks 8 KiB apart)
@@ -184,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const bool mn = J.y_mn_major != 0;
+            const bool mn = MODE == GEMM_STORE && J.y_mn_major != 0;
             const uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, kTileN) | (mn ? (1u << 16) : 0u);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kStages;
@@ -207,19 +219,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
             tc05::mma_commit(tmem_full_bar);
         }
     } else {
-        // ===================== epilogue (4 warps, thread = accumulator row) =====================
-        const int e = threadIdx.x - 64;  // 0..127
-        const int q = warp & 3;          // TMEM lane quarter this warp may access
+        // ===================== epilogue: 8 warps, thread = accumulator row, two warps per lane quarter
+        // (one per 64-column half of the tile) =====================
+        const int e = threadIdx.x - 64;      // 0..255
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;    // which 64 columns
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < J.M;
         const int ncols = min(kTileN, J.N - n0);
-        const int mode = J.mode;
-        {
+        const float alpha = J.alpha;
+        if (e < kTileN) {
             const int col = n0 + e;
             float cs = 0.f, cl = 0.f;
             if (col < J.N) {
-                cs = J.alpha * (J.sy ? J.sy[col] : 1.f);
-                if (mode == GEMM_GRAD) {
+                cs = alpha * (J.sy ? J.sy[col] : 1.f);
+                if (MODE == GEMM_GRAD) {
                     if (J.lse_y) cl = J.lse_y[col];
                     else if (J.py_max) cl = merge_partials(J.py_max, J.py_sum, J.py_tiles, J.N, col);
                 }
@@ -227,17 +241,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
             col_scale[e] = cs;
             col_lse[e] = cl;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue-only named barrier
-
         const float rs = (row_ok && J.sx) ? J.sx[row] : 1.f;
         float lse_x = 0.f, u = 0.f, d = 0.f, gs = 1.f;
         int tgt = -1;
-        if (mode == GEMM_GRAD && row_ok) {
+        if (MODE == GEMM_GRAD && row_ok) {
             lse_x = J.lse_x ? J.lse_x[row] : merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
             tgt = J.tgt_vec ? J.tgt_vec[row] : row + J.tgt_offset;
             if (J.w_x) {
                 // prototype CE coefficient from the picked logit (utils/prototype_loss.py:28,37-39)
                 float dot = 0.f;
+#pragma unroll 1
                 for (int d0 = 0; d0 < J.D; d0 += 32) {
                     float xv[32], yv[32];
                     const int nv = min(32, J.D - d0);
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; ++j) dot += xv[j] * yv[j];
                 }
-                const float p = expf(dot * J.alpha - lse_x);
+                const float p = expf(dot * alpha - lse_x);
                 u = (J.w_conf[row] ? J.w_coef : 0.f) * p / (p + 1e-7f);
                 d = u;
             } else {
@@ -255,21 +268,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
             }
             gs = J.gscale ? *J.gscale : 1.f;
         }
-        const float v = (mode == GEMM_GRAD && (J.lse_y || J.py_max)) ? J.v_scalar : 0.f;
-        const bool fused_fin = mode == GEMM_STORE && J.fin_dx != nullptr;
+        const float v = (MODE == GEMM_GRAD && (J.lse_y || J.py_max)) ? J.v_scalar : 0.f;
+        const bool fused_fin = MODE == GEMM_STORE && J.fin_dx != nullptr;
         const float fsx = (fused_fin && row_ok && J.fin_sx) ? J.fin_sx[row] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue-only named barrier: col_scale / col_lse ready
 
         tc05::mbar_wait(tmem_full_bar, 0);
         tc05::fence_after_sync();
 
-        float run_max = -INFINITY, run_sum = 0.f;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int c_begin = half * 2, c_end = half * 2 + 2;   // two 32-column chunks per warp
 
         float fin_dot = 0.f;
-        if (fused_fin && J.fin_sx) {
-            // pass 1 of the normalise-backward: <xh, g> over the whole row (tile spans all of N)
+        if (MODE == GEMM_STORE && fused_fin && J.fin_sx) {
+            // pass 1 of the normalise-backward: <xh, g> over the whole row (the tile spans all of N)
+            float part = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < kTileN / 32; ++c) {
+            for (int c = c_begin; c < c_end; ++c) {
                 if (c * 32 >= ncols) break;
                 uint32_t acc[32];
                 tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
@@ -279,13 +294,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                     const int nv = min(32, ncols - c * 32);
                     load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + n0 + c * 32, nv, xv);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) fin_dot += fsx * xv[j] * (__uint_as_float(acc[j]) * rs * col_scale[c * 32 + j]);
+                    for (int j = 0; j < 32; ++j) part += xv[j] * __uint_as_float(acc[j]);
                 }
             }
+            dot_part[half * kTileM + q * 32 + lane] = part * fsx * alpha;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            fin_dot = dot_part[q * 32 + lane] + dot_part[kTileM + q * 32 + lane];
         }
 
+        float run_max = -INFINITY, run_sum = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < kTileN / 32; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             if (c * 32 >= ncols) break;  // warp-uniform
             uint32_t acc[32];
             tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
@@ -295,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 32; ++j) l[j] = __uint_as_float(acc[j]) * rs * col_scale[c * 32 + j];
 
-            if (mode == GEMM_STATS) {
+            if (MODE == GEMM_STATS) {
                 float cmax = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -308,22 +327,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 run_sum = run_sum * fast_exp2((run_max - new_max) * kLog2e) + s;
                 run_max = new_max;
             }
-            if (fused_fin) {
-                if (row_ok) {
-                    if (J.fin_sx) {
-                        float xv[32];
-                        load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + n0 + c * 32, nv, xv);
+            if (MODE == GEMM_STORE && fused_fin) {
+                if (J.fin_sx && row_ok) {
+                    float xv[32];
+                    load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + n0 + c * 32, nv, xv);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xv[j] * fin_dot);
-                    }
-                    store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + n0 + c * 32, nv, l);
+                    for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xv[j] * fin_dot);
                 }
-            } else if ((mode == GEMM_STATS || mode == GEMM_STORE) && J.out && row_ok) {
-                store32_from_float(J.out, STIL_F32, (long long)row * J.ld_out + n0 + c * 32, nv, l);
+                if (row_ok) store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + n0 + c * 32, nv, l);
+            } else if ((MODE == GEMM_STATS || MODE == GEMM_STORE) && J.out) {
+                float* dst = J.out + (long long)row * J.ld_out + n0 + c * 32;
+                // warp-uniform choice: the slow path issues warp-collective TMEM loads
+                const bool vec_ok = nv == 32 && (J.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(J.out) & 15) == 0);
+                if (vec_ok) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(l[j], l[j + 1], l[j + 2], l[j + 3]);
+                    }
+                } else {
+                    // partial / unaligned chunk: compact per-column loop
+#pragma unroll 1
+                    for (int j = 0; j < nv; ++j) {
+                        const float val = tmem_ld_col(taddr + c * 32 + j) * rs * col_scale[c * 32 + j];
+                        if (row_ok) dst[j] = val;
+                    }
+                }
             }
-            if (mode == GEMM_GRAD && row_ok) {
+            if (MODE == GEMM_GRAD && row_ok) {
                 __nv_bfloat16* hi_dst = J.gop + (long long)row * 2 * J.ld_g + n0 + c * 32;
                 __nv_bfloat16* lo_dst = hi_dst + J.ld_g;
+                // gop rows are padded to 32 columns (ld_g % 32 == 0), so full 16-byte stores are always in bounds;
+                // columns >= N hold finite garbage that the dX GEMM never reads (its contraction extent is N)
                 uint32_t hi_pk[16], lo_pk[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
@@ -336,33 +371,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                         if (n0 + c * 32 + jj == tgt) g -= d;
                         g2[h] = g * col_scale[c * 32 + jj] * gs;
                     }
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(g2[0]), h1 = __float2bfloat16_rn(g2[1]);
-                    const __nv_bfloat16 l0 = __float2bfloat16_rn(g2[0] - __bfloat162float(h0));
-                    const __nv_bfloat16 l1 = __float2bfloat16_rn(g2[1] - __bfloat162float(h1));
-                    hi_pk[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo_pk[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(g2[0], g2[1]);
+                    const float2 hf = __bfloat1622float2(hh);
+                    const __nv_bfloat162 ll = __floats2bfloat162_rn(g2[0] - hf.x, g2[1] - hf.y);
+                    hi_pk[j / 2] = *reinterpret_cast<const uint32_t*>(&hh);
+                    lo_pk[j / 2] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
-                if (nv == 32 && ((reinterpret_cast<uintptr_t>(hi_dst) & 15) == 0) &&
-                    ((reinterpret_cast<uintptr_t>(lo_dst) & 15) == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        *reinterpret_cast<uint4*>(hi_dst + 2 * j) = make_uint4(hi_pk[j], hi_pk[j + 1], hi_pk[j + 2], hi_pk[j + 3]);
-                        *reinterpret_cast<uint4*>(lo_dst + 2 * j) = make_uint4(lo_pk[j], lo_pk[j + 1], lo_pk[j + 2], lo_pk[j + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nv) {
-                            const uint32_t hp = hi_pk[j / 2], lp = lo_pk[j / 2];
-                            hi_dst[j] = __ushort_as_bfloat16((unsigned short)((j & 1) ? (hp >> 16) : (hp & 0xffff)));
-                            lo_dst[j] = __ushort_as_bfloat16((unsigned short)((j & 1) ? (lp >> 16) : (lp & 0xffff)));
-                        }
+                for (int j = 0; j < 16; j += 4) {
+                    *reinterpret_cast<uint4*>(hi_dst + 2 * j) = make_uint4(hi_pk[j], hi_pk[j + 1], hi_pk[j + 2], hi_pk[j + 3]);
+                    *reinterpret_cast<uint4*>(lo_dst + 2 * j) = make_uint4(lo_pk[j], lo_pk[j + 1], lo_pk[j + 2], lo_pk[j + 3]);
                 }
             }
         }
-        if (mode == GEMM_STATS && row_ok) {
-            J.part_max[(long long)tn * J.M + row] = run_max;
-            J.part_sum[(long long)tn * J.M + row] = run_sum;
+        if (MODE == GEMM_STATS && row_ok) {
+            // one (max, sum) partial per 64-column half tile; an empty half contributes (-inf, 0)
+            J.part_max[(long long)(tn * 2 + half) * J.M + row] = run_max;
+            J.part_sum[(long long)(tn * 2 + half) * J.M + row] = run_sum;
         }
     }
 
@@ -427,17 +452,28 @@ void gemm_job_tiles(GemmLaunch& L) {
     L.total_tiles = begin;
 }
 
-int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
-    STIL_REQUIRE(L.njobs >= 1 && L.njobs <= kMaxGemmJobs, STIL_E_ARG, "gemm launch with %d jobs", L.njobs);
-    if (L.total_tiles == 0) return STIL_OK;
+template <int MODE>
+static int launch_gemm_mode(const GemmLaunch& L, cudaStream_t stream) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        attr_err = cudaFuncSetAttribute(gemm_tc05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     });
     STIL_CUDA(attr_err);
-    STIL_CUDA(launch_pdl(gemm_tc05_kernel, dim3(L.total_tiles), dim3(kThreads), kSmemBytes, stream, L));
+    STIL_CUDA(launch_pdl(gemm_tc05_kernel<MODE>, dim3(L.total_tiles), dim3(kThreads), kSmemBytes, stream, L));
     return STIL_OK;
+}
+
+// All jobs of one launch share the epilogue mode (the kernel is specialised per mode to keep it small).
+int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
+    STIL_REQUIRE(L.njobs >= 1 && L.njobs <= kMaxGemmJobs, STIL_E_ARG, "gemm launch with %d jobs", L.njobs);
+    if (L.total_tiles == 0) return STIL_OK;
+    const int mode = L.job[0].mode;
+    for (int j = 1; j < L.njobs; ++j)
+        STIL_REQUIRE(L.job[j].mode == mode, STIL_E_ARG, "gemm launch mixes epilogue modes");
+    if (mode == GEMM_STATS) return launch_gemm_mode<GEMM_STATS>(L, stream);
+    if (mode == GEMM_STORE) return launch_gemm_mode<GEMM_STORE>(L, stream);
+    return launch_gemm_mode<GEMM_GRAD>(L, stream);
 }
 
 }  // namespace stil
