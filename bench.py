@@ -256,7 +256,7 @@ def run_gpu_arm(args):
     pk = peaks()
 
     # enough distinct batches that inputs+outputs+scratch touched between two uses of a buffer exceed L2
-    Head = (lambda c, device: S.DistributedSTiLHead(c, device=device)) if dist_on else \
+    Head = (lambda c, device: S.DistributedSTiLHead(c, device=device, use_graph=not args.no_graph)) if dist_on else \
            (lambda c, device: S.STiLHead(c, device=device))
     probe = Head(cfg, device=dev)
     per_head = probe.h2d_bytes + sum(t.numel() * t.element_size() for t in probe.out.values()) + probe._ws.numel()
@@ -265,7 +265,7 @@ def run_gpu_arm(args):
     host_batches = [synth.make_batch(cfg, seed=2022 + i, rank=rank) for i in range(min(nbuf, 8))]
     for i, h in enumerate(heads):
         h.load(host_batches[i % len(host_batches)])
-        if not dist_on:
+        if not (dist_on and args.no_graph):
             h.capture()
     pinned = [heads[0].pin(b) for b in host_batches]
     torch.cuda.synchronize(dev)
@@ -292,7 +292,7 @@ def run_gpu_arm(args):
         "data": "synthetic",
         "config": {"workload": workload_name(cfg, args.config), "per_gpu_batch": cfg.batch,
                    "l2": f"inputs larger than L2: {nbuf} rotating batches x {per_head / 2**20:.1f} MiB touched per step",
-                   "parallelism": f"dp{world}", "cuda_graph": not dist_on},
+                   "parallelism": f"dp{world}", "cuda_graph": True},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": heads[0].h2d_bytes,
                 "d2h_bytes_per_step": heads[0].d2h_bytes},
         "gpu_launches": heads[0].launches_per_step * args.steps,
@@ -309,9 +309,9 @@ def run_gpu_arm(args):
                 per.setdefault(name, []).append(ms1)
     kern = {k: sum(v) / len(v) * 1e3 for k, v in per.items()}      # us per launch
     if rank == 0 and dist_on:
-        line["config"]["cuda_graph"] = False
-        line["config"]["collectives"] = ("NCCL: 2x all_gather(embeddings) overlapped with the row-local step, "
-                                         "all_gather(LSE), 1 packed all_reduce(loss, class_sum, class_count)")
+        line["config"]["cuda_graph"] = not args.no_graph
+        line["config"]["collectives"] = ("NCCL, captured in the CUDA graph: 1 all_gather([feat_i|feat_t]) overlapped with the row-local "
+                                         "step, all_reduce(loss, LSE slots), all_reduce(class_sum|class_count); InfoNCE chain on its own stream")
         line["config"]["infonce"] = f"global batch {cfg.batch * world} (all-gathered)"
         print(json.dumps(line), flush=True)
     if rank == 0 and not dist_on:
@@ -341,8 +341,16 @@ def run_gpu_arm(args):
                                               f"{ms_cpu:.2f} ms/step, best thread count of 1..{len(os.sched_getaffinity(0))} = {n}"}
         print(json.dumps(line), flush=True)
     if dist_on:
+        # graphs that captured NCCL work must die before the communicator; then leave without the (slow, and with
+        # captured collectives occasionally hanging) process-group teardown
+        torch.cuda.synchronize(dev)
         dist.barrier()
-        dist.destroy_process_group()
+        for h in heads:
+            h.release()
+        del heads
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
@@ -353,6 +361,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
+    ap.add_argument("--no-graph", action="store_true", help="N>1 only: do not capture kernels+NCCL in a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

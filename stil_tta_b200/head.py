@@ -203,7 +203,6 @@ class DistributedSTiLHead(STiLHead):
     """
 
     def __init__(self, cfg: HeadConfig, device="cuda", group=None, **kw) -> None:
-        kw["use_graph"] = False          # NCCL collectives are issued between the kernels
         super().__init__(cfg, device=device, **kw)
         import torch.distributed as dist
         from .distributed import GlobalBatch
@@ -211,51 +210,97 @@ class DistributedSTiLHead(STiLHead):
         self.world, self.rank = self.gb.world_size, self.gb.rank
         B, K, P = cfg.batch, cfg.num_classes, cfg.proj_dim
         n = B * self.world
+        W = self.world
         dev, edt = self.dev, self.inp["feat_i"].dtype
-        self._a_all = torch.empty(n, P, dtype=edt, device=dev)
-        self._b_all = torch.empty(n, P, dtype=edt, device=dev)
-        self._lse_loc = torch.empty(2, B, dtype=torch.float32, device=dev)
-        self._lse_all = torch.empty(self.world, 2, B, dtype=torch.float32, device=dev)
-        self._lse_cat = torch.empty(2, n, dtype=torch.float32, device=dev)
-        # [loss partial | class_sum | class_count] reduced with one collective
-        self._packed = torch.zeros(1 + K * P + K, dtype=torch.float32, device=dev)
+        # one all-gather for both modalities: rows [feat_i | feat_t] side by side, leading dimension 2P
+        self._ab_loc = torch.empty(B, 2 * P, dtype=edt, device=dev)
+        self._ab_all = torch.empty(n, 2 * P, dtype=edt, device=dev)
+        # two small all-reduces on one buffer: [loss partial (4) | LSE slots [2, W, B]] for the InfoNCE chain and
+        # [class_sum | class_count] for the prototype bank (STiLModel.py:377-379, one collective instead of two);
+        # every rank fills only its own LSE slot, so SUM over ranks is the gather of the LSE vectors
+        self._o_lse, self._o_cs, self._o_cc = 4, 4 + 2 * n, 4 + 2 * n + K * P
+        self._packed = torch.zeros(self._o_cc + K, dtype=torch.float32, device=dev)
+        self._lse = self._packed[self._o_lse:self._o_cs].view(2, W, B)
+        self._nce_stream = None
         lib = _lib.load()
         code = _lib.dtype_code(self.inp["feat_i"])
         self._nce_ws = torch.empty(lib.stil_infonce_workspace_bytes(B, n, P, code), dtype=torch.uint8, device=dev)
         a = self._args
         a.skip_infonce = 1
-        a.class_sum = self._packed[1:1 + K * P].data_ptr()
-        a.class_count = self._packed[1 + K * P:].data_ptr()
+        a.class_sum = self._packed[self._o_cs:].data_ptr()
+        a.class_count = self._packed[self._o_cc:].data_ptr()
         a.prototypes_sum, a.prototypes_count_sum = None, None
-        self.out["class_sum"] = self._packed[1:1 + K * P].view(K, P)
-        self.out["class_count"] = self._packed[1 + K * P:].view(K, 1)
-        self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 4 + 3 + 1   # + infonce fwd/bwd + add
+        self.out["class_sum"] = self._packed[self._o_cs:self._o_cc].view(K, P)
+        self.out["class_count"] = self._packed[self._o_cc:].view(K, 1)
+        # + cat, zero, infonce fwd (prep, gemm, finish), bwd (prep, gemm, gemm), proto_add, loss copy
+        self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 2 + 3 + 3 + 2
+
+    def capture(self) -> None:
+        """Record kernels AND the NCCL collectives of one step into a CUDA graph (every rank must call this
+        and later replay in lockstep)."""
+        with torch.cuda.device(self.dev):
+            keep = (self.prototypes_sum.clone(), self.prototypes_count_sum.clone())
+            s = torch.cuda.Stream(self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._run_eager()
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            torch.cuda.synchronize(self.dev)
+            self.dist.barrier(group=self.group)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_eager()
+            self.prototypes_sum.copy_(keep[0])
+            self.prototypes_count_sum.copy_(keep[1])
+            torch.cuda.synchronize(self.dev)
+            self._graph = g
 
     def run(self) -> None:
+        with torch.cuda.device(self.dev):
+            if self.use_graph:
+                if self._graph is None:
+                    self.capture()
+                self._graph.replay()
+            else:
+                self._run_eager()
+
+    def _run_eager(self) -> None:
         cfg, dist, lib = self.cfg, self.dist, _lib.load()
         B, K, P, W = cfg.batch, cfg.num_classes, cfg.proj_dim, self.world
-        n, off = B * W, B * self.rank
+        n, off, r = B * W, B * self.rank, self.rank
         code = _lib.dtype_code(self.inp["feat_i"])
         p = lambda t: t.data_ptr()
+        esz = self._ab_all.element_size()
         with torch.cuda.device(self.dev):
-            # the gathers fly while the row-local part of the step runs
-            h1 = dist.all_gather_into_tensor(self._a_all, self.inp["feat_i"], group=self.group, async_op=True)
-            h2 = dist.all_gather_into_tensor(self._b_all, self.inp["feat_t"], group=self.group, async_op=True)
+            cur = torch.cuda.current_stream(self.dev)
+            if self._nce_stream is None:
+                self._nce_stream = torch.cuda.Stream(self.dev)
+            sb = self._nce_stream
+            torch.cat((self.inp["feat_i"], self.inp["feat_t"]), dim=1, out=self._ab_loc)
+            sb.wait_stream(cur)
+            # chain B (own stream): gather -> global InfoNCE forward -> all-reduce(loss, LSE) -> backward
+            with torch.cuda.stream(sb):
+                dist.all_gather_into_tensor(self._ab_all, self._ab_loc, group=self.group)
+                self._lse.zero_()
+                a_all, b_all = p(self._ab_all), p(self._ab_all) + P * esz
+                a_loc, b_loc = a_all + off * 2 * P * esz, b_all + off * 2 * P * esz
+                check(lib.stil_infonce_fwd(a_loc, b_loc, a_all, b_all, code, B, n, P, 2 * P, off, cfg.temperature,
+                                           cfg.lambda_0, p(self._packed), p(self._lse[0, r]), p(self._lse[1, r]), None, 0,
+                                           p(self._nce_ws), self._nce_ws.numel(), sb.cuda_stream))
+                dist.all_reduce(self._packed[:self._o_cs], op=dist.ReduceOp.SUM, group=self.group)
+                check(lib.stil_infonce_bwd(a_loc, b_loc, a_all, b_all, code, B, n, P, 2 * P, off, cfg.temperature,
+                                           cfg.lambda_0, p(self._lse[0]), p(self._lse[1]), None, p(self.out["d_feat_i"]),
+                                           p(self.out["d_feat_t"]), _lib.dtype_code(self.out["d_feat_i"]), P,
+                                           p(self._nce_ws), self._nce_ws.numel(), sb.cuda_stream))
+                self.out["losses"][0:1].copy_(self._packed[0:1], non_blocking=True)
+            # chain A (current stream): everything row-local, then the prototype partials over all ranks
             self._enqueue()
-            h1.wait(); h2.wait()
-            st = torch.cuda.current_stream(self.dev).cuda_stream
-            check(lib.stil_infonce_fwd(p(self.inp["feat_i"]), p(self.inp["feat_t"]), p(self._a_all), p(self._b_all), code,
-                                       B, n, P, P, off, cfg.temperature, cfg.lambda_0, p(self._packed),
-                                       p(self._lse_loc[0]), p(self._lse_loc[1]), None, 0, p(self._nce_ws),
-                                       self._nce_ws.numel(), st))
-            dist.all_gather_into_tensor(self._lse_all, self._lse_loc, group=self.group)
-            dist.all_reduce(self._packed, op=dist.ReduceOp.SUM, group=self.group)
-            self._lse_cat.view(2, W, B).copy_(self._lse_all.transpose(0, 1))
-            st = torch.cuda.current_stream(self.dev).cuda_stream
-            check(lib.stil_infonce_bwd(p(self.inp["feat_i"]), p(self.inp["feat_t"]), p(self._a_all), p(self._b_all), code,
-                                       B, n, P, P, off, cfg.temperature, cfg.lambda_0, p(self._lse_cat[0]),
-                                       p(self._lse_cat[1]), None, p(self.out["d_feat_i"]), p(self.out["d_feat_t"]),
-                                       _lib.dtype_code(self.out["d_feat_i"]), P, p(self._nce_ws), self._nce_ws.numel(), st))
+            dist.all_reduce(self._packed[self._o_cs:], op=dist.ReduceOp.SUM, group=self.group)
             check(lib.stil_proto_add(p(self.out["class_sum"]), p(self.out["class_count"]), K, P, p(self.prototypes_sum),
-                                     p(self.prototypes_count_sum), st))
-            self.out["losses"][0:1].copy_(self._packed[0:1], non_blocking=True)
+                                     p(self.prototypes_count_sum), cur.cuda_stream))
+            cur.wait_stream(sb)
+
+    def release(self) -> None:
+        """Drop the captured graph (it pins the NCCL communicator) before the process group is destroyed."""
+        self._graph = None

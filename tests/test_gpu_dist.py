@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, batch):
+def _worker(rank, world, port, batch, use_graph):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -29,7 +29,7 @@ def _worker(rank, world, port, batch):
         from oracle import stil_head_oracle as O
         cfg = synth.dvm_config(batch)
         batches = [synth.make_batch(cfg, seed=2022, rank=r) for r in range(world)]
-        head = S.DistributedSTiLHead(cfg, device=f"cuda:{rank}")
+        head = S.DistributedSTiLHead(cfg, device=f"cuda:{rank}", use_graph=use_graph)
         head.load(batches[rank])
         for _ in range(2):          # second run accumulates again
             head.run()
@@ -54,11 +54,22 @@ def _worker(rank, world, port, batch):
         assert float((head.out["class_sum"].cpu() - cs).abs().max()) <= 1e-4
         assert float((head.prototypes_sum.cpu() - 2 * cs).abs().max()) <= 2e-4
         assert float((head.prototypes_count_sum.cpu() - 2 * cc).abs().max()) <= 2e-5
-    finally:
-        dist.destroy_process_group()
+        ok = True
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        ok = False
+    # a graph that captured NCCL work pins the communicator: drop it, then leave without the process-group teardown
+    try:
+        head.release()
+        torch.cuda.synchronize()
+    except BaseException:
+        pass
+    os._exit(0 if ok else 1)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_distributed_head_two_ranks():
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_distributed_head_two_ranks(use_graph):
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), 256), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), 256, use_graph), nprocs=2, join=True)
