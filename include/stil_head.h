@@ -50,6 +50,9 @@ typedef enum {
 
 STIL_API int stil_version(void);
 STIL_API const char* stil_last_error(void);
+/* Debug aid: install (or clear with NULL) a device buffer of [64 launches][64 CTAs][8] uint64 into which the GEMM
+ * kernel's CTAs store %globaltimer stamps of their phases (scripts/gemm_timeline.py).  Not for production use. */
+STIL_API int stil_debug_trace(void* buffer);
 /* 0 if the current device can run the kernels (compute capability 10.x), STIL_E_ARCH otherwise. */
 STIL_API int stil_check_device(void);
 

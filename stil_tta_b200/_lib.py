@@ -52,6 +52,7 @@ SIGNATURES = {
     "stil_version": (i32, []),
     "stil_last_error": (C.c_char_p, []),
     "stil_check_device": (i32, []),
+    "stil_debug_trace": (i32, [vp]),
     "stil_infonce_workspace_bytes": (i64, [i64, i64, i64, i32]),
     "stil_infonce_fwd": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, vp, i64, vp]),
     "stil_infonce_bwd": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, vp, i32, i64,

@@ -369,6 +369,8 @@ extern "C" {
 STIL_API int stil_version(void) { return STIL_VERSION; }
 STIL_API const char* stil_last_error(void) { return stil::last_error(); }
 
+STIL_API int stil_debug_trace(void* buffer) { return gemm_set_trace(buffer); }
+
 STIL_API int stil_check_device(void) {
     int dev = 0;
     STIL_CUDA(cudaGetDevice(&dev));

@@ -108,6 +108,21 @@ __device__ __forceinline__ void store32_from_float(void* base, int dtype, long l
     }
 }
 
+// Optional timeline instrumentation (stil_debug_trace): when a buffer is installed every CTA stores %globaltimer
+// stamps of its phases: [launch_id][cta][8] = start, prologue done, last TMA issued, last MMA committed, accumulator
+// ready (epilogue), epilogue math done, epilogue end, mode.
+__device__ unsigned long long* g_trace = nullptr;
+constexpr int kTraceCtas = 64, kTraceSlots = 8, kTraceLaunches = 64;
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define STIL_TRACE(slot)                                                                              \
+    do {                                                                                              \
+        if (trace && blockIdx.x < kTraceCtas) trace[(blockIdx.x) * kTraceSlots + (slot)] = gtime();   \
+    } while (0)
+
 // Slow-path helpers for a partial / unaligned 32-column chunk: compact loops over single TMEM columns so that
 // the unrolled fast paths stay small (code size is what bounds these short kernels' start-up).
 __device__ __forceinline__ float tmem_ld_col(uint32_t taddr) {
@@ -135,6 +150,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: next kernel may begin its prologue
+    unsigned long long* trace = g_trace ? g_trace + (size_t)(L.trace_id % kTraceLaunches) * kTraceCtas * kTraceSlots : nullptr;
+    if (threadIdx.x == 0) { STIL_TRACE(0); if (trace && blockIdx.x < kTraceCtas) trace[blockIdx.x * kTraceSlots + 7] = MODE; }
 
     // ---- which job / tile
     int jid = 0;
@@ -170,6 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     tc05::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: predecessor's results are visible from here on
+    if (threadIdx.x == 0) STIL_TRACE(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -192,6 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                     tc05::tma_load_3d(b_dst + 64 * kTileK * 2, &J.tmy, &full_bar[s], n0 + 64, kk * kTileK, J.yseg[p]);
                 }
             }
+            STIL_TRACE(2);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -217,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 tc05::mma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
             }
             tc05::mma_commit(tmem_full_bar);
+            STIL_TRACE(3);
         }
     } else {
         // ===================== epilogue: 8 warps, thread = accumulator row, two warps per lane quarter
@@ -273,8 +293,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
         const float fsx = (fused_fin && row_ok && J.fin_sx) ? J.fin_sx[row] : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue-only named barrier: col_scale / col_lse ready
 
+        if (e == 0) STIL_TRACE(4);   // epilogue prologue (scales, merges, coefficients) done
         tc05::mbar_wait(tmem_full_bar, 0);
         tc05::fence_after_sync();
+        if (e == 0) STIL_TRACE(5);   // accumulator ready
 
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int c_begin = half * 2, c_end = half * 2 + 2;   // two 32-column chunks per warp
@@ -394,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     // ---- teardown: all TMEM reads done before dealloc
     tc05::fence_before_sync();
     __syncthreads();
+    if (threadIdx.x == 0) STIL_TRACE(6);
     if (warp == 1) {
         tc05::fence_after_sync();
         tc05::tmem_dealloc(tmem_base, kTmemCols);
@@ -452,6 +475,12 @@ void gemm_job_tiles(GemmLaunch& L) {
     L.total_tiles = begin;
 }
 
+int gemm_set_trace(void* buf) {
+    unsigned long long* p = static_cast<unsigned long long*>(buf);
+    STIL_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+    return STIL_OK;
+}
+
 template <int MODE>
 static int launch_gemm_mode(const GemmLaunch& L, cudaStream_t stream) {
     static std::once_flag once;
@@ -471,6 +500,8 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
     const int mode = L.job[0].mode;
     for (int j = 1; j < L.njobs; ++j)
         STIL_REQUIRE(L.job[j].mode == mode, STIL_E_ARG, "gemm launch mixes epilogue modes");
+    static unsigned int launch_counter = 0;
+    const_cast<GemmLaunch&>(L).trace_id = launch_counter++;
     if (mode == GEMM_STATS) return launch_gemm_mode<GEMM_STATS>(L, stream);
     if (mode == GEMM_STORE) return launch_gemm_mode<GEMM_STORE>(L, stream);
     return launch_gemm_mode<GEMM_GRAD>(L, stream);

@@ -74,6 +74,7 @@ struct GemmLaunch {
     GemmJob job[kMaxGemmJobs];
     int njobs;
     int total_tiles;
+    unsigned int trace_id;   // launch ordinal for the optional timeline trace
 };
 
 // Build the operand tensor map.  `base` bf16, logical [rows, nseg, inner]; strides in elements.
@@ -81,6 +82,7 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t r
                      int64_t row_stride, int64_t seg_stride, int box_rows = 128);
 void gemm_job_tiles(GemmLaunch& L);  // fills tiles_m/tiles_n/tile_begin/total_tiles
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream);
+int gemm_set_trace(void* buf);   // debug: device buffer of [64 launches][64 CTAs][8] u64 %globaltimer stamps, or nullptr
 
 // --------------------------------------------------------------------------- row kernels (row_kernels.cu)
 // Operand preparation: for every row of x (f32 or bf16) write the bf16 segments (hi[,lo[,lolo]]) into
