@@ -145,6 +145,18 @@ STIL_API int stil_proto_finalize(float* prototypes, float* psum, float* pcount, 
                         int32_t* empty_classes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a6 — distribution alignment.  Replaces STiLModel.distribution_alignment (STiLModel.py:171-180; same code in
+ * simmatch_model.py:151-163, MMatch.py:136-148), split at its all-reduce:
+ *   stil_da_batch_mean : mean[k] = probs.mean(0)                                   (:173)
+ *   (caller: all-reduce mean over ranks and divide by the world size, :174-176 — a no-op on one rank)
+ *   stil_da_apply      : DA_queue[ptr] = mean; ptr = (ptr+1) % da_len; out = probs / DA_queue.mean(0), rows
+ *                        renormalised (:176-179).  da_ptr is the reference's int64 [1] buffer ON THE DEVICE (no
+ *                        host sync, unlike `int(self.DA_ptr)`); qmean_scratch is k floats of scratch. */
+STIL_API int stil_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, void* stream);
+STIL_API int stil_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* da_queue,
+                  int64_t da_len, int64_t* da_ptr, float* qmean_scratch, float* out, int64_t ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * f-1 — masked soft-target CE of the three student heads on the unlabelled rows, forward and
  * gradient in one pass.  Replaces STiLModel.py:301-303.
  *   losses[3]  = (loss_m_u, loss_i_u, loss_t_u), each a mean over `rows`
@@ -184,8 +196,10 @@ typedef struct stil_head_step_args {
     float *prototypes_sum, *prototypes_count_sum;     /* accumulated in place when non-NULL */
     float rate_uce_scale;                             /* grad_scale of the f-1 gradients */
     void* workspace; int64_t workspace_bytes; void* stream;
-    /* optional instrumentation (bench.py): cudaEvent_t[n_timing_events] recorded on `stream` before each
-     * main-chain launch and after the last one; leave NULL/0 otherwise (and always during graph capture) */
+    /* optional instrumentation (bench.py): cudaEvent_t[9] recorded around the launches of the two critical chains —
+     * 0|prep|1|gemm stats|5|cgpl_pgls|6|gemm grad (prototype CE)|7|gemm dX (prototype CE)|8 on `stream`;
+     * 2|gemm grad (InfoNCE)|3|gemm dX (InfoNCE)|4 on the internal InfoNCE-backward stream.  Leave NULL/0 otherwise (and
+     * always during graph capture). */
     void** timing_events; int n_timing_events;
     /* 1: leave the InfoNCE (losses[0], d_feat_i, d_feat_t) to the caller — the data-parallel path computes it on
      * the all-gathered global batch with stil_infonce_fwd/bwd while this call does everything row-local */

@@ -10,7 +10,7 @@ from .synth import HeadConfig, cardiac_config, dvm_config, make_batch  # noqa: F
 
 _LAZY = {
     "CLIPLoss": "losses", "PrototypeLoss": "losses", "masked_soft_ce": "losses", "label_argmax": "losses",
-    "cgpl_pgls": "pseudo_label", "prototype_logits": "pseudo_label", "PseudoLabels": "pseudo_label",
+    "cgpl_pgls": "pseudo_label", "distribution_alignment": "pseudo_label", "prototype_logits": "pseudo_label", "PseudoLabels": "pseudo_label",
     "cal_prototypes": "prototypes", "cal_prototypes_separate": "prototypes", "PrototypeBank": "prototypes",
     "STiLHead": "head", "DistributedSTiLHead": "head", "GlobalBatch": "distributed", "all_reduce_prototype_partials": "distributed",
 }

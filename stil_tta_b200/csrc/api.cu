@@ -140,11 +140,14 @@ Operand rowmajor_operand(const void* x, int dtype, int64_t dim, int64_t ld, cons
     }
     return O;
 }
-Operand grad_operand(const __nv_bfloat16* gop, int64_t ldg) {
+// G = dLoss/dLogits as bf16: hi+lo segments when the gradients are wanted in fp32, hi only for bf16 gradients
+// (whose own rounding is 2^-9 already)
+inline int grad_nseg(int grad_dtype) { return grad_dtype == STIL_BF16 ? 1 : 2; }
+Operand grad_operand(const __nv_bfloat16* gop, int64_t ldg, int nseg) {
     Operand O;
     O.base = gop;
-    O.nseg = 2;
-    O.row_stride = 2 * ldg;
+    O.nseg = nseg;
+    O.row_stride = (int64_t)nseg * ldg;
     O.seg_stride = ldg;
     return O;
 }
@@ -255,7 +258,7 @@ void infonce_finish_jobs(FinishJob* F2, const InfoncePlan& P, const void* a_all,
 
 int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const Operand& B, int64_t m, int64_t n,
                       int64_t dim, int64_t off, float inv_t, float lambda0, const float* lse_row_all,
-                      const float* lse_col_all, const float* grad_loss) {
+                      const float* lse_col_all, const float* grad_loss, int grad_dtype) {
     for (int s = 0; s < 2; ++s) {
         const Operand& X = s == 0 ? A : B;
         const Operand& Y = s == 0 ? B : A;
@@ -283,6 +286,7 @@ int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const
         J.gscale = grad_loss;
         J.gop = P.gop[s];
         J.ld_g = P.ldg;
+        J.g_nseg = grad_nseg(grad_dtype);
     }
     return STIL_OK;
 }
@@ -294,7 +298,7 @@ int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, cons
     const int esz = dtype == STIL_BF16 ? 2 : 4;
     *fused = dim <= kTileN;
     for (int s = 0; s < 2; ++s) {
-        const Operand X = grad_operand(P.gop[s], P.ldg);
+        const Operand X = grad_operand(P.gop[s], P.ldg, grad_nseg(grad_dtype));
         const Operand& Y = s == 0 ? B : A;
         int rc = fill_gemm_store_mn(J2[s], X, m, Y, n, dim);
         if (rc) return rc;
@@ -333,9 +337,10 @@ void infonce_gradfinish_jobs(GradFinishJob* G2, const InfoncePlan& P, const void
 }
 
 // side streams for the independent branches of the step (fork/join with events; capturable)
+constexpr int kSide = 4;   // 0: losses, 1: prototype sums, 2: masked CE, 3: pseudo-label + prototype-CE backward chain
 struct SideStreams {
-    cudaStream_t s[3];
-    cudaEvent_t fork, join[3];
+    cudaStream_t s[kSide];
+    cudaEvent_t fork, fork2, join[kSide];
     bool ready;
 };
 SideStreams g_side[64];
@@ -348,11 +353,12 @@ int get_side_streams(SideStreams** out) {
     std::lock_guard<std::mutex> lock(g_side_mutex);
     SideStreams& S = g_side[dev];
     if (!S.ready) {
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < kSide; ++i) {
             STIL_CUDA(cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking));
             STIL_CUDA(cudaEventCreateWithFlags(&S.join[i], cudaEventDisableTiming));
         }
         STIL_CUDA(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
+        STIL_CUDA(cudaEventCreateWithFlags(&S.fork2, cudaEventDisableTiming));
         S.ready = true;
     }
     *out = &S;
@@ -454,7 +460,7 @@ STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* 
     GemmLaunch GL;
     std::memset(&GL, 0, sizeof(GL));
     if ((rc = infonce_grad_jobs(GL.job, P, A, B, m, n, dim, row_offset, inv_t, lambda0, lse_row_all, lse_col_all,
-                                grad_loss)))
+                                grad_loss, grad_dtype)))
         return rc;
     GL.njobs = 2;
     gemm_job_tiles(GL);
@@ -571,7 +577,7 @@ void proto_finish_job(FinishJob& F, const ProtoPlan& P, const void* feat, int dt
 }
 int proto_grad_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, int64_t rows, int64_t dim, int64_t ld,
                    int64_t k, float inv_t, const int32_t* cls, const float* lse, const float* w,
-                   const float* grad_loss, const float* prototypes, const uint8_t* conf) {
+                   const float* grad_loss, const float* z, int64_t ldz, const uint8_t* conf, int grad_dtype) {
     const Operand X = rowmajor_operand(feat, dtype, dim, ld, P.feat_op, P.feat_nseg);
     const Operand Y = rowmajor_operand(nullptr, STIL_F32, dim, dim, P.proto_op, P.proto_nseg);
     int rc = fill_gemm_common(J, X, 0, rows, Y, k, dim);
@@ -582,6 +588,7 @@ int proto_grad_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, 
     J.gscale = grad_loss;
     J.gop = P.gop;
     J.ld_g = P.ldg;
+    J.g_nseg = grad_nseg(grad_dtype);
     if (lse) {
         J.lse_x = lse;
         J.u_vec = w;
@@ -589,8 +596,7 @@ int proto_grad_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, 
         // fused: LSE from the GEMM_STATS partials, coefficient from the picked logit, both in the kernel
         J.px_max = P.pmax; J.px_sum = P.psum;
         J.px_tiles = (int)stat_slots(k);
-        J.w_x = feat; J.w_x_dtype = dtype; J.w_ldx = ld;
-        J.w_y = prototypes; J.w_ldy = dim;
+        J.w_z = z; J.w_ldz = ldz;
         J.w_conf = conf;
         J.w_coef = 1.f / (float)rows;
     }
@@ -599,7 +605,7 @@ int proto_grad_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, 
 // d_feat = G · prototypes (prototypes read in place, MN-major); cast to grad_dtype in the epilogue when possible
 int proto_store_job(GemmJob& J, const ProtoPlan& P, int64_t rows, int64_t dim, int64_t k, void* d_feat, int grad_dtype,
                     int64_t ld_grad, bool* fused) {
-    const Operand X = grad_operand(P.gop, P.ldg);
+    const Operand X = grad_operand(P.gop, P.ldg, grad_nseg(grad_dtype));
     const Operand Y = rowmajor_operand(nullptr, STIL_F32, dim, dim, P.proto_op, P.proto_nseg);
     int rc = fill_gemm_store_mn(J, X, rows, Y, k, dim);
     if (rc) return rc;
@@ -676,8 +682,8 @@ STIL_API int stil_proto_ce_bwd(const void* feat, int dtype, int64_t rows, int64_
     if ((rc = launch_prep(PL, S(stream)))) return rc;
     GemmLaunch GL;
     std::memset(&GL, 0, sizeof(GL));
-    if ((rc = proto_grad_job(GL.job[0], P, feat, dtype, rows, dim, ld, k, inv_t, cls, lse, w, grad_loss, prototypes,
-                             nullptr)))
+    if ((rc = proto_grad_job(GL.job[0], P, feat, dtype, rows, dim, ld, k, inv_t, cls, lse, w, grad_loss, nullptr, 0,
+                             nullptr, grad_dtype)))
         return rc;
     GL.njobs = 1;
     gemm_job_tiles(GL);
@@ -725,6 +731,19 @@ STIL_API int stil_proto_finalize(float* prototypes, float* psum, float* pcount, 
     return launch_proto_finalize(prototypes, psum, pcount, k, dim, empty_classes, S(stream));
 }
 
+// =============================================================================================== a6
+STIL_API int stil_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, void* stream) {
+    STIL_REQUIRE(probs && mean && rows >= 1 && ld >= k, STIL_E_ARG, "da_batch_mean: bad arguments");
+    return launch_da_batch_mean(probs, ld, rows, k, mean, S(stream));
+}
+
+STIL_API int stil_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* da_queue,
+                  int64_t da_len, int64_t* da_ptr, float* qmean_scratch, float* out, int64_t ld_out, void* stream) {
+    STIL_REQUIRE(probs && batch_mean && da_queue && da_ptr && qmean_scratch && out && da_len >= 1 && ld >= k && ld_out >= k,
+                 STIL_E_ARG, "da_apply: bad arguments");
+    return launch_da_apply(probs, ld, rows, k, batch_mean, da_queue, da_len, da_ptr, qmean_scratch, out, ld_out, S(stream));
+}
+
 // =============================================================================================== f-1
 STIL_API int64_t stil_masked_softce_workspace_bytes(int64_t rows) {
     Workspace W(nullptr, 0);
@@ -762,6 +781,7 @@ struct StepPlan {
     __nv_bfloat16* teach_op;   // teacher feat_m_e operand (fp32 input only)
     float* teacher_logits;     // [b_u, ldk]
     float *teach_pmax, *teach_psum;
+    float* z_pt;               // [batch, ldk] student prototype logits (for the CE coefficient)
     int64_t ldk;
     int32_t* cls;              // [batch]
     uint8_t* conf;             // [batch]
@@ -786,6 +806,7 @@ StepPlan plan_step(void* ws, int64_t ws_bytes, int64_t batch, int64_t b_l, int64
     P.teacher_logits = W.take<float>(b_u * P.ldk);
     P.teach_pmax = W.take<float>(stat_slots(k) * b_u);
     P.teach_psum = W.take<float>(stat_slots(k) * b_u);
+    P.z_pt = W.take<float>(batch * P.ldk);
     P.cls = W.take<int32_t>(batch);
     P.conf = W.take<uint8_t>(batch);
     P.lse_row = W.take<float>(batch);
@@ -805,11 +826,11 @@ STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int6
 
 STIL_API int stil_head_step_launches(const stil_head_step_args* a) {
     if (!a) return 0;
-    // main chain: prep, gemm(stats+teacher), cgpl_pgls, gemm(grad), gemm(dX) [+ grad_finish when dim > 128]
-    // side branches: finish (losses), proto_accumulate, masked soft CE
+    // prep, gemm(stats), cgpl_pgls, gemm(grad)+gemm(dX) for the prototype CE, finish, proto_accumulate
     int n = 7;
-    if (a->dim > kTileN) n += 1;
-    if (a->y_m) n += 1;
+    if (!a->skip_infonce) n += 2;          // gemm(grad)+gemm(dX) for the InfoNCE
+    if (a->dim > kTileN) n += a->skip_infonce ? 1 : 2;   // un-fused normalise-backward / cast
+    if (a->y_m) n += 1;                    // masked soft CE
     return n;
 }
 
@@ -837,13 +858,16 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
                  (long long)P.bytes);
     SideStreams* SS = nullptr;
     if ((rc = get_side_streams(&SS))) return rc;
+    cudaStream_t s_loss = SS->s[0], s_acc = SS->s[1], s_ce = SS->s[2], s_nce = SS->s[3];
+    cudaStream_t s_pl = st;   // the pseudo-label -> prototype-CE backward chain is the critical one: main stream
     const float inv_t = 1.0f / a->temperature;
     const int esz = dt == STIL_BF16 ? 2 : 4;
     const void* feat_m_ue = static_cast<const char*>(a->feat_m_e) + B_l * D * esz;
-    cudaEvent_t* tev = reinterpret_cast<cudaEvent_t*>(a->timing_events);   // optional: bench instrumentation
-    int tev_i = 0;
-    auto mark = [&]() -> int {
-        if (tev && tev_i < a->n_timing_events) STIL_CUDA(cudaEventRecord(tev[tev_i++], st));
+    const bool nce = !a->skip_infonce;
+    // optional instrumentation (bench.py): event pairs around the GEMM launches and the pseudo-label kernel
+    cudaEvent_t* tev = reinterpret_cast<cudaEvent_t*>(a->timing_events);
+    auto mark = [&](int i, cudaStream_t s) -> int {
+        if (tev && i < a->n_timing_events) STIL_CUDA(cudaEventRecord(tev[i], s));
         return STIL_OK;
     };
 
@@ -851,7 +875,6 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     PrepLaunch PL;
     std::memset(&PL, 0, sizeof(PL));
     PL.zero_words = P.nce.ticket; PL.n_zero = 32;   // [0] finish ticket, [16] masked-CE ticket
-    const bool nce = !a->skip_infonce;
     if (nce) {
         prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, nullptr, 0, 0, P.nce.ra));
         prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, nullptr, 0, 0, P.nce.rb));
@@ -861,10 +884,11 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         prep_add(PL, prep_job(feat_m_ue, dt, B_u, D, D, 3, P.teach_op, nullptr, 0, 0, nullptr));
     }
     prep_add(PL, prep_job(a->prototypes, STIL_F32, K, D, D, P.pt.proto_nseg, P.pt.proto_op, nullptr, 0, 0, nullptr));
-    if ((rc = mark())) return rc;
+    if ((rc = mark(0, st))) return rc;
     if ((rc = launch_prep(PL, st))) return rc;
 
-    // 2. forward GEMMs: InfoNCE both sides (stats), prototype CE (stats), teacher prototype logits (store)
+    // 2. forward GEMMs, one launch: InfoNCE both sides (statistics), student prototype logits (statistics + store),
+    //    teacher prototype logits (store)
     const Operand A = rowmajor_operand(a->feat_i, dt, D, D, P.nce.a_op, P.nce.nseg);
     const Operand Bm = rowmajor_operand(a->feat_t, dt, D, D, P.nce.b_op, P.nce.nseg);
     GemmLaunch GL;
@@ -874,7 +898,10 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         if ((rc = infonce_stats_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, nullptr, 0))) return rc;
         nj = 2;
     }
-    if ((rc = proto_stats_job(GL.job[nj++], P.pt, a->feat_m, dt, B, D, D, K, inv_t))) return rc;
+    if ((rc = proto_stats_job(GL.job[nj], P.pt, a->feat_m, dt, B, D, D, K, inv_t))) return rc;
+    GL.job[nj].out = P.z_pt;
+    GL.job[nj].ld_out = P.ldk;
+    ++nj;
     if (B_u > 0) {
         const Operand X = rowmajor_operand(feat_m_ue, dt, D, D, P.teach_op, 3);
         const Operand Y = rowmajor_operand(nullptr, STIL_F32, D, D, P.pt.proto_op, P.pt.proto_nseg);
@@ -888,72 +915,89 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     }
     GL.njobs = nj;
     gemm_job_tiles(GL);
-    if ((rc = mark())) return rc;
+    if ((rc = mark(1, st))) return rc;
     if ((rc = launch_gemm(GL, st))) return rc;
+    if ((rc = mark(5, st))) return rc;
 
-    // 3. CGPL + PGLS on the unlabelled rows; (cls, conf) of every row for the prototype kernels
-    if ((rc = mark())) return rc;
+    // ---- fork A: the InfoNCE backward leaves the main stream here (it does not need the pseudo labels)
+    STIL_CUDA(cudaEventRecord(SS->fork, st));
+    STIL_CUDA(cudaStreamWaitEvent(s_nce, SS->fork, 0));
+
+    // 4. main stream: CGPL + PGLS on the unlabelled rows, (cls, conf) of every row ...
     if ((rc = launch_cgpl_pgls(a->y_m_ue, a->y_i_ue, a->y_t_ue, a->logit_dtype, K, P.teacher_logits, P.ldk, B_u, K,
                                a->temperature, a->rate_pseudo, a->th1, a->past_start_epoch, a->pseudo_label, K, nullptr,
                                0, a->max_prob, a->max_idx, a->mask1, a->case1, a->case2_i, a->case2_t, a->case3,
-                               nullptr, P.cls + B_l, P.conf + B_l, a->y_l, B_l, P.cls, P.conf, st)))
+                               nullptr, P.cls + B_l, P.conf + B_l, a->y_l, B_l, P.cls, P.conf, s_pl)))
         return rc;
-
-    // ---- fork point: three independent branches run beside the backward GEMM chain (enqueued below)
-    STIL_CUDA(cudaEventRecord(SS->fork, st));
-    for (int i = 0; i < 3; ++i) STIL_CUDA(cudaStreamWaitEvent(SS->s[i], SS->fork, 0));
-
-    // 4. backward on the main stream: G tiles (bf16 hi/lo; statistics merged in-kernel) ...
-    std::memset(&GL, 0, sizeof(GL));
-    nj = 0;
-    if (nce) {
-        if ((rc = infonce_grad_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, a->lambda0, nullptr, nullptr, nullptr))) return rc;
-        nj = 2;
+    if ((rc = mark(6, s_pl))) return rc;
+    // ---- fork B: everything that only needs the pseudo labels
+    STIL_CUDA(cudaEventRecord(SS->fork2, s_pl));
+    STIL_CUDA(cudaStreamWaitEvent(s_loss, SS->fork2, 0));
+    STIL_CUDA(cudaStreamWaitEvent(s_acc, SS->fork2, 0));
+    STIL_CUDA(cudaStreamWaitEvent(s_ce, SS->fork2, 0));
+    //    ... then the prototype-CE backward on the same stream
+    bool fused_pt = false;
+    {
+        std::memset(&GL, 0, sizeof(GL));
+        if ((rc = proto_grad_job(GL.job[0], P.pt, a->feat_m, dt, B, D, D, K, inv_t, P.cls, nullptr, nullptr, nullptr,
+                                 P.z_pt, P.ldk, P.conf, a->grad_dtype)))
+            return rc;
+        GL.njobs = 1;
+        gemm_job_tiles(GL);
+        if ((rc = launch_gemm(GL, s_pl))) return rc;
+        if ((rc = mark(7, s_pl))) return rc;
+        std::memset(&GL, 0, sizeof(GL));
+        if ((rc = proto_store_job(GL.job[0], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
+        GL.njobs = 1;
+        gemm_job_tiles(GL);
+        if ((rc = launch_gemm(GL, s_pl))) return rc;
+        if ((rc = mark(8, s_pl))) return rc;
+        if (!fused_pt) {
+            GradFinishLaunch GF;
+            std::memset(&GF, 0, sizeof(GF));
+            GradFinishJob& j = GF.job[0];
+            j.g = P.pt.g; j.dx = a->d_feat_m; j.dx_dtype = a->grad_dtype; j.ld_dx = D;
+            j.rows = (int)B; j.dim = (int)D; j.row_begin = 0;
+            GF.njobs = 1;
+            GF.total_rows = (int)B;
+            if ((rc = launch_grad_finish(GF, s_pl))) return rc;
+        }
     }
-    if ((rc = proto_grad_job(GL.job[nj++], P.pt, a->feat_m, dt, B, D, D, K, inv_t, P.cls, nullptr, nullptr, nullptr,
-                             a->prototypes, P.conf)))
-        return rc;
-    GL.njobs = nj;
-    gemm_job_tiles(GL);
-    if ((rc = mark())) return rc;
-    if ((rc = launch_gemm(GL, st))) return rc;
-    // 5. ... then dX = G · Y with the normalise-backward / cast in the epilogue
-    std::memset(&GL, 0, sizeof(GL));
-    bool fused = false, fused_pt = false;
-    nj = 0;
+
+    // 3. side stream: InfoNCE backward — G tiles (statistics merged in-kernel), then dX = G · Y with the
+    //    normalise-backward in the epilogue.  Independent of the pseudo labels.
+    bool fused = true;
     if (nce) {
+        std::memset(&GL, 0, sizeof(GL));
+        if ((rc = infonce_grad_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, a->lambda0, nullptr, nullptr, nullptr,
+                                    a->grad_dtype)))
+            return rc;
+        GL.njobs = 2;
+        gemm_job_tiles(GL);
+        if ((rc = mark(2, s_nce))) return rc;
+        if ((rc = launch_gemm(GL, s_nce))) return rc;
+        if ((rc = mark(3, s_nce))) return rc;
+        std::memset(&GL, 0, sizeof(GL));
         if ((rc = infonce_store_jobs(GL.job, P.nce, A, Bm, a->feat_i, a->feat_t, dt, B, B, D, D, 0, a->d_feat_i,
                                      a->d_feat_t, a->grad_dtype, D, &fused)))
             return rc;
-        nj = 2;
-    }
-    if ((rc = proto_store_job(GL.job[nj++], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
-    GL.njobs = nj;
-    gemm_job_tiles(GL);
-    if ((rc = mark())) return rc;
-    if ((rc = launch_gemm(GL, st))) return rc;
-    if (!fused_pt) {
-        GradFinishLaunch GF;
-        std::memset(&GF, 0, sizeof(GF));
-        int gj = 0;
-        if (nce) {
+        GL.njobs = 2;
+        gemm_job_tiles(GL);
+        if ((rc = launch_gemm(GL, s_nce))) return rc;
+        if ((rc = mark(4, s_nce))) return rc;
+        if (!fused) {
+            GradFinishLaunch GF;
+            std::memset(&GF, 0, sizeof(GF));
             infonce_gradfinish_jobs(GF.job, P.nce, a->feat_i, a->feat_t, dt, B, D, D, 0, a->d_feat_i, a->d_feat_t,
                                     a->grad_dtype, D);
-            gj = 2;
+            GF.njobs = 2;
+            GF.total_rows = (int)(2 * B);
+            if ((rc = launch_grad_finish(GF, s_nce))) return rc;
         }
-        GradFinishJob& j = GF.job[gj];
-        j.g = P.pt.g; j.dx = a->d_feat_m; j.dx_dtype = a->grad_dtype; j.ld_dx = D;
-        j.rows = (int)B; j.dim = (int)D; j.row_begin = (int)(gj * B);
-        GF.njobs = gj + 1;
-        GF.total_rows = (int)((gj + 1) * B);
-        if ((rc = mark())) return rc;
-        if ((rc = launch_grad_finish(GF, st))) return rc;
     }
-    if ((rc = mark())) return rc;
 
-    // ---- side branches (enqueued after the critical path; they only depend on the fork event)
-    // side 0: merge statistics -> losses (and LSE vectors)
-    {
+    // 5. side branches
+    {   // losses and LSE vectors
         FinishLaunch FL;
         std::memset(&FL, 0, sizeof(FL));
         int fj = 0;
@@ -972,13 +1016,13 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         FL.block_partials = P.nce.block_partials;
         FL.ticket = P.nce.ticket;
         FL.out_loss = a->losses;   // [0] = itc, [1] = pt
-        if ((rc = launch_finish(FL, SS->s[0]))) return rc;
+        if ((rc = launch_finish(FL, s_loss))) return rc;
     }
-    // side 1: prototype partial sums (+ in-place accumulate) from the teacher features (STiLModel.py:376-381)
+    // prototype partial sums (+ in-place accumulate) from the teacher features (STiLModel.py:376-381)
     if ((rc = launch_proto_accumulate(a->feat_m_e, dt, B, D, D, P.cls, P.conf, B_l, a->repeat_ratio, K, a->class_sum,
-                                      a->class_count, a->prototypes_sum, a->prototypes_count_sum, SS->s[1])))
+                                      a->class_count, a->prototypes_sum, a->prototypes_count_sum, s_acc)))
         return rc;
-    // side 2: masked soft-target CE of the student heads (f-1)
+    // masked soft-target CE of the student heads (f-1)
     if (a->y_m) {
         STIL_REQUIRE(a->y_i && a->y_t && a->mask_random, STIL_E_ARG, "head_step: student logits need y_i, y_t, mask_random");
         const int lsz = a->logit_dtype == STIL_BF16 ? 2 : 4;
@@ -987,12 +1031,12 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         if ((rc = launch_masked_softce(urow(a->y_m), urow(a->y_i), urow(a->y_t), a->logit_dtype, K, a->pseudo_label, K,
                                        a->mask1, a->case1, a->case2_i, a->case2_t, a->case3, a->mask_random, B_u, K,
                                        a->losses + 2, grow(a->d_y_m), grow(a->d_y_i), grow(a->d_y_t), K,
-                                       a->rate_uce_scale, P.ce_partials, P.ce_ticket, SS->s[2])))
+                                       a->rate_uce_scale, P.ce_partials, P.ce_ticket, s_ce)))
             return rc;
     }
 
     // ---- join
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < kSide; ++i) {
         STIL_CUDA(cudaEventRecord(SS->join[i], SS->s[i]));
         STIL_CUDA(cudaStreamWaitEvent(st, SS->join[i], 0));
     }

@@ -33,14 +33,30 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-// log-sum-exp of one row/column from its per-tile (max, sum) partials laid out [tiles, stride]
-__device__ __forceinline__ float merge_partials(const float* pmax, const float* psum, int tiles, long long stride,
+// log-sum-exp of one row/column from its (max, sum) partials laid out [slots, stride]; eight slots are loaded
+// together so the merge costs one memory round trip
+__device__ __forceinline__ float merge_partials(const float* pmax, const float* psum, int slots, long long stride,
                                                 int idx) {
-    float m = -INFINITY;
-    for (int t = 0; t < tiles; ++t) m = fmaxf(m, pmax[t * stride + idx]);
-    float s = 0.f;
-    for (int t = 0; t < tiles; ++t) s += psum[t * stride + idx] * expf(pmax[t * stride + idx] - m);
-    return m + logf(s);
+    float run_m = -INFINITY, run_s = 0.f;
+    for (int t0 = 0; t0 < slots; t0 += 8) {
+        float m[8], s[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = t0 + j < slots;
+            m[j] = ok ? pmax[(long long)(t0 + j) * stride + idx] : -INFINITY;
+            s[j] = ok ? psum[(long long)(t0 + j) * stride + idx] : 0.f;
+        }
+        float nm = run_m;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nm = fmaxf(nm, m[j]);
+        if (nm == -INFINITY) continue;
+        float acc = run_s * __expf(run_m - nm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += s[j] * __expf(m[j] - nm);
+        run_m = nm;
+        run_s = acc;
+    }
+    return run_m + logf(run_s);
 }
 
 __device__ __forceinline__ void load32_as_float(const void* base, int dtype, long long off, int nv, float (&x)[32]) {
@@ -267,19 +283,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
         if (MODE == GEMM_GRAD && row_ok) {
             lse_x = J.lse_x ? J.lse_x[row] : merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
             tgt = J.tgt_vec ? J.tgt_vec[row] : row + J.tgt_offset;
-            if (J.w_x) {
+            if (J.w_z) {
                 // prototype CE coefficient from the picked logit (utils/prototype_loss.py:28,37-39)
-                float dot = 0.f;
-#pragma unroll 1
-                for (int d0 = 0; d0 < J.D; d0 += 32) {
-                    float xv[32], yv[32];
-                    const int nv = min(32, J.D - d0);
-                    load32_as_float(J.w_x, J.w_x_dtype, (long long)row * J.w_ldx + d0, nv, xv);
-                    load32_as_float(J.w_y, STIL_F32, (long long)tgt * J.w_ldy + d0, nv, yv);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) dot += xv[j] * yv[j];
-                }
-                const float p = expf(dot * alpha - lse_x);
+                const float p = expf(J.w_z[(long long)row * J.w_ldz + tgt] - lse_x);
                 u = (J.w_conf[row] ? J.w_coef : 0.f) * p / (p + 1e-7f);
                 d = u;
             } else {
@@ -291,6 +297,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
         const float v = (MODE == GEMM_GRAD && (J.lse_y || J.py_max)) ? J.v_scalar : 0.f;
         const bool fused_fin = MODE == GEMM_STORE && J.fin_dx != nullptr;
         const float fsx = (fused_fin && row_ok && J.fin_sx) ? J.fin_sx[row] : 0.f;
+        // this thread's 64 columns of x for the normalise-backward, fetched while the MMAs run
+        float xrow[2][32];
+        if (MODE == GEMM_STORE && fused_fin && J.fin_sx) {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = half * 2 + cc;
+                const int nv = max(0, min(32, ncols - c * 32));
+                if (row_ok && nv > 0)
+                    load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + n0 + c * 32, nv, xrow[cc]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) xrow[cc][j] = 0.f;
+                }
+            }
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue-only named barrier: col_scale / col_lse ready
 
         if (e == 0) STIL_TRACE(4);   // epilogue prologue (scales, merges, coefficients) done
@@ -305,18 +326,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
         if (MODE == GEMM_STORE && fused_fin && J.fin_sx) {
             // pass 1 of the normalise-backward: <xh, g> over the whole row (the tile spans all of N)
             float part = 0.f;
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; ++c) {
-                if (c * 32 >= ncols) break;
-                uint32_t acc[32];
-                tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
-                tc05::tmem_ld_wait();
-                if (row_ok) {
-                    float xv[32];
-                    const int nv = min(32, ncols - c * 32);
-                    load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + n0 + c * 32, nv, xv);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) part += xv[j] * __uint_as_float(acc[j]);
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = c_begin + cc;
+                if (c * 32 < ncols) {   // warp-uniform
+                    uint32_t acc[32];
+                    tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
+                    tc05::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) part += xrow[cc][j] * __uint_as_float(acc[j]);
                 }
             }
             dot_part[half * kTileM + q * 32 + lane] = part * fsx * alpha;
@@ -351,10 +369,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
             }
             if (MODE == GEMM_STORE && fused_fin) {
                 if (J.fin_sx && row_ok) {
-                    float xv[32];
-                    load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + n0 + c * 32, nv, xv);
+                    if (c == c_begin) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xv[j] * fin_dot);
+                        for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xrow[0][j] * fin_dot);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xrow[1][j] * fin_dot);
+                    }
                 }
                 if (row_ok) store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + n0 + c * 32, nv, l);
             } else if ((MODE == GEMM_STATS || MODE == GEMM_STORE) && J.out) {
@@ -377,7 +398,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 }
             }
             if (MODE == GEMM_GRAD && row_ok) {
-                __nv_bfloat16* hi_dst = J.gop + (long long)row * 2 * J.ld_g + n0 + c * 32;
+                const bool want_lo = J.g_nseg > 1;
+                __nv_bfloat16* hi_dst = J.gop + (long long)row * J.g_nseg * J.ld_g + n0 + c * 32;
                 __nv_bfloat16* lo_dst = hi_dst + J.ld_g;
                 // gop rows are padded to 32 columns (ld_g % 32 == 0), so full 16-byte stores are always in bounds;
                 // columns >= N hold finite garbage that the dX GEMM never reads (its contraction extent is N)
@@ -400,9 +422,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                     lo_pk[j / 2] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
+                for (int j = 0; j < 16; j += 4)
                     *reinterpret_cast<uint4*>(hi_dst + 2 * j) = make_uint4(hi_pk[j], hi_pk[j + 1], hi_pk[j + 2], hi_pk[j + 3]);
-                    *reinterpret_cast<uint4*>(lo_dst + 2 * j) = make_uint4(lo_pk[j], lo_pk[j + 1], lo_pk[j + 2], lo_pk[j + 3]);
+                if (want_lo) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<uint4*>(lo_dst + 2 * j) = make_uint4(lo_pk[j], lo_pk[j + 1], lo_pk[j + 2], lo_pk[j + 3]);
                 }
             }
         }

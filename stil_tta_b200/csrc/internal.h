@@ -43,20 +43,19 @@ struct alignas(64) GemmJob {
     const int* tgt_vec;      // [M] or nullptr -> tgt = row + tgt_offset
     int tgt_offset;
     const float* gscale;     // device scalar or nullptr (1.0)
-    __nv_bfloat16* gop;      // [M, 2, ld_g]
+    __nv_bfloat16* gop;      // [M, g_nseg, ld_g]
     long long ld_g;
     // GRAD with the statistics merge fused in (used when lse_x == nullptr): per-column-tile (max, sum)
     // partials of GEMM_STATS for this job's rows (px_*) and, for the symmetric InfoNCE, columns (py_*)
     const float *px_max, *px_sum, *py_max, *py_sum;
     int px_tiles, py_tiles;
-    // GRAD for the prototype CE: u_i = d_i = conf_i*w_coef*p/(p+1e-7), p = exp(alpha*<x_i, proto[tgt_i]> - lse_i)
-    const void* w_x;         // raw feat rows (nullptr -> u/d as above)
-    int w_x_dtype;
-    long long w_ldx;
-    const float* w_y;        // raw fp32 prototypes
-    long long w_ldy;
+    // GRAD for the prototype CE: u_i = d_i = conf_i*w_coef*p/(p+1e-7), p = exp(z[i, tgt_i] - lse_i), with z the
+    // logits stored by the GEMM_STATS job of the same problem
+    const float* w_z;        // [M, w_ldz] (nullptr -> u/d as above)
+    long long w_ldz;
     const unsigned char* w_conf;
     float w_coef;
+    int g_nseg;              // 2: G as bf16 hi+lo (fp32 gradients), 1: hi only (bf16 gradients)
     // STORE with Y given MN-major ([contraction rows, N contiguous]) — the backward's dX = G · Y
     int y_mn_major;
     // STORE with the normalise-backward / cast fused in (needs tiles_n == 1):
@@ -197,5 +196,8 @@ int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int 
                          unsigned int* ticket, cudaStream_t stream);
 int64_t masked_softce_blocks(int64_t rows, int64_t k);
 int launch_zero_u32(unsigned int* p, int n, cudaStream_t stream);
+int launch_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, cudaStream_t stream);
+int launch_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* da_queue,
+                    int64_t da_len, int64_t* da_ptr, float* qmean, float* out, int64_t ld_out, cudaStream_t stream);
 
 }  // namespace stil

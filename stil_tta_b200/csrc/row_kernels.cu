@@ -7,7 +7,11 @@ namespace stil {
 
 namespace {
 
-constexpr int kRowBlock = 256;  // 8 warps
+constexpr int kRowBlock = 256;  // 8 warps (upper bound; small problems use 2-warp blocks to spread over the SMs)
+
+// Warp-per-row kernels are latency-bound at the reference sizes (a few hundred rows): fewer warps per block means
+// more SMs busy and a whole issue slot per warp.
+inline int row_block_threads(int64_t warps_needed) { return warps_needed <= 4096 ? 64 : kRowBlock; }
 
 // =====================================================================================
 // Operand preparation
@@ -222,11 +226,11 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
     constexpr int RPW = 32 / LPR;
     pdl_launch_dependents();
     pdl_wait();
-    for (int i = blockIdx.x * kRowBlock + threadIdx.x; i < A.b_l; i += gridDim.x * kRowBlock) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.b_l; i += gridDim.x * blockDim.x) {
         A.cls_l[i] = (int)A.y_l[i];
         A.conf_l[i] = 1.0f >= A.th1;
     }
-    const int warp_global = blockIdx.x * (kRowBlock / 32) + (threadIdx.x >> 5);
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
     const int row = warp_global * RPW + lane / LPR;
@@ -410,7 +414,7 @@ __global__ void labelled_cls_kernel(const long long* y_l, int b_l, float th, int
 // =====================================================================================
 __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant__ FinishLaunch L) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grow = blockIdx.x * (kRowBlock / 32) + warp;
+    const int grow = blockIdx.x * (blockDim.x >> 5) + warp;
     float term[2] = {0.f, 0.f};
     if (grow < L.total_rows) {
         int jid = 0;
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
     __syncthreads();
     if (threadIdx.x == 0) {
         float a = 0.f, b = 0.f;
-        for (int w = 0; w < kRowBlock / 32; ++w) {
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
             a += sred[0][w];
             b += sred[1][w];
         }
@@ -469,17 +473,20 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
         is_last = atomicAdd(L.ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last && warp < 2) {
-        // warp `w` reduces slot `w`: lane-strided partial sums in block order, then a fixed shuffle tree
+    if (is_last && warp == 0) {
+        // deterministic: lane-strided partial sums in block order, then a fixed shuffle tree, per loss slot
         __threadfence();
-        float sum = 0.f;
         const volatile float* bp = L.block_partials;
-        for (unsigned int b = lane; b < gridDim.x; b += 32) sum += bp[2 * b + warp];
-        sum = warp_sum(sum);
-        bool used = false;
-        for (int j = 0; j < L.njobs; ++j) used |= L.job[j].loss_slot == warp;
-        if (used && lane == 0) L.out_loss[warp] = sum;
-        if (threadIdx.x == 0) *L.ticket = 0u;
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+            float sum = 0.f;
+            for (unsigned int b = lane; b < gridDim.x; b += 32) sum += bp[2 * b + slot];
+            sum = warp_sum(sum);
+            bool used = false;
+            for (int j = 0; j < L.njobs; ++j) used |= L.job[j].loss_slot == slot;
+            if (used && lane == 0) L.out_loss[slot] = sum;
+        }
+        if (lane == 0) *L.ticket = 0u;
     }
 }
 
@@ -540,7 +547,7 @@ __global__ void __launch_bounds__(kRowBlock) proto_accumulate_kernel(const void*
                                                                      float repeat_ratio, int k, float* class_sum,
                                                                      float* class_count, float* psum, float* pcount) {
     __shared__ int codes[kAccChunk];   // class of a confident row, -1 otherwise
-    const int c = blockIdx.x * (kRowBlock / 32) + (threadIdx.x >> 5);
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const bool vec = (dim % 4 == 0) && (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(feat) % 16 == 0);
     for (int d0 = 0; d0 < dim; d0 += 128) {
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(kRowBlock) proto_accumulate_kernel(const void*
         for (int base = 0; base < rows; base += kAccChunk) {
             const int nrow = min(kAccChunk, rows - base);
             __syncthreads();
-            for (int i = threadIdx.x; i < nrow; i += kRowBlock) codes[i] = conf[base + i] ? cls[base + i] : -1;
+            for (int i = threadIdx.x; i < nrow; i += blockDim.x) codes[i] = conf[base + i] ? cls[base + i] : -1;
             __syncthreads();
             if (c >= k) continue;
             for (int r0 = 0; r0 < nrow; r0 += 32) {
@@ -647,7 +654,7 @@ struct SoftCeArgs {
 template <int NV>
 __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeArgs A) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (kRowBlock / 32) + warp;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     float lossv[3] = {0.f, 0.f, 0.f};
     if (row < A.rows) {
         const int k = A.k;
@@ -707,22 +714,75 @@ __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeAr
     if (threadIdx.x == 0) {
         for (int h = 0; h < 3; ++h) {
             float a = 0.f;
-            for (int w = 0; w < kRowBlock / 32; ++w) a += sred[h][w];
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sred[h][w];
             A.block_partials[3 * blockIdx.x + h] = a;
         }
         __threadfence();
         is_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last && warp < 3) {
+    if (is_last && warp == 0) {
+        // deterministic: lane-strided partial sums in block order, then a fixed shuffle tree, per loss
         __threadfence();
-        float sum = 0.f;
         const volatile float* bp = A.block_partials;
-        for (unsigned int b = lane; b < gridDim.x; b += 32) sum += bp[3 * b + warp];
-        sum = warp_sum(sum);
-        if (lane == 0) A.losses[warp] = sum / (float)A.rows;   // .mean() over B_u
-        if (threadIdx.x == 0) *A.ticket = 0u;
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            float sum = 0.f;
+            for (unsigned int b = lane; b < gridDim.x; b += 32) sum += bp[3 * b + h];
+            sum = warp_sum(sum);
+            if (lane == 0) A.losses[h] = sum / (float)A.rows;   // .mean() over B_u
+        }
+        if (lane == 0) *A.ticket = 0u;
     }
+}
+
+// =====================================================================================
+// distribution alignment (STiLModel.py:171-180)
+// =====================================================================================
+// mean over rows of each column; one thread per column inside a 32-column slab, rows split over 8 groups and
+// combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) da_batch_mean_kernel(const float* __restrict__ probs, long long ld, int rows, int k,
+                                                            float* __restrict__ mean) {
+    __shared__ float part[8][33];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int grp = threadIdx.x >> 5;
+    float s = 0.f;
+    if (col < k)
+        for (int r = grp; r < rows; r += 8) s += probs[(long long)r * ld + col];
+    part[grp][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (grp == 0 && col < k) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += part[g][threadIdx.x];
+        mean[col] = t / (float)rows;                                   // probs.mean(0), :173
+    }
+}
+// queue[ptr] = batch_mean (already averaged over ranks); ptr = (ptr+1) % len; qmean = queue.mean(0) over ALL rows
+__global__ void __launch_bounds__(256) da_update_kernel(const float* __restrict__ batch_mean, float* da_queue, int da_len,
+                                                        int k, long long* da_ptr, float* qmean) {
+    const int ptr = (int)(*da_ptr);
+    for (int c = threadIdx.x; c < k; c += blockDim.x) da_queue[(long long)ptr * k + c] = batch_mean[c];   // :176
+    __syncthreads();
+    for (int c = threadIdx.x; c < k; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < da_len; ++r) s += da_queue[(long long)r * k + c];
+        qmean[c] = s / (float)da_len;                                                                   // :178
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *da_ptr = (ptr + 1) % da_len;                                                  // :177
+}
+// probs / qmean, rows renormalised (:178-179); one warp per row
+__global__ void __launch_bounds__(kRowBlock) da_apply_kernel(const float* __restrict__ probs, long long ld, int rows, int k,
+                                                             const float* __restrict__ qmean, float* out, long long ld_out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float s = 0.f;
+    for (int c = lane; c < k; c += 32) s += __fdiv_rn(probs[(long long)row * ld + c], qmean[c]);
+    s = warp_sum(s);
+    for (int c = lane; c < k; c += 32)
+        out[(long long)row * ld_out + c] = __fdiv_rn(__fdiv_rn(probs[(long long)row * ld + c], qmean[c]), s);
 }
 
 __global__ void zero_u32_kernel(unsigned int* p, int n) {
@@ -732,9 +792,10 @@ __global__ void zero_u32_kernel(unsigned int* p, int n) {
 
 template <int LPR, int NV>
 int launch_cgpl_t(const CgplArgs& A, cudaStream_t stream) {
-    const int rows_per_block = (kRowBlock / 32) * (32 / LPR);
+    const int threads = row_block_threads(ceil_div(A.rows, 32 / LPR));
+    const int rows_per_block = (threads / 32) * (32 / LPR);
     const int blocks = (int)ceil_div(A.rows, rows_per_block);
-    STIL_CUDA(launch_pdl(cgpl_pgls_kernel<LPR, NV>, dim3(blocks), dim3(kRowBlock), 0, stream, A));
+    STIL_CUDA(launch_pdl(cgpl_pgls_kernel<LPR, NV>, dim3(blocks), dim3(threads), 0, stream, A));
     return STIL_OK;
 }
 
@@ -765,11 +826,11 @@ int launch_zero_u32(unsigned int* p, int n, cudaStream_t stream) {
     return STIL_OK;
 }
 
-int64_t finish_blocks(int total_rows) { return ceil_div(total_rows, kRowBlock / 32); }
+int64_t finish_blocks(int total_rows) { return ceil_div(total_rows, row_block_threads(total_rows) / 32); }
 
 int launch_finish(const FinishLaunch& L, cudaStream_t stream) {
     if (L.total_rows == 0) return STIL_OK;
-    finish_kernel<<<(int)finish_blocks(L.total_rows), kRowBlock, 0, stream>>>(L);
+    finish_kernel<<<(int)finish_blocks(L.total_rows), row_block_threads(L.total_rows), 0, stream>>>(L);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }
@@ -846,7 +907,8 @@ int launch_proto_accumulate(const void* feat, int dtype, int64_t rows, int64_t d
                             const uint8_t* conf, int64_t b_l, float repeat_ratio, int64_t k, float* class_sum,
                             float* class_count, float* psum, float* pcount, cudaStream_t stream) {
     if (k == 0) return STIL_OK;
-    proto_accumulate_kernel<<<(int)ceil_div(k, kRowBlock / 32), kRowBlock, 0, stream>>>(
+    const int acc_threads = k <= 1024 ? 128 : kRowBlock;
+    proto_accumulate_kernel<<<(int)ceil_div(k, acc_threads / 32), acc_threads, 0, stream>>>(
         feat, dtype, (int)rows, (int)dim, ld, cls, conf, (int)b_l, repeat_ratio, (int)k, class_sum, class_count, psum,
         pcount);
     STIL_LAUNCH_CHECK();
@@ -871,7 +933,26 @@ int launch_proto_finalize(float* prototypes, float* psum, float* pcount, int64_t
     return STIL_OK;
 }
 
-int64_t masked_softce_blocks(int64_t rows, int64_t) { return ceil_div(rows, kRowBlock / 32); }
+int launch_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, cudaStream_t stream) {
+    if (k == 0) return STIL_OK;
+    da_batch_mean_kernel<<<(int)ceil_div(k, 32), 256, 0, stream>>>(probs, ld, (int)rows, (int)k, mean);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+int launch_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* da_queue,
+                    int64_t da_len, int64_t* da_ptr, float* qmean, float* out, int64_t ld_out, cudaStream_t stream) {
+    da_update_kernel<<<1, 256, 0, stream>>>(batch_mean, da_queue, (int)da_len, (int)k, reinterpret_cast<long long*>(da_ptr),
+                                            qmean);
+    STIL_LAUNCH_CHECK();
+    if (rows == 0) return STIL_OK;
+    const int threads = row_block_threads(rows);
+    da_apply_kernel<<<(int)ceil_div(rows, threads / 32), threads, 0, stream>>>(probs, ld, (int)rows, (int)k, qmean, out,
+                                                                               ld_out);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int64_t masked_softce_blocks(int64_t rows, int64_t) { return ceil_div(rows, row_block_threads(rows) / 32); }
 
 int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
                          const float* pseudo_label, int64_t ld_pl, const uint8_t* mask1, const uint8_t* case1,
@@ -900,10 +981,11 @@ int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int 
     A.vec_pl = (ld_pl % 2 == 0) && al(pseudo_label, 8);
     A.vec_g = (ld_g % 2 == 0) && al(d_y_m, 8) && al(d_y_i, 8) && al(d_y_t, 8);
     const int blocks = (int)masked_softce_blocks(rows, k);
-    if (k <= 64) masked_softce_kernel<1><<<blocks, kRowBlock, 0, stream>>>(A);
-    else if (k <= 320) masked_softce_kernel<5><<<blocks, kRowBlock, 0, stream>>>(A);
-    else if (k <= 512) masked_softce_kernel<8><<<blocks, kRowBlock, 0, stream>>>(A);
-    else masked_softce_kernel<16><<<blocks, kRowBlock, 0, stream>>>(A);
+    const int threads = row_block_threads(rows);
+    if (k <= 64) masked_softce_kernel<1><<<blocks, threads, 0, stream>>>(A);
+    else if (k <= 320) masked_softce_kernel<5><<<blocks, threads, 0, stream>>>(A);
+    else if (k <= 512) masked_softce_kernel<8><<<blocks, threads, 0, stream>>>(A);
+    else masked_softce_kernel<16><<<blocks, threads, 0, stream>>>(A);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }

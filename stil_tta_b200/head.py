@@ -38,12 +38,19 @@ class STiLHead:
         edt = torch.bfloat16 if cfg.embed_dtype == "bf16" else torch.float32
         dev = self.dev
         z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)
-        self.inp: Dict[str, torch.Tensor] = {k: z(B, P, dtype=edt) for k in _IN_EMBED}
-        self.inp.update({k: z(B_u, K, dtype=logit_dtype) for k in _IN_TEACHER})
+        # every per-batch input lives in ONE device allocation (and one pinned host mirror, see pin()), so that a
+        # batch arrives with a single host->device copy
+        spec = [(k, (B, P), edt) for k in _IN_EMBED] + [(k, (B_u, K), logit_dtype) for k in _IN_TEACHER]
         if student_ce:
-            self.inp.update({k: z(B, K, dtype=logit_dtype) for k in _IN_STUDENT})
-        self.inp["y_l"] = z(B_l, dtype=torch.int64)
-        self.inp["mask_random"] = z(B_u, dtype=torch.bool)
+            spec += [(k, (B, K), logit_dtype) for k in _IN_STUDENT]
+        spec += [("y_l", (B_l,), torch.int64), ("mask_random", (B_u,), torch.bool)]
+        self._layout, off = [], 0
+        for name, shape, dtype in spec:
+            nbytes = int(torch.tensor([], dtype=dtype).element_size()) * int(torch.Size(shape).numel())
+            self._layout.append((name, shape, dtype, off, nbytes))
+            off += (nbytes + 255) // 256 * 256
+        self._packed_in = torch.zeros(max(off, 256), dtype=torch.uint8, device=dev)
+        self.inp: Dict[str, torch.Tensor] = self._views(self._packed_in)
         # state buffers carry the reference names (STiLModel.py:94-96)
         self.prototypes = z(K, P)
         self.prototypes_sum = z(K, P)
@@ -66,10 +73,18 @@ class STiLHead:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._pinned: Optional[Dict[str, torch.Tensor]] = None
         self._losses_host = torch.zeros(5, dtype=torch.float32).pin_memory()
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.inp.values())
+        self.h2d_bytes = self._packed_in.numel()
         self.d2h_bytes = self._losses_host.numel() * 4
 
     # ------------------------------------------------------------------------------------------
+    def _views(self, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Typed views of a packed input buffer (device or pinned host) following self._layout."""
+        out = {}
+        for name, shape, dtype, off, nbytes in self._layout:
+            out[name] = buf[off:off + nbytes].view(dtype).view(shape) if nbytes else torch.empty(shape, dtype=dtype,
+                                                                                                 device=buf.device)
+        return out
+
     def _make_args(self, embed_code: int, logit_code: int) -> HeadStepArgs:
         c, i, o = self.cfg, self.inp, self.out
         p = lambda t: t.data_ptr()
@@ -126,11 +141,13 @@ class STiLHead:
             self._graph = g
 
     def timed_run(self, names=False):
-        """One un-captured step with a CUDA event before every main-chain launch and after the last one;
-        returns the per-launch durations in milliseconds (bench.py's live kernel timing)."""
-        labels = ["prep_kernel", "gemm_tc05_kernel[stats+teacher]", "cgpl_pgls_kernel", "gemm_tc05_kernel[grad]",
-                  "gemm_tc05_kernel[dX]"] + (["grad_finish_kernel"] if self.cfg.proj_dim > 128 else [])
-        n = len(labels) + 1
+        """One un-captured step with CUDA events recorded (on the launching streams) around the launches of the two
+        critical chains; returns the per-launch durations in milliseconds (bench.py's live kernel timing)."""
+        pairs = [("prep_kernel", 0, 1), ("gemm_tc05_kernel<STATS>[infonce x2, proto, teacher]", 1, 5),
+                 ("gemm_tc05_kernel<GRAD>[infonce x2]", 2, 3), ("gemm_tc05_kernel<STORE>[infonce x2]", 3, 4),
+                 ("cgpl_pgls_kernel", 5, 6), ("gemm_tc05_kernel<GRAD>[proto]", 6, 7),
+                 ("gemm_tc05_kernel<STORE>[proto]", 7, 8)]
+        n = 9
         with torch.cuda.device(self.dev):
             st = torch.cuda.current_stream(self.dev)
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
@@ -148,8 +165,8 @@ class STiLHead:
                 self._args.timing_events = None
                 self._args.n_timing_events = 0
             torch.cuda.synchronize(self.dev)
-            ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(n - 1)]
-        return list(zip(labels, ms)) if names else ms
+            ms = [evs[i].elapsed_time(evs[j]) for _, i, j in pairs]
+        return list(zip([p[0] for p in pairs], ms)) if names else ms
 
     def run(self) -> None:
         """Enqueue one head step on the current stream (graph replay when captured)."""
@@ -162,19 +179,23 @@ class STiLHead:
                 self._enqueue()
 
     # ------------------------------------------------------------------------------------------ end to end
-    def pin(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        """Stage a host batch in pinned memory (done once per batch by a data loader, outside the step)."""
-        pinned = {}
-        for k, dst in self.inp.items():
-            pinned[k] = batch[k].to(dst.dtype).contiguous().pin_memory()
-        return pinned
+    def pin(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Stage a host batch in ONE pinned buffer laid out like the device inputs (a data loader's job, done
+        once per batch outside the step)."""
+        buf = torch.zeros(self._packed_in.numel(), dtype=torch.uint8).pin_memory()
+        for k, v in self._views(buf).items():
+            v.copy_(batch[k].to(v.dtype))
+        return buf
 
-    def step_host(self, pinned: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """One end-to-end step from HOST buffers: H2D of every input, the head, D2H of the five losses.
+    def copy_in(self, pinned: torch.Tensor) -> None:
+        """Host -> device copy of one packed batch on the current stream."""
+        self._packed_in.copy_(pinned, non_blocking=True)
+
+    def step_host(self, pinned: torch.Tensor) -> torch.Tensor:
+        """One end-to-end step from HOST buffers: H2D of every input (one copy), the head, D2H of the five losses.
         Returns the pinned host tensor of losses (valid after the stream synchronises)."""
         with torch.cuda.device(self.dev):
-            for k, dst in self.inp.items():
-                dst.copy_(pinned[k], non_blocking=True)
+            self.copy_in(pinned)
             self.run()
             self._losses_host.copy_(self.out["losses"], non_blocking=True)
         return self._losses_host

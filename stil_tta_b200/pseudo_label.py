@@ -86,3 +86,31 @@ def cgpl_pgls(y_m: torch.Tensor, y_i: torch.Tensor, y_t: torch.Tensor, feat_m_ue
                                          ptr(flags[0]), ptr(flags[1]), ptr(flags[2]), ptr(flags[3]), ptr(flags[4]),
                                          ptr(top1), None, None, _lib.stream_ptr(dev)))
     return PseudoLabels(pl, pred, max_prob, max_idx, flags[0], flags[1], flags[2], flags[3], flags[4], top1, tl)
+
+
+@torch.no_grad()
+def distribution_alignment(probs: torch.Tensor, DA_queue: torch.Tensor, DA_ptr: torch.Tensor, group=None
+                           ) -> torch.Tensor:
+    """Drop-in for ``STiLModel.distribution_alignment`` (``STiLModel.py:171-180``): the batch-mean class
+    distribution (all-reduced over ranks when a process group is initialised) enters the ring buffer ``DA_queue``
+    [256, K] at ``DA_ptr`` (int64 [1], advanced on the device — no host sync), ``probs`` are divided by the queue
+    mean and row-renormalised.  ``DA_queue`` / ``DA_ptr`` are the caller's ``register_buffer``s, updated in place."""
+    import torch.distributed as dist
+    p = probs.detach().to(torch.float32).contiguous()
+    dev = _lib.require_cuda(p, DA_queue, DA_ptr)
+    _lib.ensure_device(dev)
+    if DA_queue.dtype != torch.float32 or DA_ptr.dtype != torch.int64 or not DA_queue.is_contiguous():
+        raise ValueError("DA_queue must be a contiguous float32 [len, K] buffer and DA_ptr an int64 [1] buffer")
+    rows, k = p.shape
+    lib = _lib.load()
+    mean = torch.empty(k, dtype=torch.float32, device=dev)
+    scratch = torch.empty(k, dtype=torch.float32, device=dev)
+    out = torch.empty_like(p)
+    with torch.cuda.device(dev):
+        check(lib.stil_da_batch_mean(ptr(p), k, rows, k, ptr(mean), _lib.stream_ptr(dev)))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(mean, group=group)                     # STiLModel.py:174
+            mean /= dist.get_world_size(group)                     # :176
+        check(lib.stil_da_apply(ptr(p), k, rows, k, ptr(mean), ptr(DA_queue), DA_queue.shape[0], ptr(DA_ptr),
+                                ptr(scratch), ptr(out), k, _lib.stream_ptr(dev)))
+    return out

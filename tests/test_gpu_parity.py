@@ -192,6 +192,23 @@ def test_cgpl_pgls_bf16_logits_and_odd_k(S, O):
         assert agree >= 0.99      # bf16 logits tie often; ties resolved identically unless fp32-ambiguous
 
 
+# ----------------------------------------------------------------------------------------------- a6
+def test_distribution_alignment_matches_oracle(S, O):
+    g = torch.Generator().manual_seed(4)
+    for k, rows in ((286, 448), (2, 896), (10, 33)):
+        q_ref, p_ref = torch.zeros(256, k), torch.zeros(1, dtype=torch.int64)
+        q, p = dev(q_ref.clone()), dev(p_ref.clone())
+        p_ref[0] = p[0] = 254                       # exercise the ring-buffer wrap-around
+        for step in range(4):
+            probs = torch.softmax(torch.randn(rows, k, generator=g) * 2, dim=1)
+            ref = O.distribution_alignment(probs, q_ref, p_ref)
+            out = S.distribution_alignment(dev(probs), q, p)
+            assert int(p) == int(p_ref) == (254 + step + 1) % 256
+            assert float((q.cpu() - q_ref).abs().max()) <= 1e-7
+            assert float(((out.cpu() - ref).abs() / ref.abs().clamp_min(1e-6)).max()) <= 1e-4
+            assert float((out.sum(1) - 1).abs().max()) <= 1e-5
+
+
 # ----------------------------------------------------------------------------------------------- a5
 @pytest.mark.parametrize("name", STEP_CASES)
 def test_cal_prototypes_separate_golden(S, name):
