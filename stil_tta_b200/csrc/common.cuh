@@ -54,6 +54,13 @@ struct Workspace {
 #ifdef __CUDACC__
 // Launch with programmatic dependent launch allowed: the kernel may start while its stream predecessor is
 // still draining; kernels call griddepcontrol.wait before touching global memory.
+// All kernels of the library ask for the same (maximum-shared) L1/shared split as the GEMM kernel needs, so that
+// back-to-back launches never make the SMs reconfigure their carve-out.
+template <class K>
+inline void prefer_max_shared(K kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args&&... args) {

@@ -127,7 +127,7 @@ __device__ __forceinline__ void store32_from_float(void* base, int dtype, long l
 // Optional timeline instrumentation (stil_debug_trace): when a buffer is installed every CTA stores %globaltimer
 // stamps of its phases: [launch_id][cta][8] = start, prologue done, last TMA issued, last MMA committed, accumulator
 // ready (epilogue), epilogue math done, epilogue end, mode.
-__device__ unsigned long long* g_trace = nullptr;
+unsigned long long* g_trace_host = nullptr;   // host copy; travels to the kernel in its parameters
 constexpr int kTraceCtas = 64, kTraceSlots = 8, kTraceLaunches = 64;
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: next kernel may begin its prologue
-    unsigned long long* trace = g_trace ? g_trace + (size_t)(L.trace_id % kTraceLaunches) * kTraceCtas * kTraceSlots : nullptr;
+    unsigned long long* trace = L.trace ? L.trace + (size_t)(L.trace_id % kTraceLaunches) * kTraceCtas * kTraceSlots : nullptr;
     if (threadIdx.x == 0) { STIL_TRACE(0); if (trace && blockIdx.x < kTraceCtas) trace[blockIdx.x * kTraceSlots + 7] = MODE; }
 
     // ---- which job / tile
@@ -501,8 +501,7 @@ void gemm_job_tiles(GemmLaunch& L) {
 }
 
 int gemm_set_trace(void* buf) {
-    unsigned long long* p = static_cast<unsigned long long*>(buf);
-    STIL_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+    g_trace_host = static_cast<unsigned long long*>(buf);
     return STIL_OK;
 }
 
@@ -527,6 +526,7 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
         STIL_REQUIRE(L.job[j].mode == mode, STIL_E_ARG, "gemm launch mixes epilogue modes");
     static unsigned int launch_counter = 0;
     const_cast<GemmLaunch&>(L).trace_id = launch_counter++;
+    const_cast<GemmLaunch&>(L).trace = g_trace_host;
     if (mode == GEMM_STATS) return launch_gemm_mode<GEMM_STATS>(L, stream);
     if (mode == GEMM_STORE) return launch_gemm_mode<GEMM_STORE>(L, stream);
     return launch_gemm_mode<GEMM_GRAD>(L, stream);

@@ -74,6 +74,7 @@ struct GemmLaunch {
     int njobs;
     int total_tiles;
     unsigned int trace_id;   // launch ordinal for the optional timeline trace
+    unsigned long long* trace;   // nullptr unless stil_debug_trace installed a buffer
 };
 
 // Build the operand tensor map.  `base` bf16, logical [rows, nseg, inner]; strides in elements.

@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
 #pragma unroll
     for (int j = 0; j < 2 * NV; ++j) pm[j] = ym[j];
     const float sm = softmax_exp<LPR, NV>(pm);
+    const float rsm = __frcp_rn(sm);   // p = e * (1/s): within 1 ulp of torch's e / s (same class as exp differences)
     int top_m;
     {
         float bv = -1.f;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int idx = 2 * (sub + LPR * it) + h;
-                pm[2 * it + h] = __fdiv_rn(pm[2 * it + h], sm);
+                pm[2 * it + h] = __fmul_rn(pm[2 * it + h], rsm);
                 if (idx < k && pm[2 * it + h] > bv) {
                     bv = pm[2 * it + h];
                     bi = idx;
@@ -302,17 +303,17 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
                 a = __fmul_rn(__fadd_rn(ym[j], yt[j]), 0.5f);
             pl[j] = a;
         }
-        const float s = softmax_exp<LPR, NV>(pl);
+        const float rs = __frcp_rn(softmax_exp<LPR, NV>(pl));
 #pragma unroll
-        for (int j = 0; j < 2 * NV; ++j) pl[j] = __fdiv_rn(pl[j], s);
+        for (int j = 0; j < 2 * NV; ++j) pl[j] = __fmul_rn(pl[j], rs);
     }
     // ---- :293-294 teacher prototype probabilities
 #pragma unroll
     for (int j = 0; j < 2 * NV; ++j) tp[j] = __fdiv_rn(tp[j], A.temperature);
     {
-        const float s = softmax_exp<LPR, NV>(tp);
+        const float rs = __frcp_rn(softmax_exp<LPR, NV>(tp));
 #pragma unroll
-        for (int j = 0; j < 2 * NV; ++j) tp[j] = __fdiv_rn(tp[j], s);
+        for (int j = 0; j < 2 * NV; ++j) tp[j] = __fmul_rn(tp[j], rs);
     }
     // ---- :295-298 smoothing mix, max/argmax, threshold
     float bv = -1.f;
@@ -795,6 +796,8 @@ int launch_cgpl_t(const CgplArgs& A, cudaStream_t stream) {
     const int threads = row_block_threads(ceil_div(A.rows, 32 / LPR));
     const int rows_per_block = (threads / 32) * (32 / LPR);
     const int blocks = (int)ceil_div(A.rows, rows_per_block);
+    static const bool once = (prefer_max_shared(cgpl_pgls_kernel<LPR, NV>), true);
+    (void)once;
     STIL_CUDA(launch_pdl(cgpl_pgls_kernel<LPR, NV>, dim3(blocks), dim3(threads), 0, stream, A));
     return STIL_OK;
 }
@@ -816,6 +819,8 @@ int launch_prep(const PrepLaunch& L, cudaStream_t stream) {
         if (L.n_zero > 0) return launch_zero_u32(L.zero_words, L.n_zero, stream);
         return STIL_OK;
     }
+    static const bool once = (prefer_max_shared(prep_kernel), true);
+    (void)once;
     STIL_CUDA(launch_pdl(prep_kernel, dim3(L.total_blocks), dim3(kRowBlock), 0, stream, L));
     return STIL_OK;
 }
@@ -830,6 +835,8 @@ int64_t finish_blocks(int total_rows) { return ceil_div(total_rows, row_block_th
 
 int launch_finish(const FinishLaunch& L, cudaStream_t stream) {
     if (L.total_rows == 0) return STIL_OK;
+    static const bool once = (prefer_max_shared(finish_kernel), true);
+    (void)once;
     finish_kernel<<<(int)finish_blocks(L.total_rows), row_block_threads(L.total_rows), 0, stream>>>(L);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
@@ -907,6 +914,8 @@ int launch_proto_accumulate(const void* feat, int dtype, int64_t rows, int64_t d
                             const uint8_t* conf, int64_t b_l, float repeat_ratio, int64_t k, float* class_sum,
                             float* class_count, float* psum, float* pcount, cudaStream_t stream) {
     if (k == 0) return STIL_OK;
+    static const bool once = (prefer_max_shared(proto_accumulate_kernel), true);
+    (void)once;
     const int acc_threads = k <= 1024 ? 128 : kRowBlock;
     proto_accumulate_kernel<<<(int)ceil_div(k, acc_threads / 32), acc_threads, 0, stream>>>(
         feat, dtype, (int)rows, (int)dim, ld, cls, conf, (int)b_l, repeat_ratio, (int)k, class_sum, class_count, psum,
@@ -981,6 +990,9 @@ int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int 
     A.vec_pl = (ld_pl % 2 == 0) && al(pseudo_label, 8);
     A.vec_g = (ld_g % 2 == 0) && al(d_y_m, 8) && al(d_y_i, 8) && al(d_y_t, 8);
     const int blocks = (int)masked_softce_blocks(rows, k);
+    static const bool once = (prefer_max_shared(masked_softce_kernel<1>), prefer_max_shared(masked_softce_kernel<5>),
+                              prefer_max_shared(masked_softce_kernel<8>), prefer_max_shared(masked_softce_kernel<16>), true);
+    (void)once;
     const int threads = row_block_threads(rows);
     if (k <= 64) masked_softce_kernel<1><<<blocks, threads, 0, stream>>>(A);
     else if (k <= 320) masked_softce_kernel<5><<<blocks, threads, 0, stream>>>(A);
