@@ -10,13 +10,16 @@ from stil_tta_b200 import _lib, synth  # noqa: E402
 
 cfg = synth.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "C2"]()
 graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
-head = S.STiLHead(cfg, device="cuda", use_graph=graph)
-head.load(synth.make_batch(cfg, seed=2022))
-for _ in range(3):
-    head.run()
-torch.cuda.synchronize()
+# the trace pointer travels in the kernel parameters, so install it before a graph is captured
 buf = torch.zeros(64, 64, 8, dtype=torch.int64, device="cuda")
 _lib.check(_lib.load().stil_debug_trace(buf.data_ptr()))
+head = S.STiLHead(cfg, device="cuda", use_graph=graph)
+head.load(synth.make_batch(cfg, seed=2022))
+for _ in range(4):
+    head.run()
+torch.cuda.synchronize()
+buf.zero_()
+torch.cuda.synchronize()
 for _ in range(2):
     head.run()
 torch.cuda.synchronize()
