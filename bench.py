@@ -251,6 +251,9 @@ def run_gpu_arm(args):
     dist_on = world > 1
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep NCCL's version banner (printed at NCCL_DEBUG=VERSION/WARN) off stdout: rank 0 prints ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG_FILE"] = os.devnull
         dist.init_process_group("nccl", device_id=dev)
     cfg = get_cfg(args.config)
     pk = peaks()
