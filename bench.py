@@ -254,7 +254,18 @@ def run_gpu_arm(args):
         # keep NCCL's version banner (printed at NCCL_DEBUG=VERSION/WARN) off stdout: rank 0 prints ONE JSON line
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
             os.environ["NCCL_DEBUG_FILE"] = os.devnull
-        dist.init_process_group("nccl", device_id=dev)
+        # ... and whatever else the communicator set-up prints goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg = get_cfg(args.config)
     pk = peaks()
 
