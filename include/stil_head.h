@@ -157,6 +157,23 @@ STIL_API int stil_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t
                   int64_t da_len, int64_t* da_ptr, float* qmean_scratch, float* out, int64_t ld_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a7 — SimMatch memory-bank block.  Replaces models/MatchModel/simmatch_model.py:268-286 (start_unlabel branch).
+ *   bank    [dim, k_bank] in the REFERENCE layout (unit columns, :68-69), same dtype as the features, read in place
+ *   labels  [k_bank] int64 (:70);  prob_ku_orig [rows, num_classes] f32 (after the optional DA, :264-266)
+ * fwd writes prob_ku [rows, num_classes] (:280) and loss_in [rows] (:286, per row — the caller takes .mean(),
+ * SimMatch.py:92) and leaves dLoss/dLogits (bf16) in the workspace; bwd turns grad_loss_in [rows] into
+ * d_feat_qu [rows, dim] (only the student feature gets a gradient).  The workspace must be the same, untouched,
+ * buffer for the forward and its backward (it holds the [rows, k_bank] teacher/student logits, fp32). */
+STIL_API int64_t stil_simmatch_workspace_bytes(int64_t rows, int64_t k_bank, int64_t dim, int dtype);
+STIL_API int stil_simmatch_fwd(const void* feat_ku, const void* feat_qu, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                      const void* bank, int64_t ld_bank, const int64_t* labels, int64_t k_bank,
+                      const float* prob_ku_orig, int64_t num_classes, float tt, float st, float c_smooth, float* prob_ku,
+                      float* loss_in, int grad_dtype, void* workspace, int64_t workspace_bytes, void* stream);
+STIL_API int stil_simmatch_bwd(const void* feat_qu, int dtype, int64_t rows, int64_t dim, const void* bank, int64_t ld_bank,
+                      int64_t k_bank, const float* grad_loss_in, void* d_feat_qu, int grad_dtype, int64_t ld_grad,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * f-1 — masked soft-target CE of the three student heads on the unlabelled rows, forward and
  * gradient in one pass.  Replaces STiLModel.py:301-303.
  *   losses[3]  = (loss_m_u, loss_i_u, loss_t_u), each a mean over `rows`

@@ -70,6 +70,10 @@ SIGNATURES = {
     "stil_proto_finalize": (i32, [vp, vp, vp, i64, i64, vp, vp]),
     "stil_da_batch_mean": (i32, [vp, i64, i64, i64, vp, vp]),
     "stil_da_apply": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
+    "stil_simmatch_workspace_bytes": (i64, [i64, i64, i64, i32]),
+    "stil_simmatch_fwd": (i32, [vp, vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, f32, f32, f32, vp, vp, i32, vp,
+                                i64, vp]),
+    "stil_simmatch_bwd": (i32, [vp, i32, i64, i64, vp, i64, i64, vp, vp, i32, i64, vp, i64, vp]),
     "stil_masked_softce_workspace_bytes": (i64, [i64]),
     "stil_masked_softce": (i32, [vp, vp, vp, i32, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64,
                                  f32, vp, i64, vp]),

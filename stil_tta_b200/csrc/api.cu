@@ -1,5 +1,6 @@
 // extern "C" entry points of libstil_head.so (see include/stil_head.h).  Host-side composition only:
 // plans the caller-provided workspace, builds TMA descriptors and job tables, enqueues kernels.
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -742,6 +743,142 @@ STIL_API int stil_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t
     STIL_REQUIRE(probs && batch_mean && da_queue && da_ptr && qmean_scratch && out && da_len >= 1 && ld >= k && ld_out >= k,
                  STIL_E_ARG, "da_apply: bad arguments");
     return launch_da_apply(probs, ld, rows, k, batch_mean, da_queue, da_len, da_ptr, qmean_scratch, out, ld_out, S(stream));
+}
+
+// =============================================================================================== a7
+namespace {
+struct SimPlan {
+    int nseg;                        // feature / bank operand segments (bf16: 1)
+    __nv_bfloat16 *fk_op, *fq_op, *bank_op;
+    float *zt, *zs;                  // [rows, ldz]
+    int64_t ldz;
+    __nv_bfloat16* gop;              // [rows, g_nseg, ldg]
+    int64_t ldg;
+    float* g;                        // [rows, dim] fp32 accumulation target of the split-K dX GEMM
+    int64_t bytes;
+};
+SimPlan plan_sim(void* ws, int64_t ws_bytes, int64_t rows, int64_t kb, int64_t dim, int dtype) {
+    SimPlan P;
+    Workspace W(ws, ws_bytes);
+    P.nseg = dtype == STIL_BF16 ? 1 : 3;
+    P.ldz = round_up(kb, 4);
+    P.ldg = pad32(kb);
+    P.fk_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(rows * 3 * dim);
+    P.fq_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(rows * 3 * dim);
+    P.bank_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(dim * 3 * P.ldg);
+    P.zt = W.take<float>(rows * P.ldz);
+    P.zs = W.take<float>(rows * P.ldz);
+    P.gop = W.take<__nv_bfloat16>(rows * 2 * P.ldg);
+    P.g = W.take<float>(rows * dim);
+    P.bytes = W.off;
+    return P;
+}
+// the bank in the reference layout [dim, k_bank] (simmatch_model.py:68-69): k_bank contiguous
+Operand bank_operand(const void* bank, int dtype, int64_t kb, int64_t ld_bank, const __nv_bfloat16* op, int64_t ldg) {
+    Operand O;
+    if (dtype == STIL_BF16) {
+        O.base = static_cast<const __nv_bfloat16*>(bank);
+        O.nseg = 1; O.row_stride = ld_bank; O.seg_stride = pad32(kb);
+    } else {
+        O.base = op;
+        O.nseg = 3; O.row_stride = 3 * ldg; O.seg_stride = ldg;
+    }
+    return O;
+}
+}  // namespace
+
+STIL_API int64_t stil_simmatch_workspace_bytes(int64_t rows, int64_t k_bank, int64_t dim, int dtype) {
+    return plan_sim(nullptr, 0, rows, k_bank, dim, dtype).bytes;
+}
+
+STIL_API int stil_simmatch_fwd(const void* feat_ku, const void* feat_qu, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                      const void* bank, int64_t ld_bank, const int64_t* labels, int64_t k_bank,
+                      const float* prob_ku_orig, int64_t num_classes, float tt, float st, float c_smooth, float* prob_ku,
+                      float* loss_in, int grad_dtype, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_embed(feat_ku, dtype, rows, dim, ld, "simmatch feat_ku");
+    if (rc) return rc;
+    if ((rc = check_embed(feat_qu, dtype, rows, dim, ld, "simmatch feat_qu"))) return rc;
+    const int per16 = dtype == STIL_BF16 ? 8 : 4;
+    STIL_REQUIRE(bank && k_bank >= 1 && ld_bank >= k_bank && ld_bank % per16 == 0 &&
+                     (reinterpret_cast<uintptr_t>(bank) & 15) == 0,
+                 STIL_E_ALIGN, "simmatch bank [dim, k_bank]: leading dimension %lld must be >= k_bank and a multiple of %d, "
+                 "base 16-byte aligned", (long long)ld_bank, per16);
+    STIL_REQUIRE(labels && prob_ku_orig && prob_ku && loss_in && tt > 0.f && st > 0.f && num_classes >= 1, STIL_E_ARG,
+                 "simmatch_fwd: bad arguments");
+    SimPlan P = plan_sim(workspace, workspace_bytes, rows, k_bank, dim, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "simmatch workspace too small: need %lld",
+                 (long long)P.bytes);
+    if (rows == 0) return STIL_OK;
+    if (dtype != STIL_BF16) {
+        PrepLaunch PL;
+        std::memset(&PL, 0, sizeof(PL));
+        prep_add(PL, prep_job(feat_ku, dtype, rows, dim, ld, 3, P.fk_op, nullptr, 0, 0, nullptr));
+        prep_add(PL, prep_job(feat_qu, dtype, rows, dim, ld, 3, P.fq_op, nullptr, 0, 0, nullptr));
+        if ((rc = launch_prep(PL, S(stream)))) return rc;
+        // the bank's segment layout is [dim, 3, ldg]: prep writes [rows=dim, nseg, "dim"=k_bank] with row pitch 3*k_bank,
+        // so it needs k_bank == ldg
+        STIL_REQUIRE(k_bank % 32 == 0, STIL_E_ALIGN, "simmatch: an fp32 bank needs k_bank %% 32 == 0 (got %lld)", (long long)k_bank);
+        std::memset(&PL, 0, sizeof(PL));
+        prep_add(PL, prep_job(bank, dtype, dim, k_bank, ld_bank, 3, P.bank_op, nullptr, 0, 0, nullptr));
+        if ((rc = launch_prep(PL, S(stream)))) return rc;
+    }
+    const Operand Bk = bank_operand(bank, dtype, k_bank, ld_bank, P.bank_op, P.ldg);
+    // teacher and student logits: X = features (K-major), Y = bank read in place as an MN-major operand
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    for (int s = 0; s < 2; ++s) {
+        const Operand X = rowmajor_operand(s == 0 ? feat_ku : feat_qu, dtype, dim, ld, s == 0 ? P.fk_op : P.fq_op, 3);
+        if ((rc = fill_gemm_store_mn(GL.job[s], X, rows, Bk, dim, k_bank))) return rc;
+        GL.job[s].npair = seg_pairs(X.nseg, Bk.nseg, 2, GL.job[s].xseg, GL.job[s].yseg);
+        GL.job[s].out = s == 0 ? P.zt : P.zs;
+        GL.job[s].ld_out = P.ldz;
+    }
+    GL.njobs = 2;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    return launch_simmatch_rows(P.zt, P.zs, P.ldz, reinterpret_cast<const long long*>(labels), (int)rows, (int)k_bank,
+                                prob_ku_orig, (int)num_classes, tt, st, c_smooth, prob_ku, loss_in, P.gop, P.ldg,
+                                grad_nseg(grad_dtype), S(stream));
+}
+
+STIL_API int stil_simmatch_bwd(const void* feat_qu, int dtype, int64_t rows, int64_t dim, const void* bank, int64_t ld_bank,
+                      int64_t k_bank, const float* grad_loss_in, void* d_feat_qu, int grad_dtype, int64_t ld_grad,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+    (void)feat_qu;
+    STIL_REQUIRE(grad_loss_in && d_feat_qu && bank, STIL_E_ARG, "simmatch_bwd: null pointer");
+    STIL_REQUIRE(grad_dtype == STIL_F32 || grad_dtype == STIL_BF16, STIL_E_DTYPE, "bad grad dtype");
+    SimPlan P = plan_sim(workspace, workspace_bytes, rows, k_bank, dim, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "simmatch workspace too small");
+    if (rows == 0) return STIL_OK;
+    int rc;
+    // d_feat_q[i,:] = grad_i * sum_j G_ij bank[:, j]; G (bf16) was left in the workspace by the forward.
+    // The contraction runs over k_bank: split it across CTAs so the whole chip works on it.
+    const Operand X = grad_operand(P.gop, P.ldg, grad_nseg(grad_dtype));
+    const Operand Bk = bank_operand(bank, dtype, k_bank, ld_bank, P.bank_op, P.ldg);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    // bank as a K-major Y operand: rows = dim (N), contraction = k_bank contiguous
+    if ((rc = fill_gemm_common(GL.job[0], X, 0, rows, Bk, dim, k_bank, 1))) return rc;
+    GemmJob& J = GL.job[0];
+    J.mode = GEMM_STORE;
+    J.sx = grad_loss_in;
+    J.out = P.g;
+    J.ld_out = dim;
+    const int64_t tiles = ceil_div(rows, kTileM) * ceil_div(dim, kTileN);
+    const int64_t kblocks = ceil_div(k_bank, kTileK);
+    J.ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(kblocks / 8, (2 * 148 + tiles - 1) / tiles));
+    if (J.ksplit > 1) STIL_CUDA(cudaMemsetAsync(P.g, 0, rows * dim * sizeof(float), S(stream)));
+    GL.njobs = 1;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    GradFinishLaunch GF;
+    std::memset(&GF, 0, sizeof(GF));
+    GradFinishJob& j = GF.job[0];
+    j.g = P.g; j.dx = d_feat_qu; j.dx_dtype = grad_dtype; j.ld_dx = ld_grad;
+    j.rows = (int)rows; j.dim = (int)dim;
+    GF.njobs = 1;
+    GF.total_rows = (int)rows;
+    return launch_grad_finish(GF, S(stream));
 }
 
 // =============================================================================================== f-1

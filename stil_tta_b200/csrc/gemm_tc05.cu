@@ -175,10 +175,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     for (int j = 1; j < kMaxGemmJobs; ++j)
         if (j < L.njobs && (int)blockIdx.x >= L.job[j].tile_begin) jid = j;
     const GemmJob& J = L.job[jid];
-    const int t = blockIdx.x - J.tile_begin;
+    int t = blockIdx.x - J.tile_begin;
+    const int ksplit = (MODE == GEMM_STORE && J.ksplit > 1) ? J.ksplit : 1;
+    const int ks = t % ksplit;
+    t /= ksplit;
     const int tm = t / J.tiles_n, tn = t % J.tiles_n;
     const int m0 = tm * kTileM, n0 = tn * kTileN;
-    const int kper = (J.D + kTileK - 1) / kTileK;
+    const int kper_all = (J.D + kTileK - 1) / kTileK;
+    // this CTA's slice of the contraction (whole range unless split)
+    const int kchunk = (kper_all + ksplit - 1) / ksplit;
+    const int kk0 = ks * kchunk;
+    const int kper = max(0, min(kchunk, kper_all - kk0));
     const int nkb = J.npair * kper;
 
     if (warp == 0 && lane == 0) {
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 const int s = kb % kStages;
                 const uint32_t ph = (kb / kStages) & 1;
                 tc05::mbar_wait(&empty_bar[s], ph ^ 1);
-                const int p = kb / kper, kk = kb - p * kper;
+                const int p = kb / kper, kk = kk0 + kb - p * kper;
                 uint8_t* a_dst = tiles + s * kStageBytes;
                 uint8_t* b_dst = a_dst + kTileM * kTileK * 2;
                 tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
@@ -251,7 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                     tc05::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + b_step * k, idesc, (kb | k) ? 1u : 0u);
                 tc05::mma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
             }
-            tc05::mma_commit(tmem_full_bar);
+            if (nkb > 0) tc05::mma_commit(tmem_full_bar);
+            else tc05::mbar_arrive(tmem_full_bar);   // empty slice of a split contraction: nothing to wait for
             STIL_TRACE(3);
         }
     } else {
@@ -378,6 +386,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                     }
                 }
                 if (row_ok) store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + n0 + c * 32, nv, l);
+            } else if (MODE == GEMM_STORE && ksplit > 1) {
+                // split contraction: add this CTA's partial tile (an empty slice adds nothing)
+                if (row_ok && nkb > 0) {
+                    float* dst = J.out + (long long)row * J.ld_out + n0 + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nv) atomicAdd(dst + j, l[j]);
+                }
             } else if ((MODE == GEMM_STATS || MODE == GEMM_STORE) && J.out) {
                 float* dst = J.out + (long long)row * J.ld_out + n0 + c * 32;
                 // warp-uniform choice: the slow path issues warp-collective TMEM loads
@@ -495,7 +511,7 @@ void gemm_job_tiles(GemmLaunch& L) {
         J.tiles_m = (int)ceil_div(J.M, kTileM);
         J.tiles_n = (int)ceil_div(J.N, kTileN);
         J.tile_begin = begin;
-        begin += J.tiles_m * J.tiles_n;
+        begin += J.tiles_m * J.tiles_n * (J.mode == GEMM_STORE && J.ksplit > 1 ? J.ksplit : 1);
     }
     L.total_tiles = begin;
 }

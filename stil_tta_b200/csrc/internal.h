@@ -56,6 +56,9 @@ struct alignas(64) GemmJob {
     const unsigned char* w_conf;
     float w_coef;
     int g_nseg;              // 2: G as bf16 hi+lo (fp32 gradients), 1: hi only (bf16 gradients)
+    // STORE: split the contraction over `ksplit` CTAs per tile; partial tiles are added to `out` with red.global
+    // (out must be zero on entry).  1 = plain store.
+    int ksplit;
     // STORE with Y given MN-major ([contraction rows, N contiguous]) — the backward's dX = G · Y
     int y_mn_major;
     // STORE with the normalise-backward / cast fused in (needs tiles_n == 1):
@@ -197,6 +200,10 @@ int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int 
                          unsigned int* ticket, cudaStream_t stream);
 int64_t masked_softce_blocks(int64_t rows, int64_t k);
 int launch_zero_u32(unsigned int* p, int n, cudaStream_t stream);
+// SimMatch bank rows (simmatch_model.py:268-286) on materialised teacher / student logits
+int launch_simmatch_rows(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_bank,
+                         const float* p_orig, int num_classes, float tt, float st, float c_smooth, float* p_out,
+                         float* loss_in, __nv_bfloat16* gop, long long ld_g, int g_nseg, cudaStream_t stream);
 int launch_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, cudaStream_t stream);
 int launch_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* da_queue,
                     int64_t da_len, int64_t* da_ptr, float* qmean, float* out, int64_t ld_out, cudaStream_t stream);

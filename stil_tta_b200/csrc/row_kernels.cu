@@ -786,6 +786,89 @@ __global__ void __launch_bounds__(kRowBlock) da_apply_kernel(const float* __rest
         out[(long long)row * ld_out + c] = __fdiv_rn(__fdiv_rn(probs[(long long)row * ld + c], qmean[c]), s);
 }
 
+// =====================================================================================
+// SimMatch bank block on materialised logits (simmatch_model.py:268-286): one block per unlabelled row
+// =====================================================================================
+//   T = softmax(zt/tt), F_j = p[y_j], T' = T∘F / sum(T∘F), A_c = sum_{j: y_j=c} T_j, p' = cs*p + (1-cs)*A,
+//   S = softmax(zs/st), loss_in = -sum_j T'_j log S_j = lse_s - (sum_c p_c Q_c)/den with Q_c = sum_{j in c} T_j zs_j/st
+//   and den = sum_c p_c A_c;   G_j = d loss_in / d zs_j (before the 1/st of the logits) = S_j - T'_j
+constexpr int kSimBlock = 256;
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float r = is_max ? -INFINITY : 0.f;
+    for (int i = 0; i < kSimBlock / 32; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+    return r;
+}
+
+__global__ void __launch_bounds__(kSimBlock) simmatch_rows_kernel(const float* __restrict__ zt, const float* __restrict__ zs,
+                                                                  long long ldz, const long long* __restrict__ labels,
+                                                                  int k_bank, const float* __restrict__ p_orig, int C,
+                                                                  float inv_tt, float inv_st, float c_smooth, float* p_out,
+                                                                  float* loss_in, __nv_bfloat16* gop, long long ld_g,
+                                                                  int g_nseg) {
+    extern __shared__ float sm[];   // p[C] | A[C] | Q[C] | red[8]
+    float* sp = sm;
+    float* sA = sm + C;
+    float* sQ = sm + 2 * C;
+    float* red = sm + 3 * C;
+    const int row = blockIdx.x;
+    const float* rt = zt + (long long)row * ldz;
+    const float* rs = zs + (long long)row * ldz;
+    for (int c = threadIdx.x; c < C; c += kSimBlock) {
+        sp[c] = p_orig[(long long)row * C + c];
+        sA[c] = 0.f;
+        sQ[c] = 0.f;
+    }
+    float mt = -INFINITY, ms = -INFINITY;
+    for (int j = threadIdx.x; j < k_bank; j += kSimBlock) {
+        mt = fmaxf(mt, rt[j] * inv_tt);
+        ms = fmaxf(ms, rs[j] * inv_st);
+    }
+    mt = block_reduce(mt, red, true);
+    ms = block_reduce(ms, red, true);
+    float st_ = 0.f, ss_ = 0.f;
+    for (int j = threadIdx.x; j < k_bank; j += kSimBlock) {
+        st_ += expf(rt[j] * inv_tt - mt);
+        ss_ += expf(rs[j] * inv_st - ms);
+    }
+    st_ = block_reduce(st_, red, false);
+    ss_ = block_reduce(ss_, red, false);
+    const float lse_t = mt + logf(st_), lse_s = ms + logf(ss_);
+    __syncthreads();
+    for (int j = threadIdx.x; j < k_bank; j += kSimBlock) {
+        const float T = expf(rt[j] * inv_tt - lse_t);
+        const int y = (int)labels[j];
+        atomicAdd(&sA[y], T);                              // :276-279 scatter_add (order not reproducible, like the reference)
+        atomicAdd(&sQ[y], T * (rs[j] * inv_st));
+    }
+    __syncthreads();
+    float den = 0.f, num = 0.f;
+    for (int c = threadIdx.x; c < C; c += kSimBlock) {
+        den += sp[c] * sA[c];
+        num += sp[c] * sQ[c];
+        p_out[(long long)row * C + c] = c_smooth < 1.f ? sp[c] * c_smooth + sA[c] * (1.f - c_smooth) : sp[c];   // :280
+    }
+    den = block_reduce(den, red, false);
+    num = block_reduce(num, red, false);
+    if (threadIdx.x == 0) loss_in[row] = lse_s - num / den;                                                       // :286
+    if (gop) {
+        const float inv_den = 1.f / den;
+        __nv_bfloat16* gh = gop + (long long)row * g_nseg * ld_g;
+        for (int j = threadIdx.x; j < k_bank; j += kSimBlock) {
+            const float T = expf(rt[j] * inv_tt - lse_t);
+            const float S = expf(rs[j] * inv_st - lse_s);
+            const float g = (S - T * sp[(int)labels[j]] * inv_den) * inv_st;
+            const __nv_bfloat16 h = __float2bfloat16_rn(g);
+            gh[j] = h;
+            if (g_nseg > 1) gh[ld_g + j] = __float2bfloat16_rn(g - __bfloat162float(h));
+        }
+    }
+}
+
 __global__ void zero_u32_kernel(unsigned int* p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0u;
@@ -957,6 +1040,18 @@ int launch_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, con
     const int threads = row_block_threads(rows);
     da_apply_kernel<<<(int)ceil_div(rows, threads / 32), threads, 0, stream>>>(probs, ld, (int)rows, (int)k, qmean, out,
                                                                                ld_out);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int launch_simmatch_rows(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_bank,
+                         const float* p_orig, int num_classes, float tt, float st, float c_smooth, float* p_out,
+                         float* loss_in, __nv_bfloat16* gop, long long ld_g, int g_nseg, cudaStream_t stream) {
+    if (rows == 0) return STIL_OK;
+    const size_t smem = (3 * (size_t)num_classes + 8) * sizeof(float);
+    STIL_REQUIRE(smem <= 48 * 1024, STIL_E_SHAPE, "simmatch: too many classes (%d)", num_classes);
+    simmatch_rows_kernel<<<rows, kSimBlock, smem, stream>>>(zt, zs, ldz, labels, k_bank, p_orig, num_classes, 1.0f / tt,
+                                                            1.0f / st, c_smooth, p_out, loss_in, gop, ld_g, g_nseg);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }

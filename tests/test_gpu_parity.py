@@ -192,6 +192,36 @@ def test_cgpl_pgls_bf16_logits_and_odd_k(S, O):
         assert agree >= 0.99      # bf16 logits tie often; ties resolved identically unless fp32-ambiguous
 
 
+# ----------------------------------------------------------------------------------------------- a7
+@pytest.mark.parametrize("rows,kb,d,c,dtype,cs", [
+    (56, 706, 128, 286, torch.bfloat16, 0.9), (448, 4096, 128, 286, torch.bfloat16, 0.9),
+    (64, 640, 64, 10, torch.float32, 0.9), (33, 2560, 128, 2, torch.bfloat16, 1.0), (128, 16384, 512, 286, torch.bfloat16, 0.9),
+])
+def test_simmatch_bank_matches_oracle(S, O, rows, kb, d, c, dtype, cs):
+    g = torch.Generator().manual_seed(rows + kb)
+    unit = torch.nn.functional.normalize
+    bank_rows = unit(torch.randn(kb, d, generator=g)).to(dtype)           # [K_b, D]; the module keeps the transpose
+    labels = torch.randint(0, c, (kb,), generator=g)
+    fk = unit(bank_rows.float()[torch.randint(0, kb, (rows,), generator=g)] + 0.3 * torch.randn(rows, d, generator=g)).to(dtype)
+    fq = unit(fk.float() + 0.2 * torch.randn(rows, d, generator=g)).to(dtype)
+    p = torch.softmax(torch.randn(rows, c, generator=g) * 3, 1)
+    fqr = fq.float().requires_grad_(True)
+    ref = O.simmatch_bank(fk.float(), fqr, p, bank_rows.float(), labels, 0.1, 0.1, cs)
+    (g_ref,) = torch.autograd.grad(ref["loss_in"].mean(), fqr)
+    bank = S.alloc_bank(d, kb, dtype)                                      # reference layout [D, K_b]
+    bank.copy_(bank_rows.t())
+    fqc = dev(fq).requires_grad_(True)
+    prob_ku, loss_in = S.simmatch_bank(dev(fk), fqc, dev(p), bank, dev(labels), 0.1, 0.1, cs)
+    (g_c,) = torch.autograd.grad(loss_in.mean(), fqc)
+    assert float((prob_ku.cpu() - ref["prob_ku"]).abs().max()) <= 2e-5
+    assert_rel(loss_in, ref["loss_in"].detach(), REL, "loss_in")
+    assert_rel(g_c, g_ref, REL if dtype == torch.float32 else 1e-2, "d_feat_qu")
+    # consumer decision (SimMatch.py:87-88) on non-ambiguous rows
+    mp_ref = ref["prob_ku"].max(1).values
+    keep = (mp_ref - 0.95).abs() > 1e-4
+    assert torch.equal((prob_ku.cpu().max(1).values >= 0.95)[keep], (mp_ref >= 0.95)[keep])
+
+
 # ----------------------------------------------------------------------------------------------- a6
 def test_distribution_alignment_matches_oracle(S, O):
     g = torch.Generator().manual_seed(4)
