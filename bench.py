@@ -270,7 +270,7 @@ def run_gpu_arm(args):
     pk = peaks()
 
     # enough distinct batches that inputs+outputs+scratch touched between two uses of a buffer exceed L2
-    Head = (lambda c, device: S.DistributedSTiLHead(c, device=device, use_graph=not args.no_graph)) if dist_on else \
+    Head = (lambda c, device: S.DistributedSTiLHead(c, device=device, use_graph=not args.no_graph, transport=args.transport)) if dist_on else \
            (lambda c, device: S.STiLHead(c, device=device))
     probe = Head(cfg, device=dev)
     per_head = probe.h2d_bytes + sum(t.numel() * t.element_size() for t in probe.out.values()) + probe._ws.numel()
@@ -345,8 +345,12 @@ def run_gpu_arm(args):
     kern = {k: sum(v) / len(v) * 1e3 for k, v in per.items()}      # us per launch
     if rank == 0 and dist_on:
         line["config"]["cuda_graph"] = not args.no_graph
-        line["config"]["collectives"] = ("NCCL, captured in the CUDA graph: 1 all_gather([feat_i|feat_t]) overlapped with the row-local "
-                                         "step, all_reduce(loss, LSE slots), all_reduce(class_sum|class_count); InfoNCE chain on its own stream")
+        line["config"]["collectives"] = (
+            "peer-memory exchange kernels over NVLink (CUDA IPC; remote stores + flags), captured in the CUDA graphs: "
+            "gather([feat_i|feat_t]), gather(loss, LSE), gather(class partials); InfoNCE chain on its own stream"
+            if args.transport == "p2p" else
+            "NCCL, captured in the CUDA graph: all_gather([feat_i|feat_t]), all_reduce(loss, LSE slots), "
+            "all_reduce(class_sum|class_count); InfoNCE chain on its own stream")
         line["config"]["infonce"] = f"global batch {cfg.batch * world} (all-gathered)"
         print(json.dumps(line), flush=True)
     if rank == 0 and not dist_on:
@@ -396,6 +400,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 exchange: peer-memory kernels or NCCL")
     ap.add_argument("--no-graph", action="store_true", help="N>1 only: do not capture kernels+NCCL in a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -187,6 +187,34 @@ STIL_API int stil_masked_softce(const void* y_m, const void* y_i, const void* y_
                        int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU exchange over peer-mapped memory (NVLink) for the two coupled steps of the data-parallel head (SURVEY
+ * §8e; the reference's `dist.all_reduce` at STiLModel.py:377-379 and its `concat_all_gather` helpers).
+ *   stil_p2p_alloc/free            one cudaMalloc'ed, zeroed buffer per rank (same size on every rank)
+ *   stil_p2p_export / import/close 64-byte CUDA IPC handle of the buffer / peer mapping of another rank's buffer
+ *   stil_p2p_exchange              all-gather: this rank's `nseg` segments are stored into EVERY rank's buffer at
+ *       dst_offset[s] (the caller makes the offsets rank-specific), then arrival flags are exchanged and the call's
+ *       kernel only finishes once every peer's segments have landed in the local buffer.  `bases` is a HOST array of
+ *       the `world` buffer addresses as seen from this rank.  flags_offset: 8*8*8 bytes of u64 flags, ctrl_offset:
+ *       64*8+64*4 bytes of local control words (both inside the buffer, zero-initialised); `channel` (0..7) separates
+ *       independent exchanges of one step.  A peer that never arrives turns into a CUDA error (bounded spin).
+ *       Callers must not overwrite a destination region a slower peer may still be reading: the head alternates
+ *       between two regions on successive steps. */
+STIL_API int stil_p2p_alloc(int64_t bytes, void** ptr);
+STIL_API int stil_p2p_free(void* ptr);
+STIL_API int stil_p2p_export(void* ptr, uint8_t* handle64);
+STIL_API int stil_p2p_import(const uint8_t* handle64, void** peer_ptr);
+STIL_API int stil_p2p_close(void* peer_ptr);
+STIL_API int stil_p2p_exchange(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset,
+                               int channel, int nseg, const void* const* src, const int64_t* nbytes,
+                               const int64_t* dst_offset, void* stream);
+
+/* prototypes_sum += sum_w parts[w].class_sum; prototypes_count_sum += sum_w parts[w].class_count, with the ranks added
+ * in index order (deterministic); parts is the gathered [world][k*dim + k] buffer; also writes the reduced
+ * class_sum / class_count.  The distributed form of STiLModel.py:377-381. */
+STIL_API int stil_proto_add_gathered(const float* parts, int64_t world, int64_t slot_floats, int64_t k, int64_t dim,
+                                     float* class_sum, float* class_count, float* psum, float* pcount, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * The whole per-batch head in one call (what STiLModel.training_step lines 262-303, 317-322, 339,
  * 374-381 do), with launches batched across the sub-problems.  Used by bench.py and STiLHead.step. */
 typedef struct stil_head_step_args {

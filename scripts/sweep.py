@@ -104,6 +104,29 @@ def gemm_sweep():
                           "alg_GFLOP": fl / 1e9, "TFLOPs": fl / t / 1e12, "frac_tensor": fl / t / 1e12 / TF}), flush=True)
 
 
+def bank_sweep():
+    """BASELINE config C5 on one GPU: SimMatch bank block, bank 65536 x 512 bf16, 448 unlabelled rows, 286 classes."""
+    g = torch.Generator().manual_seed(2)
+    for rows, kb, d, c in ((448, 65536, 512, 286), (448, 2560, 128, 286)):
+        unit = torch.nn.functional.normalize
+        bank = S.alloc_bank(d, kb, torch.bfloat16)
+        bank.copy_(unit(torch.randn(kb, d, generator=g)).t())
+        labels = torch.randint(0, c, (kb,), generator=g).to(dev)
+        fk = unit(torch.randn(rows, d, generator=g)).to(torch.bfloat16).to(dev)
+        fq = unit(torch.randn(rows, d, generator=g)).to(torch.bfloat16).to(dev).requires_grad_(True)
+        p = torch.softmax(torch.randn(rows, c, generator=g) * 3, 1).to(dev)
+
+        def fb():
+            fq.grad = None
+            prob_ku, loss_in = S.simmatch_bank(fk, fq, p, bank, labels, 0.1, 0.1, 0.9)
+            loss_in.mean().backward()
+        t = time_fn(fb, iters=5, warm=2)
+        fl = 6.0 * rows * kb * d
+        print(json.dumps({"op": "simmatch_bank fwd+bwd (a7)", "rows": rows, "k_bank": kb, "d": d, "ms": t * 1e3,
+                          "samples_per_s": rows / t, "alg_GFLOP": fl / 1e9, "TFLOPs": fl / t / 1e12,
+                          "frac_tensor": fl / t / 1e12 / TF}), flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "hbm_peak_GBps": HBM, "bf16_peak_TFLOPs": TF}))
@@ -111,3 +134,5 @@ if __name__ == "__main__":
         rows_sweep()
     if what in ("gemm", "all"):
         gemm_sweep()
+    if what in ("bank", "all"):
+        bank_sweep()

@@ -12,7 +12,7 @@ _LAZY = {
     "CLIPLoss": "losses", "PrototypeLoss": "losses", "masked_soft_ce": "losses", "label_argmax": "losses",
     "cgpl_pgls": "pseudo_label", "distribution_alignment": "pseudo_label", "prototype_logits": "pseudo_label", "PseudoLabels": "pseudo_label",
     "cal_prototypes": "prototypes", "cal_prototypes_separate": "prototypes", "PrototypeBank": "prototypes",
-    "simmatch_bank": "bank", "alloc_bank": "bank", "STiLHead": "head", "DistributedSTiLHead": "head", "GlobalBatch": "distributed", "all_reduce_prototype_partials": "distributed",
+    "simmatch_bank": "bank", "alloc_bank": "bank", "STiLHead": "head", "DistributedSTiLHead": "head", "GlobalBatch": "distributed", "P2PBuffer": "distributed", "all_reduce_prototype_partials": "distributed",
 }
 
 

@@ -68,6 +68,14 @@ SIGNATURES = {
     "stil_proto_accumulate": (i32, [vp, i32, i64, i64, i64, vp, vp, i64, f32, i64, vp, vp, vp, vp, vp]),
     "stil_proto_add": (i32, [vp, vp, i64, i64, vp, vp, vp]),
     "stil_proto_finalize": (i32, [vp, vp, vp, i64, i64, vp, vp]),
+    "stil_proto_add_gathered": (i32, [vp, i64, i64, i64, i64, vp, vp, vp, vp, vp]),
+    "stil_p2p_alloc": (i32, [i64, C.POINTER(vp)]),
+    "stil_p2p_free": (i32, [vp]),
+    "stil_p2p_export": (i32, [vp, C.c_char_p]),
+    "stil_p2p_import": (i32, [C.c_char_p, C.POINTER(vp)]),
+    "stil_p2p_close": (i32, [vp]),
+    "stil_p2p_exchange": (i32, [C.POINTER(vp), i32, i32, i64, i64, i32, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64),
+                                vp]),
     "stil_da_batch_mean": (i32, [vp, i64, i64, i64, vp, vp]),
     "stil_da_apply": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
     "stil_simmatch_workspace_bytes": (i64, [i64, i64, i64, i32]),

@@ -726,6 +726,13 @@ STIL_API int stil_proto_add(const float* class_sum, const float* class_count, in
     return launch_proto_add(class_sum, class_count, k, dim, psum, pcount, S(stream));
 }
 
+STIL_API int stil_proto_add_gathered(const float* parts, int64_t world, int64_t slot_floats, int64_t k, int64_t dim,
+                                     float* class_sum, float* class_count, float* psum, float* pcount, void* stream) {
+    STIL_REQUIRE(parts && class_sum && class_count && psum && pcount && world >= 1 && slot_floats >= k * dim + k, STIL_E_ARG,
+                 "proto_add_gathered: bad arguments");
+    return launch_proto_add_gathered(parts, world, slot_floats, k, dim, class_sum, class_count, psum, pcount, S(stream));
+}
+
 STIL_API int stil_proto_finalize(float* prototypes, float* psum, float* pcount, int64_t k, int64_t dim,
                         int32_t* empty_classes, void* stream) {
     STIL_REQUIRE(prototypes && psum && pcount && empty_classes, STIL_E_ARG, "proto_finalize: null pointer");

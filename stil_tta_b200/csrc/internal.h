@@ -190,6 +190,8 @@ int launch_proto_accumulate(const void* feat, int dtype, int64_t rows, int64_t d
                             float* class_count, float* psum, float* pcount, cudaStream_t stream);
 int launch_proto_add(const float* class_sum, const float* class_count, int64_t k, int64_t dim, float* psum,
                      float* pcount, cudaStream_t stream);
+int launch_proto_add_gathered(const float* parts, int64_t world, int64_t slot, int64_t k, int64_t dim, float* class_sum,
+                              float* class_count, float* psum, float* pcount, cudaStream_t stream);
 int launch_proto_finalize(float* prototypes, float* psum, float* pcount, int64_t k, int64_t dim,
                           int32_t* empty_classes, cudaStream_t stream);
 int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,

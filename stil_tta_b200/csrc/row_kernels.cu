@@ -618,6 +618,23 @@ __global__ void proto_add_kernel(const float* class_sum, const float* class_coun
     if (i < k) pcount[i] += class_count[i];
 }
 
+__global__ void proto_add_gathered_kernel(const float* parts, int world, long long slot, int k, int dim, float* class_sum,
+                                          float* class_count, float* psum, float* pcount) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nsum = (long long)k * dim;
+    if (i < nsum + k) {
+        float s = 0.f;
+        for (int w = 0; w < world; ++w) s += parts[(long long)w * slot + i];   // rank order: deterministic
+        if (i < nsum) {
+            class_sum[i] = s;
+            psum[i] += s;
+        } else {
+            class_count[i - nsum] = s;
+            pcount[i - nsum] += s;
+        }
+    }
+}
+
 __global__ void proto_finalize_kernel(float* prototypes, float* psum, float* pcount, int dim, int* empty) {
     const int c = blockIdx.x;
     const float cnt = pcount[c];
@@ -1012,6 +1029,15 @@ int launch_proto_add(const float* class_sum, const float* class_count, int64_t k
     if (k == 0) return STIL_OK;
     proto_add_kernel<<<(int)ceil_div(k * dim, 256), 256, 0, stream>>>(class_sum, class_count, (int)k, (int)dim, psum,
                                                                        pcount);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+int launch_proto_add_gathered(const float* parts, int64_t world, int64_t slot, int64_t k, int64_t dim, float* class_sum,
+                              float* class_count, float* psum, float* pcount, cudaStream_t stream) {
+    if (k == 0) return STIL_OK;
+    proto_add_gathered_kernel<<<(int)ceil_div(k * dim + k, 256), 256, 0, stream>>>(parts, (int)world, slot, (int)k, (int)dim,
+                                                                                class_sum, class_count, psum, pcount);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }

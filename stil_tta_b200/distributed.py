@@ -80,3 +80,84 @@ def sharded_infonce(a_loc: torch.Tensor, b_loc: torch.Tensor, temperature: float
     lse_row_all, lse_col_all = gb.gather_rows(lse_row), gb.gather_rows(lse_col)
     d_a, d_b = bwd_local(a_all, b_all, off, m, lse_row_all, lse_col_all)
     return loss, d_a, d_b
+
+
+class P2PBuffer:
+    """One zeroed device buffer per rank, mapped into every peer of the node with CUDA IPC, plus the
+    ``stil_p2p_exchange`` all-gather over it (remote NVLink stores + arrival flags; see csrc/p2p.cu).
+
+    Layout: ``[flags 512 B | control 768 B | pad to 4096 | user bytes]``.  ``view(offset, shape, dtype)`` gives a
+    torch tensor over the local buffer; ``exchange(channel, [(src_tensor, dst_offset_bytes), ...])`` stores the
+    segments at the same offsets of every rank's buffer."""
+
+    HEADER = 4096
+
+    def __init__(self, user_bytes: int, device: torch.device, group=None) -> None:
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib, self.group, self.dev = C, _lib, group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("P2PBuffer supports up to 8 ranks (one NVSwitch node)")
+        self.nbytes = self.HEADER + (int(user_bytes) + 255) // 256 * 256
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            p = C.c_void_p()
+            _lib.check(lib.stil_p2p_alloc(self.nbytes, C.byref(p)))
+            self.local = p.value
+            h = C.create_string_buffer(64)
+            _lib.check(lib.stil_p2p_export(self.local, h))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(h.raw), group=group)
+            self.peers = []
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    self.peers.append(self.local)
+                else:
+                    q = C.c_void_p()
+                    _lib.check(lib.stil_p2p_import(hb, C.byref(q)))
+                    self.peers.append(q.value)
+        self._bases = (C.c_void_p * self.world)(*self.peers)
+        dist.barrier(group=group)
+
+    def view(self, offset: int, shape, dtype) -> torch.Tensor:
+        """Tensor over ``[HEADER + offset, ...)`` of the LOCAL buffer."""
+        n = 1
+        for s in shape:
+            n *= int(s)
+        esz = torch.tensor([], dtype=dtype).element_size()
+        tstr = {torch.float32: "<f4", torch.bfloat16: "<u2", torch.uint8: "|u1", torch.int64: "<i8"}[dtype]
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (n,), "typestr": tstr, "data": (self.local + self.HEADER + offset, False),
+                                        "version": 3}
+        t = torch.as_tensor(raw, device=self.dev)
+        if dtype == torch.bfloat16:
+            t = t.view(torch.bfloat16)
+        assert t.numel() * esz == n * esz
+        return t.view(*shape)
+
+    def exchange(self, channel: int, segments, stream_ptr: int) -> None:
+        C, lib = self._C, self._lib.load()
+        n = len(segments)
+        src = (C.c_void_p * n)(*[t.data_ptr() for t, _ in segments])
+        nb = (C.c_int64 * n)(*[t.numel() * t.element_size() for t, _ in segments])
+        off = (C.c_int64 * n)(*[self.HEADER + o for _, o in segments])
+        self._lib.check(lib.stil_p2p_exchange(self._bases, self.world, self.rank, 0, 512, channel, n, src, nb, off,
+                                              stream_ptr))
+
+    def close(self) -> None:
+        if self.local is None:
+            return
+        lib = self._lib.load()
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.group)
+        with torch.cuda.device(self.dev):
+            for r, p in enumerate(self.peers):
+                if r != self.rank:
+                    lib.stil_p2p_close(p)
+            dist.barrier(group=self.group)
+            lib.stil_p2p_free(self.local)
+        self.local = None

@@ -212,87 +212,121 @@ class STiLHead:
 
 
 class DistributedSTiLHead(STiLHead):
-    """Data-parallel head over one node (one process per GPU, ``torch.distributed`` / NCCL over NVLink).
+    """Data-parallel head over one node (one process per GPU, ``torch.distributed``; NVLink).
 
     Everything row-local runs in ``stil_head_step`` with ``skip_infonce``; the two coupled pieces follow
-    SURVEY §8e: (i) InfoNCE on the GLOBAL batch — both embeddings all-gathered, local rows scored against all
-    columns, only the two LSE vectors gathered again for the backward (oracle: reference ``CLIPLoss`` on the
-    concatenated batch); (ii) prototype partial sums all-reduced before they are accumulated
-    (``STiLModel.py:377-379``) — packed with the InfoNCE loss partial into ONE all-reduce.
-    ``losses[0]`` is the global InfoNCE loss (same on every rank); ``d_feat_i/t`` are its gradients w.r.t. the
-    local rows.
+    SURVEY §8e: (i) InfoNCE on the GLOBAL batch — ``[feat_i | feat_t]`` rows all-gathered (one exchange, leading
+    dimension 2P), local rows scored against all columns, only the loss partial and the two LSE vectors exchanged
+    before the backward (oracle: reference ``CLIPLoss`` on the concatenated batch) — no gradient reduce-scatter;
+    (ii) the prototype partial sums of all ranks are summed before they are accumulated (``STiLModel.py:377-379``).
+
+    ``transport="p2p"`` (default): the three exchanges are ``stil_p2p_exchange`` kernels over CUDA-IPC peer memory
+    (remote NVLink stores + flags, a few microseconds each); destination regions alternate between two halves on
+    successive steps, so two CUDA graphs (even / odd) are captured and replayed in turn.
+    ``transport="nccl"``: one NCCL all-gather and two all-reduces, captured in one graph.
+    ``losses[0]`` is the global InfoNCE loss (same on every rank); ``d_feat_i/t`` its gradients w.r.t. the local rows.
     """
 
-    def __init__(self, cfg: HeadConfig, device="cuda", group=None, **kw) -> None:
+    def __init__(self, cfg: HeadConfig, device="cuda", group=None, transport: str = "p2p", **kw) -> None:
         super().__init__(cfg, device=device, **kw)
         import torch.distributed as dist
         from .distributed import GlobalBatch
         self.dist, self.group, self.gb = dist, group, GlobalBatch(group)
         self.world, self.rank = self.gb.world_size, self.gb.rank
+        self.transport = transport if self.world > 1 else "nccl"
         B, K, P = cfg.batch, cfg.num_classes, cfg.proj_dim
-        n = B * self.world
-        W = self.world
+        n, W = B * self.world, self.world
         dev, edt = self.dev, self.inp["feat_i"].dtype
-        # one all-gather for both modalities: rows [feat_i | feat_t] side by side, leading dimension 2P
-        self._ab_loc = torch.empty(B, 2 * P, dtype=edt, device=dev)
-        self._ab_all = torch.empty(n, 2 * P, dtype=edt, device=dev)
-        # two small all-reduces on one buffer: [loss partial (4) | LSE slots [2, W, B]] for the InfoNCE chain and
-        # [class_sum | class_count] for the prototype bank (STiLModel.py:377-379, one collective instead of two);
-        # every rank fills only its own LSE slot, so SUM over ranks is the gather of the LSE vectors
-        self._o_lse, self._o_cs, self._o_cc = 4, 4 + 2 * n, 4 + 2 * n + K * P
-        self._packed = torch.zeros(self._o_cc + K, dtype=torch.float32, device=dev)
-        self._lse = self._packed[self._o_lse:self._o_cs].view(2, W, B)
+        esz = 2 if edt == torch.bfloat16 else 4
+        self._slot = (K * P + K + 3) // 4 * 4                       # floats per rank: [class_sum | class_count]
+        self._ab_loc = torch.empty(B, 2 * P, dtype=edt, device=dev)  # [feat_i | feat_t], leading dimension 2P
+        self._cls_loc = torch.zeros(self._slot, dtype=torch.float32, device=dev)
+        self._nce_loc = torch.zeros(4 + 2 * B, dtype=torch.float32, device=dev)   # [loss partial (4) | lse_row | lse_col]
         self._nce_stream = None
+        self._graphs = [None, None]
+        self._parity = 0
         lib = _lib.load()
         code = _lib.dtype_code(self.inp["feat_i"])
         self._nce_ws = torch.empty(lib.stil_infonce_workspace_bytes(B, n, P, code), dtype=torch.uint8, device=dev)
         a = self._args
         a.skip_infonce = 1
-        a.class_sum = self._packed[self._o_cs:].data_ptr()
-        a.class_count = self._packed[self._o_cc:].data_ptr()
+        a.class_sum = self._cls_loc.data_ptr()
+        a.class_count = self._cls_loc[K * P:].data_ptr()
         a.prototypes_sum, a.prototypes_count_sum = None, None
-        self.out["class_sum"] = self._packed[self._o_cs:self._o_cc].view(K, P)
-        self.out["class_count"] = self._packed[self._o_cc:].view(K, 1)
-        # + cat, zero, infonce fwd (prep, gemm, finish), bwd (prep, gemm, gemm), proto_add, loss copy
-        self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 2 + 3 + 3 + 2
+        self._sum_out = torch.zeros(K, P, dtype=torch.float32, device=dev)
+        self._cnt_out = torch.zeros(K, 1, dtype=torch.float32, device=dev)
+        self.out["class_sum"], self.out["class_count"] = self._sum_out, self._cnt_out
+        if self.transport == "p2p":
+            from .distributed import P2PBuffer
+            r256 = lambda x: (x + 255) // 256 * 256
+            self._o_ab = 0
+            self._o_loss = self._o_ab + r256(n * 2 * P * esz)
+            self._o_lr = self._o_loss + r256(W * 16)
+            self._o_lc = self._o_lr + r256(n * 4)
+            self._o_cls = self._o_lc + r256(n * 4)
+            self._half = self._o_cls + r256(W * self._slot * 4)
+            self._p2p = P2PBuffer(2 * self._half, dev, group)
+            v = self._p2p.view
+            self._r = []
+            for h in (0, 1):
+                o = h * self._half
+                self._r.append(dict(
+                    off=o, ab=v(o + self._o_ab, (n, 2 * P), edt), loss=v(o + self._o_loss, (W, 4), torch.float32),
+                    lse_row=v(o + self._o_lr, (n,), torch.float32), lse_col=v(o + self._o_lc, (n,), torch.float32),
+                    cls=v(o + self._o_cls, (W, self._slot), torch.float32)))
+        else:
+            # NCCL: [loss partial (4) | LSE slots [2, W, B]] all-reduced for the InfoNCE chain (every rank fills only
+            # its own LSE slot, so SUM is the gather) and [class_sum | class_count] all-reduced for the bank
+            self._ab_all = torch.empty(n, 2 * P, dtype=edt, device=dev)
+            self._packed = torch.zeros(4 + 2 * n, dtype=torch.float32, device=dev)
+            self._lse = self._packed[4:].view(2, W, B)
+        # + cat, exchanges / collectives, infonce fwd (prep, gemm, finish), bwd (prep, gemm, gemm), add, loss
+        self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 3 + 3 + 3 + 2
 
+    # ------------------------------------------------------------------------------------------
     def capture(self) -> None:
-        """Record kernels AND the NCCL collectives of one step into a CUDA graph (every rank must call this
-        and later replay in lockstep)."""
+        """Record kernels AND exchanges of one step into CUDA graphs (every rank must call this and later replay
+        in lockstep).  The p2p transport alternates destination halves, hence one graph per parity."""
         with torch.cuda.device(self.dev):
             keep = (self.prototypes_sum.clone(), self.prototypes_count_sum.clone())
             s = torch.cuda.Stream(self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
-                for _ in range(2):
-                    self._run_eager()
+                for i in range(2):
+                    self._run_eager(i & 1)
             torch.cuda.current_stream(self.dev).wait_stream(s)
             torch.cuda.synchronize(self.dev)
             self.dist.barrier(group=self.group)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._run_eager()
+            for parity in ((0, 1) if self.transport == "p2p" else (0,)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_eager(parity)
+                self._graphs[parity] = g
             self.prototypes_sum.copy_(keep[0])
             self.prototypes_count_sum.copy_(keep[1])
             torch.cuda.synchronize(self.dev)
-            self._graph = g
+            self.dist.barrier(group=self.group)
+            self._graph = self._graphs[0]
 
     def run(self) -> None:
         with torch.cuda.device(self.dev):
+            parity = self._parity if self.transport == "p2p" else 0
+            self._parity ^= 1
             if self.use_graph:
                 if self._graph is None:
                     self.capture()
-                self._graph.replay()
+                self._graphs[parity].replay()
             else:
-                self._run_eager()
+                self._run_eager(parity)
 
-    def _run_eager(self) -> None:
+    def _run_eager(self, parity: int = 0) -> None:
         cfg, dist, lib = self.cfg, self.dist, _lib.load()
         B, K, P, W = cfg.batch, cfg.num_classes, cfg.proj_dim, self.world
         n, off, r = B * W, B * self.rank, self.rank
         code = _lib.dtype_code(self.inp["feat_i"])
         p = lambda t: t.data_ptr()
-        esz = self._ab_all.element_size()
+        esz = self._ab_loc.element_size()
+        p2p = self.transport == "p2p"
         with torch.cuda.device(self.dev):
             cur = torch.cuda.current_stream(self.dev)
             if self._nce_stream is None:
@@ -300,28 +334,55 @@ class DistributedSTiLHead(STiLHead):
             sb = self._nce_stream
             torch.cat((self.inp["feat_i"], self.inp["feat_t"]), dim=1, out=self._ab_loc)
             sb.wait_stream(cur)
-            # chain B (own stream): gather -> global InfoNCE forward -> all-reduce(loss, LSE) -> backward
+            # chain B (own stream): gather -> global InfoNCE forward -> exchange(loss, LSE) -> backward
             with torch.cuda.stream(sb):
-                dist.all_gather_into_tensor(self._ab_all, self._ab_loc, group=self.group)
-                self._lse.zero_()
-                a_all, b_all = p(self._ab_all), p(self._ab_all) + P * esz
+                if p2p:
+                    R = self._r[parity]
+                    self._p2p.exchange(0, [(self._ab_loc, R["off"] + self._o_ab + off * 2 * P * esz)], sb.cuda_stream)
+                    ab_all, loss_dst = R["ab"], self._nce_loc
+                    lse_row_loc, lse_col_loc = self._nce_loc[4:4 + B], self._nce_loc[4 + B:]
+                else:
+                    dist.all_gather_into_tensor(self._ab_all, self._ab_loc, group=self.group)
+                    self._lse.zero_()
+                    ab_all, loss_dst = self._ab_all, self._packed
+                    lse_row_loc, lse_col_loc = self._lse[0, r], self._lse[1, r]
+                a_all, b_all = p(ab_all), p(ab_all) + P * esz
                 a_loc, b_loc = a_all + off * 2 * P * esz, b_all + off * 2 * P * esz
                 check(lib.stil_infonce_fwd(a_loc, b_loc, a_all, b_all, code, B, n, P, 2 * P, off, cfg.temperature,
-                                           cfg.lambda_0, p(self._packed), p(self._lse[0, r]), p(self._lse[1, r]), None, 0,
+                                           cfg.lambda_0, p(loss_dst), p(lse_row_loc), p(lse_col_loc), None, 0,
                                            p(self._nce_ws), self._nce_ws.numel(), sb.cuda_stream))
-                dist.all_reduce(self._packed[:self._o_cs], op=dist.ReduceOp.SUM, group=self.group)
+                if p2p:
+                    self._p2p.exchange(1, [(self._nce_loc[:4], R["off"] + self._o_loss + r * 16),
+                                           (lse_row_loc, R["off"] + self._o_lr + off * 4),
+                                           (lse_col_loc, R["off"] + self._o_lc + off * 4)], sb.cuda_stream)
+                    lse_row_all, lse_col_all = R["lse_row"], R["lse_col"]
+                    torch.sum(R["loss"][:, 0], dim=0, keepdim=True, out=self.out["losses"][0:1])
+                else:
+                    dist.all_reduce(self._packed, op=dist.ReduceOp.SUM, group=self.group)
+                    lse_row_all, lse_col_all = self._lse[0].reshape(-1), self._lse[1].reshape(-1)
+                    self.out["losses"][0:1].copy_(self._packed[0:1], non_blocking=True)
                 check(lib.stil_infonce_bwd(a_loc, b_loc, a_all, b_all, code, B, n, P, 2 * P, off, cfg.temperature,
-                                           cfg.lambda_0, p(self._lse[0]), p(self._lse[1]), None, p(self.out["d_feat_i"]),
+                                           cfg.lambda_0, p(lse_row_all), p(lse_col_all), None, p(self.out["d_feat_i"]),
                                            p(self.out["d_feat_t"]), _lib.dtype_code(self.out["d_feat_i"]), P,
                                            p(self._nce_ws), self._nce_ws.numel(), sb.cuda_stream))
-                self.out["losses"][0:1].copy_(self._packed[0:1], non_blocking=True)
-            # chain A (current stream): everything row-local, then the prototype partials over all ranks
+            # chain A (current stream): everything row-local, then the prototype partials of all ranks
             self._enqueue()
-            dist.all_reduce(self._packed[self._o_cs:], op=dist.ReduceOp.SUM, group=self.group)
-            check(lib.stil_proto_add(p(self.out["class_sum"]), p(self.out["class_count"]), K, P, p(self.prototypes_sum),
-                                     p(self.prototypes_count_sum), cur.cuda_stream))
+            if p2p:
+                self._p2p.exchange(2, [(self._cls_loc, R["off"] + self._o_cls + r * self._slot * 4)], cur.cuda_stream)
+                parts, nparts = R["cls"], W
+            else:
+                dist.all_reduce(self._cls_loc, op=dist.ReduceOp.SUM, group=self.group)
+                parts, nparts = self._cls_loc, 1
+            check(lib.stil_proto_add_gathered(p(parts), nparts, self._slot, K, P, p(self._sum_out), p(self._cnt_out),
+                                              p(self.prototypes_sum), p(self.prototypes_count_sum), cur.cuda_stream))
             cur.wait_stream(sb)
 
     def release(self) -> None:
-        """Drop the captured graph (it pins the NCCL communicator) before the process group is destroyed."""
+        """Drop the captured graphs (they pin the communicator / peer mappings) and unmap the peer memory; call on
+        every rank before the process group is destroyed."""
         self._graph = None
+        self._graphs = [None, None]
+        if getattr(self, "_p2p", None) is not None:
+            self._r = None
+            self._p2p.close()
+            self._p2p = None

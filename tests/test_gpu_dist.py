@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, batch, use_graph):
+def _worker(rank, world, port, batch, use_graph, transport):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -29,9 +29,9 @@ def _worker(rank, world, port, batch, use_graph):
         from oracle import stil_head_oracle as O
         cfg = synth.dvm_config(batch)
         batches = [synth.make_batch(cfg, seed=2022, rank=r) for r in range(world)]
-        head = S.DistributedSTiLHead(cfg, device=f"cuda:{rank}", use_graph=use_graph)
+        head = S.DistributedSTiLHead(cfg, device=f"cuda:{rank}", use_graph=use_graph, transport=transport)
         head.load(batches[rank])
-        for _ in range(2):          # second run accumulates again
+        for _ in range(4):          # every run accumulates again; p2p alternates its two regions
             head.run()
         torch.cuda.synchronize()
         # oracle: reference CLIPLoss on the concatenation of all ranks' rows
@@ -52,8 +52,8 @@ def _worker(rank, world, port, batch, use_graph):
         cs = sum(o["class_sum"] for o in os_)
         cc = sum(o["class_count"] for o in os_)
         assert float((head.out["class_sum"].cpu() - cs).abs().max()) <= 1e-4
-        assert float((head.prototypes_sum.cpu() - 2 * cs).abs().max()) <= 2e-4
-        assert float((head.prototypes_count_sum.cpu() - 2 * cc).abs().max()) <= 2e-5
+        assert float((head.prototypes_sum.cpu() - 4 * cs).abs().max()) <= 4e-4
+        assert float((head.prototypes_count_sum.cpu() - 4 * cc).abs().max()) <= 4e-5
         ok = True
     except BaseException:
         import traceback
@@ -69,7 +69,7 @@ def _worker(rank, world, port, batch, use_graph):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_distributed_head_two_ranks(use_graph):
+@pytest.mark.parametrize("use_graph,transport", [(False, "p2p"), (True, "p2p"), (True, "nccl")])
+def test_distributed_head_two_ranks(use_graph, transport):
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), 256, use_graph), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), 256, use_graph, transport), nprocs=2, join=True)
