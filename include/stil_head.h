@@ -13,6 +13,7 @@
  *     aligned (dim % 8 == 0 for bf16, % 4 for f32, base pointers 16-B aligned).
  *   - every function returns 0 (STIL_OK) or a negative stil_status_t, never throws, never aborts,
  *     never synchronises the device; stil_last_error() gives the message (thread-local).
+ *   - workspaces of stil_head_step must be zero-filled once before their first use (reduction tickets live there)
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are CUDA-graph
  *     capturable.  The library allocates no device memory: scratch comes from the caller through
  *     `workspace` (size from the matching *_workspace_bytes query; 256-B aligned).
@@ -241,17 +242,23 @@ typedef struct stil_head_step_args {
     float *prototypes_sum, *prototypes_count_sum;     /* accumulated in place when non-NULL */
     float rate_uce_scale;                             /* grad_scale of the f-1 gradients */
     void* workspace; int64_t workspace_bytes; void* stream;
-    /* optional instrumentation (bench.py): cudaEvent_t[9] recorded around the launches of the two critical chains —
-     * 0|prep|1|gemm stats|5|cgpl_pgls|6|gemm grad (prototype CE)|7|gemm dX (prototype CE)|8 on `stream`;
-     * 2|gemm grad (InfoNCE)|3|gemm dX (InfoNCE)|4 on the internal InfoNCE-backward stream.  Leave NULL/0 otherwise (and
+    /* optional instrumentation (bench.py): cudaEvent_t[11] recorded around the launches of the two chains —
+     * 0|prep|1|gemm stats (prototypes)|5|cgpl_pgls|6|gemm grad (prototype CE)|7|gemm dX (prototype CE)|8 on `stream`;
+     * 9|prep|10|gemm stats (InfoNCE)|2|gemm grad (InfoNCE)|3|gemm dX (InfoNCE)|4 on the internal InfoNCE stream.  Leave NULL/0 otherwise (and
      * always during graph capture). */
     void** timing_events; int n_timing_events;
     /* 1: leave the InfoNCE (losses[0], d_feat_i, d_feat_t) to the caller — the data-parallel path computes it on
      * the all-gathered global batch with stil_infonce_fwd/bwd while this call does everything row-local */
     int skip_infonce;
+    /* 1: the bf16 operand form of `prototypes` is already in the workspace (stil_head_prepare_prototypes was called
+     * with the same workspace after the prototypes last changed) — the step then skips that conversion */
+    int prototypes_prepared;
 } stil_head_step_args;
 STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int64_t k, int64_t dim, int embed_dtype);
 STIL_API int stil_head_step(const stil_head_step_args* args);
+/* Convert args->prototypes to the tensor-core operand form kept in args->workspace (the prototypes only change at
+ * epoch end, STiLModel.py:408-415, so this runs once per change, not once per step). */
+STIL_API int stil_head_prepare_prototypes(const stil_head_step_args* args);
 /* number of kernel launches one stil_head_step enqueues for these args (for bench.py's gpu_launches) */
 STIL_API int stil_head_step_launches(const stil_head_step_args* args);
 

@@ -43,7 +43,7 @@ class HeadStepArgs(C.Structure):
         ("prototypes_sum", vp), ("prototypes_count_sum", vp),
         ("rate_uce_scale", f32),
         ("workspace", vp), ("workspace_bytes", i64), ("stream", vp),
-        ("timing_events", vp), ("n_timing_events", i32), ("skip_infonce", i32),
+        ("timing_events", vp), ("n_timing_events", i32), ("skip_infonce", i32), ("prototypes_prepared", i32),
     ]
 
 
@@ -88,6 +88,7 @@ SIGNATURES = {
     "stil_head_step_workspace_bytes": (i64, [i64, i64, i64, i64, i32]),
     "stil_head_step": (i32, [C.POINTER(HeadStepArgs)]),
     "stil_head_step_launches": (i32, [C.POINTER(HeadStepArgs)]),
+    "stil_head_prepare_prototypes": (i32, [C.POINTER(HeadStepArgs)]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -341,7 +341,7 @@ void infonce_gradfinish_jobs(GradFinishJob* G2, const InfoncePlan& P, const void
 constexpr int kSide = 4;   // 0: losses, 1: prototype sums, 2: masked CE, 3: pseudo-label + prototype-CE backward chain
 struct SideStreams {
     cudaStream_t s[kSide];
-    cudaEvent_t fork, fork2, join[kSide];
+    cudaEvent_t fork, fork2, nce_stats, join[kSide];
     bool ready;
 };
 SideStreams g_side[64];
@@ -360,6 +360,7 @@ int get_side_streams(SideStreams** out) {
         }
         STIL_CUDA(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
         STIL_CUDA(cudaEventCreateWithFlags(&S.fork2, cudaEventDisableTiming));
+        STIL_CUDA(cudaEventCreateWithFlags(&S.nce_stats, cudaEventDisableTiming));
         S.ready = true;
     }
     *out = &S;
@@ -968,11 +969,22 @@ STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int6
     return plan_step(nullptr, 0, batch, b_l, k, dim, embed_dtype).bytes;
 }
 
+STIL_API int stil_head_prepare_prototypes(const stil_head_step_args* a) {
+    STIL_REQUIRE(a != nullptr && a->prototypes && a->workspace, STIL_E_ARG, "head_prepare_prototypes: null argument");
+    StepPlan P = plan_step(a->workspace, a->workspace_bytes, a->batch, a->b_l, a->k, a->dim, a->embed_dtype);
+    STIL_REQUIRE(P.bytes <= a->workspace_bytes, STIL_E_WORKSPACE, "head_step workspace too small: need %lld", (long long)P.bytes);
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    prep_add(PL, prep_job(a->prototypes, STIL_F32, a->k, a->dim, a->dim, P.pt.proto_nseg, P.pt.proto_op, nullptr, 0, 0, nullptr));
+    return launch_prep(PL, S(a->stream));
+}
+
 STIL_API int stil_head_step_launches(const stil_head_step_args* a) {
     if (!a) return 0;
-    // prep, gemm(stats), cgpl_pgls, gemm(grad)+gemm(dX) for the prototype CE, finish, proto_accumulate
-    int n = 7;
-    if (!a->skip_infonce) n += 2;          // gemm(grad)+gemm(dX) for the InfoNCE
+    // gemm(stats), cgpl_pgls, gemm(grad)+gemm(dX) for the prototype CE, finish, proto_accumulate
+    int n = 6;
+    if (a->embed_dtype != STIL_BF16 || !a->prototypes_prepared) n += 1;   // main-stream prep
+    if (!a->skip_infonce) n += 4;          // prep, gemm(stats), gemm(grad), gemm(dX) for the InfoNCE
     if (a->dim > kTileN) n += a->skip_infonce ? 1 : 2;   // un-fused normalise-backward / cast
     if (a->y_m) n += 1;                    // masked soft CE
     return n;
@@ -1003,7 +1015,6 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     SideStreams* SS = nullptr;
     if ((rc = get_side_streams(&SS))) return rc;
     cudaStream_t s_loss = SS->s[0], s_acc = SS->s[1], s_ce = SS->s[2], s_nce = SS->s[3];
-    cudaStream_t s_pl = st;   // the pseudo-label -> prototype-CE backward chain is the critical one: main stream
     const float inv_t = 1.0f / a->temperature;
     const int esz = dt == STIL_BF16 ? 2 : 4;
     const void* feat_m_ue = static_cast<const char*>(a->feat_m_e) + B_l * D * esz;
@@ -1015,33 +1026,31 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         return STIL_OK;
     };
 
-    // 1. operand preparation (all matrices, one launch): inverse norms, fp32 -> bf16 segment split
-    PrepLaunch PL;
-    std::memset(&PL, 0, sizeof(PL));
-    PL.zero_words = P.nce.ticket; PL.n_zero = 32;   // [0] finish ticket, [16] masked-CE ticket
-    if (nce) {
-        prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, nullptr, 0, 0, P.nce.ra));
-        prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, nullptr, 0, 0, P.nce.rb));
-    }
-    if (dt != STIL_BF16) {
-        prep_add(PL, prep_job(a->feat_m, dt, B, D, D, P.pt.feat_nseg, P.pt.feat_op, nullptr, 0, 0, nullptr));
-        prep_add(PL, prep_job(feat_m_ue, dt, B_u, D, D, 3, P.teach_op, nullptr, 0, 0, nullptr));
-    }
-    prep_add(PL, prep_job(a->prototypes, STIL_F32, K, D, D, P.pt.proto_nseg, P.pt.proto_op, nullptr, 0, 0, nullptr));
-    if ((rc = mark(0, st))) return rc;
-    if ((rc = launch_prep(PL, st))) return rc;
-
-    // 2. forward GEMMs, one launch: InfoNCE both sides (statistics), student prototype logits (statistics + store),
-    //    teacher prototype logits (store)
+    // ---- fork A: the InfoNCE (forward statistics and backward) is independent of the pseudo-label chain and runs on
+    //      its own stream from the start of the step
+    STIL_CUDA(cudaEventRecord(SS->fork, st));
     const Operand A = rowmajor_operand(a->feat_i, dt, D, D, P.nce.a_op, P.nce.nseg);
     const Operand Bm = rowmajor_operand(a->feat_t, dt, D, D, P.nce.b_op, P.nce.nseg);
     GemmLaunch GL;
+
+    // 1. main stream: operand preparation — fp32 -> bf16 segment split of the prototypes (skipped when the caller
+    //    prepared them once with stil_head_prepare_prototypes and they have not changed) and of fp32 features
+    {
+        PrepLaunch PL;
+        std::memset(&PL, 0, sizeof(PL));
+        if (dt != STIL_BF16) {
+            prep_add(PL, prep_job(a->feat_m, dt, B, D, D, P.pt.feat_nseg, P.pt.feat_op, nullptr, 0, 0, nullptr));
+            prep_add(PL, prep_job(feat_m_ue, dt, B_u, D, D, 3, P.teach_op, nullptr, 0, 0, nullptr));
+        }
+        if (!a->prototypes_prepared)
+            prep_add(PL, prep_job(a->prototypes, STIL_F32, K, D, D, P.pt.proto_nseg, P.pt.proto_op, nullptr, 0, 0, nullptr));
+        if ((rc = mark(0, st))) return rc;
+        if (PL.njobs > 0 && (rc = launch_prep(PL, st))) return rc;
+    }
+
+    // 2. main stream: student prototype logits (statistics + store) and teacher prototype logits (store), one launch
     std::memset(&GL, 0, sizeof(GL));
     int nj = 0;
-    if (nce) {
-        if ((rc = infonce_stats_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, nullptr, 0))) return rc;
-        nj = 2;
-    }
     if ((rc = proto_stats_job(GL.job[nj], P.pt, a->feat_m, dt, B, D, D, K, inv_t))) return rc;
     GL.job[nj].out = P.z_pt;
     GL.job[nj].ld_out = P.ldk;
@@ -1050,7 +1059,7 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         const Operand X = rowmajor_operand(feat_m_ue, dt, D, D, P.teach_op, 3);
         const Operand Y = rowmajor_operand(nullptr, STIL_F32, D, D, P.pt.proto_op, P.pt.proto_nseg);
         if ((rc = fill_gemm_common(GL.job[nj], X, 0, B_u, Y, K, D))) return rc;
-        GL.job[nj].mode = GEMM_STATS;            // same launch as the statistics jobs; its partials are unused
+        GL.job[nj].mode = GEMM_STATS;            // same launch as the statistics job; its partials are unused
         GL.job[nj].part_max = P.teach_pmax;
         GL.job[nj].part_sum = P.teach_psum;
         GL.job[nj].out = P.teacher_logits;
@@ -1063,22 +1072,15 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     if ((rc = launch_gemm(GL, st))) return rc;
     if ((rc = mark(5, st))) return rc;
 
-    // ---- fork A: the InfoNCE backward leaves the main stream here (it does not need the pseudo labels)
-    STIL_CUDA(cudaEventRecord(SS->fork, st));
-    STIL_CUDA(cudaStreamWaitEvent(s_nce, SS->fork, 0));
-
-    // 4. main stream: CGPL + PGLS on the unlabelled rows, (cls, conf) of every row ...
+    // 3. main stream: CGPL + PGLS on the unlabelled rows, (cls, conf) of every row ...
     if ((rc = launch_cgpl_pgls(a->y_m_ue, a->y_i_ue, a->y_t_ue, a->logit_dtype, K, P.teacher_logits, P.ldk, B_u, K,
                                a->temperature, a->rate_pseudo, a->th1, a->past_start_epoch, a->pseudo_label, K, nullptr,
                                0, a->max_prob, a->max_idx, a->mask1, a->case1, a->case2_i, a->case2_t, a->case3,
-                               nullptr, P.cls + B_l, P.conf + B_l, a->y_l, B_l, P.cls, P.conf, s_pl)))
+                               nullptr, P.cls + B_l, P.conf + B_l, a->y_l, B_l, P.cls, P.conf, st)))
         return rc;
-    if ((rc = mark(6, s_pl))) return rc;
+    if ((rc = mark(6, st))) return rc;
     // ---- fork B: everything that only needs the pseudo labels
-    STIL_CUDA(cudaEventRecord(SS->fork2, s_pl));
-    STIL_CUDA(cudaStreamWaitEvent(s_loss, SS->fork2, 0));
-    STIL_CUDA(cudaStreamWaitEvent(s_acc, SS->fork2, 0));
-    STIL_CUDA(cudaStreamWaitEvent(s_ce, SS->fork2, 0));
+    STIL_CUDA(cudaEventRecord(SS->fork2, st));
     //    ... then the prototype-CE backward on the same stream
     bool fused_pt = false;
     {
@@ -1088,14 +1090,14 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
             return rc;
         GL.njobs = 1;
         gemm_job_tiles(GL);
-        if ((rc = launch_gemm(GL, s_pl))) return rc;
-        if ((rc = mark(7, s_pl))) return rc;
+        if ((rc = launch_gemm(GL, st))) return rc;
+        if ((rc = mark(7, st))) return rc;
         std::memset(&GL, 0, sizeof(GL));
         if ((rc = proto_store_job(GL.job[0], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
         GL.njobs = 1;
         gemm_job_tiles(GL);
-        if ((rc = launch_gemm(GL, s_pl))) return rc;
-        if ((rc = mark(8, s_pl))) return rc;
+        if ((rc = launch_gemm(GL, st))) return rc;
+        if ((rc = mark(8, st))) return rc;
         if (!fused_pt) {
             GradFinishLaunch GF;
             std::memset(&GF, 0, sizeof(GF));
@@ -1104,21 +1106,35 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
             j.rows = (int)B; j.dim = (int)D; j.row_begin = 0;
             GF.njobs = 1;
             GF.total_rows = (int)B;
-            if ((rc = launch_grad_finish(GF, s_pl))) return rc;
+            if ((rc = launch_grad_finish(GF, st))) return rc;
         }
     }
 
-    // 3. side stream: InfoNCE backward — G tiles (statistics merged in-kernel), then dX = G · Y with the
-    //    normalise-backward in the epilogue.  Independent of the pseudo labels.
-    bool fused = true;
+    // 4. InfoNCE stream: inverse norms (+ fp32 split) -> statistics of a·bT and b·aT -> G tiles (statistics merged
+    //    in-kernel) -> dX = G · Y with the normalise-backward in the epilogue
     if (nce) {
+        STIL_CUDA(cudaStreamWaitEvent(s_nce, SS->fork, 0));
+        PrepLaunch PL;
+        std::memset(&PL, 0, sizeof(PL));
+        prep_add(PL, prep_job(a->feat_i, dt, B, D, D, P.nce.nseg, P.nce.a_op, nullptr, 0, 0, P.nce.ra));
+        prep_add(PL, prep_job(a->feat_t, dt, B, D, D, P.nce.nseg, P.nce.b_op, nullptr, 0, 0, P.nce.rb));
+        if ((rc = mark(9, s_nce))) return rc;
+        if ((rc = launch_prep(PL, s_nce))) return rc;
+        std::memset(&GL, 0, sizeof(GL));
+        if ((rc = infonce_stats_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, nullptr, 0))) return rc;
+        GL.njobs = 2;
+        gemm_job_tiles(GL);
+        if ((rc = mark(10, s_nce))) return rc;
+        if ((rc = launch_gemm(GL, s_nce))) return rc;
+        if ((rc = mark(2, s_nce))) return rc;
+        STIL_CUDA(cudaEventRecord(SS->nce_stats, s_nce));
+        bool fused = true;
         std::memset(&GL, 0, sizeof(GL));
         if ((rc = infonce_grad_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, a->lambda0, nullptr, nullptr, nullptr,
                                     a->grad_dtype)))
             return rc;
         GL.njobs = 2;
         gemm_job_tiles(GL);
-        if ((rc = mark(2, s_nce))) return rc;
         if ((rc = launch_gemm(GL, s_nce))) return rc;
         if ((rc = mark(3, s_nce))) return rc;
         std::memset(&GL, 0, sizeof(GL));
@@ -1139,6 +1155,11 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
             if ((rc = launch_grad_finish(GF, s_nce))) return rc;
         }
     }
+
+    STIL_CUDA(cudaStreamWaitEvent(s_loss, SS->fork2, 0));
+    if (nce) STIL_CUDA(cudaStreamWaitEvent(s_loss, SS->nce_stats, 0));
+    STIL_CUDA(cudaStreamWaitEvent(s_acc, SS->fork2, 0));
+    STIL_CUDA(cudaStreamWaitEvent(s_ce, SS->fork2, 0));
 
     // 5. side branches
     {   // losses and LSE vectors

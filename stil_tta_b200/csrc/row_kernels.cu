@@ -196,24 +196,22 @@ __device__ __forceinline__ void group_argmax(float& v, int& idx) {
     }
 }
 
-// argmax_k softmax(a)_k with torch's first-index rule, without dividing every element: e_max = exp(0) = 1
-// exactly, and fl(e/s) can only tie with fl(1/s) for e within a few ulp of 1, so only those are divided.
+// argmax_k softmax(y)_k for a head whose probabilities are not needed: softmax is monotone, so this is the first
+// index of the largest LOGIT.  (torch takes the argmax of the rounded probabilities, STiLModel.py:263; the two can
+// only differ when an earlier, smaller logit rounds to the same probability — logits closer than one ulp, rows that
+// DESIGN.md §2 classifies as ambiguous.)
 template <int LPR, int NV>
-__device__ __forceinline__ int argmax_of_softmax(float (&e)[2 * NV], float s, int sub, int k) {
-    float bv = -1.f;
+__device__ __forceinline__ int argmax_logits(const float (&y)[2 * NV], int sub, int k) {
+    float bv = -INFINITY;
     int bi = 0x7fffffff;
 #pragma unroll
     for (int it = 0; it < NV; ++it) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int idx = 2 * (sub + LPR * it) + h;
-            const float ev = e[2 * it + h];
-            if (idx < k && ev >= 0.9999f) {
-                const float p = __fdiv_rn(ev, s);
-                if (p > bv) {  // ascending idx within a lane: strict > keeps the first
-                    bv = p;
-                    bi = idx;
-                }
+            if (idx < k && (y[2 * it + h] > bv || bi == 0x7fffffff)) {   // ascending idx within a lane: strict > keeps the first
+                bv = y[2 * it + h];
+                bi = idx;
             }
         }
     }
@@ -269,18 +267,8 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
         group_argmax<LPR>(bv, bi);
         top_m = bi;
     }
-    int top_i, top_t;
-    {
-        float w[2 * NV];
-#pragma unroll
-        for (int j = 0; j < 2 * NV; ++j) w[j] = yi[j];
-        float s = softmax_exp<LPR, NV>(w);
-        top_i = argmax_of_softmax<LPR, NV>(w, s, sub, k);
-#pragma unroll
-        for (int j = 0; j < 2 * NV; ++j) w[j] = yt[j];
-        s = softmax_exp<LPR, NV>(w);
-        top_t = argmax_of_softmax<LPR, NV>(w, s, sub, k);
-    }
+    const int top_i = argmax_logits<LPR, NV>(yi, sub, k);
+    const int top_t = argmax_logits<LPR, NV>(yt, sub, k);
     // ---- :264-267 agreement cases
     const bool mi = top_m == top_i, mt = top_m == top_t;
     const bool c1 = mi && mt, c2i = mi && !mt, c2t = mt && !mi;

@@ -67,7 +67,8 @@ class STiLHead:
             self.out.update({"d_y_m": z(B, K), "d_y_i": z(B, K), "d_y_t": z(B, K)})
         lib = _lib.load()
         code = _lib.STIL_BF16 if edt == torch.bfloat16 else _lib.STIL_F32
-        self._ws = torch.empty(lib.stil_head_step_workspace_bytes(B, B_l, K, P, code), dtype=torch.uint8, device=dev)
+        self._ws = torch.zeros(lib.stil_head_step_workspace_bytes(B, B_l, K, P, code), dtype=torch.uint8, device=dev)
+        self._proto_version = None       # torch version counter of `prototypes` at the last operand conversion
         self._args = self._make_args(code, _lib.STIL_BF16 if logit_dtype == torch.bfloat16 else _lib.STIL_F32)
         self.launches_per_step = lib.stil_head_step_launches(C.byref(self._args))
         self._graph: Optional[torch.cuda.CUDAGraph] = None
@@ -118,6 +119,17 @@ class STiLHead:
         if "prototypes" in batch:
             self.prototypes.copy_(batch["prototypes"], non_blocking=True)
 
+    def _ensure_prototypes(self) -> None:
+        """The prototypes change once per epoch (STiLModel.py:408-415), their tensor-core operand form is cached in
+        the workspace and refreshed only when the tensor's version counter moved (any in-place torch write) or
+        finalize_prototypes() ran."""
+        v = self.prototypes._version
+        if v != self._proto_version:
+            self._args.stream = torch.cuda.current_stream(self.dev).cuda_stream
+            check(_lib.load().stil_head_prepare_prototypes(C.byref(self._args)))
+            self._args.prototypes_prepared = 1
+            self._proto_version = v
+
     def _enqueue(self) -> None:
         self._args.stream = torch.cuda.current_stream(self.dev).cuda_stream
         check(_lib.load().stil_head_step(C.byref(self._args)))
@@ -125,6 +137,7 @@ class STiLHead:
     def capture(self) -> None:
         """Warm up once, then record the step into a CUDA graph (kernel params are baked in)."""
         with torch.cuda.device(self.dev):
+            self._ensure_prototypes()
             # the warm-up run must not leave a trace in the running accumulators (STiLModel.py:380-381)
             keep = (self.prototypes_sum.clone(), self.prototypes_count_sum.clone())
             s = torch.cuda.Stream(self.dev)
@@ -143,11 +156,13 @@ class STiLHead:
     def timed_run(self, names=False):
         """One un-captured step with CUDA events recorded (on the launching streams) around the launches of the two
         critical chains; returns the per-launch durations in milliseconds (bench.py's live kernel timing)."""
-        pairs = [("prep_kernel", 0, 1), ("gemm_tc05_kernel<STATS>[infonce x2, proto, teacher]", 1, 5),
-                 ("gemm_tc05_kernel<GRAD>[infonce x2]", 2, 3), ("gemm_tc05_kernel<STORE>[infonce x2]", 3, 4),
-                 ("cgpl_pgls_kernel", 5, 6), ("gemm_tc05_kernel<GRAD>[proto]", 6, 7),
-                 ("gemm_tc05_kernel<STORE>[proto]", 7, 8)]
-        n = 9
+        pairs = [("gemm_tc05_kernel<STATS>[proto, teacher]", 1, 5), ("cgpl_pgls_kernel", 5, 6),
+                 ("gemm_tc05_kernel<GRAD>[proto]", 6, 7), ("gemm_tc05_kernel<STORE>[proto]", 7, 8),
+                 ("prep_kernel[infonce]", 9, 10), ("gemm_tc05_kernel<STATS>[infonce x2]", 10, 2),
+                 ("gemm_tc05_kernel<GRAD>[infonce x2]", 2, 3), ("gemm_tc05_kernel<STORE>[infonce x2]", 3, 4)]
+        if self.cfg.embed_dtype != "bf16":
+            pairs.insert(0, ("prep_kernel[fp32 split]", 0, 1))
+        n = 11
         with torch.cuda.device(self.dev):
             st = torch.cuda.current_stream(self.dev)
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
@@ -156,6 +171,7 @@ class STiLHead:
             arr = (C.c_void_p * n)(*[e.cuda_event for e in evs])
             self._args.timing_events = C.cast(arr, C.c_void_p)
             self._args.n_timing_events = n
+            self._ensure_prototypes()
             try:
                 # keep the GPU busy while the host enqueues the whole step, so the event intervals are GPU-side
                 # durations rather than host launch gaps
@@ -171,6 +187,7 @@ class STiLHead:
     def run(self) -> None:
         """Enqueue one head step on the current stream (graph replay when captured)."""
         with torch.cuda.device(self.dev):
+            self._ensure_prototypes()
             if self.use_graph:
                 if self._graph is None:
                     self.capture()
@@ -208,6 +225,7 @@ class STiLHead:
             check(_lib.load().stil_proto_finalize(self.prototypes.data_ptr(), self.prototypes_sum.data_ptr(),
                                                   self.prototypes_count_sum.data_ptr(), k, d, empty.data_ptr(),
                                                   torch.cuda.current_stream(self.dev).cuda_stream))
+        self._proto_version = None      # written by the kernel, not through torch: force the operand refresh
         return empty
 
 
@@ -288,6 +306,7 @@ class DistributedSTiLHead(STiLHead):
         """Record kernels AND exchanges of one step into CUDA graphs (every rank must call this and later replay
         in lockstep).  The p2p transport alternates destination halves, hence one graph per parity."""
         with torch.cuda.device(self.dev):
+            self._ensure_prototypes()
             keep = (self.prototypes_sum.clone(), self.prototypes_count_sum.clone())
             s = torch.cuda.Stream(self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -310,6 +329,7 @@ class DistributedSTiLHead(STiLHead):
 
     def run(self) -> None:
         with torch.cuda.device(self.dev):
+            self._ensure_prototypes()
             parity = self._parity if self.transport == "p2p" else 0
             self._parity ^= 1
             if self.use_graph:

@@ -387,6 +387,40 @@ def test_head_step_full_size_vs_oracle(S, O, cfg_name, batch, graph):
     assert float((head.prototypes_count_sum.cpu() - 2 * o["class_count"]).abs().max()) <= 2e-5
 
 
+def test_head_prototype_operand_cache_follows_changes(S, O):
+    """The cached tensor-core form of the prototypes is refreshed after in-place torch writes and after the
+    epoch-end finalise (STiLModel.py:408-415) — graph replays included."""
+    from stil_tta_b200 import synth
+    cfg = synth.cardiac_config(256)
+    b = synth.make_batch(cfg, seed=3)
+    head = S.STiLHead(cfg, device="cuda", use_graph=True)
+    head.load(b)
+    head.run()
+    torch.cuda.synchronize()
+    l0 = head.out["losses"].clone()
+    # 1. in-place torch write
+    b2 = dict(b)
+    b2["prototypes"] = b["prototypes"] * 0.5
+    head.prototypes.copy_(b2["prototypes"])
+    head.run()
+    torch.cuda.synchronize()
+    o2 = O.head_step(b2, cfg, with_grads=False)
+    assert abs(float(head.out["losses"][1]) - float(o2["loss_pt"])) <= REL * abs(float(o2["loss_pt"])) + 1e-6
+    assert not torch.equal(l0, head.out["losses"])
+    # 2. epoch-end finalise writes the prototypes from a kernel
+    head.prototypes_sum.copy_(torch.randn(cfg.num_classes, cfg.proj_dim) * 0.1)
+    head.prototypes_count_sum.fill_(2.0)
+    expect = (head.prototypes_sum / head.prototypes_count_sum).cpu()
+    head.finalize_prototypes()
+    head.run()
+    torch.cuda.synchronize()
+    b3 = dict(b)
+    b3["prototypes"] = expect
+    o3 = O.head_step(b3, cfg, with_grads=False)
+    assert abs(float(head.out["losses"][1]) - float(o3["loss_pt"])) <= REL * abs(float(o3["loss_pt"])) + 1e-6
+    assert torch.equal(head.out["mask1"].cpu(), o3["mask1"]) or int(O.ambiguous_rows(b3, cfg).sum()) > 0
+
+
 def test_head_step_host_end_to_end(S, O):
     from stil_tta_b200 import synth
     cfg = synth.dvm_config(512)
