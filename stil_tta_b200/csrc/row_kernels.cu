@@ -529,15 +529,20 @@ __device__ __forceinline__ void load4_as_float(const void* feat, int dtype, long
     }
 }
 
+// One block per class; the block's warps split the rows (contiguous ranges), each warp adds its matching rows in
+// index order, and the per-warp partials are combined in warp order — the result does not depend on scheduling.
 __global__ void __launch_bounds__(kRowBlock) proto_accumulate_kernel(const void* __restrict__ feat, int dtype, int rows,
                                                                      int dim, long long ld,
                                                                      const int* __restrict__ cls,
                                                                      const unsigned char* __restrict__ conf, int b_l,
                                                                      float repeat_ratio, int k, float* class_sum,
                                                                      float* class_count, float* psum, float* pcount) {
-    __shared__ int codes[kAccChunk];   // class of a confident row, -1 otherwise
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    __shared__ int codes[kAccChunk];                       // class of a confident row, -1 otherwise
+    __shared__ float part[2][kRowBlock / 32][128];         // [labelled | unlabelled][warp][dim slab]
+    __shared__ float cnt[2][kRowBlock / 32];
+    const int c = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarp = blockDim.x >> 5;
     const bool vec = (dim % 4 == 0) && (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(feat) % 16 == 0);
     for (int d0 = 0; d0 < dim; d0 += 128) {
         float al[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
@@ -548,12 +553,15 @@ __global__ void __launch_bounds__(kRowBlock) proto_accumulate_kernel(const void*
             __syncthreads();
             for (int i = threadIdx.x; i < nrow; i += blockDim.x) codes[i] = conf[base + i] ? cls[base + i] : -1;
             __syncthreads();
-            if (c >= k) continue;
-            for (int r0 = 0; r0 < nrow; r0 += 32) {
+            // this warp's contiguous share of the chunk, in units of 32 rows
+            const int groups = (nrow + 31) / 32;
+            const int per = (groups + nwarp - 1) / nwarp;
+            for (int gi = warp * per; gi < min(groups, (warp + 1) * per); ++gi) {
+                const int r0 = gi * 32;
                 const bool hit = (r0 + lane < nrow) && codes[r0 + lane] == c;
                 unsigned int ballot = __ballot_sync(0xffffffffu, hit);
                 while (ballot) {
-                    // up to four matching rows in flight, added in ascending row order (deterministic)
+                    // up to four matching rows in flight, added in ascending row order
                     int idx[4];
                     int n = 0;
 #pragma unroll
@@ -582,17 +590,38 @@ __global__ void __launch_bounds__(kRowBlock) proto_accumulate_kernel(const void*
                 }
             }
         }
-        if (c >= k) continue;
+        // combine the warps' partials in warp order
+        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (d + j < dim) {
-                const float v = __fadd_rn(__fdiv_rn(al[j], repeat_ratio), au[j]);   // :224
-                class_sum[(long long)c * dim + d + j] = v;
-                if (psum) psum[(long long)c * dim + d + j] += v;                     // :380
+        for (int q = 0; q < 4; ++q) {
+            part[0][warp][lane * 4 + q] = al[q];
+            part[1][warp][lane * 4 + q] = au[q];
+        }
+        if (lane == 0) {
+            cnt[0][warp] = nl;
+            cnt[1][warp] = nu;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < 128; t += blockDim.x) {
+            const int dd = d0 + t;
+            if (dd < dim) {
+                float sl = 0.f, su = 0.f;
+                for (int w = 0; w < nwarp; ++w) {
+                    sl += part[0][w][t];
+                    su += part[1][w][t];
+                }
+                const float v = __fadd_rn(__fdiv_rn(sl, repeat_ratio), su);         // :224
+                class_sum[(long long)c * dim + dd] = v;
+                if (psum) psum[(long long)c * dim + dd] += v;                        // :380
             }
         }
-        if (d0 == 0 && lane == 0) {
-            const float v = __fadd_rn(__fdiv_rn(nl, repeat_ratio), nu);             // :225
+        if (d0 == 0 && threadIdx.x == 0) {
+            float sl = 0.f, su = 0.f;
+            for (int w = 0; w < nwarp; ++w) {
+                sl += cnt[0][w];
+                su += cnt[1][w];
+            }
+            const float v = __fadd_rn(__fdiv_rn(sl, repeat_ratio), su);             // :225
             class_count[c] = v;
             if (pcount) pcount[c] += v;                                              // :381
         }
@@ -1004,8 +1033,9 @@ int launch_proto_accumulate(const void* feat, int dtype, int64_t rows, int64_t d
     if (k == 0) return STIL_OK;
     static const bool once = (prefer_max_shared(proto_accumulate_kernel), true);
     (void)once;
-    const int acc_threads = k <= 1024 ? 128 : kRowBlock;
-    proto_accumulate_kernel<<<(int)ceil_div(k, acc_threads / 32), acc_threads, 0, stream>>>(
+    // one block per class; few classes with many rows each (cardiac, K=2) get 8 warps, many small classes 2
+    const int acc_threads = (rows / (k > 0 ? k : 1)) >= 16 ? kRowBlock : 64;
+    proto_accumulate_kernel<<<(int)k, acc_threads, 0, stream>>>(
         feat, dtype, (int)rows, (int)dim, ld, cls, conf, (int)b_l, repeat_ratio, (int)k, class_sum, class_count, psum,
         pcount);
     STIL_LAUNCH_CHECK();
