@@ -1159,7 +1159,7 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     STIL_CUDA(cudaStreamWaitEvent(s_loss, SS->fork2, 0));
     if (nce) STIL_CUDA(cudaStreamWaitEvent(s_loss, SS->nce_stats, 0));
     STIL_CUDA(cudaStreamWaitEvent(s_acc, SS->fork2, 0));
-    STIL_CUDA(cudaStreamWaitEvent(s_ce, SS->fork2, 0));
+    if (a->y_m) STIL_CUDA(cudaStreamWaitEvent(s_ce, SS->fork2, 0));
 
     // 5. side branches
     {   // losses and LSE vectors
@@ -1202,6 +1202,8 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
 
     // ---- join
     for (int i = 0; i < kSide; ++i) {
+        if (SS->s[i] == s_nce && !nce) continue;   // that stream never joined this step (nothing was forked to it)
+        if (SS->s[i] == s_ce && !a->y_m) continue;
         STIL_CUDA(cudaEventRecord(SS->join[i], SS->s[i]));
         STIL_CUDA(cudaStreamWaitEvent(st, SS->join[i], 0));
     }
