@@ -41,6 +41,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/), or None."""
+    f = REPO / "profiles" / "r1_traffic.json"
+    if f.exists():
+        d = json.loads(f.read_text()).get(kernel)
+        if d:
+            return d["dram_bytes_per_launch"]
+    return None
+
+
 def get_cfg(name: str):
     from stil_tta_b200 import synth
     return synth.CONFIGS[name]()
@@ -386,7 +396,8 @@ def run_gpu_arm(args):
         t_avg = sum(gemm_us) / n_l * 1e-6
         ach = flops_step / n_l / t_avg / 1e12
         line["roofline"] = {"kernel": "gemm_tc05_kernel", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"],
-                            "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+                            "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                            "traffic": ncu_traffic("gemm_tc05_kernel") if args.config == "C2" else None,
                             "peak_source": pk["src"] + " bf16 sustained", "launches_per_step": n_l,
                             "us_per_launch": t_avg * 1e6, "alg_flops_per_launch": flops_step / n_l,
                             "share_of_timed_launches": sum(gemm_us) / sum(kern.values())}
@@ -394,7 +405,8 @@ def run_gpu_arm(args):
         top = rl["cgpl_pgls_kernel"]
         line["roofline_hbm_kernel"] = {"kernel": "cgpl_pgls_kernel", "bound": "hbm", "achieved": top["achieved"],
                                        "peak": top["peak"], "unit": "GB/s", "frac": top["achieved"] / top["peak"],
-                                       "us_per_launch": top["seconds"] * 1e6, "alg_bytes_per_launch": top["alg_bytes"]}
+                                       "us_per_launch": top["seconds"] * 1e6, "alg_bytes_per_launch": top["alg_bytes"],
+                                       "traffic": ncu_traffic("cgpl_pgls_kernel") if args.config == "C2" else None}
         line["kernel_us"] = {k: round(v, 2) for k, v in kern.items()}
         if world == 1 and not args.no_cpu_baseline:
             ms_cpu, done, n = cpu_reference_steps(cfg, 400, 3, budget_s=15.0)
