@@ -175,6 +175,73 @@ STIL_API int stil_simmatch_bwd(const void* feat_qu, int dtype, int64_t rows, int
                       void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a8 / a9 — memory-bank smoothing of a pseudo-label distribution.  Replaces comatch_model.py:288-293 (c_keep = alpha,
+ * c_bank = 1 - alpha) and MMatch.py:222-227 (the literals 0.9 / 0.1), followed by the max / argmax / threshold of
+ * MMatch.py:229-230 / CoMatch.py:92-93:
+ *   A = rownorm(exp(feat · queue_feat / T));   out = c_keep * probs + c_bank * (A · queue_probsᵀ)
+ *   max_prob, max_idx = max(out, dim=1);  mask = max_prob >= th            (each output pointer may be NULL)
+ *   feat [rows, dim]; queue_feat [dim, k_q] in the REFERENCE layout, same dtype as feat, read in place;
+ *   queue_probs [num_classes, k_q] f32.  queue_feat == NULL: no bank yet (epoch gate) — out = probs. */
+STIL_API int64_t stil_bank_smooth_workspace_bytes(int64_t rows, int64_t k_q, int64_t dim, int64_t num_classes, int dtype);
+STIL_API int stil_bank_smooth(const float* probs, int64_t ld_p, int64_t rows, int64_t num_classes, const void* feat, int dtype,
+                              int64_t dim, int64_t ld_f, const void* queue_feat, int64_t ld_q, const float* queue_probs,
+                              int64_t ld_qp, int64_t k_q, float temperature, float c_keep, float c_bank, float* out,
+                              int64_t ld_out, float th, float* max_prob, int64_t* max_idx, uint8_t* mask, void* workspace,
+                              int64_t workspace_bytes, void* stream);
+
+/* a8 — CoMatch pseudo-label graph and embedding graph.  Replaces comatch_model.py:298-312:
+ *   Q   = [probs · probsᵀ with diagonal 1 | probs · probs_u]                  [rows, rows + k_q] f32
+ *   sim = exp([feat_s0 · feat_s1ᵀ | feat_s0 · queue_s] / T)                    [rows, rows + k_q] f32
+ *   probs [rows, C] f32; probs_u [C, k_q] f32; queue_s [dim, k_q] (reference layouts), same dtype as the features.
+ * stil_comatch_sim_bwd turns grad_sim into d_feat_s0 (the only differentiable input, :309-311); it has its own
+ * workspace. */
+STIL_API int64_t stil_comatch_graphs_workspace_bytes(int64_t rows, int64_t k_q, int64_t dim, int64_t num_classes, int dtype);
+STIL_API int stil_comatch_graphs_fwd(const float* probs, int64_t ld_p, int64_t rows, int64_t num_classes,
+                                     const float* probs_u, int64_t ld_pu, const void* feat_s0, const void* feat_s1, int dtype,
+                                     int64_t dim, int64_t ld_f, const void* queue_s, int64_t ld_q, int64_t k_q,
+                                     float temperature, float* Q, float* sim, int64_t ld_out, void* workspace,
+                                     int64_t workspace_bytes, void* stream);
+STIL_API int64_t stil_comatch_sim_bwd_workspace_bytes(int64_t rows, int64_t k_q, int64_t dim, int dtype);
+STIL_API int stil_comatch_sim_bwd(const float* grad_sim, const float* sim, int64_t ld, int64_t rows, int64_t k_q,
+                                  const void* feat_s1, int dtype, int64_t dim, int64_t ld_f, const void* queue_s,
+                                  int64_t ld_q, float temperature, void* d_feat_s0, int grad_dtype, int64_t ld_grad,
+                                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* a8 consumer — CoMatch graph contrastive loss.  Replaces CoMatch.py:100-110:
+ *   pos = Q >= contrast_th;  w = Q*pos / rowsum;  p = sim*pos / rowsum(sim);  loss = mean_i -sum_j w log(p + 1e-7) pos
+ *   d_sim (NULL to skip) = d loss / d sim * grad_scale, [rows, ld].
+ * stil_row_loss_workspace_bytes sizes the scratch of this and of stil_weighted_softce. */
+STIL_API int64_t stil_row_loss_workspace_bytes(int64_t rows);
+STIL_API int stil_graph_contrast_loss(const float* Q, const float* sim, int64_t ld, int64_t rows, int64_t cols,
+                                      float contrast_th, float* loss, float* d_sim, float grad_scale, void* workspace,
+                                      int64_t workspace_bytes, void* stream);
+
+/* f-1 for the single-head consumers of a7-a9: loss = mean_i mask_i * CE(logits_i, target_i), forward + gradient.
+ * Exactly one of target_probs [rows, k] f32 (SimMatch.py:91, CoMatch.py:96-97) and target_idx [rows] int64 (the dense
+ * one-hot hard label of MMatch.py:231-234) is given; mask may be NULL (all rows); d_logits may be NULL. */
+STIL_API int stil_weighted_softce(const void* logits, int logit_dtype, int64_t ld_y, const float* target_probs, int64_t ld_t,
+                                  const int64_t* target_idx, const uint8_t* mask, int64_t rows, int64_t k, float* loss,
+                                  float* d_logits, int64_t ld_g, float grad_scale, void* workspace, int64_t workspace_bytes,
+                                  void* stream);
+
+/* Queue / bank maintenance next to a7-a9 (SURVEY f-4).
+ *   stil_queue_enqueue : queue_feat[:, ptr:ptr+n'] = z[:n'].T; queue_probs[:, ptr:ptr+n'] = t[:n'].T with
+ *                        n' = min(n, k_q - ptr); ptr = (ptr + n') % k_q     (comatch_model.py:117-146, MMatch.py:102-117).
+ *                        ptr is the reference's int64 [1] buffer ON THE DEVICE (no host sync, unlike `int(self.queue_ptr)`).
+ *   stil_bank_update   : bank[:, index] = k.T; labels[index] = y             (simmatch_model.py:141-147)
+ *   stil_da_apply_hist : CoMatch's list-based distribution alignment (comatch_model.py:271-285) as a ring of the last
+ *                        hist_len batch means: hist[count % hist_len] = batch_mean; count += 1;
+ *                        out = rownorm(probs / mean(valid rows of hist)); count is an int64 [1] on the device. */
+STIL_API int stil_queue_enqueue(void* queue_feat, int q_dtype, int64_t ld_q, float* queue_probs, int64_t ld_qp, int64_t k_q,
+                                int64_t* ptr, const void* z, int z_dtype, int64_t ld_z, int64_t n, int64_t dim, const float* t,
+                                int64_t ld_t, int64_t num_classes, void* stream);
+STIL_API int stil_bank_update(void* bank, int b_dtype, int64_t ld_bank, int64_t* labels, const void* k, int k_dtype,
+                              int64_t ld_k, const int64_t* y, const int64_t* index, int64_t n, int64_t dim, void* stream);
+STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* hist,
+                                int64_t hist_len, int64_t* count, float* qmean_scratch, float* out, int64_t ld_out,
+                                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * f-1 — masked soft-target CE of the three student heads on the unlabelled rows, forward and
  * gradient in one pass.  Replaces STiLModel.py:301-303.
  *   losses[3]  = (loss_m_u, loss_i_u, loss_t_u), each a mean over `rows`

@@ -12,7 +12,11 @@ _LAZY = {
     "CLIPLoss": "losses", "PrototypeLoss": "losses", "masked_soft_ce": "losses", "label_argmax": "losses",
     "cgpl_pgls": "pseudo_label", "distribution_alignment": "pseudo_label", "prototype_logits": "pseudo_label", "PseudoLabels": "pseudo_label",
     "cal_prototypes": "prototypes", "cal_prototypes_separate": "prototypes", "PrototypeBank": "prototypes",
-    "simmatch_bank": "bank", "alloc_bank": "bank", "STiLHead": "head", "DistributedSTiLHead": "head", "GlobalBatch": "distributed", "P2PBuffer": "distributed", "all_reduce_prototype_partials": "distributed",
+    "simmatch_bank": "bank", "alloc_bank": "bank",
+    "bank_smooth": "bank_blocks", "mmatch_pseudo_label": "bank_blocks", "comatch_smooth": "bank_blocks",
+    "comatch_graphs": "bank_blocks", "graph_contrast_loss": "bank_blocks", "masked_ce": "bank_blocks",
+    "queue_enqueue": "bank_blocks", "update_bank": "bank_blocks", "HistAlignment": "bank_blocks",
+    "SmoothedLabels": "bank_blocks", "STiLHead": "head", "DistributedSTiLHead": "head", "GlobalBatch": "distributed", "P2PBuffer": "distributed", "all_reduce_prototype_partials": "distributed",
 }
 
 

@@ -82,6 +82,20 @@ SIGNATURES = {
     "stil_simmatch_fwd": (i32, [vp, vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, f32, f32, f32, vp, vp, i32, vp,
                                 i64, vp]),
     "stil_simmatch_bwd": (i32, [vp, i32, i64, i64, vp, i64, i64, vp, vp, i32, i64, vp, i64, vp]),
+    "stil_bank_smooth_workspace_bytes": (i64, [i64, i64, i64, i64, i32]),
+    "stil_bank_smooth": (i32, [vp, i64, i64, i64, vp, i32, i64, i64, vp, i64, vp, i64, i64, f32, f32, f32, vp, i64, f32,
+                               vp, vp, vp, vp, i64, vp]),
+    "stil_comatch_graphs_workspace_bytes": (i64, [i64, i64, i64, i64, i32]),
+    "stil_comatch_graphs_fwd": (i32, [vp, i64, i64, i64, vp, i64, vp, vp, i32, i64, i64, vp, i64, i64, f32, vp, vp, i64,
+                                      vp, i64, vp]),
+    "stil_comatch_sim_bwd_workspace_bytes": (i64, [i64, i64, i64, i32]),
+    "stil_comatch_sim_bwd": (i32, [vp, vp, i64, i64, i64, vp, i32, i64, i64, vp, i64, f32, vp, i32, i64, vp, i64, vp]),
+    "stil_row_loss_workspace_bytes": (i64, [i64]),
+    "stil_graph_contrast_loss": (i32, [vp, vp, i64, i64, i64, f32, vp, vp, f32, vp, i64, vp]),
+    "stil_weighted_softce": (i32, [vp, i32, i64, vp, i64, vp, vp, i64, i64, vp, vp, i64, f32, vp, i64, vp]),
+    "stil_queue_enqueue": (i32, [vp, i32, i64, vp, i64, i64, vp, vp, i32, i64, i64, i64, vp, i64, i64, vp]),
+    "stil_bank_update": (i32, [vp, i32, i64, vp, vp, i32, i64, vp, vp, i64, i64, vp]),
+    "stil_da_apply_hist": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
     "stil_masked_softce_workspace_bytes": (i64, [i64]),
     "stil_masked_softce": (i32, [vp, vp, vp, i32, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64,
                                  f32, vp, i64, vp]),

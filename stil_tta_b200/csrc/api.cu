@@ -918,6 +918,338 @@ STIL_API int stil_masked_softce(const void* y_m, const void* y_i, const void* y_
                                 ticket, S(stream));
 }
 
+// =============================================================================================== a8 / a9
+namespace {
+inline int64_t pad8(int64_t n) { return round_up(n, 8); }
+
+// a matrix stored [contraction rows, n contiguous] (the reference's queue layout [dim, K_q] / [C, K_q]) presented as
+// an MN-major Y operand: bf16 in place, fp32 via its segment form [rows, 3, pad8(n)]
+Operand colmajor_operand(const void* x, int dtype, int64_t n, int64_t ld, const __nv_bfloat16* op) {
+    Operand O;
+    if (dtype == STIL_BF16) {
+        O.base = static_cast<const __nv_bfloat16*>(x);
+        O.nseg = 1; O.row_stride = ld; O.seg_stride = pad8(n);
+    } else {
+        O.base = op;
+        O.nseg = 3; O.row_stride = 3 * pad8(n); O.seg_stride = pad8(n);
+    }
+    return O;
+}
+PrepJob prep_job_padded(const void* x, int dtype, int64_t rows, int64_t dim, int64_t ld, __nv_bfloat16* op, int64_t op_dim) {
+    PrepJob j = prep_job(x, dtype, rows, dim, ld, 3, op, nullptr, 0, 0, nullptr);
+    j.op_dim = (int)op_dim;
+    return j;
+}
+int check_queue(const void* q, int dtype, int64_t k_q, int64_t ld_q, const char* what) {
+    const int per16 = dtype == STIL_BF16 ? 8 : 4;
+    STIL_REQUIRE(q && k_q >= 1 && ld_q >= k_q && ld_q % per16 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
+                 STIL_E_ALIGN, "%s [dim, k_q]: leading dimension %lld must be >= k_q and a multiple of %d, base 16-byte aligned",
+                 what, (long long)ld_q, per16);
+    return STIL_OK;
+}
+
+struct SmoothPlan {
+    __nv_bfloat16 *f_op, *q_op, *qp_op;   // feat [rows,3,dim] | queue [dim,3,pad8(k_q)] (fp32 only) | queue_probs [C,3,pad8(k_q)]
+    float* z;                              // [rows, ldz]
+    int64_t ldz;
+    __nv_bfloat16* a_op;                   // [rows, 2, ldg]
+    int64_t ldg;
+    float* s;                              // [rows, lds] = A · queue_probsᵀ
+    int64_t lds;
+    int64_t bytes;
+};
+SmoothPlan plan_smooth(void* ws, int64_t ws_bytes, int64_t rows, int64_t k_q, int64_t dim, int64_t c, int dtype) {
+    SmoothPlan P;
+    Workspace W(ws, ws_bytes);
+    P.ldz = round_up(k_q, 4);
+    P.ldg = pad32(k_q);
+    P.lds = round_up(c, 4);
+    P.f_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(rows * 3 * dim);
+    P.q_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(dim * 3 * pad8(k_q));
+    P.qp_op = W.take<__nv_bfloat16>(c * 3 * pad8(k_q));
+    P.z = W.take<float>(rows * P.ldz);
+    P.a_op = W.take<__nv_bfloat16>(rows * 2 * P.ldg);
+    P.s = W.take<float>(rows * P.lds);
+    P.bytes = W.off;
+    return P;
+}
+}  // namespace
+
+STIL_API int64_t stil_bank_smooth_workspace_bytes(int64_t rows, int64_t k_q, int64_t dim, int64_t num_classes, int dtype) {
+    return plan_smooth(nullptr, 0, rows, k_q, dim, num_classes, dtype).bytes;
+}
+
+STIL_API int stil_bank_smooth(const float* probs, int64_t ld_p, int64_t rows, int64_t num_classes, const void* feat, int dtype,
+                              int64_t dim, int64_t ld_f, const void* queue_feat, int64_t ld_q, const float* queue_probs,
+                              int64_t ld_qp, int64_t k_q, float temperature, float c_keep, float c_bank, float* out,
+                              int64_t ld_out, float th, float* max_prob, int64_t* max_idx, uint8_t* mask, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+    STIL_REQUIRE(probs && num_classes >= 1 && ld_p >= num_classes && (out == nullptr || ld_out >= num_classes), STIL_E_ARG,
+                 "bank_smooth: bad probs / out arguments");
+    if (queue_feat == nullptr)   // before the bank is used (MMatch.py:221 `current_epoch > 0`, comatch_model.py:288)
+        return launch_smooth_mix(probs, ld_p, nullptr, 0, rows, num_classes, 1.f, 0.f, out, ld_out, th, max_prob, max_idx,
+                                 mask, S(stream));
+    int rc = check_embed(feat, dtype, rows, dim, ld_f, "bank_smooth feat");
+    if (rc) return rc;
+    if ((rc = check_queue(queue_feat, dtype, k_q, ld_q, "bank_smooth queue_feat"))) return rc;
+    STIL_REQUIRE(queue_probs && ld_qp >= k_q && temperature > 0.f, STIL_E_ARG, "bank_smooth: bad queue_probs / temperature");
+    SmoothPlan P = plan_smooth(workspace, workspace_bytes, rows, k_q, dim, num_classes, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "bank_smooth workspace too small: need %lld",
+                 (long long)P.bytes);
+    if (rows == 0) return STIL_OK;
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    if (dtype != STIL_BF16) {
+        prep_add(PL, prep_job(feat, dtype, rows, dim, ld_f, 3, P.f_op, nullptr, 0, 0, nullptr));
+        prep_add(PL, prep_job_padded(queue_feat, dtype, dim, k_q, ld_q, P.q_op, pad8(k_q)));
+    }
+    prep_add(PL, prep_job_padded(queue_probs, STIL_F32, num_classes, k_q, ld_qp, P.qp_op, pad8(k_q)));
+    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    // z = feat · queue_feat (queue read in place in the reference layout)
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    const Operand X = rowmajor_operand(feat, dtype, dim, ld_f, P.f_op, 3);
+    const Operand Qf = colmajor_operand(queue_feat, dtype, k_q, ld_q, P.q_op);
+    if ((rc = fill_gemm_store_mn(GL.job[0], X, rows, Qf, dim, k_q))) return rc;
+    GL.job[0].npair = seg_pairs(X.nseg, Qf.nseg, 2, GL.job[0].xseg, GL.job[0].yseg);
+    GL.job[0].out = P.z;
+    GL.job[0].ld_out = P.ldz;
+    GL.njobs = 1;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    // A = rownorm(exp(z / T)) as a bf16 hi/lo operand, then s = A · queue_probsᵀ
+    if ((rc = launch_bank_softmax_rows(P.z, P.ldz, rows, k_q, temperature, P.a_op, P.ldg, 2, S(stream)))) return rc;
+    std::memset(&GL, 0, sizeof(GL));
+    const Operand A = grad_operand(P.a_op, P.ldg, 2);
+    Operand Qp;
+    Qp.base = P.qp_op; Qp.nseg = 3; Qp.row_stride = 3 * pad8(k_q); Qp.seg_stride = pad8(k_q);
+    if ((rc = fill_gemm_common(GL.job[0], A, 0, rows, Qp, num_classes, k_q, 2))) return rc;
+    GL.job[0].mode = GEMM_STORE;
+    GL.job[0].out = P.s;
+    GL.job[0].ld_out = P.lds;
+    GL.njobs = 1;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    return launch_smooth_mix(probs, ld_p, P.s, P.lds, rows, num_classes, c_keep, c_bank, out, ld_out, th, max_prob, max_idx,
+                             mask, S(stream));
+}
+
+namespace {
+struct GraphPlan {
+    __nv_bfloat16 *p_op, *pu_op;          // probs [rows,3,pad8(C)] | probs_u [C,3,pad8(k_q)]
+    __nv_bfloat16 *f0_op, *f1_op, *qs_op; // fp32 features / queue only
+    int64_t bytes;
+};
+GraphPlan plan_graph(void* ws, int64_t ws_bytes, int64_t rows, int64_t k_q, int64_t dim, int64_t c, int dtype) {
+    GraphPlan P;
+    Workspace W(ws, ws_bytes);
+    P.p_op = W.take<__nv_bfloat16>(rows * 3 * pad8(c));
+    P.pu_op = W.take<__nv_bfloat16>(c * 3 * pad8(k_q));
+    const bool f32 = dtype != STIL_BF16;
+    P.f0_op = f32 ? W.take<__nv_bfloat16>(rows * 3 * dim) : nullptr;
+    P.f1_op = f32 ? W.take<__nv_bfloat16>(rows * 3 * dim) : nullptr;
+    P.qs_op = f32 ? W.take<__nv_bfloat16>(dim * 3 * pad8(k_q)) : nullptr;
+    P.bytes = W.off;
+    return P;
+}
+}  // namespace
+
+STIL_API int64_t stil_comatch_graphs_workspace_bytes(int64_t rows, int64_t k_q, int64_t dim, int64_t num_classes, int dtype) {
+    return plan_graph(nullptr, 0, rows, k_q, dim, num_classes, dtype).bytes;
+}
+
+STIL_API int stil_comatch_graphs_fwd(const float* probs, int64_t ld_p, int64_t rows, int64_t num_classes,
+                                     const float* probs_u, int64_t ld_pu, const void* feat_s0, const void* feat_s1, int dtype,
+                                     int64_t dim, int64_t ld_f, const void* queue_s, int64_t ld_q, int64_t k_q,
+                                     float temperature, float* Q, float* sim, int64_t ld_out, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+    int rc = check_embed(feat_s0, dtype, rows, dim, ld_f, "comatch feat_s0");
+    if (rc) return rc;
+    if ((rc = check_embed(feat_s1, dtype, rows, dim, ld_f, "comatch feat_s1"))) return rc;
+    if ((rc = check_queue(queue_s, dtype, k_q, ld_q, "comatch queue_s"))) return rc;
+    STIL_REQUIRE(probs && probs_u && Q && sim && num_classes >= 1 && ld_p >= num_classes && ld_pu >= k_q &&
+                     ld_out >= rows + k_q && temperature > 0.f,
+                 STIL_E_ARG, "comatch_graphs_fwd: bad arguments");
+    GraphPlan P = plan_graph(workspace, workspace_bytes, rows, k_q, dim, num_classes, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "comatch_graphs workspace too small: need %lld",
+                 (long long)P.bytes);
+    if (rows == 0) return STIL_OK;
+    const int64_t cp = pad8(num_classes);
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    prep_add(PL, prep_job_padded(probs, STIL_F32, rows, num_classes, ld_p, P.p_op, cp));
+    prep_add(PL, prep_job_padded(probs_u, STIL_F32, num_classes, k_q, ld_pu, P.pu_op, pad8(k_q)));
+    if (dtype != STIL_BF16) {
+        prep_add(PL, prep_job(feat_s0, dtype, rows, dim, ld_f, 3, P.f0_op, nullptr, 0, 0, nullptr));
+        prep_add(PL, prep_job(feat_s1, dtype, rows, dim, ld_f, 3, P.f1_op, nullptr, 0, 0, nullptr));
+        prep_add(PL, prep_job_padded(queue_s, dtype, dim, k_q, ld_q, P.qs_op, pad8(k_q)));
+    }
+    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    Operand Pr;
+    Pr.base = P.p_op; Pr.nseg = 3; Pr.row_stride = 3 * cp; Pr.seg_stride = cp;
+    Operand Pu;
+    Pu.base = P.pu_op; Pu.nseg = 3; Pu.row_stride = 3 * pad8(k_q); Pu.seg_stride = pad8(k_q);
+    const Operand F0 = rowmajor_operand(feat_s0, dtype, dim, ld_f, P.f0_op, 3);
+    const Operand F1 = rowmajor_operand(feat_s1, dtype, dim, ld_f, P.f1_op, 3);
+    const Operand Qs = colmajor_operand(queue_s, dtype, k_q, ld_q, P.qs_op);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    // Q_self = probs · probsᵀ with the diagonal forced to 1 (comatch_model.py:299-300)
+    if ((rc = fill_gemm_common(GL.job[0], Pr, 0, rows, Pr, rows, num_classes, 2))) return rc;
+    GL.job[0].mode = GEMM_STORE; GL.job[0].out = Q; GL.job[0].ld_out = ld_out; GL.job[0].post_op = 2;
+    // Q_past = probs · probs_u (:303-304), probs_u [C, k_q] read as an MN-major operand
+    if ((rc = fill_gemm_store_mn(GL.job[1], Pr, rows, Pu, num_classes, k_q))) return rc;
+    GL.job[1].npair = seg_pairs(3, 3, 2, GL.job[1].xseg, GL.job[1].yseg);
+    GL.job[1].out = Q + rows; GL.job[1].ld_out = ld_out;
+    // sim_self = exp(f_s0 · f_s1ᵀ / T) (:310)
+    if ((rc = fill_gemm_common(GL.job[2], F0, 0, rows, F1, rows, dim, 2))) return rc;
+    GL.job[2].mode = GEMM_STORE; GL.job[2].alpha = 1.0f / temperature; GL.job[2].out = sim; GL.job[2].ld_out = ld_out;
+    GL.job[2].post_op = 1;
+    // sim_past = exp(f_s0 · queue_s / T) (:311-312)
+    if ((rc = fill_gemm_store_mn(GL.job[3], F0, rows, Qs, dim, k_q))) return rc;
+    GL.job[3].npair = seg_pairs(F0.nseg, Qs.nseg, 2, GL.job[3].xseg, GL.job[3].yseg);
+    GL.job[3].alpha = 1.0f / temperature; GL.job[3].out = sim + rows; GL.job[3].ld_out = ld_out; GL.job[3].post_op = 1;
+    GL.njobs = 4;
+    gemm_job_tiles(GL);
+    return launch_gemm(GL, S(stream));
+}
+
+STIL_API int stil_comatch_sim_bwd(const float* grad_sim, const float* sim, int64_t ld, int64_t rows, int64_t k_q,
+                                  const void* feat_s1, int dtype, int64_t dim, int64_t ld_f, const void* queue_s,
+                                  int64_t ld_q, float temperature, void* d_feat_s0, int grad_dtype, int64_t ld_grad,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+    STIL_REQUIRE(grad_sim && sim && d_feat_s0 && ld >= rows + k_q && temperature > 0.f, STIL_E_ARG,
+                 "comatch_sim_bwd: bad arguments");
+    STIL_REQUIRE(grad_dtype == STIL_F32 || grad_dtype == STIL_BF16, STIL_E_DTYPE, "bad grad dtype");
+    int rc = check_embed(feat_s1, dtype, rows, dim, ld_f, "comatch feat_s1");
+    if (rc) return rc;
+    if ((rc = check_queue(queue_s, dtype, k_q, ld_q, "comatch queue_s"))) return rc;
+    STIL_REQUIRE(workspace != nullptr, STIL_E_WORKSPACE, "comatch_sim_bwd: null workspace");
+    if (rows == 0) return STIL_OK;
+    // the backward has its own workspace (stil_comatch_sim_bwd_workspace_bytes): [gs | gp | g | (fp32) f1_op, qs_op]
+    Workspace W(workspace, workspace_bytes);
+    const int nseg = grad_nseg(grad_dtype);
+    __nv_bfloat16* gs = W.take<__nv_bfloat16>(rows * 2 * pad32(rows));
+    __nv_bfloat16* gp = W.take<__nv_bfloat16>(rows * 2 * pad32(k_q));
+    float* g = W.take<float>(rows * dim);
+    __nv_bfloat16* f1_op = dtype != STIL_BF16 ? W.take<__nv_bfloat16>(rows * 3 * dim) : nullptr;
+    __nv_bfloat16* qs_op = dtype != STIL_BF16 ? W.take<__nv_bfloat16>(dim * 3 * pad8(k_q)) : nullptr;
+    STIL_REQUIRE(W.off <= workspace_bytes, STIL_E_WORKSPACE, "comatch_sim_bwd workspace too small: need %lld", (long long)W.off);
+    if (dtype != STIL_BF16) {
+        PrepLaunch PL;
+        std::memset(&PL, 0, sizeof(PL));
+        prep_add(PL, prep_job(feat_s1, dtype, rows, dim, ld_f, 3, f1_op, nullptr, 0, 0, nullptr));
+        prep_add(PL, prep_job_padded(queue_s, dtype, dim, k_q, ld_q, qs_op, pad8(k_q)));
+        if ((rc = launch_prep(PL, S(stream)))) return rc;
+    }
+    if ((rc = launch_sim_grad(grad_sim, sim, ld, rows, rows, k_q, temperature, gs, pad32(rows), gp, pad32(k_q), nseg,
+                              S(stream))))
+        return rc;
+    STIL_CUDA(cudaMemsetAsync(g, 0, rows * dim * sizeof(float), S(stream)));
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    // d_f_s0 = G_self · f_s1 (f_s1 [rows, dim] as an MN-major operand) + G_past · queue_sᵀ (queue_s [dim, k_q] K-major);
+    // both jobs add into g (split-contraction mode)
+    const Operand Gs = grad_operand(gs, pad32(rows), nseg), Gp = grad_operand(gp, pad32(k_q), nseg);
+    const Operand F1 = rowmajor_operand(feat_s1, dtype, dim, ld_f, f1_op, 3);
+    const Operand Qs = colmajor_operand(queue_s, dtype, k_q, ld_q, qs_op);
+    if ((rc = fill_gemm_store_mn(GL.job[0], Gs, rows, F1, rows, dim))) return rc;
+    GL.job[0].out = g; GL.job[0].ld_out = dim;
+    GL.job[0].ksplit = (int)std::max<int64_t>(2, std::min<int64_t>(ceil_div(rows, kTileK), 8));
+    if ((rc = fill_gemm_common(GL.job[1], Gp, 0, rows, Qs, dim, k_q, 1))) return rc;
+    GL.job[1].mode = GEMM_STORE; GL.job[1].out = g; GL.job[1].ld_out = dim;
+    GL.job[1].ksplit = (int)std::max<int64_t>(2, std::min<int64_t>(ceil_div(k_q, kTileK) / 2, 16));
+    GL.njobs = 2;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    GradFinishLaunch GF;
+    std::memset(&GF, 0, sizeof(GF));
+    GradFinishJob& j = GF.job[0];
+    j.g = g; j.dx = d_feat_s0; j.dx_dtype = grad_dtype; j.ld_dx = ld_grad;
+    j.rows = (int)rows; j.dim = (int)dim;
+    GF.njobs = 1;
+    GF.total_rows = (int)rows;
+    return launch_grad_finish(GF, S(stream));
+}
+
+STIL_API int64_t stil_comatch_sim_bwd_workspace_bytes(int64_t rows, int64_t k_q, int64_t dim, int dtype) {
+    Workspace W(nullptr, 0);
+    W.take<__nv_bfloat16>(rows * 2 * pad32(rows));
+    W.take<__nv_bfloat16>(rows * 2 * pad32(k_q));
+    W.take<float>(rows * dim);
+    if (dtype != STIL_BF16) {
+        W.take<__nv_bfloat16>(rows * 3 * dim);
+        W.take<__nv_bfloat16>(dim * 3 * pad8(k_q));
+    }
+    return W.off;
+}
+
+STIL_API int64_t stil_row_loss_workspace_bytes(int64_t rows) {
+    Workspace W(nullptr, 0);
+    W.take<unsigned int>(64);
+    W.take<float>(std::max<int64_t>(rows, weighted_softce_blocks(rows)) + 8);
+    return W.off;
+}
+
+STIL_API int stil_graph_contrast_loss(const float* Q, const float* sim, int64_t ld, int64_t rows, int64_t cols,
+                                      float contrast_th, float* loss, float* d_sim, float grad_scale, void* workspace,
+                                      int64_t workspace_bytes, void* stream) {
+    STIL_REQUIRE(Q && sim && loss && rows >= 1 && cols >= 1 && ld >= cols, STIL_E_ARG, "graph_contrast_loss: bad arguments");
+    STIL_REQUIRE(workspace && workspace_bytes >= stil_row_loss_workspace_bytes(rows), STIL_E_WORKSPACE,
+                 "graph_contrast_loss workspace too small");
+    Workspace W(workspace, workspace_bytes);
+    unsigned int* ticket = W.take<unsigned int>(64);
+    float* partials = W.take<float>(rows + 8);
+    STIL_CUDA(cudaMemsetAsync(ticket, 0, 16, S(stream)));
+    return launch_graph_contrast(Q, sim, ld, rows, cols, contrast_th, d_sim, grad_scale, partials, ticket, loss, S(stream));
+}
+
+STIL_API int stil_weighted_softce(const void* logits, int logit_dtype, int64_t ld_y, const float* target_probs, int64_t ld_t,
+                                  const int64_t* target_idx, const uint8_t* mask, int64_t rows, int64_t k, float* loss,
+                                  float* d_logits, int64_t ld_g, float grad_scale, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
+    STIL_REQUIRE(logit_dtype == STIL_F32 || logit_dtype == STIL_BF16, STIL_E_DTYPE, "weighted_softce: bad logit dtype");
+    STIL_REQUIRE(logits && loss && rows >= 1 && k >= 1 && ((target_probs != nullptr) != (target_idx != nullptr)), STIL_E_ARG,
+                 "weighted_softce: needs logits, loss and exactly one of target_probs / target_idx");
+    STIL_REQUIRE(workspace && workspace_bytes >= stil_row_loss_workspace_bytes(rows), STIL_E_WORKSPACE,
+                 "weighted_softce workspace too small");
+    Workspace W(workspace, workspace_bytes);
+    unsigned int* ticket = W.take<unsigned int>(64);
+    float* partials = W.take<float>(std::max<int64_t>(rows, weighted_softce_blocks(rows)) + 8);
+    STIL_CUDA(cudaMemsetAsync(ticket, 0, 16, S(stream)));
+    return launch_weighted_softce(logits, logit_dtype, ld_y, target_probs, ld_t, target_idx, mask, rows, k, d_logits, ld_g,
+                                  grad_scale, partials, ticket, loss, S(stream));
+}
+
+STIL_API int stil_queue_enqueue(void* queue_feat, int q_dtype, int64_t ld_q, float* queue_probs, int64_t ld_qp, int64_t k_q,
+                                int64_t* ptr, const void* z, int z_dtype, int64_t ld_z, int64_t n, int64_t dim, const float* t,
+                                int64_t ld_t, int64_t num_classes, void* stream) {
+    STIL_REQUIRE(queue_feat && queue_probs && ptr && k_q >= 1 && ld_q >= k_q && ld_qp >= k_q && n >= 0 && (n == 0 || (z && t)),
+                 STIL_E_ARG, "queue_enqueue: bad arguments");
+    STIL_REQUIRE((q_dtype == STIL_F32 || q_dtype == STIL_BF16) && (z_dtype == STIL_F32 || z_dtype == STIL_BF16), STIL_E_DTYPE,
+                 "queue_enqueue: bad dtype");
+    return launch_queue_enqueue(queue_feat, q_dtype, ld_q, queue_probs, ld_qp, k_q, ptr, z, z_dtype, ld_z, n, dim, t, ld_t,
+                                num_classes, S(stream));
+}
+
+STIL_API int stil_bank_update(void* bank, int b_dtype, int64_t ld_bank, int64_t* labels, const void* k, int k_dtype,
+                              int64_t ld_k, const int64_t* y, const int64_t* index, int64_t n, int64_t dim, void* stream) {
+    STIL_REQUIRE(bank && labels && n >= 0 && (n == 0 || (k && y && index)), STIL_E_ARG, "bank_update: bad arguments");
+    STIL_REQUIRE((b_dtype == STIL_F32 || b_dtype == STIL_BF16) && (k_dtype == STIL_F32 || k_dtype == STIL_BF16), STIL_E_DTYPE,
+                 "bank_update: bad dtype");
+    return launch_bank_update(bank, b_dtype, ld_bank, labels, k, k_dtype, ld_k, y, index, n, dim, S(stream));
+}
+
+STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* hist,
+                                int64_t hist_len, int64_t* count, float* qmean_scratch, float* out, int64_t ld_out,
+                                void* stream) {
+    STIL_REQUIRE(probs && batch_mean && hist && count && qmean_scratch && out && hist_len >= 1, STIL_E_ARG,
+                 "da_apply_hist: bad arguments");
+    int rc = launch_da_hist_update(batch_mean, hist, hist_len, k, count, qmean_scratch, S(stream));
+    if (rc) return rc;
+    return launch_da_rows(probs, ld, rows, k, qmean_scratch, out, ld_out, S(stream));
+}
+
 // =============================================================================================== whole step
 namespace {
 struct StepPlan {

@@ -148,6 +148,14 @@ __device__ __forceinline__ float tmem_ld_col(uint32_t taddr) {
     return __uint_as_float(v);
 }
 
+// GEMM_STORE post-ops: 1 = exp(value) (embedding graph, comatch_model.py:309-311), 2 = diagonal forced to 1
+// (pseudo-label graph, comatch_model.py:299-300)
+__device__ __forceinline__ float store_post(float v, int op, int row, int col) {
+    if (op == 1) return fast_exp2(v * kLog2e);
+    if (op == 2) return row == col ? 1.f : v;
+    return v;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_constant__ GemmLaunch L) {
     extern __shared__ uint8_t smem_raw[];
@@ -396,6 +404,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 }
             } else if ((MODE == GEMM_STATS || MODE == GEMM_STORE) && J.out) {
                 float* dst = J.out + (long long)row * J.ld_out + n0 + c * 32;
+                if (MODE == GEMM_STORE && J.post_op) {
+                    // graph epilogues of the CoMatch block (comatch_model.py:299-300, 309-311)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) l[j] = store_post(l[j], J.post_op, row, n0 + c * 32 + j);
+                }
                 // warp-uniform choice: the slow path issues warp-collective TMEM loads
                 const bool vec_ok = nv == 32 && (J.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(J.out) & 15) == 0);
                 if (vec_ok) {
@@ -408,7 +421,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                     // partial / unaligned chunk: compact per-column loop
 #pragma unroll 1
                     for (int j = 0; j < nv; ++j) {
-                        const float val = tmem_ld_col(taddr + c * 32 + j) * rs * col_scale[c * 32 + j];
+                        float val = tmem_ld_col(taddr + c * 32 + j) * rs * col_scale[c * 32 + j];
+                        if (MODE == GEMM_STORE && J.post_op) val = store_post(val, J.post_op, row, n0 + c * 32 + j);
                         if (row_ok) dst[j] = val;
                     }
                 }

@@ -70,6 +70,8 @@ struct alignas(64) GemmJob {
     int fin_x_dtype;
     long long fin_ldx;
     const float* fin_sx;
+    // plain STORE post-op on the scaled value: 0 none, 1 exp, 2 diagonal (row == column) forced to 1
+    int post_op;
 };
 
 struct GemmLaunch {
@@ -102,6 +104,7 @@ struct PrepJob {
     long long ld_t;
     int nseg_t;
     float* inv_norm;         // nullable
+    int op_dim;              // per-segment row length of `op` (>= dim, zero-filled beyond dim); 0 = dim
     int block_begin;
 };
 constexpr int kMaxPrepJobs = 8;
@@ -209,5 +212,31 @@ int launch_simmatch_rows(const float* zt, const float* zs, long long ldz, const 
 int launch_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, cudaStream_t stream);
 int launch_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* da_queue,
                     int64_t da_len, int64_t* da_ptr, float* qmean, float* out, int64_t ld_out, cudaStream_t stream);
+
+// --------------------------------------------------------------------------- bank blocks a8/a9 (bank_kernels.cu)
+int launch_bank_softmax_rows(const float* z, int64_t ldz, int64_t rows, int64_t k_q, float temperature,
+                             __nv_bfloat16* gop, int64_t ldg, int nseg, cudaStream_t stream);
+int launch_smooth_mix(const float* p, int64_t ld_p, const float* s, int64_t ld_s, int64_t rows, int64_t k, float c_keep,
+                      float c_bank, float* out, int64_t ld_out, float th, float* max_prob, int64_t* max_idx,
+                      uint8_t* mask, cudaStream_t stream);
+int launch_sim_grad(const float* gsim, const float* sim, int64_t ld, int64_t rows, int64_t n_self, int64_t k_q,
+                    float temperature, __nv_bfloat16* gs, int64_t ldg_s, __nv_bfloat16* gp, int64_t ldg_p, int nseg,
+                    cudaStream_t stream);
+int launch_graph_contrast(const float* Q, const float* sim, int64_t ld, int64_t rows, int64_t cols, float th, float* d_sim,
+                          float grad_scale, float* partials, unsigned int* ticket, float* loss, cudaStream_t stream);
+int64_t weighted_softce_blocks(int64_t rows);
+int launch_weighted_softce(const void* y, int dtype, int64_t ld_y, const float* tp, int64_t ld_t, const int64_t* tidx,
+                           const uint8_t* mask, int64_t rows, int64_t k, float* d_y, int64_t ld_g, float grad_scale,
+                           float* partials, unsigned int* ticket, float* loss, cudaStream_t stream);
+int launch_queue_enqueue(void* queue, int q_dtype, int64_t ld_q, float* qprobs, int64_t ld_qp, int64_t k_q, int64_t* ptr,
+                         const void* z, int z_dtype, int64_t ld_z, int64_t n, int64_t dim, const float* t, int64_t ld_t,
+                         int64_t num_classes, cudaStream_t stream);
+int launch_bank_update(void* bank, int b_dtype, int64_t ld_b, int64_t* labels, const void* k, int k_dtype, int64_t ld_k,
+                       const int64_t* y, const int64_t* index, int64_t n, int64_t dim, cudaStream_t stream);
+int launch_da_hist_update(const float* batch_mean, float* hist, int64_t hist_len, int64_t k, int64_t* count, float* qmean,
+                          cudaStream_t stream);
+// probs / qmean with rows renormalised (the second half of launch_da_apply)
+int launch_da_rows(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* qmean, float* out, int64_t ld_out,
+                   cudaStream_t stream);
 
 }  // namespace stil

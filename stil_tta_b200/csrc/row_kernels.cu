@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kRowBlock) prep_kernel(const __grid_constant__
     const int r = (blockIdx.x - J.block_begin) * kPrepRows + warp;
     if (r >= J.rows) return;
     float ss = 0.f;
-    const bool vec = (J.dim % 128 == 0) && (J.ld % 4 == 0) &&
+    const int odim = J.op_dim > 0 ? J.op_dim : J.dim;
+    const bool vec = (J.dim % 128 == 0) && (odim == J.dim) && (J.ld % 4 == 0) &&
                      (reinterpret_cast<uintptr_t>(J.x) % (J.dtype == STIL_BF16 ? 8 : 16) == 0);
     if (vec) {
         // each lane owns 4 consecutive elements of every 128-element slab
@@ -75,16 +76,16 @@ __global__ void __launch_bounds__(kRowBlock) prep_kernel(const __grid_constant__
             }
         }
     } else {
-        for (int d = lane; d < J.dim; d += 32) {
-            const float x = ld_as_float(J.x, J.dtype, (long long)r * J.ld + d);
+        for (int d = lane; d < odim; d += 32) {
+            const float x = d < J.dim ? ld_as_float(J.x, J.dtype, (long long)r * J.ld + d) : 0.f;
             ss += x * x;
             if (J.op) {
                 __nv_bfloat16 h, l, ll;
                 split3(x, h, l, ll);
-                __nv_bfloat16* o = J.op + ((long long)r * J.nseg) * J.dim + d;
+                __nv_bfloat16* o = J.op + ((long long)r * J.nseg) * odim + d;
                 o[0] = h;
-                if (J.nseg > 1) o[J.dim] = l;
-                if (J.nseg > 2) o[2 * J.dim] = ll;
+                if (J.nseg > 1) o[odim] = l;
+                if (J.nseg > 2) o[2 * odim] = ll;
             }
         }
     }
@@ -1080,6 +1081,10 @@ int launch_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, con
     da_update_kernel<<<1, 256, 0, stream>>>(batch_mean, da_queue, (int)da_len, (int)k, reinterpret_cast<long long*>(da_ptr),
                                             qmean);
     STIL_LAUNCH_CHECK();
+    return launch_da_rows(probs, ld, rows, k, qmean, out, ld_out, stream);
+}
+int launch_da_rows(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* qmean, float* out, int64_t ld_out,
+                   cudaStream_t stream) {
     if (rows == 0) return STIL_OK;
     const int threads = row_block_threads(rows);
     da_apply_kernel<<<(int)ceil_div(rows, threads / 32), threads, 0, stream>>>(probs, ld, (int)rows, (int)k, qmean, out,
