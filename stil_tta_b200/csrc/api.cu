@@ -72,6 +72,16 @@ int fill_gemm_common(GemmJob& J, const Operand& X, int64_t xrow0, int64_t M, con
     return STIL_OK;
 }
 
+// Mark operands the kernel launched immediately before this one (on the same stream, by this library) does not write:
+// the TMA producer then streams them before griddepcontrol.wait (gemm_tc05.cu).  Never set for the first kernel of a
+// call — its stream predecessor is the caller's.
+inline void set_early(GemmLaunch& GL, bool x, bool y) {
+    for (int j = 0; j < GL.njobs; ++j) {
+        GL.job[j].early_x = x ? 1 : 0;
+        GL.job[j].early_y = y ? 1 : 0;
+    }
+}
+
 // dX[M, ncols] = G[M, (hi,lo), n] · Y[n, ncols]: X = G (K-major), Y read in place as an MN-major operand
 int fill_gemm_store_mn(GemmJob& J, const Operand& G, int64_t M, const Operand& Y, int64_t n, int64_t ncols) {
     std::memset(&J, 0, sizeof(J));
@@ -423,6 +433,7 @@ STIL_API int stil_infonce_fwd(const void* a_loc, const void* b_loc, const void* 
     if ((rc = infonce_stats_jobs(GL.job, P, A, B, m, n, dim, row_offset, inv_t, logits, ld_logits))) return rc;
     GL.njobs = 2;
     gemm_job_tiles(GL);
+    set_early(GL, dtype == STIL_BF16, dtype == STIL_BF16);   // predecessor = prep: bf16 operands are the caller's inputs
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
     FinishLaunch FL;
     std::memset(&FL, 0, sizeof(FL));
@@ -474,6 +485,7 @@ STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* 
         return rc;
     GL.njobs = 2;
     gemm_job_tiles(GL);
+    set_early(GL, false, true);   // predecessor = GRAD (writes X = G); Y is an input / an operand of the forward call
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
     if (fused) return STIL_OK;
     GradFinishLaunch GF;
@@ -1422,12 +1434,14 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
             return rc;
         GL.njobs = 1;
         gemm_job_tiles(GL);
+        set_early(GL, true, true);    // predecessor = cgpl_pgls: both operands were final two kernels ago
         if ((rc = launch_gemm(GL, st))) return rc;
         if ((rc = mark(7, st))) return rc;
         std::memset(&GL, 0, sizeof(GL));
         if ((rc = proto_store_job(GL.job[0], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
         GL.njobs = 1;
         gemm_job_tiles(GL);
+        set_early(GL, false, true);   // predecessor = GRAD (writes X = G); Y = prototype operand
         if ((rc = launch_gemm(GL, st))) return rc;
         if ((rc = mark(8, st))) return rc;
         if (!fused_pt) {
@@ -1456,6 +1470,7 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         if ((rc = infonce_stats_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, nullptr, 0))) return rc;
         GL.njobs = 2;
         gemm_job_tiles(GL);
+        set_early(GL, dt == STIL_BF16, dt == STIL_BF16);   // predecessor = prep: bf16 operands are the caller's inputs
         if ((rc = mark(10, s_nce))) return rc;
         if ((rc = launch_gemm(GL, s_nce))) return rc;
         if ((rc = mark(2, s_nce))) return rc;
@@ -1467,6 +1482,7 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
             return rc;
         GL.njobs = 2;
         gemm_job_tiles(GL);
+        set_early(GL, true, true);    // predecessor = STATS: operands were final two kernels ago
         if ((rc = launch_gemm(GL, s_nce))) return rc;
         if ((rc = mark(3, s_nce))) return rc;
         std::memset(&GL, 0, sizeof(GL));
@@ -1475,6 +1491,7 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
             return rc;
         GL.njobs = 2;
         gemm_job_tiles(GL);
+        set_early(GL, false, true);   // predecessor = GRAD (writes X = G)
         if ((rc = launch_gemm(GL, s_nce))) return rc;
         if ((rc = mark(4, s_nce))) return rc;
         if (!fused) {

@@ -41,8 +41,8 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* hi, long long seg_str
 __global__ void __launch_bounds__(kBlk) bank_softmax_rows_kernel(const float* __restrict__ z, long long ldz, int k_q,
                                                                  float inv_t, __nv_bfloat16* gop, long long ldg, int nseg) {
     __shared__ float red[kBlk / 32];
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait();                 // predecessor complete and visible ...
+    pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
     const int row = blockIdx.x;
     const float* r = z + (long long)row * ldz;
     float m = -INFINITY;
@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(kBlk) smooth_mix_kernel(const float* __restric
                                                           float c_keep, float c_bank, float* out, long long ld_out,
                                                           float th, float* max_prob, long long* max_idx,
                                                           unsigned char* mask) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait();                 // predecessor complete and visible ...
+    pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kBlk) sim_grad_kernel(const float* __restrict_
                                                         long long ld, int n_self, int k_q, float inv_t,
                                                         __nv_bfloat16* gs, long long ldg_s, __nv_bfloat16* gp,
                                                         long long ldg_p, int nseg) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait();                 // predecessor complete and visible ...
+    pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
     const int row = blockIdx.y;
     const long long j = (long long)blockIdx.x * kBlk + threadIdx.x;
     const long long base = (long long)row * ld;
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(kBlk) graph_contrast_kernel(const float* __res
                                                               float grad_scale, float* partials, unsigned int* ticket,
                                                               float* loss) {
     __shared__ float red[kBlk / 32];
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait();                 // predecessor complete and visible ...
+    pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
     const int row = blockIdx.x;
     const float* q = Q + (long long)row * ld;
     const float* s = sim + (long long)row * ld;
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(kBlk) weighted_softce_kernel(const void* __res
                                                                const unsigned char* __restrict__ mask, int rows, int k,
                                                                float* d_y, long long ld_g, float grad_scale,
                                                                float* partials, unsigned int* ticket, float* loss) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait();                 // predecessor complete and visible ...
+    pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     float lrow = 0.f;

@@ -20,10 +20,16 @@ namespace stil {
 
 namespace {
 
-constexpr int kStages = 6;
+// Ring depth by occupancy: small grids (<= one CTA per SM) run one CTA per SM with a 6-deep ring (the whole K loop of
+// the reference sizes is in flight at once); grids of more than 148 tiles run TWO CTAs per SM with 3-deep rings so that
+// one CTA's epilogue overlaps the other's TMA/MMA main loop (the accumulator is single-buffered).
+constexpr int kMaxStages = 6;
 constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kStageBytes = (kTileM + kTileN) * kTileK * 2;  // 32 KiB
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 2048 /*scales, dot partials*/ + 256 /*barriers*/;
+constexpr int smem_bytes_for(int stages) {
+    return stages * kStageBytes + 1024 /*align slack*/ + 2048 /*scales, dot partials*/ + 256 /*barriers*/;
+}
+constexpr int kStageFloats = 32 * 33;   // per-warp staging tile for coalesced epilogue stores (reuses the ring)
 constexpr uint32_t kTmemCols = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -139,15 +145,6 @@ __device__ __forceinline__ unsigned long long gtime() {
         if (trace && blockIdx.x < kTraceCtas) trace[(blockIdx.x) * kTraceSlots + (slot)] = gtime();   \
     } while (0)
 
-// Slow-path helpers for a partial / unaligned 32-column chunk: compact loops over single TMEM columns so that
-// the unrolled fast paths stay small (code size is what bounds these short kernels' start-up).
-__device__ __forceinline__ float tmem_ld_col(uint32_t taddr) {
-    uint32_t v;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
-    tc05::tmem_ld_wait();
-    return __uint_as_float(v);
-}
-
 // GEMM_STORE post-ops: 1 = exp(value) (embedding graph, comatch_model.py:309-311), 2 = diagonal forced to 1
 // (pseudo-label graph, comatch_model.py:299-300)
 __device__ __forceinline__ float store_post(float v, int op, int row, int col) {
@@ -156,9 +153,10 @@ __device__ __forceinline__ float store_post(float v, int op, int row, int col) {
     return v;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_constant__ GemmLaunch L) {
+template <int MODE, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_constant__ GemmLaunch L) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int kStages = OCC == 1 ? kMaxStages : 3;
     // carve: [stages x (A 16K | B 16K)] 1024-aligned, then scales, then barriers
     const uint32_t raw = tc05::smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
@@ -167,13 +165,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     float* col_lse = col_scale + kTileN;                                          // [128]
     float* dot_part = col_lse + kTileN;                                           // [2][128]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(dot_part + 2 * kTileM);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: next kernel may begin its prologue
     unsigned long long* trace = L.trace ? L.trace + (size_t)(L.trace_id % kTraceLaunches) * kTraceCtas * kTraceSlots : nullptr;
     if (threadIdx.x == 0) { STIL_TRACE(0); if (trace && blockIdx.x < kTraceCtas) trace[blockIdx.x * kTraceSlots + 7] = MODE; }
 
@@ -217,22 +214,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
     __syncthreads();
     tc05::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: predecessor's results are visible from here on
-    if (threadIdx.x == 0) STIL_TRACE(1);
-
+    // Programmatic dependent launch.  Every thread that touches global memory the stream predecessor may have written
+    // waits for it first; `launch_dependents` is issued AFTER that wait, so by the time the next kernel of the chain
+    // starts, everything two or more kernels back is complete.  That is what lets the TMA producer stream operands the
+    // immediate predecessor does not write (J.early_x / J.early_y) before its own wait: the main loop of this kernel then
+    // overlaps the predecessor's execution and only the epilogue depends on it.
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             const bool mn = MODE == GEMM_STORE && J.y_mn_major != 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
-                tc05::mbar_wait(&empty_bar[s], ph ^ 1);
+            auto load_x = [&](int kb, int s) {
                 const int p = kb / kper, kk = kk0 + kb - p * kper;
-                uint8_t* a_dst = tiles + s * kStageBytes;
-                uint8_t* b_dst = a_dst + kTileM * kTileK * 2;
-                tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                tc05::tma_load_3d(a_dst, &J.tmx, &full_bar[s], kk * kTileK, m0, J.xseg[p]);
+                tc05::tma_load_3d(tiles + s * kStageBytes, &J.tmx, &full_bar[s], kk * kTileK, m0, J.xseg[p]);
+            };
+            auto load_y = [&](int kb, int s) {
+                const int p = kb / kper, kk = kk0 + kb - p * kper;
+                uint8_t* b_dst = tiles + s * kStageBytes + kTileM * kTileK * 2;
                 if (!mn) {
                     tc05::tma_load_3d(b_dst, &J.tmy, &full_bar[s], kk * kTileK, n0, J.yseg[p]);
                 } else {
@@ -240,6 +237,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                     tc05::tma_load_3d(b_dst, &J.tmy, &full_bar[s], n0, kk * kTileK, J.yseg[p]);
                     tc05::tma_load_3d(b_dst + 64 * kTileK * 2, &J.tmy, &full_bar[s], n0 + 64, kk * kTileK, J.yseg[p]);
                 }
+            };
+            // first pass over the ring: operands that do not depend on the predecessor go out before the wait
+            const int first = min(nkb, kStages);
+            const bool ex = J.early_x != 0, ey = J.early_y != 0;
+            if (ex || ey) {
+                for (int kb = 0; kb < first; ++kb) {
+                    tc05::mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
+                    if (ex) load_x(kb, kb);
+                    if (ey) load_y(kb, kb);
+                }
+            }
+            if (!(ex && ey)) {
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                for (int kb = 0; kb < first; ++kb) {
+                    if (!(ex || ey)) tc05::mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
+                    if (!ex) load_x(kb, kb);
+                    if (!ey) load_y(kb, kb);
+                }
+            }
+            int s = 0;
+            uint32_t ph = 1;            // second pass over the ring waits for the first release of each slot
+            for (int kb = first; kb < nkb; ++kb) {
+                tc05::mbar_wait(&empty_bar[s], ph ^ 1);
+                tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                load_x(kb, s);
+                load_y(kb, s);
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
             STIL_TRACE(2);
         }
@@ -248,9 +272,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
         if (lane == 0) {
             const bool mn = MODE == GEMM_STORE && J.y_mn_major != 0;
             const uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, kTileN) | (mn ? (1u << 16) : 0u);
+            int s = 0;
+            uint32_t ph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (kb / kStages) & 1;
                 tc05::mbar_wait(&full_bar[s], ph);
                 tc05::fence_after_sync();
                 const uint32_t a_addr = tc05::smem_u32(tiles + s * kStageBytes);
@@ -265,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                 for (int k = 0; k < kTileK / 16; ++k)
                     tc05::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + b_step * k, idesc, (kb | k) ? 1u : 0u);
                 tc05::mma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
             if (nkb > 0) tc05::mma_commit(tmem_full_bar);
             else tc05::mbar_arrive(tmem_full_bar);   // empty slice of a split contraction: nothing to wait for
@@ -280,6 +305,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
         const bool row_ok = row < J.M;
         const int ncols = min(kTileN, J.N - n0);
         const float alpha = J.alpha;
+        asm volatile("griddepcontrol.wait;" ::: "memory");               // predecessor's results visible from here on
+        if (e == 0) {
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // next kernel may begin its prologue
+            STIL_TRACE(1);
+        }
         if (e < kTileN) {
             const int col = n0 + e;
             float cs = 0.f, cl = 0.f;
@@ -403,29 +433,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc05_kernel(const __grid_con
                         if (j < nv) atomicAdd(dst + j, l[j]);
                 }
             } else if ((MODE == GEMM_STATS || MODE == GEMM_STORE) && J.out) {
-                float* dst = J.out + (long long)row * J.ld_out + n0 + c * 32;
                 if (MODE == GEMM_STORE && J.post_op) {
                     // graph epilogues of the CoMatch block (comatch_model.py:299-300, 309-311)
 #pragma unroll
                     for (int j = 0; j < 32; ++j) l[j] = store_post(l[j], J.post_op, row, n0 + c * 32 + j);
                 }
-                // warp-uniform choice: the slow path issues warp-collective TMEM loads
-                const bool vec_ok = nv == 32 && (J.ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(J.out) & 15) == 0);
-                if (vec_ok) {
-                    if (row_ok) {
+                // coalesced store through a per-warp staging tile (the operand ring is idle once the accumulator is
+                // complete): registers (thread = row) -> smem [32][33] -> 32 rows of up to 128 contiguous bytes; no
+                // alignment or leading-dimension requirement on `out`
+                float* stg = reinterpret_cast<float*>(tiles) + (warp - 2) * kStageFloats;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(l[j], l[j + 1], l[j + 2], l[j + 3]);
-                    }
-                } else {
-                    // partial / unaligned chunk: compact per-column loop
-#pragma unroll 1
-                    for (int j = 0; j < nv; ++j) {
-                        float val = tmem_ld_col(taddr + c * 32 + j) * rs * col_scale[c * 32 + j];
-                        if (MODE == GEMM_STORE && J.post_op) val = store_post(val, J.post_op, row, n0 + c * 32 + j);
-                        if (row_ok) dst[j] = val;
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = l[j];
+                __syncwarp();
+                {
+                    const int rbase = m0 + q * 32;
+                    float* obase = J.out + (long long)rbase * J.ld_out + n0 + c * 32 + lane;
+                    const int rmax = min(32, J.M - rbase);
+                    if (lane < nv) {
+#pragma unroll 8
+                        for (int r = 0; r < rmax; ++r) obase[(long long)r * J.ld_out] = stg[r * 33 + lane];
                     }
                 }
+                __syncwarp();
             }
             if (MODE == GEMM_GRAD && row_ok) {
                 const bool want_lo = J.g_nseg > 1;
@@ -535,15 +564,17 @@ int gemm_set_trace(void* buf) {
     return STIL_OK;
 }
 
-template <int MODE>
+template <int MODE, int OCC>
 static int launch_gemm_mode(const GemmLaunch& L, cudaStream_t stream) {
+    constexpr int smem = smem_bytes_for(OCC == 1 ? kMaxStages : 3);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_tc05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        attr_err = cudaFuncSetAttribute(gemm_tc05_kernel<MODE, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (attr_err == cudaSuccess) prefer_max_shared(gemm_tc05_kernel<MODE, OCC>);
     });
     STIL_CUDA(attr_err);
-    STIL_CUDA(launch_pdl(gemm_tc05_kernel<MODE>, dim3(L.total_tiles), dim3(kThreads), kSmemBytes, stream, L));
+    STIL_CUDA(launch_pdl(gemm_tc05_kernel<MODE, OCC>, dim3(L.total_tiles), dim3(kThreads), smem, stream, L));
     return STIL_OK;
 }
 
@@ -557,9 +588,11 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
     static unsigned int launch_counter = 0;
     const_cast<GemmLaunch&>(L).trace_id = launch_counter++;
     const_cast<GemmLaunch&>(L).trace = g_trace_host;
-    if (mode == GEMM_STATS) return launch_gemm_mode<GEMM_STATS>(L, stream);
-    if (mode == GEMM_STORE) return launch_gemm_mode<GEMM_STORE>(L, stream);
-    return launch_gemm_mode<GEMM_GRAD>(L, stream);
+    // more tiles than SMs: two CTAs per SM (3-deep rings) so epilogues overlap main loops
+    const bool two = L.total_tiles > 148;
+    if (mode == GEMM_STATS) return two ? launch_gemm_mode<GEMM_STATS, 2>(L, stream) : launch_gemm_mode<GEMM_STATS, 1>(L, stream);
+    if (mode == GEMM_STORE) return two ? launch_gemm_mode<GEMM_STORE, 2>(L, stream) : launch_gemm_mode<GEMM_STORE, 1>(L, stream);
+    return two ? launch_gemm_mode<GEMM_GRAD, 2>(L, stream) : launch_gemm_mode<GEMM_GRAD, 1>(L, stream);
 }
 
 }  // namespace stil

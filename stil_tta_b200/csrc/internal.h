@@ -70,6 +70,9 @@ struct alignas(64) GemmJob {
     int fin_x_dtype;
     long long fin_ldx;
     const float* fin_sx;
+    // programmatic dependent launch: the X / Y operand bytes are not written by the kernel launched immediately before
+    // this one on the stream, so the TMA producer may stream them before griddepcontrol.wait (see gemm_tc05.cu)
+    int early_x, early_y;
     // plain STORE post-op on the scaled value: 0 none, 1 exp, 2 diagonal (row == column) forced to 1
     int post_op;
 };

@@ -32,8 +32,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kRowBlock) prep_kernel(const __grid_constant__ PrepLaunch L) {
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait();                 // predecessor complete and visible ...
+    pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
     // reduction tickets of the later kernels of this op start from zero (workspace content is arbitrary)
     if (blockIdx.x == 0 && (int)threadIdx.x < L.n_zero) L.zero_words[threadIdx.x] = 0u;
     int jid = 0;
@@ -223,8 +223,8 @@ __device__ __forceinline__ int argmax_logits(const float (&y)[2 * NV], int sub, 
 template <int LPR, int NV>
 __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) {
     constexpr int RPW = 32 / LPR;
-    pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait();                 // predecessor complete and visible ...
+    pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.b_l; i += gridDim.x * blockDim.x) {
         A.cls_l[i] = (int)A.y_l[i];
         A.conf_l[i] = 1.0f >= A.th1;
