@@ -382,6 +382,11 @@ def run_gpu_arm(args):
             "peer-memory exchange kernels over NVLink (CUDA IPC; remote stores + flags), captured in the CUDA graphs: "
             "gather([feat_i|feat_t]), gather(loss, LSE), gather(class partials); InfoNCE chain on its own stream"
             if args.transport == "p2p" else
+            "fused compute + exchange over NVLink peer memory (CUDA IPC; remote stores + arrival flags), captured in the CUDA "
+            "graphs: one kernel packs [feat_i|feat_t], normalises and stores the rows into every rank's buffer; the statistics "
+            "GEMM consumes each peer's rows as its flag lands; one kernel merges and stores the row LSEs; the gradient GEMM's "
+            "epilogue waits for the column LSEs it reads; class partials pushed at the end of the row-local chain"
+            if args.transport == "fused" else
             "NCCL, captured in the CUDA graph: all_gather([feat_i|feat_t]), all_reduce(loss, LSE slots), "
             "all_reduce(class_sum|class_count); InfoNCE chain on its own stream")
         line["config"]["infonce"] = f"global batch {cfg.batch * world} (all-gathered)"
@@ -435,7 +440,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
-    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="N>1 exchange: peer-memory kernels or NCCL")
+    ap.add_argument("--transport", default="fused", choices=["fused", "p2p", "nccl"],
+                    help="N>1 exchange: fused peer-memory schedule, blocking peer-memory all-gathers, or NCCL")
     ap.add_argument("--nbuf", type=int, default=0, help="experiments: override the number of rotating batches")
     ap.add_argument("--no-graph", action="store_true", help="N>1 only: do not capture kernels+NCCL in a CUDA graph")
     args = ap.parse_args()

@@ -81,6 +81,14 @@ STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* 
                      float lambda0, const float* lse_row_all, const float* lse_col_all, const float* grad_loss,
                      void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, void* workspace,
                      int64_t workspace_bytes, void* stream);
+/* Same as stil_infonce_bwd when it directly follows stil_infonce_fwd with the same inputs on the same, untouched,
+ * workspace (the data-parallel head: forward, LSE exchange, backward): the inverse norms / operand split left there
+ * by the forward are reused instead of recomputed. */
+STIL_API int stil_infonce_bwd_after_fwd(const void* a_all, const void* b_all, int dtype, int64_t m, int64_t n, int64_t dim,
+                                        int64_t ld, int64_t row_offset, float temperature, float lambda0,
+                                        const float* lse_row_all, const float* lse_col_all, const float* grad_loss,
+                                        void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, void* workspace,
+                                        int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a3 (first half) — raw prototype similarities out[r,k] = feat[r,:]·prototypes[k,:] in fp32.
@@ -275,6 +283,47 @@ STIL_API int stil_p2p_close(void* peer_ptr);
 STIL_API int stil_p2p_exchange(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset,
                                int channel, int nseg, const void* const* src, const int64_t* nbytes,
                                const int64_t* dst_offset, void* stream);
+
+/* Fused compute + exchange schedule of the data-parallel head (no kernel sits waiting for a peer; consumers wait, tile by
+ * tile, for exactly the arrivals they read).  All take the channel description of stil_p2p_exchange.
+ *   stil_p2p_push            : stil_p2p_exchange without the final wait (store to every rank, publish the flag, retire)
+ *   stil_p2p_wait            : retire once every peer's latest push on `channel` has landed (for plain consumers)
+ *   stil_p2p_push_embeddings : rows of [feat_i | feat_t] (leading dimension 2*dim) and their inverse L2 norms written into
+ *                              every rank's gathered matrix (byte offset ab_offset) and norm vectors (ra/rb_offset, f32
+ *                              [n]) at global rows row0.. — pack + F.normalize pass + all-gather in one kernel
+ *   stil_p2p_push_lse        : row LSEs of the local rows of both InfoNCE sides, merged from the statistics partials in
+ *                              the stil_infonce workspace and written into every rank's gathered lse_row / lse_col
+ *   stil_infonce_stats_gathered / _loss_gathered / _bwd_gathered : stil_infonce_fwd / _bwd on buffers gathered that way
+ *       (bf16 only).  wait_flags = this rank's flag words of the channel (buffer + flags_offset + channel*64),
+ *       wait_seq = its sequence counter (buffer + ctrl_offset + channel*8); rows_per_peer = rows each rank owns.
+ *       stats: statistics GEMM only, every tile waits for the owner of its columns.  bwd: gradient GEMMs, the epilogue
+ *       waits for the owner of the column LSEs it reads.  loss: loss partial + LSEs of the local rows from the
+ *       statistics (off the critical chain); its workspace ticket words (first 256 bytes) must start out zero. */
+STIL_API int stil_p2p_push(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset, int channel,
+                           int nseg, const void* const* src, const int64_t* nbytes, const int64_t* dst_offset, void* stream);
+STIL_API int stil_p2p_wait(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset, int channel,
+                           void* stream);
+STIL_API int stil_p2p_push_embeddings(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset,
+                                      int channel, const void* feat_i, const void* feat_t, int dtype, int64_t rows,
+                                      int64_t dim, int64_t row0, int64_t ab_offset, int64_t ra_offset, int64_t rb_offset,
+                                      void* stream);
+STIL_API int stil_p2p_push_lse(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset,
+                               int channel, const void* infonce_workspace, int64_t m, int64_t n, int64_t dim, int dtype,
+                               int64_t row0, int64_t lse_row_offset, int64_t lse_col_offset, void* stream);
+STIL_API int stil_infonce_stats_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
+                                         int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
+                                         float temperature, const void* wait_flags, const void* wait_seq,
+                                         int64_t rows_per_peer, void* workspace, int64_t workspace_bytes, void* stream);
+STIL_API int stil_infonce_loss_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
+                                        int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
+                                        float temperature, float lambda0, float* loss_sum, float* lse_row, float* lse_col,
+                                        void* workspace, int64_t workspace_bytes, void* stream);
+STIL_API int stil_infonce_bwd_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
+                                       int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
+                                       float temperature, float lambda0, const float* lse_row_all,
+                                       const float* lse_col_all, const void* wait_flags, const void* wait_seq,
+                                       int64_t rows_per_peer, const float* grad_loss, void* d_a, void* d_b, int grad_dtype,
+                                       int64_t ld_grad, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* prototypes_sum += sum_w parts[w].class_sum; prototypes_count_sum += sum_w parts[w].class_count, with the ranks added
  * in index order (deterministic); parts is the gathered [world][k*dim + k] buffer; also writes the reduced

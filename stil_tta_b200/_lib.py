@@ -57,6 +57,8 @@ SIGNATURES = {
     "stil_infonce_fwd": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, vp, i64, vp]),
     "stil_infonce_bwd": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, vp, i32, i64,
                                vp, i64, vp]),
+    "stil_infonce_bwd_after_fwd": (i32, [vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, vp, i32, i64,
+                                         vp, i64, vp]),
     "stil_proto_logits_workspace_bytes": (i64, [i64, i64, i64, i32]),
     "stil_proto_logits": (i32, [vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
     "stil_cgpl_pgls": (i32, [vp, vp, vp, i32, i64, vp, i64, i64, i64, f32, f32, f32, i32, vp, i64, vp, i64, vp, vp, vp,
@@ -76,6 +78,14 @@ SIGNATURES = {
     "stil_p2p_close": (i32, [vp]),
     "stil_p2p_exchange": (i32, [C.POINTER(vp), i32, i32, i64, i64, i32, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64),
                                 vp]),
+    "stil_p2p_push": (i32, [C.POINTER(vp), i32, i32, i64, i64, i32, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), vp]),
+    "stil_p2p_wait": (i32, [C.POINTER(vp), i32, i32, i64, i64, i32, vp]),
+    "stil_p2p_push_embeddings": (i32, [C.POINTER(vp), i32, i32, i64, i64, i32, vp, vp, i32, i64, i64, i64, i64, i64, i64, vp]),
+    "stil_p2p_push_lse": (i32, [C.POINTER(vp), i32, i32, i64, i64, i32, vp, i64, i64, i64, i32, i64, i64, i64, vp]),
+    "stil_infonce_stats_gathered": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, vp, vp, i64, vp, i64, vp]),
+    "stil_infonce_loss_gathered": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, vp]),
+    "stil_infonce_bwd_gathered": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, vp, vp,
+                                        vp, i32, i64, vp, i64, vp]),
     "stil_da_batch_mean": (i32, [vp, i64, i64, i64, vp, vp]),
     "stil_da_apply": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
     "stil_simmatch_workspace_bytes": (i64, [i64, i64, i64, i32]),

@@ -97,6 +97,8 @@ int fill_gemm_store_mn(GemmJob& J, const Operand& G, int64_t M, const Operand& Y
     return STIL_OK;
 }
 
+int infonce_dx_ksplit(int64_t m, int64_t n, int64_t dim);
+
 // ------------------------------------------------------------------------------------------ InfoNCE plan
 struct InfoncePlan {
     int nseg;
@@ -125,11 +127,11 @@ InfoncePlan plan_infonce(void* ws, int64_t ws_bytes, int64_t m, int64_t n, int64
         P.pmax[s] = W.take<float>(stat_slots(n) * m);
         P.psum[s] = W.take<float>(stat_slots(n) * m);
     }
-    P.block_partials = W.take<float>(2 * finish_blocks((int)(3 * m)) + 8);  // 3m rows: the fused step adds the prototype rows
+    P.block_partials = W.take<float>(2 * ceil_div(3 * m, 2) + 8);   // upper bound of finish_blocks():  // 3m rows: the fused step adds the prototype rows
     // backward-only regions (the forward never touches them, the query always counts them)
     for (int s = 0; s < 2; ++s) {
         P.gop[s] = W.take<__nv_bfloat16>(m * 2 * P.ldg);
-        P.g[s] = W.take<float>(m * dim);
+        P.g[s] = W.take<float>(m * dim * infonce_dx_ksplit(m, n, dim));   // one slice per contraction split
     }
     (void)bwd;
     P.bytes = W.off;
@@ -187,7 +189,7 @@ ProtoPlan plan_proto(void* ws, int64_t ws_bytes, int64_t rows, int64_t k, int64_
     P.proto_op = W.take<__nv_bfloat16>(k * P.proto_nseg * dim);
     P.pmax = W.take<float>(stat_slots(k) * rows);
     P.psum = W.take<float>(stat_slots(k) * rows);
-    P.block_partials = W.take<float>(2 * finish_blocks((int)rows) + 8);
+    P.block_partials = W.take<float>(2 * ceil_div(rows, 2) + 8);
     P.gop = W.take<__nv_bfloat16>(rows * 2 * P.ldg);
     P.g = W.take<float>(rows * dim);
     P.bytes = W.off;
@@ -302,17 +304,28 @@ int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const
     return STIL_OK;
 }
 
+// The dX GEMM of a global batch contracts over all n columns on only 2*ceil(m/128)*ceil(dim/128) tiles: split the
+// contraction over CTAs (partial tiles are added with 16-byte reductions into P.g, which the GRAD launch cleared)
+// when the loop is long and the grid small.
+int infonce_dx_ksplit(int64_t m, int64_t n, int64_t dim) {
+    const int64_t kblocks = ceil_div(n, kTileK), tiles = 2 * ceil_div(m, kTileM) * ceil_div(dim, kTileN);
+    if (kblocks < 16 || tiles * 2 > 148) return 1;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(kblocks / 8, 148 / tiles));
+}
+
 // d(x̂_i) = sum_j G'_ij y_j, then the backward of F.normalize in the epilogue when one tile spans `dim`
 int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const Operand& B, const void* a_all,
                        const void* b_all, int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t off,
                        void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, bool* fused) {
     const int esz = dtype == STIL_BF16 ? 2 : 4;
-    *fused = dim <= kTileN;
+    const int ksplit = infonce_dx_ksplit(m, n, dim);
+    *fused = dim <= kTileN && ksplit == 1;
     for (int s = 0; s < 2; ++s) {
         const Operand X = grad_operand(P.gop[s], P.ldg, grad_nseg(grad_dtype));
         const Operand& Y = s == 0 ? B : A;
         int rc = fill_gemm_store_mn(J2[s], X, m, Y, n, dim);
         if (rc) return rc;
+        J2[s].ksplit = ksplit;
         if (*fused) {
             J2[s].fin_dx = s == 0 ? d_a : d_b;
             J2[s].fin_dx_dtype = grad_dtype;
@@ -324,13 +337,14 @@ int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, cons
         } else {
             J2[s].out = P.g[s];
             J2[s].ld_out = dim;
+            J2[s].slice_stride = ksplit > 1 ? m * dim : 0;
         }
     }
     return STIL_OK;
 }
 
 void infonce_gradfinish_jobs(GradFinishJob* G2, const InfoncePlan& P, const void* a_all, const void* b_all, int dtype,
-                             int64_t m, int64_t dim, int64_t ld, int64_t off, void* d_a, void* d_b, int grad_dtype,
+                             int64_t m, int64_t n_cols, int64_t dim, int64_t ld, int64_t off, void* d_a, void* d_b, int grad_dtype,
                              int64_t ld_grad) {
     const int esz = dtype == STIL_BF16 ? 2 : 4;
     for (int s = 0; s < 2; ++s) {
@@ -344,6 +358,8 @@ void infonce_gradfinish_jobs(GradFinishJob* G2, const InfoncePlan& P, const void
         j.dx_dtype = grad_dtype; j.ld_dx = ld_grad;
         j.rows = (int)m; j.dim = (int)dim;
         j.row_begin = (int)(s * m);
+        j.nslices = infonce_dx_ksplit(m, n_cols, dim);
+        j.slice_stride = m * dim;
     }
 }
 
@@ -448,12 +464,13 @@ STIL_API int stil_infonce_fwd(const void* a_loc, const void* b_loc, const void* 
     return launch_finish(FL, S(stream));
 }
 
-STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* a_all, const void* b_all, int dtype,
+}  // extern "C"
+namespace {
+int infonce_bwd_impl(const void* a_all, const void* b_all, int dtype,
                      int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset, float temperature,
                      float lambda0, const float* lse_row_all, const float* lse_col_all, const float* grad_loss,
                      void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, void* workspace,
-                     int64_t workspace_bytes, void* stream) {
-    (void)a_loc; (void)b_loc;
+                     int64_t workspace_bytes, void* stream, bool after_fwd) {
     int rc = infonce_args_check(a_all, b_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0);
     if (rc) return rc;
     STIL_REQUIRE(lse_row_all && lse_col_all && d_a && d_b, STIL_E_ARG, "infonce_bwd: null pointer");
@@ -463,11 +480,14 @@ STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* 
                  (long long)P.bytes);
     if (m == 0) return STIL_OK;
     const float inv_t = 1.0f / temperature;
-    PrepLaunch PL;
-    std::memset(&PL, 0, sizeof(PL));
-    prep_add(PL, prep_job(a_all, dtype, n, dim, ld, P.nseg, P.a_op, nullptr, 0, 0, P.ra));
-    prep_add(PL, prep_job(b_all, dtype, n, dim, ld, P.nseg, P.b_op, nullptr, 0, 0, P.rb));
-    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    if (!after_fwd) {
+        // inverse norms (and the fp32 operand split): still in the workspace when the forward just ran on it
+        PrepLaunch PL;
+        std::memset(&PL, 0, sizeof(PL));
+        prep_add(PL, prep_job(a_all, dtype, n, dim, ld, P.nseg, P.a_op, nullptr, 0, 0, P.ra));
+        prep_add(PL, prep_job(b_all, dtype, n, dim, ld, P.nseg, P.b_op, nullptr, 0, 0, P.rb));
+        if ((rc = launch_prep(PL, S(stream)))) return rc;
+    }
     const Operand A = rowmajor_operand(a_all, dtype, dim, ld, P.a_op, P.nseg);
     const Operand B = rowmajor_operand(b_all, dtype, dim, ld, P.b_op, P.nseg);
     GemmLaunch GL;
@@ -477,6 +497,8 @@ STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* 
         return rc;
     GL.njobs = 2;
     gemm_job_tiles(GL);
+    // predecessor = this call's prep: bf16 operands are the caller's inputs (after_fwd: the predecessor is the caller's)
+    if (!after_fwd) set_early(GL, dtype == STIL_BF16, dtype == STIL_BF16);
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
     std::memset(&GL, 0, sizeof(GL));
     bool fused = false;
@@ -490,7 +512,162 @@ STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* 
     if (fused) return STIL_OK;
     GradFinishLaunch GF;
     std::memset(&GF, 0, sizeof(GF));
-    infonce_gradfinish_jobs(GF.job, P, a_all, b_all, dtype, m, dim, ld, row_offset, d_a, d_b, grad_dtype, ld_grad);
+    infonce_gradfinish_jobs(GF.job, P, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype, ld_grad);
+    GF.njobs = 2;
+    GF.total_rows = (int)(2 * m);
+    return launch_grad_finish(GF, S(stream));
+}
+}  // namespace
+extern "C" {
+STIL_API int stil_infonce_bwd(const void* a_loc, const void* b_loc, const void* a_all, const void* b_all, int dtype,
+                     int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset, float temperature,
+                     float lambda0, const float* lse_row_all, const float* lse_col_all, const float* grad_loss,
+                     void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    (void)a_loc; (void)b_loc;
+    return infonce_bwd_impl(a_all, b_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0, lse_row_all, lse_col_all,
+                            grad_loss, d_a, d_b, grad_dtype, ld_grad, workspace, workspace_bytes, stream, false);
+}
+STIL_API int stil_infonce_bwd_after_fwd(const void* a_all, const void* b_all, int dtype, int64_t m, int64_t n, int64_t dim,
+                                        int64_t ld, int64_t row_offset, float temperature, float lambda0,
+                                        const float* lse_row_all, const float* lse_col_all, const float* grad_loss,
+                                        void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, void* workspace,
+                                        int64_t workspace_bytes, void* stream) {
+    return infonce_bwd_impl(a_all, b_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0, lse_row_all, lse_col_all,
+                            grad_loss, d_a, d_b, grad_dtype, ld_grad, workspace, workspace_bytes, stream, true);
+}
+
+// --------------------------------------------------------------------------- global-batch InfoNCE on gathered buffers
+// The data-parallel head's fused schedule (csrc/p2p.cu): the embeddings and their inverse norms are pushed into every
+// rank's buffer by stil_p2p_push_embeddings, the statistics GEMM consumes them tile by tile as they arrive (arrival
+// flags), stil_p2p_push_lse merges and pushes the row LSEs, and the gradient GEMM waits for the LSEs it needs.
+}  // extern "C"
+namespace stil {
+void infonce_stat_partials(void* workspace, int64_t m, int64_t n, int64_t dim, int dtype, const float** pmax,
+                           const float** psum, int* slots) {
+    InfoncePlan P = plan_infonce(workspace, 1ll << 60, m, n, dim, dtype, true);
+    for (int s = 0; s < 2; ++s) { pmax[s] = P.pmax[s]; psum[s] = P.psum[s]; }
+    *slots = (int)stat_slots(n);
+}
+}  // namespace stil
+namespace {
+void set_wait(GemmLaunch& GL, const void* flags, const void* seq, int64_t rows_per_peer, int wait_y) {
+    for (int j = 0; j < GL.njobs; ++j) {
+        GL.job[j].wait_flags = static_cast<const unsigned long long*>(flags);
+        GL.job[j].wait_seq = static_cast<const unsigned long long*>(seq);
+        GL.job[j].wait_rows_per_peer = (int)rows_per_peer;
+        GL.job[j].wait_y = wait_y;
+    }
+}
+int gathered_check(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all, int dtype, int64_t m,
+                   int64_t n, int64_t dim, int64_t ld, int64_t row_offset, float temperature, float lambda0,
+                   const void* wait_flags, const void* wait_seq, int64_t rows_per_peer) {
+    STIL_REQUIRE(dtype == STIL_BF16, STIL_E_DTYPE, "gathered InfoNCE: bf16 embeddings only (fp32 uses stil_infonce_fwd/bwd)");
+    int rc = infonce_args_check(a_all, b_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0);
+    if (rc) return rc;
+    STIL_REQUIRE(ra_all && rb_all && ((wait_flags == nullptr) == (wait_seq == nullptr)) &&
+                     (wait_flags == nullptr || rows_per_peer >= 1),
+                 STIL_E_ARG, "gathered InfoNCE: bad norm / flag arguments");
+    return STIL_OK;
+}
+}  // namespace
+extern "C" {
+STIL_API int stil_infonce_stats_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
+                                         int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
+                                         float temperature, const void* wait_flags, const void* wait_seq,
+                                         int64_t rows_per_peer, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = gathered_check(a_all, b_all, ra_all, rb_all, dtype, m, n, dim, ld, row_offset, temperature, 0.5f, wait_flags,
+                            wait_seq, rows_per_peer);
+    if (rc) return rc;
+    InfoncePlan P = plan_infonce(workspace, workspace_bytes, m, n, dim, dtype, false);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "infonce workspace too small: need %lld bytes",
+                 (long long)P.bytes);
+    if (m == 0) return STIL_OK;
+    P.ra = const_cast<float*>(ra_all);
+    P.rb = const_cast<float*>(rb_all);
+    const Operand A = rowmajor_operand(a_all, dtype, dim, ld, nullptr, 1);
+    const Operand B = rowmajor_operand(b_all, dtype, dim, ld, nullptr, 1);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = infonce_stats_jobs(GL.job, P, A, B, m, n, dim, row_offset, 1.0f / temperature, nullptr, 0))) return rc;
+    GL.njobs = 2;
+    gemm_job_tiles(GL);
+    set_wait(GL, wait_flags, wait_seq, rows_per_peer, 1);
+    return launch_gemm(GL, S(stream));
+}
+
+/* loss partial of the local rows (and their LSEs) from the statistics left by stil_infonce_stats_gathered — off the
+ * critical chain.  The workspace's first 256 bytes must have been zero when it was first used (reduction ticket). */
+STIL_API int stil_infonce_loss_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
+                                        int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
+                                        float temperature, float lambda0, float* loss_sum, float* lse_row, float* lse_col,
+                                        void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = gathered_check(a_all, b_all, ra_all, rb_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0, nullptr,
+                            nullptr, 0);
+    if (rc) return rc;
+    STIL_REQUIRE(loss_sum && lse_row && lse_col, STIL_E_ARG, "infonce_loss_gathered: null output");
+    InfoncePlan P = plan_infonce(workspace, workspace_bytes, m, n, dim, dtype, false);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "infonce workspace too small");
+    if (m == 0) return STIL_OK;
+    P.ra = const_cast<float*>(ra_all);
+    P.rb = const_cast<float*>(rb_all);
+    FinishLaunch FL;
+    std::memset(&FL, 0, sizeof(FL));
+    infonce_finish_jobs(FL.job, P, a_all, b_all, dtype, m, n, dim, ld, row_offset, 1.0f / temperature, lambda0, lse_row,
+                        lse_col, 0);
+    FL.job[0].row_begin = 0;
+    FL.job[1].row_begin = (int)m;
+    FL.njobs = 2;
+    FL.total_rows = (int)(2 * m);
+    FL.block_partials = P.block_partials;
+    FL.ticket = P.ticket;
+    FL.out_loss = loss_sum;
+    return launch_finish(FL, S(stream));
+}
+
+STIL_API int stil_infonce_bwd_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
+                                       int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
+                                       float temperature, float lambda0, const float* lse_row_all,
+                                       const float* lse_col_all, const void* wait_flags, const void* wait_seq,
+                                       int64_t rows_per_peer, const float* grad_loss, void* d_a, void* d_b, int grad_dtype,
+                                       int64_t ld_grad, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = gathered_check(a_all, b_all, ra_all, rb_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0, wait_flags,
+                            wait_seq, rows_per_peer);
+    if (rc) return rc;
+    STIL_REQUIRE(lse_row_all && lse_col_all && d_a && d_b, STIL_E_ARG, "infonce_bwd_gathered: null pointer");
+    STIL_REQUIRE(grad_dtype == STIL_F32 || grad_dtype == STIL_BF16, STIL_E_DTYPE, "bad grad dtype");
+    InfoncePlan P = plan_infonce(workspace, workspace_bytes, m, n, dim, dtype, true);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "infonce workspace too small");
+    if (m == 0) return STIL_OK;
+    P.ra = const_cast<float*>(ra_all);
+    P.rb = const_cast<float*>(rb_all);
+    const Operand A = rowmajor_operand(a_all, dtype, dim, ld, nullptr, 1);
+    const Operand B = rowmajor_operand(b_all, dtype, dim, ld, nullptr, 1);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = infonce_grad_jobs(GL.job, P, A, B, m, n, dim, row_offset, 1.0f / temperature, lambda0, lse_row_all, lse_col_all,
+                                grad_loss, grad_dtype)))
+        return rc;
+    GL.njobs = 2;
+    gemm_job_tiles(GL);
+    // every embedding row landed before the statistics GEMM finished (it waited for each peer): the operands stream
+    // before the wait; only the epilogue needs the peers' LSEs
+    set_early(GL, true, true);
+    set_wait(GL, wait_flags, wait_seq, rows_per_peer, 0);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    std::memset(&GL, 0, sizeof(GL));
+    bool fused = false;
+    if ((rc = infonce_store_jobs(GL.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
+                                 ld_grad, &fused)))
+        return rc;
+    GL.njobs = 2;
+    gemm_job_tiles(GL);
+    set_early(GL, false, true);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    if (fused) return STIL_OK;
+    GradFinishLaunch GF;
+    std::memset(&GF, 0, sizeof(GF));
+    infonce_gradfinish_jobs(GF.job, P, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype, ld_grad);
     GF.njobs = 2;
     GF.total_rows = (int)(2 * m);
     return launch_grad_finish(GF, S(stream));
@@ -1497,7 +1674,7 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         if (!fused) {
             GradFinishLaunch GF;
             std::memset(&GF, 0, sizeof(GF));
-            infonce_gradfinish_jobs(GF.job, P.nce, a->feat_i, a->feat_t, dt, B, D, D, 0, a->d_feat_i, a->d_feat_t,
+            infonce_gradfinish_jobs(GF.job, P.nce, a->feat_i, a->feat_t, dt, B, B, D, D, 0, a->d_feat_i, a->d_feat_t,
                                     a->grad_dtype, D);
             GF.njobs = 2;
             GF.total_rows = (int)(2 * B);

@@ -145,6 +145,21 @@ __device__ __forceinline__ unsigned long long gtime() {
         if (trace && blockIdx.x < kTraceCtas) trace[(blockIdx.x) * kTraceSlots + (slot)] = gtime();   \
     } while (0)
 
+// Arrival flags of the peer-memory all-gathers (csrc/p2p.cu): a consumer tile waits only for the peers whose rows it reads,
+// so the transfer overlaps the tiles that need local data.  Bounded spin: a lost peer is a CUDA error, not a hang.
+__device__ __forceinline__ void wait_peer_rows(const unsigned long long* flags, const unsigned long long* seq_ptr, int rpp,
+                                               int r0, int r1) {
+    unsigned long long seq;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seq) : "l"(seq_ptr) : "memory");
+    for (int p = r0 / rpp; p <= r1 / rpp; ++p) {
+        unsigned long long v, spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
+            if (++spins > (1ull << 26)) __trap();
+        } while (v < seq);
+    }
+}
+
 // GEMM_STORE post-ops: 1 = exp(value) (embedding graph, comatch_model.py:309-311), 2 = diagonal forced to 1
 // (pseudo-label graph, comatch_model.py:299-300)
 __device__ __forceinline__ float store_post(float v, int op, int row, int col) {
@@ -250,6 +265,12 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
             }
             if (!(ex && ey)) {
                 asm volatile("griddepcontrol.wait;" ::: "memory");
+                if (J.wait_flags && J.wait_y) {
+                    // the Y rows of this tile were stored by their owner rank(s): wait for exactly those arrivals, then
+                    // order the acquire before the TMA (async proxy) reads
+                    wait_peer_rows(J.wait_flags, J.wait_seq, J.wait_rows_per_peer, n0, min(n0 + kTileN, J.N) - 1);
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                }
                 for (int kb = 0; kb < first; ++kb) {
                     if (!(ex || ey)) tc05::mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
                     if (!ex) load_x(kb, kb);
@@ -314,9 +335,11 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
             const int col = n0 + e;
             float cs = 0.f, cl = 0.f;
             if (col < J.N) {
-                cs = alpha * (J.sy ? J.sy[col] : 1.f);
+                // column scales / LSEs gathered from peer ranks: wait for the owner's arrival, read through L2
+                if (J.wait_flags) wait_peer_rows(J.wait_flags, J.wait_seq, J.wait_rows_per_peer, col, col);
+                cs = alpha * (J.sy ? __ldcg(J.sy + col) : 1.f);
                 if (MODE == GEMM_GRAD) {
-                    if (J.lse_y) cl = J.lse_y[col];
+                    if (J.lse_y) cl = __ldcg(J.lse_y + col);
                     else if (J.py_max) cl = merge_partials(J.py_max, J.py_sum, J.py_tiles, J.N, col);
                 }
             }
@@ -424,13 +447,21 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
                     }
                 }
                 if (row_ok) store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + n0 + c * 32, nv, l);
-            } else if (MODE == GEMM_STORE && ksplit > 1) {
+            } else if (MODE == GEMM_STORE && ksplit > 1 && J.slice_stride == 0) {
                 // split contraction: add this CTA's partial tile (an empty slice adds nothing)
                 if (row_ok && nkb > 0) {
                     float* dst = J.out + (long long)row * J.ld_out + n0 + c * 32;
+                    if (nv == 32 && (J.ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(J.out) & 15) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nv) atomicAdd(dst + j, l[j]);
+                        for (int j = 0; j < 32; j += 4)   // one 16-byte reduction per 4 columns
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(l[j]),
+                                         "f"(l[j + 1]), "f"(l[j + 2]), "f"(l[j + 3])
+                                         : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nv) atomicAdd(dst + j, l[j]);
+                    }
                 }
             } else if ((MODE == GEMM_STATS || MODE == GEMM_STORE) && J.out) {
                 if (MODE == GEMM_STORE && J.post_op) {
@@ -442,12 +473,16 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
                 // complete): registers (thread = row) -> smem [32][33] -> 32 rows of up to 128 contiguous bytes; no
                 // alignment or leading-dimension requirement on `out`
                 float* stg = reinterpret_cast<float*>(tiles) + (warp - 2) * kStageFloats;
+                // split contraction with per-slice outputs (deterministic: the consumer adds the slices in order);
+                // an empty slice stores zeros (its accumulator was never written)
+                const bool empty_slice = MODE == GEMM_STORE && ksplit > 1 && nkb == 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = l[j];
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = empty_slice ? 0.f : l[j];
                 __syncwarp();
                 {
                     const int rbase = m0 + q * 32;
-                    float* obase = J.out + (long long)rbase * J.ld_out + n0 + c * 32 + lane;
+                    float* obase = J.out + (MODE == GEMM_STORE ? (long long)ks * J.slice_stride : 0ll) +
+                                   (long long)rbase * J.ld_out + n0 + c * 32 + lane;
                     const int rmax = min(32, J.M - rbase);
                     if (lane < nv) {
 #pragma unroll 8

@@ -57,8 +57,10 @@ struct alignas(64) GemmJob {
     float w_coef;
     int g_nseg;              // 2: G as bf16 hi+lo (fp32 gradients), 1: hi only (bf16 gradients)
     // STORE: split the contraction over `ksplit` CTAs per tile; partial tiles are added to `out` with red.global
-    // (out must be zero on entry).  1 = plain store.
+    // (out must be zero on entry).  1 = plain store.  With slice_stride > 0 (floats) slice k instead STORES its partial
+    // tile to out + k*slice_stride — deterministic, nothing to clear; the consumer adds the slices in index order.
     int ksplit;
+    long long slice_stride;
     // STORE with Y given MN-major ([contraction rows, N contiguous]) — the backward's dX = G · Y
     int y_mn_major;
     // STORE with the normalise-backward / cast fused in (needs tiles_n == 1):
@@ -73,6 +75,13 @@ struct alignas(64) GemmJob {
     // programmatic dependent launch: the X / Y operand bytes are not written by the kernel launched immediately before
     // this one on the stream, so the TMA producer may stream them before griddepcontrol.wait (see gemm_tc05.cu)
     int early_x, early_y;
+    // Peer-memory gather consumed in place (data-parallel head): wait_flags[p] (local, one u64 per peer) must reach
+    // *wait_seq before rows [p*wait_rows_per_peer, ...) of the gathered Y-side data are read — by the TMA producer for
+    // the Y operand tile (wait_y) and by the epilogue for sy / lse_y.  nullptr = no waiting.
+    const unsigned long long* wait_flags;
+    const unsigned long long* wait_seq;
+    int wait_rows_per_peer;
+    int wait_y;
     // plain STORE post-op on the scaled value: 0 none, 1 exp, 2 diagonal (row == column) forced to 1
     int post_op;
 };
@@ -91,6 +100,10 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t r
 void gemm_job_tiles(GemmLaunch& L);  // fills tiles_m/tiles_n/tile_begin/total_tiles
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream);
 int gemm_set_trace(void* buf);   // debug: device buffer of [64 launches][64 CTAs][8] u64 %globaltimer stamps, or nullptr
+
+// (max, sum) statistics partials of the two InfoNCE sides inside an stil_infonce workspace (api.cu; used by p2p.cu)
+void infonce_stat_partials(void* workspace, int64_t m, int64_t n, int64_t dim, int dtype, const float** pmax,
+                           const float** psum, int* slots);
 
 // --------------------------------------------------------------------------- row kernels (row_kernels.cu)
 // Operand preparation: for every row of x (f32 or bf16) write the bf16 segments (hi[,lo[,lolo]]) into
@@ -162,7 +175,9 @@ int64_t finish_blocks(int total_rows);
 
 // dx = sx*(g - xh*(xh·g)) with xh = sx*x  (backward of F.normalize) or dx = g when sx == nullptr.
 struct GradFinishJob {
-    const float* g;  // [rows, dim] f32
+    const float* g;  // [nslices][rows, dim] f32, slices `slice_stride` floats apart, added in index order
+    int nslices;     // 0/1 = a single matrix
+    long long slice_stride;
     const void* x;
     int x_dtype;
     long long ldx;

@@ -406,6 +406,8 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grow = blockIdx.x * (blockDim.x >> 5) + warp;
     float term[2] = {0.f, 0.f};
+    pdl_wait();
+    pdl_launch_dependents();
     if (grow < L.total_rows) {
         int jid = 0;
 #pragma unroll
@@ -413,24 +415,38 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
             if (j < L.njobs && grow >= L.job[j].row_begin) jid = j;
         const FinishJob& J = L.job[jid];
         const int i = grow - J.row_begin;
+        // every global load of the row is issued before the first reduction (one memory round trip, not five):
+        // the first 64 statistics slots and 128 row elements live in registers
+        const long long yrow = J.kind == 0 ? (long long)(i + J.y_offset) : (long long)J.cls[i];
+        float pm[2], ps[2], xv[4], yv[4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int t = lane + 32 * q;
+            pm[q] = t < J.tiles_n ? J.part_max[(long long)t * J.M + i] : -INFINITY;
+            ps[q] = t < J.tiles_n ? J.part_sum[(long long)t * J.M + i] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int d = lane + 32 * q;
+            xv[q] = d < J.dim ? ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d) : 0.f;
+            yv[q] = d < J.dim ? ld_as_float(J.y, J.y_dtype, yrow * J.ldy + d) : 0.f;
+        }
+        const float sxv = J.sx ? J.sx[i] : 1.f, syv = J.sy ? J.sy[i + J.y_offset] : 1.f;
         // merge (max, sum) partials over column tiles
-        float m = -INFINITY;
-        for (int t = lane; t < J.tiles_n; t += 32) m = fmaxf(m, J.part_max[(long long)t * J.M + i]);
+        float m = fmaxf(pm[0], pm[1]);
+        for (int t = lane + 64; t < J.tiles_n; t += 32) m = fmaxf(m, J.part_max[(long long)t * J.M + i]);
         m = warp_max(m);
-        float s = 0.f;
-        for (int t = lane; t < J.tiles_n; t += 32)
+        float s = ps[0] * expf(pm[0] - m) + ps[1] * expf(pm[1] - m);
+        for (int t = lane + 64; t < J.tiles_n; t += 32)
             s += J.part_sum[(long long)t * J.M + i] * expf(J.part_max[(long long)t * J.M + i] - m);
         s = warp_sum(s);
         const float lse = m + logf(s);
         // dot product with the partner row
-        const long long yrow = J.kind == 0 ? (long long)(i + J.y_offset) : (long long)J.cls[i];
-        float dot = 0.f;
-        for (int d = lane; d < J.dim; d += 32)
+        float dot = xv[0] * yv[0] + xv[1] * yv[1] + xv[2] * yv[2] + xv[3] * yv[3];
+        for (int d = lane + 128; d < J.dim; d += 32)
             dot += ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d) * ld_as_float(J.y, J.y_dtype, yrow * J.ldy + d);
         dot = warp_sum(dot);
-        float z = dot * J.alpha;
-        if (J.sx) z *= J.sx[i];
-        if (J.sy) z *= J.sy[i + J.y_offset];
+        const float z = dot * J.alpha * sxv * syv;
         if (lane == 0) {
             J.lse[i] = lse;
             if (J.kind == 0) {
@@ -466,12 +482,22 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
     if (is_last && warp == 0) {
         // deterministic: lane-strided partial sums in block order, then a fixed shuffle tree, per loss slot
         __threadfence();
-        const volatile float* bp = L.block_partials;
+        const float2* bp = reinterpret_cast<const float2*>(L.block_partials);
+        // batches of 8 independent L2 loads per lane (one round trip per 256 blocks), added in a fixed order
+        float sum2[2] = {0.f, 0.f};
+        for (unsigned int b0 = 0; b0 < gridDim.x; b0 += 256) {
+            float2 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned int b = b0 + lane + 32 * q;
+                v[q] = b < gridDim.x ? __ldcg(bp + b) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { sum2[0] += v[q].x; sum2[1] += v[q].y; }
+        }
 #pragma unroll
         for (int slot = 0; slot < 2; ++slot) {
-            float sum = 0.f;
-            for (unsigned int b = lane; b < gridDim.x; b += 32) sum += bp[2 * b + slot];
-            sum = warp_sum(sum);
+            float sum = warp_sum(sum2[slot]);
             bool used = false;
             for (int j = 0; j < L.njobs; ++j) used |= L.job[j].loss_slot == slot;
             if (used && lane == 0) L.out_loss[slot] = sum;
@@ -484,8 +510,10 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
 // backward of F.normalize (or plain cast) on the GEMM2 output
 // =====================================================================================
 __global__ void __launch_bounds__(kRowBlock) grad_finish_kernel(const __grid_constant__ GradFinishLaunch L) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grow = blockIdx.x * (kRowBlock / 32) + warp;
+    const int grow = blockIdx.x * (blockDim.x >> 5) + warp;
     if (grow >= L.total_rows) return;
     int jid = 0;
 #pragma unroll
@@ -493,18 +521,41 @@ __global__ void __launch_bounds__(kRowBlock) grad_finish_kernel(const __grid_con
         if (j < L.njobs && grow >= L.job[j].row_begin) jid = j;
     const GradFinishJob& J = L.job[jid];
     const int i = grow - J.row_begin;
-    const float* g = J.g + (long long)i * J.dim;
+    const float* g0 = J.g + (long long)i * J.dim;
+    const int ns = J.nslices > 1 ? J.nslices : 1;
+    auto gsum = [&](int d) {      // slices of a split contraction, added in index order (deterministic)
+        float v = g0[d];
+#pragma unroll 8
+        for (int k = 1; k < ns; ++k) v += g0[(long long)k * J.slice_stride + d];
+        return v;
+    };
     if (J.sx) {
         const float sx = J.sx[i];
+        // dim <= 128: the row's gradient stays in registers between the dot product and the projection
+        float gv[4];
         float dot = 0.f;
-        for (int d = lane; d < J.dim; d += 32) dot += sx * ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d) * g[d];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int d = lane + 32 * q;
+            gv[q] = d < J.dim ? gsum(d) : 0.f;
+            if (d < J.dim) dot += sx * ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d) * gv[q];
+        }
+        for (int d = lane + 128; d < J.dim; d += 32) dot += sx * ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d) * gsum(d);
         dot = warp_sum(dot);
-        for (int d = lane; d < J.dim; d += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int d = lane + 32 * q;
+            if (d < J.dim) {
+                const float xh = sx * ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d);
+                st_from_float(J.dx, J.dx_dtype, (long long)i * J.ld_dx + d, sx * (gv[q] - xh * dot));
+            }
+        }
+        for (int d = lane + 128; d < J.dim; d += 32) {
             const float xh = sx * ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d);
-            st_from_float(J.dx, J.dx_dtype, (long long)i * J.ld_dx + d, sx * (g[d] - xh * dot));
+            st_from_float(J.dx, J.dx_dtype, (long long)i * J.ld_dx + d, sx * (gsum(d) - xh * dot));
         }
     } else {
-        for (int d = lane; d < J.dim; d += 32) st_from_float(J.dx, J.dx_dtype, (long long)i * J.ld_dx + d, g[d]);
+        for (int d = lane; d < J.dim; d += 32) st_from_float(J.dx, J.dx_dtype, (long long)i * J.ld_dx + d, gsum(d));
     }
 }
 
@@ -949,21 +1000,24 @@ int launch_zero_u32(unsigned int* p, int n, cudaStream_t stream) {
     return STIL_OK;
 }
 
-int64_t finish_blocks(int total_rows) { return ceil_div(total_rows, row_block_threads(total_rows) / 32); }
+// eight rows per block once there is a row per scheduler anyway: fewer blocks = a shorter ticket reduction
+inline int finish_threads(int total_rows) { return total_rows >= 512 ? kRowBlock : 64; }
+int64_t finish_blocks(int total_rows) { return ceil_div(total_rows, finish_threads(total_rows) / 32); }
 
 int launch_finish(const FinishLaunch& L, cudaStream_t stream) {
     if (L.total_rows == 0) return STIL_OK;
     static const bool once = (prefer_max_shared(finish_kernel), true);
     (void)once;
-    finish_kernel<<<(int)finish_blocks(L.total_rows), row_block_threads(L.total_rows), 0, stream>>>(L);
-    STIL_LAUNCH_CHECK();
+    STIL_CUDA(launch_pdl(finish_kernel, dim3((unsigned)finish_blocks(L.total_rows)),
+                         dim3((unsigned)finish_threads(L.total_rows)), 0, stream, L));
     return STIL_OK;
 }
 
 int launch_grad_finish(const GradFinishLaunch& L, cudaStream_t stream) {
     if (L.total_rows == 0) return STIL_OK;
-    grad_finish_kernel<<<(int)ceil_div(L.total_rows, kRowBlock / 32), kRowBlock, 0, stream>>>(L);
-    STIL_LAUNCH_CHECK();
+    const int threads = row_block_threads(L.total_rows);
+    STIL_CUDA(launch_pdl(grad_finish_kernel, dim3((unsigned)ceil_div(L.total_rows, threads / 32)), dim3((unsigned)threads), 0,
+                         stream, L));
     return STIL_OK;
 }
 

@@ -238,19 +238,27 @@ class DistributedSTiLHead(STiLHead):
     before the backward (oracle: reference ``CLIPLoss`` on the concatenated batch) — no gradient reduce-scatter;
     (ii) the prototype partial sums of all ranks are summed before they are accumulated (``STiLModel.py:377-379``).
 
-    ``transport="p2p"`` (default): the three exchanges are ``stil_p2p_exchange`` kernels over CUDA-IPC peer memory
-    (remote NVLink stores + flags, a few microseconds each); destination regions alternate between two halves on
-    successive steps, so two CUDA graphs (even / odd) are captured and replayed in turn.
+    ``transport="fused"`` (default for bf16 embeddings): compute and exchange are fused over CUDA-IPC peer memory — one
+    kernel packs ``[feat_i | feat_t]``, computes the inverse norms and stores both into every rank's buffer; the
+    statistics GEMM consumes the gathered rows tile by tile as their owner's arrival flag lands (local tiles do not wait);
+    one kernel merges the statistics into row LSEs and stores them into every rank's buffer; the gradient GEMM's epilogue
+    waits only for the owners of the column LSEs it reads; the class partials are pushed and waited for at the very end
+    of the row-local chain.  No kernel sits waiting for a peer before useful work.
+    ``transport="p2p"``: the three exchanges are blocking ``stil_p2p_exchange`` all-gather kernels (remote NVLink stores
+    + flags).  Both peer-memory transports alternate destination regions between two halves on successive steps, so two
+    CUDA graphs (even / odd) are captured and replayed in turn.
     ``transport="nccl"``: one NCCL all-gather and two all-reduces, captured in one graph.
     ``losses[0]`` is the global InfoNCE loss (same on every rank); ``d_feat_i/t`` its gradients w.r.t. the local rows.
     """
 
-    def __init__(self, cfg: HeadConfig, device="cuda", group=None, transport: str = "p2p", **kw) -> None:
+    def __init__(self, cfg: HeadConfig, device="cuda", group=None, transport: str = "fused", **kw) -> None:
         super().__init__(cfg, device=device, **kw)
         import torch.distributed as dist
         from .distributed import GlobalBatch
         self.dist, self.group, self.gb = dist, group, GlobalBatch(group)
         self.world, self.rank = self.gb.world_size, self.gb.rank
+        if transport == "fused" and self.inp["feat_i"].dtype != torch.bfloat16:
+            transport = "p2p"           # the fused schedule reads bf16 rows in place; fp32 needs the operand split pass
         self.transport = transport if self.world > 1 else "nccl"
         B, K, P = cfg.batch, cfg.num_classes, cfg.proj_dim
         n, W = B * self.world, self.world
@@ -265,7 +273,8 @@ class DistributedSTiLHead(STiLHead):
         self._parity = 0
         lib = _lib.load()
         code = _lib.dtype_code(self.inp["feat_i"])
-        self._nce_ws = torch.empty(lib.stil_infonce_workspace_bytes(B, n, P, code), dtype=torch.uint8, device=dev)
+        self._nce_ws = torch.zeros(lib.stil_infonce_workspace_bytes(B, n, P, code), dtype=torch.uint8, device=dev)
+        self._loss_stream = None
         a = self._args
         a.skip_infonce = 1
         a.class_sum = self._cls_loc.data_ptr()
@@ -274,7 +283,7 @@ class DistributedSTiLHead(STiLHead):
         self._sum_out = torch.zeros(K, P, dtype=torch.float32, device=dev)
         self._cnt_out = torch.zeros(K, 1, dtype=torch.float32, device=dev)
         self.out["class_sum"], self.out["class_count"] = self._sum_out, self._cnt_out
-        if self.transport == "p2p":
+        if self.transport in ("p2p", "fused"):
             from .distributed import P2PBuffer
             r256 = lambda x: (x + 255) // 256 * 256
             self._o_ab = 0
@@ -282,7 +291,9 @@ class DistributedSTiLHead(STiLHead):
             self._o_lr = self._o_loss + r256(W * 16)
             self._o_lc = self._o_lr + r256(n * 4)
             self._o_cls = self._o_lc + r256(n * 4)
-            self._half = self._o_cls + r256(W * self._slot * 4)
+            self._o_ra = self._o_cls + r256(W * self._slot * 4)
+            self._o_rb = self._o_ra + r256(n * 4)
+            self._half = self._o_rb + r256(n * 4)
             self._p2p = P2PBuffer(2 * self._half, dev, group)
             v = self._p2p.view
             self._r = []
@@ -291,7 +302,8 @@ class DistributedSTiLHead(STiLHead):
                 self._r.append(dict(
                     off=o, ab=v(o + self._o_ab, (n, 2 * P), edt), loss=v(o + self._o_loss, (W, 4), torch.float32),
                     lse_row=v(o + self._o_lr, (n,), torch.float32), lse_col=v(o + self._o_lc, (n,), torch.float32),
-                    cls=v(o + self._o_cls, (W, self._slot), torch.float32)))
+                    cls=v(o + self._o_cls, (W, self._slot), torch.float32),
+                    ra=v(o + self._o_ra, (n,), torch.float32), rb=v(o + self._o_rb, (n,), torch.float32)))
         else:
             # NCCL: [loss partial (4) | LSE slots [2, W, B]] all-reduced for the InfoNCE chain (every rank fills only
             # its own LSE slot, so SUM is the gather) and [class_sum | class_count] all-reduced for the bank
@@ -316,7 +328,7 @@ class DistributedSTiLHead(STiLHead):
             torch.cuda.current_stream(self.dev).wait_stream(s)
             torch.cuda.synchronize(self.dev)
             self.dist.barrier(group=self.group)
-            for parity in ((0, 1) if self.transport == "p2p" else (0,)):
+            for parity in ((0, 1) if self.transport in ("p2p", "fused") else (0,)):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._run_eager(parity)
@@ -330,7 +342,7 @@ class DistributedSTiLHead(STiLHead):
     def run(self) -> None:
         with torch.cuda.device(self.dev):
             self._ensure_prototypes()
-            parity = self._parity if self.transport == "p2p" else 0
+            parity = self._parity if self.transport in ("p2p", "fused") else 0
             self._parity ^= 1
             if self.use_graph:
                 if self._graph is None:
@@ -339,7 +351,62 @@ class DistributedSTiLHead(STiLHead):
             else:
                 self._run_eager(parity)
 
+    def _run_fused(self, parity: int) -> None:
+        """One step of the fused compute + exchange schedule (see the class docstring)."""
+        cfg, lib = self.cfg, _lib.load()
+        B, K, P, W = cfg.batch, cfg.num_classes, cfg.proj_dim, self.world
+        n, off, r = B * W, B * self.rank, self.rank
+        code = _lib.dtype_code(self.inp["feat_i"])
+        p = lambda t: t.data_ptr()
+        pb, R = self._p2p, self._r[parity]
+        H = pb.HEADER + R["off"]                      # byte offset of this parity's region inside every buffer
+        flags = lambda ch: pb.local + ch * 64          # u64 flags[channel][8] at offset 0
+        seq = lambda ch: pb.local + 512 + ch * 8       # u64 seq[channel] at offset 512
+        chan = lambda ch: (pb._bases, W, r, 0, 512, ch)
+        with torch.cuda.device(self.dev):
+            cur = torch.cuda.current_stream(self.dev)
+            if self._nce_stream is None:
+                self._nce_stream = torch.cuda.Stream(self.dev)
+                self._loss_stream = torch.cuda.Stream(self.dev)
+            sb, sl = self._nce_stream, self._loss_stream
+            sb.wait_stream(cur)
+            a_all, b_all = p(R["ab"]), p(R["ab"]) + P * 2
+            with torch.cuda.stream(sb):
+                check(lib.stil_p2p_push_embeddings(*chan(0), p(self.inp["feat_i"]), p(self.inp["feat_t"]), code, B, P, off,
+                                                   H + self._o_ab, H + self._o_ra, H + self._o_rb, sb.cuda_stream))
+                check(lib.stil_infonce_stats_gathered(a_all, b_all, p(R["ra"]), p(R["rb"]), code, B, n, P, 2 * P, off,
+                                                      cfg.temperature, flags(0), seq(0), B, p(self._nce_ws),
+                                                      self._nce_ws.numel(), sb.cuda_stream))
+                sl.wait_stream(sb)
+                check(lib.stil_p2p_push_lse(*chan(1), p(self._nce_ws), B, n, P, code, off, H + self._o_lr, H + self._o_lc,
+                                            sb.cuda_stream))
+                check(lib.stil_infonce_bwd_gathered(a_all, b_all, p(R["ra"]), p(R["rb"]), code, B, n, P, 2 * P, off,
+                                                    cfg.temperature, cfg.lambda_0, p(R["lse_row"]), p(R["lse_col"]),
+                                                    flags(1), seq(1), B, None, p(self.out["d_feat_i"]),
+                                                    p(self.out["d_feat_t"]), _lib.dtype_code(self.out["d_feat_i"]), P,
+                                                    p(self._nce_ws), self._nce_ws.numel(), sb.cuda_stream))
+            with torch.cuda.stream(sl):
+                # loss partial of the local rows from the statistics: beside the chain, not in it
+                check(lib.stil_infonce_loss_gathered(a_all, b_all, p(R["ra"]), p(R["rb"]), code, B, n, P, 2 * P, off,
+                                                     cfg.temperature, cfg.lambda_0, p(self._nce_loc), p(self._nce_loc[4:]),
+                                                     p(self._nce_loc[4 + B:]), p(self._nce_ws), self._nce_ws.numel(),
+                                                     sl.cuda_stream))
+            self._enqueue()                          # everything row-local (current stream)
+            cur.wait_stream(sl)
+            segs = [(self._cls_loc, H + self._o_cls + r * self._slot * 4), (self._nce_loc[:4], H + self._o_loss + r * 16)]
+            src = (C.c_void_p * 2)(*[t.data_ptr() for t, _ in segs])
+            nb = (C.c_int64 * 2)(*[t.numel() * t.element_size() for t, _ in segs])
+            dst = (C.c_int64 * 2)(*[o for _, o in segs])
+            check(lib.stil_p2p_push(*chan(2), 2, src, nb, dst, cur.cuda_stream))
+            check(lib.stil_p2p_wait(*chan(2), cur.cuda_stream))
+            check(lib.stil_proto_add_gathered(p(R["cls"]), W, self._slot, K, P, p(self._sum_out), p(self._cnt_out),
+                                              p(self.prototypes_sum), p(self.prototypes_count_sum), cur.cuda_stream))
+            torch.sum(R["loss"][:, 0], dim=0, keepdim=True, out=self.out["losses"][0:1])
+            cur.wait_stream(sb)
+
     def _run_eager(self, parity: int = 0) -> None:
+        if self.transport == "fused":
+            return self._run_fused(parity)
         cfg, dist, lib = self.cfg, self.dist, _lib.load()
         B, K, P, W = cfg.batch, cfg.num_classes, cfg.proj_dim, self.world
         n, off, r = B * W, B * self.rank, self.rank
@@ -381,10 +448,12 @@ class DistributedSTiLHead(STiLHead):
                     dist.all_reduce(self._packed, op=dist.ReduceOp.SUM, group=self.group)
                     lse_row_all, lse_col_all = self._lse[0].reshape(-1), self._lse[1].reshape(-1)
                     self.out["losses"][0:1].copy_(self._packed[0:1], non_blocking=True)
-                check(lib.stil_infonce_bwd(a_loc, b_loc, a_all, b_all, code, B, n, P, 2 * P, off, cfg.temperature,
-                                           cfg.lambda_0, p(lse_row_all), p(lse_col_all), None, p(self.out["d_feat_i"]),
-                                           p(self.out["d_feat_t"]), _lib.dtype_code(self.out["d_feat_i"]), P,
-                                           p(self._nce_ws), self._nce_ws.numel(), sb.cuda_stream))
+                # the forward's inverse norms are still in the workspace: no second preparation pass
+                check(lib.stil_infonce_bwd_after_fwd(a_all, b_all, code, B, n, P, 2 * P, off, cfg.temperature,
+                                                     cfg.lambda_0, p(lse_row_all), p(lse_col_all), None,
+                                                     p(self.out["d_feat_i"]), p(self.out["d_feat_t"]),
+                                                     _lib.dtype_code(self.out["d_feat_i"]), P, p(self._nce_ws),
+                                                     self._nce_ws.numel(), sb.cuda_stream))
             # chain A (current stream): everything row-local, then the prototype partials of all ranks
             self._enqueue()
             if p2p:

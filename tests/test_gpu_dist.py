@@ -69,7 +69,7 @@ def _worker(rank, world, port, batch, use_graph, transport):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("use_graph,transport", [(False, "p2p"), (True, "p2p"), (True, "nccl")])
+@pytest.mark.parametrize("use_graph,transport", [(False, "fused"), (True, "fused"), (False, "p2p"), (True, "p2p"), (True, "nccl")])
 def test_distributed_head_two_ranks(use_graph, transport):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), 256, use_graph, transport), nprocs=2, join=True)
