@@ -292,13 +292,19 @@ STIL_API int stil_p2p_exchange(void* const* bases, int world, int rank, int64_t 
  *                              every rank's gathered matrix (byte offset ab_offset) and norm vectors (ra/rb_offset, f32
  *                              [n]) at global rows row0.. — pack + F.normalize pass + all-gather in one kernel
  *   stil_p2p_push_lse        : row LSEs of the local rows of both InfoNCE sides, merged from the statistics partials in
- *                              the stil_infonce workspace and written into every rank's gathered lse_row / lse_col
+ *                              the stil_infonce workspace and written into every rank's gathered lse_row / lse_col as
+ *                              8-byte "LL" words {f32 value, u32 tag} (ONE store each: no fence, no flag — readers spin
+ *                              on the word until the tag equals the low 32 bits of channel tag_channel's counter, which
+ *                              stil_p2p_push_embeddings advanced at the start of the step)
  *   stil_infonce_stats_gathered / _loss_gathered / _bwd_gathered : stil_infonce_fwd / _bwd on buffers gathered that way
  *       (bf16 only).  wait_flags = this rank's flag words of the channel (buffer + flags_offset + channel*64),
  *       wait_seq = its sequence counter (buffer + ctrl_offset + channel*8); rows_per_peer = rows each rank owns.
- *       stats: statistics GEMM only, every tile waits for the owner of its columns.  bwd: gradient GEMMs, the epilogue
- *       waits for the owner of the column LSEs it reads.  loss: loss partial + LSEs of the local rows from the
- *       statistics (off the critical chain); its workspace ticket words (first 256 bytes) must start out zero. */
+ *       stats: statistics GEMM only, every tile waits for the owner of its columns.  bwd: gradient GEMMs; lse_row_ll /
+ *       lse_col_ll are the gathered LL-word vectors [n] x 8 bytes of stil_p2p_push_lse and ll_tag the counter word whose low
+ *       32 bits tag this step — the epilogue spins on exactly the entries it reads.  loss: loss partial + LSEs of the
+ *       local rows from the statistics (off the critical chain); with bases != NULL the partial is also stored as an LL
+ *       word [rank] at byte loss_ll_offset of every rank's buffer (tag: low 32 bits of *ll_tag); its workspace ticket
+ *       words (first 256 bytes) must start out zero. */
 STIL_API int stil_p2p_push(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset, int channel,
                            int nseg, const void* const* src, const int64_t* nbytes, const int64_t* dst_offset, void* stream);
 STIL_API int stil_p2p_wait(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset, int channel,
@@ -308,7 +314,7 @@ STIL_API int stil_p2p_push_embeddings(void* const* bases, int world, int rank, i
                                       int64_t dim, int64_t row0, int64_t ab_offset, int64_t ra_offset, int64_t rb_offset,
                                       void* stream);
 STIL_API int stil_p2p_push_lse(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset,
-                               int channel, const void* infonce_workspace, int64_t m, int64_t n, int64_t dim, int dtype,
+                               int tag_channel, const void* infonce_workspace, int64_t m, int64_t n, int64_t dim, int dtype,
                                int64_t row0, int64_t lse_row_offset, int64_t lse_col_offset, void* stream);
 STIL_API int stil_infonce_stats_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
                                          int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
@@ -317,12 +323,19 @@ STIL_API int stil_infonce_stats_gathered(const void* a_all, const void* b_all, c
 STIL_API int stil_infonce_loss_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
                                         int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
                                         float temperature, float lambda0, float* loss_sum, float* lse_row, float* lse_col,
+                                        void* const* bases, int world, int rank, int64_t loss_ll_offset, const void* ll_tag,
                                         void* workspace, int64_t workspace_bytes, void* stream);
+/* stil_proto_add_gathered for partials that were PUSHED (stil_p2p_push / stil_head_step's partials_push): every block
+ * first waits for all ranks' arrival counters (wait_flags[w] >= *wait_target); optionally also sums the ranks' InfoNCE
+ * loss partials (LL words loss_ll[w], tag = low 32 bits of *loss_tag) into loss_out — the last kernel of the step. */
+STIL_API int stil_proto_add_gathered_wait(const float* parts, int64_t world, int64_t slot_floats, int64_t k, int64_t dim,
+                                          float* class_sum, float* class_count, float* psum, float* pcount,
+                                          const void* wait_flags, const void* wait_target, const void* loss_ll,
+                                          const void* loss_tag, float* loss_out, void* stream);
 STIL_API int stil_infonce_bwd_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
                                        int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
-                                       float temperature, float lambda0, const float* lse_row_all,
-                                       const float* lse_col_all, const void* wait_flags, const void* wait_seq,
-                                       int64_t rows_per_peer, const float* grad_loss, void* d_a, void* d_b, int grad_dtype,
+                                       float temperature, float lambda0, const void* lse_row_ll,
+                                       const void* lse_col_ll, const void* ll_tag, const float* grad_loss, void* d_a, void* d_b, int grad_dtype,
                                        int64_t ld_grad, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* prototypes_sum += sum_w parts[w].class_sum; prototypes_count_sum += sum_w parts[w].class_count, with the ranks added
@@ -334,6 +347,14 @@ STIL_API int stil_proto_add_gathered(const float* parts, int64_t world, int64_t 
 /* ---------------------------------------------------------------------------------------------
  * The whole per-batch head in one call (what STiLModel.training_step lines 262-303, 317-322, 339,
  * 374-381 do), with launches batched across the sub-problems.  Used by bench.py and STiLHead.step. */
+/* one channel of a peer-memory buffer set (see stil_p2p_exchange) */
+typedef struct stil_p2p_channel {
+    void* bases[8];
+    int world, rank;
+    int64_t flags_offset, ctrl_offset;
+    int channel;
+} stil_p2p_channel;
+
 typedef struct stil_head_step_args {
     /* sizes */
     int64_t batch, b_l, k, dim;
@@ -369,6 +390,11 @@ typedef struct stil_head_step_args {
     /* 1: the bf16 operand form of `prototypes` is already in the workspace (stil_head_prepare_prototypes was called
      * with the same workspace after the prototypes last changed) — the step then skips that conversion */
     int prototypes_prepared;
+    /* data-parallel head: non-NULL = right after the prototype partial sums exist, push the packed
+     * [class_sum | class_count] (class_count must sit right behind class_sum) to byte partials_dst_offset of every
+     * rank's buffer on this channel (stil_p2p_push); the consumer is stil_proto_add_gathered_wait */
+    const stil_p2p_channel* partials_push;
+    int64_t partials_dst_offset;
 } stil_head_step_args;
 STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int64_t k, int64_t dim, int embed_dtype);
 STIL_API int stil_head_step(const stil_head_step_args* args);

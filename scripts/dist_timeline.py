@@ -15,7 +15,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-transport = sys.argv[1] if len(sys.argv) > 1 else "p2p"
+transport = sys.argv[1] if len(sys.argv) > 1 else "fused"
 cfg = synth.CONFIGS["C2"]()
 head = S.DistributedSTiLHead(cfg, device=dev, use_graph=True, transport=transport)
 head.load(synth.make_batch(cfg, seed=2022, rank=rank))

@@ -22,6 +22,12 @@ _ERR_NAMES = {-1: "STIL_E_SHAPE", -2: "STIL_E_DTYPE", -3: "STIL_E_ALIGN", -4: "S
 i64, i32, f32, vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 
 
+class P2PChannel(C.Structure):
+    """Mirror of `stil_p2p_channel` (include/stil_head.h)."""
+    _fields_ = [("bases", vp * 8), ("world", i32), ("rank", i32), ("flags_offset", i64), ("ctrl_offset", i64),
+                ("channel", i32)]
+
+
 class HeadStepArgs(C.Structure):
     """Mirror of `stil_head_step_args` (include/stil_head.h) — field order must match."""
     _fields_ = [
@@ -44,6 +50,7 @@ class HeadStepArgs(C.Structure):
         ("rate_uce_scale", f32),
         ("workspace", vp), ("workspace_bytes", i64), ("stream", vp),
         ("timing_events", vp), ("n_timing_events", i32), ("skip_infonce", i32), ("prototypes_prepared", i32),
+        ("partials_push", C.POINTER(P2PChannel)), ("partials_dst_offset", i64),
     ]
 
 
@@ -83,8 +90,10 @@ SIGNATURES = {
     "stil_p2p_push_embeddings": (i32, [C.POINTER(vp), i32, i32, i64, i64, i32, vp, vp, i32, i64, i64, i64, i64, i64, i64, vp]),
     "stil_p2p_push_lse": (i32, [C.POINTER(vp), i32, i32, i64, i64, i32, vp, i64, i64, i64, i32, i64, i64, i64, vp]),
     "stil_infonce_stats_gathered": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, vp, vp, i64, vp, i64, vp]),
-    "stil_infonce_loss_gathered": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, vp]),
-    "stil_infonce_bwd_gathered": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, vp, vp,
+    "stil_infonce_loss_gathered": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, C.POINTER(vp),
+                                         i32, i32, i64, vp, vp, i64, vp]),
+    "stil_proto_add_gathered_wait": (i32, [vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "stil_infonce_bwd_gathered": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, vp,
                                         vp, i32, i64, vp, i64, vp]),
     "stil_da_batch_mean": (i32, [vp, i64, i64, i64, vp, vp]),
     "stil_da_apply": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),

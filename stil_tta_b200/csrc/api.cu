@@ -601,6 +601,7 @@ STIL_API int stil_infonce_stats_gathered(const void* a_all, const void* b_all, c
 STIL_API int stil_infonce_loss_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
                                         int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
                                         float temperature, float lambda0, float* loss_sum, float* lse_row, float* lse_col,
+                                        void* const* bases, int world, int rank, int64_t loss_ll_offset, const void* ll_tag,
                                         void* workspace, int64_t workspace_bytes, void* stream) {
     int rc = gathered_check(a_all, b_all, ra_all, rb_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0, nullptr,
                             nullptr, 0);
@@ -622,19 +623,30 @@ STIL_API int stil_infonce_loss_gathered(const void* a_all, const void* b_all, co
     FL.block_partials = P.block_partials;
     FL.ticket = P.ticket;
     FL.out_loss = loss_sum;
+    if (bases) {
+        // the partial also goes to every rank's LL word [rank] at loss_ll_offset (summed there in rank order)
+        STIL_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && ll_tag && loss_ll_offset % 8 == 0, STIL_E_ARG,
+                     "infonce_loss_gathered: bad peer arguments");
+        for (int p = 0; p < world; ++p)
+            FL.ll_out[p] = reinterpret_cast<unsigned long long*>(static_cast<char*>(bases[p]) + loss_ll_offset) + rank;
+        FL.ll_world = world;
+        FL.ll_tag = static_cast<const unsigned long long*>(ll_tag);
+    }
     return launch_finish(FL, S(stream));
 }
 
 STIL_API int stil_infonce_bwd_gathered(const void* a_all, const void* b_all, const float* ra_all, const float* rb_all,
                                        int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t row_offset,
-                                       float temperature, float lambda0, const float* lse_row_all,
-                                       const float* lse_col_all, const void* wait_flags, const void* wait_seq,
-                                       int64_t rows_per_peer, const float* grad_loss, void* d_a, void* d_b, int grad_dtype,
+                                       float temperature, float lambda0, const void* lse_row_ll,
+                                       const void* lse_col_ll, const void* ll_tag, const float* grad_loss, void* d_a,
+                                       void* d_b, int grad_dtype,
                                        int64_t ld_grad, void* workspace, int64_t workspace_bytes, void* stream) {
-    int rc = gathered_check(a_all, b_all, ra_all, rb_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0, wait_flags,
-                            wait_seq, rows_per_peer);
+    int rc = gathered_check(a_all, b_all, ra_all, rb_all, dtype, m, n, dim, ld, row_offset, temperature, lambda0, nullptr,
+                            nullptr, 0);
     if (rc) return rc;
-    STIL_REQUIRE(lse_row_all && lse_col_all && d_a && d_b, STIL_E_ARG, "infonce_bwd_gathered: null pointer");
+    const float* lse_row_all = static_cast<const float*>(lse_row_ll);
+    const float* lse_col_all = static_cast<const float*>(lse_col_ll);
+    STIL_REQUIRE(lse_row_all && lse_col_all && ll_tag && d_a && d_b, STIL_E_ARG, "infonce_bwd_gathered: null pointer");
     STIL_REQUIRE(grad_dtype == STIL_F32 || grad_dtype == STIL_BF16, STIL_E_DTYPE, "bad grad dtype");
     InfoncePlan P = plan_infonce(workspace, workspace_bytes, m, n, dim, dtype, true);
     STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "infonce workspace too small");
@@ -653,7 +665,11 @@ STIL_API int stil_infonce_bwd_gathered(const void* a_all, const void* b_all, con
     // every embedding row landed before the statistics GEMM finished (it waited for each peer): the operands stream
     // before the wait; only the epilogue needs the peers' LSEs
     set_early(GL, true, true);
-    set_wait(GL, wait_flags, wait_seq, rows_per_peer, 0);
+    for (int s = 0; s < 2; ++s) {
+        // LL-word vectors: entry i is 8 bytes; the job builder offset the row pointer in floats, redo it in words
+        GL.job[s].lse_x = (s == 0 ? lse_row_all : lse_col_all) + 2 * row_offset;
+        GL.job[s].lse_ll_tag = static_cast<const unsigned long long*>(ll_tag);
+    }
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
     std::memset(&GL, 0, sizeof(GL));
     bool fused = false;
@@ -916,6 +932,19 @@ STIL_API int stil_proto_add(const float* class_sum, const float* class_count, in
     return launch_proto_add(class_sum, class_count, k, dim, psum, pcount, S(stream));
 }
 
+STIL_API int stil_proto_add_gathered_wait(const float* parts, int64_t world, int64_t slot_floats, int64_t k, int64_t dim,
+                                          float* class_sum, float* class_count, float* psum, float* pcount,
+                                          const void* wait_flags, const void* wait_target, const void* loss_ll,
+                                          const void* loss_tag, float* loss_out, void* stream) {
+    STIL_REQUIRE(parts && class_sum && class_count && psum && pcount && world >= 1 && world <= 8 && wait_flags && wait_target &&
+                     ((loss_ll == nullptr) == (loss_out == nullptr)) && (loss_ll == nullptr || loss_tag != nullptr),
+                 STIL_E_ARG, "proto_add_gathered_wait: bad arguments");
+    return launch_proto_add_gathered(parts, world, slot_floats, k, dim, class_sum, class_count, psum, pcount, S(stream),
+                                     static_cast<const unsigned long long*>(wait_flags),
+                                     static_cast<const unsigned long long*>(wait_target),
+                                     static_cast<const unsigned long long*>(loss_ll),
+                                     static_cast<const unsigned long long*>(loss_tag), loss_out);
+}
 STIL_API int stil_proto_add_gathered(const float* parts, int64_t world, int64_t slot_floats, int64_t k, int64_t dim,
                                      float* class_sum, float* class_count, float* psum, float* pcount, void* stream) {
     STIL_REQUIRE(parts && class_sum && class_count && psum && pcount && world >= 1 && slot_floats >= k * dim + k, STIL_E_ARG,
@@ -1713,6 +1742,18 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
     if ((rc = launch_proto_accumulate(a->feat_m_e, dt, B, D, D, P.cls, P.conf, B_l, a->repeat_ratio, K, a->class_sum,
                                       a->class_count, a->prototypes_sum, a->prototypes_count_sum, s_acc)))
         return rc;
+    if (a->partials_push) {
+        // data-parallel head: the packed [class_sum | class_count] partial leaves for every rank as soon as it exists,
+        // mid-step on this side stream, instead of after the whole row-local chain
+        const stil_p2p_channel* ch = a->partials_push;
+        STIL_REQUIRE(a->class_count == a->class_sum + K * D, STIL_E_ARG,
+                     "head_step: partials_push needs class_count right behind class_sum (one packed partial)");
+        const void* src = a->class_sum;
+        const int64_t nbytes = round_up((K * D + K) * (int64_t)sizeof(float), 16), dst = a->partials_dst_offset;
+        if ((rc = stil_p2p_push(ch->bases, ch->world, ch->rank, ch->flags_offset, ch->ctrl_offset, ch->channel, 1, &src,
+                                &nbytes, &dst, s_acc)))
+            return rc;
+    }
     // masked soft-target CE of the student heads (f-1)
     if (a->y_m) {
         STIL_REQUIRE(a->y_i && a->y_t && a->mask_random, STIL_E_ARG, "head_step: student logits need y_i, y_t, mask_random");

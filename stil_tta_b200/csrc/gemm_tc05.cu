@@ -160,6 +160,21 @@ __device__ __forceinline__ void wait_peer_rows(const unsigned long long* flags, 
     }
 }
 
+// "LL" words of a flag-less peer exchange (csrc/p2p.cu, p2p_push_lse_kernel): value in the low 32 bits, the step tag in
+// the high 32 bits of ONE 8-byte store; the reader spins on the word itself until the tag matches — no fence anywhere.
+__device__ __forceinline__ float ll_read(const float* base, long long idx, const unsigned long long* tag_ptr) {
+    unsigned long long tag;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(tag) : "l"(tag_ptr) : "memory");
+    const unsigned int want = (unsigned int)tag;
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(base) + idx;
+    unsigned long long v, spins = 0;
+    do {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+        if (++spins > (1ull << 26)) __trap();
+    } while ((unsigned int)(v >> 32) != want);
+    return __uint_as_float((unsigned int)v);
+}
+
 // GEMM_STORE post-ops: 1 = exp(value) (embedding graph, comatch_model.py:309-311), 2 = diagonal forced to 1
 // (pseudo-label graph, comatch_model.py:299-300)
 __device__ __forceinline__ float store_post(float v, int op, int row, int col) {
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
                 if (J.wait_flags) wait_peer_rows(J.wait_flags, J.wait_seq, J.wait_rows_per_peer, col, col);
                 cs = alpha * (J.sy ? __ldcg(J.sy + col) : 1.f);
                 if (MODE == GEMM_GRAD) {
-                    if (J.lse_y) cl = __ldcg(J.lse_y + col);
+                    if (J.lse_y) cl = J.lse_ll_tag ? ll_read(J.lse_y, col, J.lse_ll_tag) : __ldcg(J.lse_y + col);
                     else if (J.py_max) cl = merge_partials(J.py_max, J.py_sum, J.py_tiles, J.N, col);
                 }
             }
@@ -350,7 +365,8 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
         float lse_x = 0.f, u = 0.f, d = 0.f, gs = 1.f;
         int tgt = -1;
         if (MODE == GEMM_GRAD && row_ok) {
-            lse_x = J.lse_x ? J.lse_x[row] : merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
+            lse_x = J.lse_x ? (J.lse_ll_tag ? ll_read(J.lse_x, row, J.lse_ll_tag) : J.lse_x[row])
+                            : merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
             tgt = J.tgt_vec ? J.tgt_vec[row] : row + J.tgt_offset;
             if (J.w_z) {
                 // prototype CE coefficient from the picked logit (utils/prototype_loss.py:28,37-39)

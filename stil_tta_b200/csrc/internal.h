@@ -82,6 +82,9 @@ struct alignas(64) GemmJob {
     const unsigned long long* wait_seq;
     int wait_rows_per_peer;
     int wait_y;
+    // GRAD: lse_x / lse_y are arrays of 8-byte LL words {f32 value, u32 tag} (flag-less peer exchange); an entry is
+    // valid once its tag equals the low 32 bits of *lse_ll_tag.  nullptr = plain f32 arrays.
+    const unsigned long long* lse_ll_tag;
     // plain STORE post-op on the scaled value: 0 none, 1 exp, 2 diagonal (row == column) forced to 1
     int post_op;
 };
@@ -169,6 +172,10 @@ struct FinishLaunch {
     float* block_partials;   // [blocks * 2]
     unsigned int* ticket;    // zeroed once by the caller's workspace init, self-resetting
     float* out_loss;         // [2]
+    // optional: loss slot 0 also goes to every rank as one 8-byte LL word {f32, u32 tag} (data-parallel head)
+    unsigned long long* ll_out[8];
+    int ll_world;
+    const unsigned long long* ll_tag;
 };
 int launch_finish(const FinishLaunch& L, cudaStream_t stream);
 int64_t finish_blocks(int total_rows);
@@ -212,7 +219,10 @@ int launch_proto_accumulate(const void* feat, int dtype, int64_t rows, int64_t d
 int launch_proto_add(const float* class_sum, const float* class_count, int64_t k, int64_t dim, float* psum,
                      float* pcount, cudaStream_t stream);
 int launch_proto_add_gathered(const float* parts, int64_t world, int64_t slot, int64_t k, int64_t dim, float* class_sum,
-                              float* class_count, float* psum, float* pcount, cudaStream_t stream);
+                              float* class_count, float* psum, float* pcount, cudaStream_t stream,
+                              const unsigned long long* wait_flags = nullptr, const unsigned long long* wait_target = nullptr,
+                              const unsigned long long* loss_ll = nullptr, const unsigned long long* loss_tag = nullptr,
+                              float* loss_out = nullptr);
 int launch_proto_finalize(float* prototypes, float* psum, float* pcount, int64_t k, int64_t dim,
                           int32_t* empty_classes, cudaStream_t stream);
 int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,

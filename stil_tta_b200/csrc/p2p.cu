@@ -45,41 +45,28 @@ struct P2PChannel {
     long long flags_offset, ctrl_offset;
     int channel;
 };
-__device__ __forceinline__ void p2p_publish(const P2PChannel& C, unsigned long long seq, bool wait) {
+__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Push protocol (no waiting, ONE system-scope release per block on the critical path — a fence.sys costs 2-4 us on
+// NVLink, so nothing here chains two of them): after the block barrier, thread p adds 1 to this rank's arrival counter in
+// peer p's buffer with a release reduction (cumulative over the block's stores).  A consumer waits until the counter
+// reaches the channel's target, which the last block to finish advances locally by the number of blocks.
+__device__ __forceinline__ void p2p_publish(const P2PChannel& C) {
     unsigned char* self = C.base[C.rank];
-    unsigned long long* seq_ctr = reinterpret_cast<unsigned long long*>(self + C.ctrl_offset) + C.channel;
+    unsigned long long* target = reinterpret_cast<unsigned long long*>(self + C.ctrl_offset) + C.channel;
     unsigned int* done_ctr = reinterpret_cast<unsigned int*>(self + C.ctrl_offset + 64 * sizeof(unsigned long long)) + C.channel;
-    __threadfence_system();
     __syncthreads();
-    __shared__ bool is_last;
-    if (threadIdx.x == 0) is_last = atomicAdd(done_ctr, 1u) == gridDim.x * gridDim.y - 1;
-    __syncthreads();
-    if (!is_last) return;
-    if ((int)threadIdx.x < C.world) {
-        const int p = threadIdx.x;
-        unsigned long long* their_flag =
-            reinterpret_cast<unsigned long long*>(C.base[p] + C.flags_offset) + C.channel * kMaxWorld + C.rank;
-        __threadfence_system();
-        st_release_sys(their_flag, seq);
-        if (wait) {
-            const unsigned long long* my_flag =
-                reinterpret_cast<const unsigned long long*>(self + C.flags_offset) + C.channel * kMaxWorld + p;
-            unsigned long long spins = 0;
-            while (ld_acquire_sys(my_flag) < seq) {
-                if (++spins > (1ull << 26)) __trap();   // a lost peer becomes a CUDA error, not a hung GPU
-            }
+    if ((int)threadIdx.x < C.world)
+        red_release_sys_add(reinterpret_cast<unsigned long long*>(C.base[threadIdx.x] + C.flags_offset) +
+                                C.channel * kMaxWorld + C.rank, 1ull);
+    if (threadIdx.x == 0) {
+        const unsigned int nblk = gridDim.x * gridDim.y;
+        if (atomicAdd(done_ctr, 1u) == nblk - 1) {
+            *done_ctr = 0u;
+            *target = *target + nblk;      // read by the consumers launched after this kernel
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        *done_ctr = 0u;
-        *seq_ctr = seq;
-        __threadfence_system();
-    }
-}
-__device__ __forceinline__ unsigned long long p2p_next_seq(const P2PChannel& C) {
-    // stable for the whole kernel: only its last block bumps the counter, after every block has read it
-    return *(reinterpret_cast<const unsigned long long*>(C.base[C.rank] + C.ctrl_offset) + C.channel) + 1;
 }
 
 // Wait until every peer's push number *seq_ctr on `channel` has landed in the local buffer (for consumers that are not
@@ -109,7 +96,6 @@ struct PushEmbed {
     int row0;                // global index of local row 0
 };
 __global__ void __launch_bounds__(kP2PBlock) p2p_push_embeddings_kernel(const PushEmbed X) {
-    const unsigned long long seq = p2p_next_seq(X.C);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * (kP2PBlock / 32) + warp;
     if (r < X.rows) {
@@ -148,13 +134,14 @@ __global__ void __launch_bounds__(kP2PBlock) p2p_push_embeddings_kernel(const Pu
             }
         }
     }
-    p2p_publish(X.C, seq, false);
+    p2p_publish(X.C);
 }
 
 // Row LSEs of the local rows of both InfoNCE sides, merged from the GEMM_STATS partials and written into every rank's
 // gathered LSE vectors (one warp per row): the statistics merge and the LSE all-gather in one kernel.
 struct PushLse {
     P2PChannel C;
+    const unsigned long long* tag;   // LL step tag: low 32 bits of this word (the embeddings channel's arrival target)
     const float* pmax[2];
     const float* psum[2];    // [slots, m] per side
     int slots, m;
@@ -162,7 +149,6 @@ struct PushLse {
     int row0;
 };
 __global__ void __launch_bounds__(kP2PBlock) p2p_push_lse_kernel(const PushLse X) {
-    const unsigned long long seq = p2p_next_seq(X.C);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gr = blockIdx.x * (kP2PBlock / 32) + warp;
     if (gr < 2 * X.m) {
@@ -183,10 +169,28 @@ __global__ void __launch_bounds__(kP2PBlock) p2p_push_lse_kernel(const PushLse X
         for (int t = lane + 64; t < X.slots; t += 32) sm += ps[(long long)t * X.m + i] * expf(pm[(long long)t * X.m + i] - mx);
         sm = warp_sum(sm);
         const float lse = mx + logf(sm);
+        // flag-less: value and step tag travel in ONE 8-byte store; readers spin on the word itself
+        const unsigned long long word = ((unsigned long long)(unsigned int)(*X.tag) << 32) | __float_as_uint(lse);
         if (lane < X.C.world)
-            reinterpret_cast<float*>(X.C.base[(X.C.rank + lane) % X.C.world] + X.lse_offset[side])[X.row0 + i] = lse;
+            reinterpret_cast<unsigned long long*>(X.C.base[(X.C.rank + lane) % X.C.world] + X.lse_offset[side])[X.row0 + i] = word;
     }
-    p2p_publish(X.C, seq, false);
+}
+
+// generic push of up to kMaxSeg byte segments (same arrival-counter protocol)
+__global__ void __launch_bounds__(kP2PBlock) p2p_push_kernel(const P2PExchange X) {
+    for (int s = 0; s < X.nseg; ++s) {
+        const uint4* src = reinterpret_cast<const uint4*>(X.src[s]);
+        const long long n16 = X.nbytes[s] >> 4;
+        for (int p = 0; p < X.world; ++p) {
+            uint4* dst = reinterpret_cast<uint4*>(X.base[(X.rank + p) % X.world] + X.dst_offset[s]);
+            for (long long i = (long long)blockIdx.x * kP2PBlock + threadIdx.x; i < n16; i += (long long)gridDim.x * kP2PBlock)
+                dst[i] = src[i];
+        }
+    }
+    P2PChannel C;
+    for (int p = 0; p < kMaxWorld; ++p) C.base[p] = X.base[p];
+    C.world = X.world; C.rank = X.rank; C.flags_offset = X.flags_offset; C.ctrl_offset = X.ctrl_offset; C.channel = X.channel;
+    p2p_publish(C);
 }
 
 __global__ void __launch_bounds__(kP2PBlock) p2p_exchange_kernel(const P2PExchange X) {
@@ -204,10 +208,13 @@ __global__ void __launch_bounds__(kP2PBlock) p2p_exchange_kernel(const P2PExchan
                 dst[i] = src[i];
         }
     }
-    __threadfence_system();
     __syncthreads();
     __shared__ bool is_last;
-    if (threadIdx.x == 0) is_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();      // one system-scope fence per block (cumulative over the block's stores)
+        is_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1;
+        __threadfence();
+    }
     __syncthreads();
     if (!is_last) return;
     // ---- last block: publish arrival to every peer, then wait until every peer's data has landed here
@@ -307,7 +314,10 @@ static int p2p_exchange_impl(void* const* bases, int world, int rank, int64_t fl
     X.world = world; X.rank = rank; X.flags_offset = flags_offset; X.ctrl_offset = ctrl_offset;
     X.channel = channel; X.nseg = nseg; X.wait = wait;
     const int blocks = (int)std::max<long long>(1, std::min<long long>(32, most / (16 * kP2PBlock * 2)));
-    p2p_exchange_kernel<<<blocks, kP2PBlock, 0, static_cast<cudaStream_t>(stream)>>>(X);
+    if (wait)
+        p2p_exchange_kernel<<<blocks, kP2PBlock, 0, static_cast<cudaStream_t>(stream)>>>(X);
+    else
+        p2p_push_kernel<<<blocks, kP2PBlock, 0, static_cast<cudaStream_t>(stream)>>>(X);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }
@@ -351,14 +361,16 @@ STIL_API int stil_p2p_push_embeddings(void* const* bases, int world, int rank, i
     return STIL_OK;
 }
 STIL_API int stil_p2p_push_lse(void* const* bases, int world, int rank, int64_t flags_offset, int64_t ctrl_offset,
-                               int channel, const void* infonce_workspace, int64_t m, int64_t n, int64_t dim, int dtype,
+                               int tag_channel, const void* infonce_workspace, int64_t m, int64_t n, int64_t dim, int dtype,
                                int64_t row0, int64_t lse_row_offset, int64_t lse_col_offset, void* stream) {
     PushLse X;
     std::memset(&X, 0, sizeof(X));
-    int rc = fill_channel(X.C, bases, world, rank, flags_offset, ctrl_offset, channel);
+    int rc = fill_channel(X.C, bases, world, rank, flags_offset, ctrl_offset, tag_channel);
     if (rc) return rc;
-    STIL_REQUIRE(infonce_workspace && m >= 1 && n >= m && lse_row_offset % 4 == 0 && lse_col_offset % 4 == 0, STIL_E_ARG,
-                 "p2p_push_lse: bad arguments");
+    STIL_REQUIRE(infonce_workspace && m >= 1 && n >= m && lse_row_offset % 8 == 0 && lse_col_offset % 8 == 0 && tag_channel >= 0 &&
+                     tag_channel < 8,
+                 STIL_E_ARG, "p2p_push_lse: bad arguments");
+    X.tag = reinterpret_cast<const unsigned long long*>(X.C.base[rank] + ctrl_offset) + tag_channel;
     int slots = 0;
     infonce_stat_partials(const_cast<void*>(infonce_workspace), m, n, dim, dtype, X.pmax, X.psum, &slots);
     X.slots = slots; X.m = (int)m; X.row0 = (int)row0;

@@ -501,6 +501,8 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
             bool used = false;
             for (int j = 0; j < L.njobs; ++j) used |= L.job[j].loss_slot == slot;
             if (used && lane == 0) L.out_loss[slot] = sum;
+            if (slot == 0 && lane < L.ll_world)
+                *L.ll_out[lane] = ((unsigned long long)(unsigned int)(*L.ll_tag) << 32) | __float_as_uint(sum);
         }
         if (lane == 0) *L.ticket = 0u;
     }
@@ -688,12 +690,42 @@ __global__ void proto_add_kernel(const float* class_sum, const float* class_coun
 }
 
 __global__ void proto_add_gathered_kernel(const float* parts, int world, long long slot, int k, int dim, float* class_sum,
-                                          float* class_count, float* psum, float* pcount) {
+                                          float* class_count, float* psum, float* pcount,
+                                          const unsigned long long* wait_flags, const unsigned long long* wait_target,
+                                          const unsigned long long* loss_ll, const unsigned long long* loss_tag,
+                                          float* loss_out) {
+    // fused schedule of the data-parallel head: the partials were pushed by the peers (csrc/p2p.cu) — wait for every
+    // rank's arrival counter here, at the consumer, instead of in a kernel of its own
+    if (wait_flags) {
+        if ((int)threadIdx.x < world) {
+            const unsigned long long target = *wait_target;
+            unsigned long long v, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + threadIdx.x) : "memory");
+                if (++spins > (1ull << 26)) __trap();
+            } while (v < target);
+        }
+        __syncthreads();
+    }
+    if (loss_ll && blockIdx.x == 0 && threadIdx.x == 0) {
+        // global InfoNCE loss = sum of the ranks' partials (LL words), in rank order
+        const unsigned int want = (unsigned int)(*loss_tag);
+        float s = 0.f;
+        for (int w = 0; w < world; ++w) {
+            unsigned long long v, spins = 0;
+            do {
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(loss_ll + w) : "memory");
+                if (++spins > (1ull << 26)) __trap();
+            } while ((unsigned int)(v >> 32) != want);
+            s += __uint_as_float((unsigned int)v);
+        }
+        *loss_out = s;
+    }
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nsum = (long long)k * dim;
     if (i < nsum + k) {
         float s = 0.f;
-        for (int w = 0; w < world; ++w) s += parts[(long long)w * slot + i];   // rank order: deterministic
+        for (int w = 0; w < world; ++w) s += __ldcg(parts + (long long)w * slot + i);   // rank order: deterministic
         if (i < nsum) {
             class_sum[i] = s;
             psum[i] += s;
@@ -1107,10 +1139,14 @@ int launch_proto_add(const float* class_sum, const float* class_count, int64_t k
 }
 
 int launch_proto_add_gathered(const float* parts, int64_t world, int64_t slot, int64_t k, int64_t dim, float* class_sum,
-                              float* class_count, float* psum, float* pcount, cudaStream_t stream) {
+                              float* class_count, float* psum, float* pcount, cudaStream_t stream,
+                              const unsigned long long* wait_flags, const unsigned long long* wait_target,
+                              const unsigned long long* loss_ll, const unsigned long long* loss_tag, float* loss_out) {
     if (k == 0) return STIL_OK;
     proto_add_gathered_kernel<<<(int)ceil_div(k * dim + k, 256), 256, 0, stream>>>(parts, (int)world, slot, (int)k, (int)dim,
-                                                                                class_sum, class_count, psum, pcount);
+                                                                                class_sum, class_count, psum, pcount,
+                                                                                wait_flags, wait_target, loss_ll, loss_tag,
+                                                                                loss_out);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }

@@ -289,12 +289,17 @@ class DistributedSTiLHead(STiLHead):
             self._o_ab = 0
             self._o_loss = self._o_ab + r256(n * 2 * P * esz)
             self._o_lr = self._o_loss + r256(W * 16)
-            self._o_lc = self._o_lr + r256(n * 4)
-            self._o_cls = self._o_lc + r256(n * 4)
+            self._o_lc = self._o_lr + r256(n * 8)       # 8 bytes per entry: the fused transport stores LL words
+            self._o_cls = self._o_lc + r256(n * 8)
             self._o_ra = self._o_cls + r256(W * self._slot * 4)
             self._o_rb = self._o_ra + r256(n * 4)
             self._half = self._o_rb + r256(n * 4)
             self._p2p = P2PBuffer(2 * self._half, dev, group)
+            ch = _lib.P2PChannel()
+            for i, b in enumerate(self._p2p.peers):
+                ch.bases[i] = b
+            ch.world, ch.rank, ch.flags_offset, ch.ctrl_offset, ch.channel = W, self.rank, 0, 512, 2
+            self._push_channel = ch
             v = self._p2p.view
             self._r = []
             for h in (0, 1):
@@ -378,30 +383,33 @@ class DistributedSTiLHead(STiLHead):
                                                       cfg.temperature, flags(0), seq(0), B, p(self._nce_ws),
                                                       self._nce_ws.numel(), sb.cuda_stream))
                 sl.wait_stream(sb)
-                check(lib.stil_p2p_push_lse(*chan(1), p(self._nce_ws), B, n, P, code, off, H + self._o_lr, H + self._o_lc,
+                # row LSEs as LL words {value, step tag}: no flag, no fence; the tag is channel 0's arrival target
+                check(lib.stil_p2p_push_lse(*chan(0), p(self._nce_ws), B, n, P, code, off, H + self._o_lr, H + self._o_lc,
                                             sb.cuda_stream))
                 check(lib.stil_infonce_bwd_gathered(a_all, b_all, p(R["ra"]), p(R["rb"]), code, B, n, P, 2 * P, off,
                                                     cfg.temperature, cfg.lambda_0, p(R["lse_row"]), p(R["lse_col"]),
-                                                    flags(1), seq(1), B, None, p(self.out["d_feat_i"]),
+                                                    seq(0), None, p(self.out["d_feat_i"]),
                                                     p(self.out["d_feat_t"]), _lib.dtype_code(self.out["d_feat_i"]), P,
                                                     p(self._nce_ws), self._nce_ws.numel(), sb.cuda_stream))
             with torch.cuda.stream(sl):
-                # loss partial of the local rows from the statistics: beside the chain, not in it
+                # loss partial of the local rows from the statistics, beside the chain: it leaves for every rank as one
+                # LL word (value + step tag in a single 8-byte store)
                 check(lib.stil_infonce_loss_gathered(a_all, b_all, p(R["ra"]), p(R["rb"]), code, B, n, P, 2 * P, off,
                                                      cfg.temperature, cfg.lambda_0, p(self._nce_loc), p(self._nce_loc[4:]),
-                                                     p(self._nce_loc[4 + B:]), p(self._nce_ws), self._nce_ws.numel(),
-                                                     sl.cuda_stream))
-            self._enqueue()                          # everything row-local (current stream)
+                                                     p(self._nce_loc[4 + B:]), pb._bases, W, r, H + self._o_loss, seq(0),
+                                                     p(self._nce_ws), self._nce_ws.numel(), sl.cuda_stream))
+            # everything row-local (current stream); the class partials are pushed from inside the step, mid-way, as soon
+            # as proto_accumulate has produced them
+            a = self._args
+            a.partials_push = C.pointer(self._push_channel)
+            a.partials_dst_offset = H + self._o_cls + r * self._slot * 4
+            self._enqueue()
             cur.wait_stream(sl)
-            segs = [(self._cls_loc, H + self._o_cls + r * self._slot * 4), (self._nce_loc[:4], H + self._o_loss + r * 16)]
-            src = (C.c_void_p * 2)(*[t.data_ptr() for t, _ in segs])
-            nb = (C.c_int64 * 2)(*[t.numel() * t.element_size() for t, _ in segs])
-            dst = (C.c_int64 * 2)(*[o for _, o in segs])
-            check(lib.stil_p2p_push(*chan(2), 2, src, nb, dst, cur.cuda_stream))
-            check(lib.stil_p2p_wait(*chan(2), cur.cuda_stream))
-            check(lib.stil_proto_add_gathered(p(R["cls"]), W, self._slot, K, P, p(self._sum_out), p(self._cnt_out),
-                                              p(self.prototypes_sum), p(self.prototypes_count_sum), cur.cuda_stream))
-            torch.sum(R["loss"][:, 0], dim=0, keepdim=True, out=self.out["losses"][0:1])
+            # last kernel of the step: waits for every rank's partials (arrival counters) and loss word, adds in rank order
+            check(lib.stil_proto_add_gathered_wait(p(R["cls"]), W, self._slot, K, P, p(self._sum_out), p(self._cnt_out),
+                                                   p(self.prototypes_sum), p(self.prototypes_count_sum), flags(2), seq(2),
+                                                   pb.local + H + self._o_loss, seq(0), p(self.out["losses"]),
+                                                   cur.cuda_stream))
             cur.wait_stream(sb)
 
     def _run_eager(self, parity: int = 0) -> None:
