@@ -151,12 +151,15 @@ __device__ __forceinline__ void wait_peer_rows(const unsigned long long* flags, 
                                                int r0, int r1) {
     unsigned long long seq;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seq) : "l"(seq_ptr) : "memory");
+    // acquire loads, polled by ONE thread per role (a trailing fence.sys instead costs microseconds: measured)
     for (int p = r0 / rpp; p <= r1 / rpp; ++p) {
         unsigned long long v, spins = 0;
-        do {
+        for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
-            if (++spins > (1ull << 26)) __trap();
-        } while (v < seq);
+            if (v >= seq) break;
+            if (++spins > (1ull << 24)) __trap();
+            __nanosleep(20);
+        }
     }
 }
 
@@ -168,10 +171,12 @@ __device__ __forceinline__ float ll_read(const float* base, long long idx, const
     const unsigned int want = (unsigned int)tag;
     const unsigned long long* w = reinterpret_cast<const unsigned long long*>(base) + idx;
     unsigned long long v, spins = 0;
-    do {
+    for (;;) {
         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
-        if (++spins > (1ull << 26)) __trap();
-    } while ((unsigned int)(v >> 32) != want);
+        if ((unsigned int)(v >> 32) == want) break;
+        if (++spins > (1ull << 24)) __trap();
+        __nanosleep(32);
+    }
     return __uint_as_float((unsigned int)v);
 }
 
@@ -346,12 +351,16 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
             asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // next kernel may begin its prologue
             STIL_TRACE(1);
         }
+        if (J.wait_flags) {
+            // column scales gathered from peer ranks: ONE thread waits for the owners of this tile's columns, the barrier
+            // passes the acquire on to the others, which then read through L2
+            if (e == 0) wait_peer_rows(J.wait_flags, J.wait_seq, J.wait_rows_per_peer, n0, min(n0 + kTileN, J.N) - 1);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         if (e < kTileN) {
             const int col = n0 + e;
             float cs = 0.f, cl = 0.f;
             if (col < J.N) {
-                // column scales / LSEs gathered from peer ranks: wait for the owner's arrival, read through L2
-                if (J.wait_flags) wait_peer_rows(J.wait_flags, J.wait_seq, J.wait_rows_per_peer, col, col);
                 cs = alpha * (J.sy ? __ldcg(J.sy + col) : 1.f);
                 if (MODE == GEMM_GRAD) {
                     if (J.lse_y) cl = J.lse_ll_tag ? ll_read(J.lse_y, col, J.lse_ll_tag) : __ldcg(J.lse_y + col);

@@ -526,9 +526,16 @@ __global__ void __launch_bounds__(kRowBlock) grad_finish_kernel(const __grid_con
     const float* g0 = J.g + (long long)i * J.dim;
     const int ns = J.nslices > 1 ? J.nslices : 1;
     auto gsum = [&](int d) {      // slices of a split contraction, added in index order (deterministic)
-        float v = g0[d];
-#pragma unroll 8
-        for (int k = 1; k < ns; ++k) v += g0[(long long)k * J.slice_stride + d];
+        // eight independent (predicated) loads per batch, then the adds: a `v += load` loop serialises one memory round
+        // trip per slice
+        float v = 0.f;
+        for (int k0 = 0; k0 < ns; k0 += 8) {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = (k0 + j < ns) ? __ldcg(g0 + (long long)(k0 + j) * J.slice_stride + d) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v += t[j];
+        }
         return v;
     };
     if (J.sx) {
@@ -697,13 +704,18 @@ __global__ void proto_add_gathered_kernel(const float* parts, int world, long lo
     // fused schedule of the data-parallel head: the partials were pushed by the peers (csrc/p2p.cu) — wait for every
     // rank's arrival counter here, at the consumer, instead of in a kernel of its own
     if (wait_flags) {
-        if ((int)threadIdx.x < world) {
+        if (threadIdx.x == 0) {
+            // one polling thread per block, acquire loads with back-off
             const unsigned long long target = *wait_target;
-            unsigned long long v, spins = 0;
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + threadIdx.x) : "memory");
-                if (++spins > (1ull << 26)) __trap();
-            } while (v < target);
+            for (int w = 0; w < world; ++w) {
+                unsigned long long v, spins = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + w) : "memory");
+                    if (v >= target) break;
+                    if (++spins > (1ull << 24)) __trap();
+                    __nanosleep(64);
+                }
+            }
         }
         __syncthreads();
     }
@@ -713,10 +725,12 @@ __global__ void proto_add_gathered_kernel(const float* parts, int world, long lo
         float s = 0.f;
         for (int w = 0; w < world; ++w) {
             unsigned long long v, spins = 0;
-            do {
+            for (;;) {
                 asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(loss_ll + w) : "memory");
-                if (++spins > (1ull << 26)) __trap();
-            } while ((unsigned int)(v >> 32) != want);
+                if ((unsigned int)(v >> 32) == want) break;
+                if (++spins > (1ull << 24)) __trap();
+                __nanosleep(64);
+            }
             s += __uint_as_float((unsigned int)v);
         }
         *loss_out = s;
