@@ -44,8 +44,8 @@ struct Operand {
 };
 
 inline int64_t pad32(int64_t n) { return round_up(n, 32); }
-// GEMM_STATS writes one (max, sum) partial per 64-column half tile
-inline int64_t stat_slots(int64_t n) { return 2 * ceil_div(n, kTileN); }
+// GEMM_STATS writes one (max, sum) partial per 32-column chunk of a tile
+inline int64_t stat_slots(int64_t n) { return 4 * ceil_div(n, kTileN); }
 
 // segment pairs (x_seg, y_seg) with x_seg + y_seg <= order, most significant first.  Segment s carries
 // ~2^-9s of the value, so order 2 keeps every product above ~2^-26 (fp32-accurate), order 1 above 2^-17.
@@ -1640,7 +1640,8 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
             return rc;
         GL.njobs = 1;
         gemm_job_tiles(GL);
-        set_early(GL, true, true);    // predecessor = cgpl_pgls: both operands were final two kernels ago
+        set_early(GL, true, true);    // predecessor = cgpl_pgls: both operands were final two kernels ago ...
+        GL.job[0].early_stats = 1;    // ... and so were the statistics of the student logits
         if ((rc = launch_gemm(GL, st))) return rc;
         if ((rc = mark(7, st))) return rc;
         std::memset(&GL, 0, sizeof(GL));

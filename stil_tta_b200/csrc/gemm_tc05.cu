@@ -24,10 +24,13 @@ namespace {
 // the reference sizes is in flight at once); grids of more than 148 tiles run TWO CTAs per SM with 3-deep rings so that
 // one CTA's epilogue overlaps the other's TMA/MMA main loop (the accumulator is single-buffered).
 constexpr int kMaxStages = 6;
-constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
+// TMA warp, MMA warp, then the epilogue warps: 16 when one CTA owns the SM (each thread drains ONE 32-column chunk of its
+// row — the epilogue is the long pole of the small, latency-bound launches), 8 when two CTAs share it (two chunks each)
+constexpr int epi_warps_for(int occ) { return occ == 1 ? 16 : 8; }
+constexpr int threads_for(int occ) { return 64 + 32 * epi_warps_for(occ); }
 constexpr int kStageBytes = (kTileM + kTileN) * kTileK * 2;  // 32 KiB
 constexpr int smem_bytes_for(int stages) {
-    return stages * kStageBytes + 1024 /*align slack*/ + 2048 /*scales, dot partials*/ + 256 /*barriers*/;
+    return stages * kStageBytes + 1024 /*align slack*/ + 3072 /*scales, dot partials*/ + 256 /*barriers*/;
 }
 constexpr int kStageFloats = 32 * 33;   // per-warp staging tile for coalesced epilogue stores (reuses the ring)
 constexpr uint32_t kTmemCols = 128;
@@ -44,21 +47,21 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __device__ __forceinline__ float merge_partials(const float* pmax, const float* psum, int slots, long long stride,
                                                 int idx) {
     float run_m = -INFINITY, run_s = 0.f;
-    for (int t0 = 0; t0 < slots; t0 += 8) {
-        float m[8], s[8];
+    for (int t0 = 0; t0 < slots; t0 += 16) {
+        float m[16], s[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
             const bool ok = t0 + j < slots;
-            m[j] = ok ? pmax[(long long)(t0 + j) * stride + idx] : -INFINITY;
-            s[j] = ok ? psum[(long long)(t0 + j) * stride + idx] : 0.f;
+            m[j] = ok ? __ldcg(pmax + (long long)(t0 + j) * stride + idx) : -INFINITY;
+            s[j] = ok ? __ldcg(psum + (long long)(t0 + j) * stride + idx) : 0.f;
         }
         float nm = run_m;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) nm = fmaxf(nm, m[j]);
+        for (int j = 0; j < 16; ++j) nm = fmaxf(nm, m[j]);
         if (nm == -INFINITY) continue;
         float acc = run_s * __expf(run_m - nm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc += s[j] * __expf(m[j] - nm);
+        for (int j = 0; j < 16; ++j) acc += s[j] * __expf(m[j] - nm);
         run_m = nm;
         run_s = acc;
     }
@@ -189,17 +192,21 @@ __device__ __forceinline__ float store_post(float v, int op, int row, int col) {
 }
 
 template <int MODE, int OCC>
-__global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_constant__ GemmLaunch L) {
+__global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const __grid_constant__ GemmLaunch L) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int kStages = OCC == 1 ? kMaxStages : 3;
+    constexpr int kEpiWarps = epi_warps_for(OCC);
+    constexpr int kEpiThreads = 32 * kEpiWarps;
+    constexpr int kParts = kEpiWarps / 4;        // column parts of the tile (one warp per TMEM lane quarter each)
+    constexpr int kCPW = 4 / kParts;             // 32-column chunks per warp
     // carve: [stages x (A 16K | B 16K)] 1024-aligned, then scales, then barriers
     const uint32_t raw = tc05::smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* tiles = smem_raw + pad;
     float* col_scale = reinterpret_cast<float*>(tiles + kStages * kStageBytes);  // [128]
     float* col_lse = col_scale + kTileN;                                          // [128]
-    float* dot_part = col_lse + kTileN;                                           // [2][128]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(dot_part + 2 * kTileM);
+    float* dot_part = col_lse + kTileN;                                           // [kParts <= 4][128]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(dot_part + 4 * kTileM);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full_bar = empty_bar + kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -231,6 +238,7 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
     if (warp == 0 && lane == 0) {
         tc05::tma_prefetch_desc(&J.tmx);
         tc05::tma_prefetch_desc(&J.tmy);
+        if (MODE == GEMM_GRAD) tc05::tma_prefetch_desc(&J.tmg);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -339,13 +347,18 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
     } else {
         // ===================== epilogue: 8 warps, thread = accumulator row, two warps per lane quarter
         // (one per 64-column half of the tile) =====================
-        const int e = threadIdx.x - 64;      // 0..255
+        const int e = threadIdx.x - 64;      // 0..kEpiThreads-1
         const int q = warp & 3;              // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;    // which 64 columns
+        const int part = (warp - 2) >> 2;    // which kCPW*32 columns
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < J.M;
         const int ncols = min(kTileN, J.N - n0);
         const float alpha = J.alpha;
+        // J.early_stats: the row statistics (and plain row/column scales) were final two kernels ago — merge them before
+        // waiting for the predecessor, overlapping its execution
+        float lse_x_early = 0.f;
+        const bool pre_stats = MODE == GEMM_GRAD && J.early_stats && J.lse_x == nullptr && J.px_max != nullptr;
+        if (pre_stats && row_ok) lse_x_early = merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
         asm volatile("griddepcontrol.wait;" ::: "memory");               // predecessor's results visible from here on
         if (e == 0) {
             asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // next kernel may begin its prologue
@@ -355,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
             // column scales gathered from peer ranks: ONE thread waits for the owners of this tile's columns, the barrier
             // passes the acquire on to the others, which then read through L2
             if (e == 0) wait_peer_rows(J.wait_flags, J.wait_seq, J.wait_rows_per_peer, n0, min(n0 + kTileN, J.N) - 1);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
         if (e < kTileN) {
             const int col = n0 + e;
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
         int tgt = -1;
         if (MODE == GEMM_GRAD && row_ok) {
             lse_x = J.lse_x ? (J.lse_ll_tag ? ll_read(J.lse_x, row, J.lse_ll_tag) : J.lse_x[row])
-                            : merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
+                    : pre_stats ? lse_x_early : merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
             tgt = J.tgt_vec ? J.tgt_vec[row] : row + J.tgt_offset;
             if (J.w_z) {
                 // prototype CE coefficient from the picked logit (utils/prototype_loss.py:28,37-39)
@@ -391,12 +404,12 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
         const float v = (MODE == GEMM_GRAD && (J.lse_y || J.py_max)) ? J.v_scalar : 0.f;
         const bool fused_fin = MODE == GEMM_STORE && J.fin_dx != nullptr;
         const float fsx = (fused_fin && row_ok && J.fin_sx) ? J.fin_sx[row] : 0.f;
-        // this thread's 64 columns of x for the normalise-backward, fetched while the MMAs run
-        float xrow[2][32];
+        // this thread's columns of x for the normalise-backward, fetched while the MMAs run
+        float xrow[kCPW][32];
         if (MODE == GEMM_STORE && fused_fin && J.fin_sx) {
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c = half * 2 + cc;
+            for (int cc = 0; cc < kCPW; ++cc) {
+                const int c = part * kCPW + cc;
                 const int nv = max(0, min(32, ncols - c * 32));
                 if (row_ok && nv > 0)
                     load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + n0 + c * 32, nv, xrow[cc]);
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
                 }
             }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue-only named barrier: col_scale / col_lse ready
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // epilogue-only named barrier: col_scale / col_lse ready
 
         if (e == 0) STIL_TRACE(4);   // epilogue prologue (scales, merges, coefficients) done
         tc05::mbar_wait(tmem_full_bar, 0);
@@ -414,32 +427,39 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
         if (e == 0) STIL_TRACE(5);   // accumulator ready
 
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const int c_begin = half * 2, c_end = half * 2 + 2;   // two 32-column chunks per warp
+        const int c_begin = part * kCPW, c_end = c_begin + kCPW;   // this warp's 32-column chunks
 
         float fin_dot = 0.f;
         if (MODE == GEMM_STORE && fused_fin && J.fin_sx) {
             // pass 1 of the normalise-backward: <xh, g> over the whole row (the tile spans all of N)
-            float part = 0.f;
+            float part_dot = 0.f;
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
+            for (int cc = 0; cc < kCPW; ++cc) {
                 const int c = c_begin + cc;
                 if (c * 32 < ncols) {   // warp-uniform
                     uint32_t acc[32];
                     tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
                     tc05::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) part += xrow[cc][j] * __uint_as_float(acc[j]);
+                    for (int j = 0; j < 32; ++j) part_dot += xrow[cc][j] * __uint_as_float(acc[j]);
                 }
             }
-            dot_part[half * kTileM + q * 32 + lane] = part * fsx * alpha;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            fin_dot = dot_part[q * 32 + lane] + dot_part[kTileM + q * 32 + lane];
+            dot_part[part * kTileM + q * 32 + lane] = part_dot * fsx * alpha;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+#pragma unroll
+            for (int pp = 0; pp < kParts; ++pp) fin_dot += dot_part[pp * kTileM + q * 32 + lane];
         }
 
-        float run_max = -INFINITY, run_sum = 0.f;
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
-            if (c * 32 >= ncols) break;  // warp-uniform
+            float run_max = -INFINITY, run_sum = 0.f;
+            if (c * 32 >= ncols) {   // warp-uniform: an empty chunk contributes the neutral statistics (-inf, 0)
+                if (MODE == GEMM_STATS && row_ok) {
+                    J.part_max[(long long)(tn * 4 + c) * J.M + row] = run_max;
+                    J.part_sum[(long long)(tn * 4 + c) * J.M + row] = run_sum;
+                }
+                continue;
+            }
             uint32_t acc[32];
             tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
             tc05::tmem_ld_wait();
@@ -460,15 +480,19 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
                     if (j < nv) s += fast_exp2((l[j] - new_max) * kLog2e);
                 run_sum = run_sum * fast_exp2((run_max - new_max) * kLog2e) + s;
                 run_max = new_max;
+                if (row_ok) {   // one (max, sum) partial per 32-column chunk
+                    J.part_max[(long long)(tn * 4 + c) * J.M + row] = run_max;
+                    J.part_sum[(long long)(tn * 4 + c) * J.M + row] = run_sum;
+                }
             }
             if (MODE == GEMM_STORE && fused_fin) {
                 if (J.fin_sx && row_ok) {
-                    if (c == c_begin) {
+                    if (kCPW == 1 || c == c_begin) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xrow[0][j] * fin_dot);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xrow[1][j] * fin_dot);
+                        for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xrow[kCPW - 1][j] * fin_dot);
                     }
                 }
                 if (row_ok) store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + n0 + c * 32, nv, l);
@@ -516,12 +540,13 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
                 }
                 __syncwarp();
             }
-            if (MODE == GEMM_GRAD && row_ok) {
+            if (MODE == GEMM_GRAD) {
                 const bool want_lo = J.g_nseg > 1;
-                __nv_bfloat16* hi_dst = J.gop + (long long)row * J.g_nseg * J.ld_g + n0 + c * 32;
-                __nv_bfloat16* lo_dst = hi_dst + J.ld_g;
-                // gop rows are padded to 32 columns (ld_g % 32 == 0), so full 16-byte stores are always in bounds;
-                // columns >= N hold finite garbage that the dX GEMM never reads (its contraction extent is N)
+                // G leaves through shared memory and TMA: thread = row stores straight to global would issue 32 scattered
+                // 16-byte sectors per instruction and make the LSU the long pole of the epilogue (2 us per tile).  Each
+                // thread writes its 64 bytes into a 128-byte-swizzled [128 rows x 64 columns] box (conflict-free), one
+                // thread then issues a bulk tensor store per box and segment.  Rows >= M and columns >= ld_g are clipped
+                // by the tensor map; columns in [N, ld_g) hold finite garbage the dX GEMM never reads.
                 uint32_t hi_pk[16], lo_pk[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
@@ -540,20 +565,29 @@ __global__ void __launch_bounds__(kThreads, OCC) gemm_tc05_kernel(const __grid_c
                     hi_pk[j / 2] = *reinterpret_cast<const uint32_t*>(&hh);
                     lo_pk[j / 2] = *reinterpret_cast<const uint32_t*>(&ll);
                 }
+                const int r_in = q * 32 + lane;                 // row inside the tile
+                const int box = c >> 1, k0 = (c & 1) * 4;       // 64-column box, first 16-byte chunk of this warp's 32 columns
+                uint8_t* hi_box = tiles + box * (kTileM * 128) + r_in * 128;
+                uint8_t* lo_box = hi_box + 2 * (kTileM * 128);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<uint4*>(hi_dst + 2 * j) = make_uint4(hi_pk[j], hi_pk[j + 1], hi_pk[j + 2], hi_pk[j + 3]);
-                if (want_lo) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<uint4*>(lo_dst + 2 * j) = make_uint4(lo_pk[j], lo_pk[j + 1], lo_pk[j + 2], lo_pk[j + 3]);
+                for (int k = 0; k < 4; ++k) {
+                    const int off = ((k0 + k) ^ (r_in & 7)) * 16;   // SWIZZLE_128B: chunk index xor (row mod 8)
+                    *reinterpret_cast<uint4*>(hi_box + off) = make_uint4(hi_pk[4 * k], hi_pk[4 * k + 1], hi_pk[4 * k + 2], hi_pk[4 * k + 3]);
+                    if (want_lo)
+                        *reinterpret_cast<uint4*>(lo_box + off) = make_uint4(lo_pk[4 * k], lo_pk[4 * k + 1], lo_pk[4 * k + 2], lo_pk[4 * k + 3]);
                 }
             }
         }
-        if (MODE == GEMM_STATS && row_ok) {
-            // one (max, sum) partial per 64-column half tile; an empty half contributes (-inf, 0)
-            J.part_max[(long long)(tn * 2 + half) * J.M + row] = run_max;
-            J.part_sum[(long long)(tn * 2 + half) * J.M + row] = run_sum;
+        if (MODE == GEMM_GRAD) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy (TMA)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (e == 0) {
+                for (int sgm = 0; sgm < J.g_nseg; ++sgm)
+                    for (int box = 0; box < 2; ++box)
+                        if (box * 64 < ncols)
+                            tc05::tma_store_3d(&J.tmg, tiles + (sgm * 2 + box) * (kTileM * 128), n0 + box * 64, m0, sgm);
+                tc05::tma_store_commit_and_wait();
+            }
         }
     }
 
@@ -634,7 +668,7 @@ static int launch_gemm_mode(const GemmLaunch& L, cudaStream_t stream) {
         if (attr_err == cudaSuccess) prefer_max_shared(gemm_tc05_kernel<MODE, OCC>);
     });
     STIL_CUDA(attr_err);
-    STIL_CUDA(launch_pdl(gemm_tc05_kernel<MODE, OCC>, dim3(L.total_tiles), dim3(kThreads), smem, stream, L));
+    STIL_CUDA(launch_pdl(gemm_tc05_kernel<MODE, OCC>, dim3(L.total_tiles), dim3(threads_for(OCC)), smem, stream, L));
     return STIL_OK;
 }
 
@@ -648,6 +682,14 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
     static unsigned int launch_counter = 0;
     const_cast<GemmLaunch&>(L).trace_id = launch_counter++;
     const_cast<GemmLaunch&>(L).trace = g_trace_host;
+    if (mode == GEMM_GRAD) {
+        // bulk-store view of G: [ld_g columns, M rows, g_nseg segments], 64 x 128 boxes, 128-byte swizzle
+        for (int j = 0; j < L.njobs; ++j) {
+            GemmJob& J = const_cast<GemmLaunch&>(L).job[j];
+            int rc = make_operand_map(&J.tmg, J.gop, J.ld_g, J.M, J.g_nseg, (int64_t)J.g_nseg * J.ld_g, J.ld_g, kTileM);
+            if (rc) return rc;
+        }
+    }
     // more tiles than SMs: two CTAs per SM (3-deep rings) so epilogues overlap main loops
     const bool two = L.total_tiles > 148;
     if (mode == GEMM_STATS) return two ? launch_gemm_mode<GEMM_STATS, 2>(L, stream) : launch_gemm_mode<GEMM_STATS, 1>(L, stream);

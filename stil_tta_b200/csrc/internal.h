@@ -21,6 +21,7 @@ constexpr int kTileM = 128, kTileN = 128, kTileK = 64;
 
 struct alignas(64) GemmJob {
     CUtensorMap tmx, tmy;  // 3-D maps (D, rows, nseg), box 64 x 128 x 1, 128-B swizzle
+    CUtensorMap tmg;       // GRAD: bulk-store map of gop [ld_g, M, g_nseg] (filled by launch_gemm)
     int M, N, D;           // X rows, Y rows, per-segment contraction length
     int npair;
     int xseg[kMaxSegPairs], yseg[kMaxSegPairs];
@@ -75,6 +76,7 @@ struct alignas(64) GemmJob {
     // programmatic dependent launch: the X / Y operand bytes are not written by the kernel launched immediately before
     // this one on the stream, so the TMA producer may stream them before griddepcontrol.wait (see gemm_tc05.cu)
     int early_x, early_y;
+    int early_stats;   // GRAD: the px_* statistics partials are that old too: merge them before the wait
     // Peer-memory gather consumed in place (data-parallel head): wait_flags[p] (local, one u64 per peer) must reach
     // *wait_seq before rows [p*wait_rows_per_peer, ...) of the gathered Y-side data are read — by the TMA producer for
     // the Y operand tile (wait_y) and by the epilogue for sy / lse_y.  nullptr = no waiting.

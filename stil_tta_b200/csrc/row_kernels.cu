@@ -1,6 +1,8 @@
 // Row-wise (HBM-bound) kernels of the STiL head: operand preparation, CGPL+PGLS pseudo-labelling,
 // soft-label argmax, statistics merge / loss terms, normalise-backward, masked soft-target CE and the
 // segmented per-class prototype sums.  Warp-shuffle reductions, vectorised coalesced row access.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace stil {
@@ -433,12 +435,26 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
         }
         const float sxv = J.sx ? J.sx[i] : 1.f, syv = J.sy ? J.sy[i + J.y_offset] : 1.f;
         // merge (max, sum) partials over column tiles
-        float m = fmaxf(pm[0], pm[1]);
-        for (int t = lane + 64; t < J.tiles_n; t += 32) m = fmaxf(m, J.part_max[(long long)t * J.M + i]);
-        m = warp_max(m);
-        float s = ps[0] * expf(pm[0] - m) + ps[1] * expf(pm[1] - m);
-        for (int t = lane + 64; t < J.tiles_n; t += 32)
-            s += J.part_sum[(long long)t * J.M + i] * expf(J.part_max[(long long)t * J.M + i] - m);
+        // slots beyond the first 64: (max, sum) pairs merged per lane in batches of four independent loads
+        float em = -INFINITY, es = 0.f;
+        for (int t0 = lane + 64; t0 < J.tiles_n; t0 += 128) {
+            float bm[4], bs[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = t0 + 32 * q;
+                bm[q] = t < J.tiles_n ? J.part_max[(long long)t * J.M + i] : -INFINITY;
+                bs[q] = t < J.tiles_n ? J.part_sum[(long long)t * J.M + i] : 0.f;
+            }
+            const float nm = fmaxf(fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3])), em);
+            if (nm == -INFINITY) continue;
+            float acc = es * expf(em - nm);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc += bs[q] * expf(bm[q] - nm);
+            em = nm;
+            es = acc;
+        }
+        float m = warp_max(fmaxf(fmaxf(pm[0], pm[1]), em));
+        float s = ps[0] * expf(pm[0] - m) + ps[1] * expf(pm[1] - m) + (em == -INFINITY ? 0.f : es * expf(em - m));
         s = warp_sum(s);
         const float lse = m + logf(s);
         // dot product with the partner row
@@ -787,9 +803,9 @@ struct SoftCeArgs {
 template <int NV>
 __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeArgs A) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
     float lossv[3] = {0.f, 0.f, 0.f};
-    if (row < A.rows) {
+    // grid-stride over rows: the grid is capped so that the final (serial, deterministic) reduction stays short
+    for (int row = blockIdx.x * (blockDim.x >> 5) + warp; row < A.rows; row += gridDim.x * (blockDim.x >> 5)) {
         const int k = A.k;
         // all four rows of this sample in flight together
         float pl[2 * NV], y[3][2 * NV];
@@ -828,7 +844,7 @@ __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeAr
                 s = warp_sum(s);
                 py = warp_sum(py);
                 const float lse = m + logf(s);
-                lossv[h] = (lse * spl - py) * wgt[h];             // -sum_k pl_k log_softmax(y)_k, times the row weight
+                lossv[h] += (lse * spl - py) * wgt[h];            // -sum_k pl_k log_softmax(y)_k, times the row weight
                 const float gs = A.grad_scale * wgt[h] * inv_rows;
 #pragma unroll
                 for (int j = 0; j < 2 * NV; ++j) dy[j] = gs * (expf(y[h][j] - lse) * spl - pl[j]);
@@ -857,12 +873,24 @@ __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeAr
     if (is_last && warp == 0) {
         // deterministic: lane-strided partial sums in block order, then a fixed shuffle tree, per loss
         __threadfence();
-        const volatile float* bp = A.block_partials;
+        const float* bp = A.block_partials;
+        float sum3[3] = {0.f, 0.f, 0.f};
+        for (unsigned int b0 = 0; b0 < gridDim.x; b0 += 128) {      // four independent L2 loads per lane and loss per batch
+            float v[4][3];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned int b = b0 + lane + 32 * q;
+#pragma unroll
+                for (int h = 0; h < 3; ++h) v[q][h] = b < gridDim.x ? __ldcg(bp + 3 * b + h) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int h = 0; h < 3; ++h) sum3[h] += v[q][h];
+        }
 #pragma unroll
         for (int h = 0; h < 3; ++h) {
-            float sum = 0.f;
-            for (unsigned int b = lane; b < gridDim.x; b += 32) sum += bp[3 * b + h];
-            sum = warp_sum(sum);
+            const float sum = warp_sum(sum3[h]);
             if (lane == 0) A.losses[h] = sum / (float)A.rows;   // .mean() over B_u
         }
         if (lane == 0) *A.ticket = 0u;
@@ -1209,7 +1237,9 @@ int launch_simmatch_rows(const float* zt, const float* zs, long long ldz, const 
     return STIL_OK;
 }
 
-int64_t masked_softce_blocks(int64_t rows, int64_t) { return ceil_div(rows, row_block_threads(rows) / 32); }
+int64_t masked_softce_blocks(int64_t rows, int64_t) {
+    return std::min<int64_t>(ceil_div(rows, row_block_threads(rows) / 32), 148 * 16);
+}
 
 int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
                          const float* pseudo_label, int64_t ld_pl, const uint8_t* mask1, const uint8_t* case1,
