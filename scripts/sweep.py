@@ -127,6 +127,40 @@ def bank_sweep():
                           "frac_tensor": fl / t / 1e12 / TF}), flush=True)
 
 
+def kernel_sweep():
+    """Tensor-pipe rate of the similarity GEMM kernel ITSELF (executed flops of one launch / its device duration from the
+    torch profiler's CUPTI kernel records) on a shape where the tensor pipe is the bound: CLIPLoss fwd+bwd, n x n x d."""
+    from torch.profiler import ProfilerActivity, profile
+    g = torch.Generator().manual_seed(3)
+    for n, d in ((4096, 2048), (8192, 1024), (4096, 512)):
+        a = torch.randn(n, d, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
+        b = torch.randn(n, d, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
+        crit = S.CLIPLoss(0.1, 0.5, return_logits=False)
+        for _ in range(3):
+            a.grad = b.grad = None
+            crit(a, b)[0].backward()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                a.grad = b.grad = None
+                crit(a, b)[0].backward()
+            torch.cuda.synchronize()
+        per = {}
+        for e in prof.events():
+            if "gemm_tc05_kernel" in e.name:
+                mode = e.name.split("gemm_tc05_kernel<")[1].split(",")[0]
+                per.setdefault(mode, []).append(e.time_range.end - e.time_range.start)
+        # every launch runs BOTH InfoNCE sides: 2 x (2 n^2 d) executed flops (statistics, recompute for G, dX)
+        fl = 2 * 2.0 * n * n * d
+        for mode, name in (("0", "STATS (logits + softmax statistics)"), ("2", "GRAD (recompute + dLogits)"), ("1", "STORE (dX = G.Y)")):
+            if mode in per:
+                us = sorted(per[mode])[len(per[mode]) // 2]
+                print(json.dumps({"kernel": f"gemm_tc05_kernel<{name}>", "n": n, "d": d, "us_per_launch": us,
+                                  "executed_GFLOP": fl / 1e9, "TFLOPs": fl / us / 1e6, "frac_tensor": fl / us / 1e6 / TF}),
+                      flush=True)
+        del a, b
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "hbm_peak_GBps": HBM, "bf16_peak_TFLOPs": TF}))
@@ -136,3 +170,5 @@ if __name__ == "__main__":
         gemm_sweep()
     if what in ("bank", "all"):
         bank_sweep()
+    if what in ("kernel", "all"):
+        kernel_sweep()

@@ -544,6 +544,7 @@ __global__ void __launch_bounds__(kRowBlock) grad_finish_kernel(const __grid_con
     auto gsum = [&](int d) {      // slices of a split contraction, added in index order (deterministic)
         // eight independent (predicated) loads per batch, then the adds: a `v += load` loop serialises one memory round
         // trip per slice
+        if (ns == 1) return g0[d];
         float v = 0.f;
         for (int k0 = 0; k0 < ns; k0 += 8) {
             float t[8];

@@ -79,8 +79,10 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_
         : "memory");
 }
 __device__ __forceinline__ void tma_store_commit_and_wait() {
+    // .read: wait until the bulk stores have READ their shared-memory source (it may then be released / the CTA may exit);
+    // the global writes themselves complete asynchronously, before the grid does
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------- tcgen05
