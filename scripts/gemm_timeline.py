@@ -26,8 +26,8 @@ torch.cuda.synchronize()
 _lib.check(_lib.load().stil_debug_trace(None))
 t = buf.cpu()
 used = (t[:, :, 0] > 0)
-names = {0: "STATS", 1: "STORE", 2: "GRAD"}
-slots = ["start", "prologue", "tma_done", "mma_done", "epi_ready", "acc_ready", "end"]
+names = {0: "STATS", 1: "STORE", 2: "GRAD", 3: "BWD (slots: start, wait passed, row/col values, first G, last G, dX ready, end)"}
+slots = ["start", "prologue", "tma_done", "mma_done", "epi_ready", "acc_ready", "end"]   # BWD: see names[3]
 launch_ids = [i for i in range(64) if used[i].any()]
 t0_all = min(int(t[i][used[i]][:, 0].min()) for i in launch_ids)
 for i in launch_ids:

@@ -82,6 +82,18 @@ inline void set_early(GemmLaunch& GL, bool x, bool y) {
     }
 }
 
+// One fused launch (gemm_bwd_kernel) instead of a GRAD launch followed by the STORE launch that consumes its G, when every
+// job pair allows it; the column tiles of a row block are dealt to as many CTAs as the STORE would have had slices.
+bool fuse_bwd(GemmLaunch& GB, const GemmLaunch& GG, const GemmLaunch& GS) {
+    std::memset(&GB, 0, sizeof(GB));
+    if (GG.njobs != GS.njobs) return false;
+    for (int j = 0; j < GG.njobs; ++j)
+        if (!make_bwd_job(GB.job[j], GG.job[j], GS.job[j], GS.job[j].ksplit > 1 ? GS.job[j].ksplit : 1)) return false;
+    GB.njobs = GG.njobs;
+    gemm_job_tiles(GB);
+    return true;
+}
+
 // dX[M, ncols] = G[M, (hi,lo), n] · Y[n, ncols]: X = G (K-major), Y read in place as an MN-major operand
 int fill_gemm_store_mn(GemmJob& J, const Operand& G, int64_t M, const Operand& Y, int64_t n, int64_t ncols) {
     std::memset(&J, 0, sizeof(J));
@@ -178,6 +190,14 @@ struct ProtoPlan {
     int64_t bytes;
 };
 
+// The fused backward of the prototype CE gives every column tile of a row block its own CTA (the three fp32-split
+// prototype segments leave room for one Y tile buffer only, so a CTA walking several tiles would serialise TMA, recompute,
+// epilogue and dX): partial dX tiles go to slices that grad_finish adds.
+inline int64_t proto_bwd_slices(int64_t k) {
+    const int64_t tiles = ceil_div(k, kTileN);
+    return tiles <= 8 ? tiles : 1;
+}
+
 ProtoPlan plan_proto(void* ws, int64_t ws_bytes, int64_t rows, int64_t k, int64_t dim, int dtype) {
     ProtoPlan P;
     Workspace W(ws, ws_bytes);
@@ -191,7 +211,7 @@ ProtoPlan plan_proto(void* ws, int64_t ws_bytes, int64_t rows, int64_t k, int64_
     P.psum = W.take<float>(stat_slots(k) * rows);
     P.block_partials = W.take<float>(2 * ceil_div(rows, 2) + 8);
     P.gop = W.take<__nv_bfloat16>(rows * 2 * P.ldg);
-    P.g = W.take<float>(rows * dim);
+    P.g = W.take<float>(rows * dim * proto_bwd_slices(k));   // one slice per column tile for the fused backward
     P.bytes = W.off;
     return P;
 }
@@ -499,16 +519,21 @@ int infonce_bwd_impl(const void* a_all, const void* b_all, int dtype,
     gemm_job_tiles(GL);
     // predecessor = this call's prep: bf16 operands are the caller's inputs (after_fwd: the predecessor is the caller's)
     if (!after_fwd) set_early(GL, dtype == STIL_BF16, dtype == STIL_BF16);
-    if ((rc = launch_gemm(GL, S(stream)))) return rc;
-    std::memset(&GL, 0, sizeof(GL));
+    GemmLaunch GS, GB;
+    std::memset(&GS, 0, sizeof(GS));
     bool fused = false;
-    if ((rc = infonce_store_jobs(GL.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
+    if ((rc = infonce_store_jobs(GS.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
                                  ld_grad, &fused)))
         return rc;
-    GL.njobs = 2;
-    gemm_job_tiles(GL);
-    set_early(GL, false, true);   // predecessor = GRAD (writes X = G); Y is an input / an operand of the forward call
-    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    GS.njobs = 2;
+    gemm_job_tiles(GS);
+    if (fuse_bwd(GB, GL, GS)) {
+        if ((rc = launch_gemm(GB, S(stream)))) return rc;       // recompute + dLogits + dX in one kernel
+    } else {
+        if ((rc = launch_gemm(GL, S(stream)))) return rc;
+        set_early(GS, false, true);   // predecessor = GRAD (writes X = G); Y is an input / an operand of the forward call
+        if ((rc = launch_gemm(GS, S(stream)))) return rc;
+    }
     if (fused) return STIL_OK;
     GradFinishLaunch GF;
     std::memset(&GF, 0, sizeof(GF));
@@ -670,16 +695,21 @@ STIL_API int stil_infonce_bwd_gathered(const void* a_all, const void* b_all, con
         GL.job[s].lse_x = (s == 0 ? lse_row_all : lse_col_all) + 2 * row_offset;
         GL.job[s].lse_ll_tag = static_cast<const unsigned long long*>(ll_tag);
     }
-    if ((rc = launch_gemm(GL, S(stream)))) return rc;
-    std::memset(&GL, 0, sizeof(GL));
+    GemmLaunch GS, GB;
+    std::memset(&GS, 0, sizeof(GS));
     bool fused = false;
-    if ((rc = infonce_store_jobs(GL.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
+    if ((rc = infonce_store_jobs(GS.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
                                  ld_grad, &fused)))
         return rc;
-    GL.njobs = 2;
-    gemm_job_tiles(GL);
-    set_early(GL, false, true);
-    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    GS.njobs = 2;
+    gemm_job_tiles(GS);
+    if (fuse_bwd(GB, GL, GS)) {
+        if ((rc = launch_gemm(GB, S(stream)))) return rc;
+    } else {
+        if ((rc = launch_gemm(GL, S(stream)))) return rc;
+        set_early(GS, false, true);
+        if ((rc = launch_gemm(GS, S(stream)))) return rc;
+    }
     if (fused) return STIL_OK;
     GradFinishLaunch GF;
     std::memset(&GF, 0, sizeof(GF));
@@ -809,6 +839,46 @@ int proto_grad_job(GemmJob& J, const ProtoPlan& P, const void* feat, int dtype, 
     }
     return STIL_OK;
 }
+// the STORE half of a fused, column-split backward: partial tiles into the slices of P.g
+int proto_store_job_split(GemmJob& J, const ProtoPlan& P, int64_t rows, int64_t dim, int64_t k, int grad_dtype) {
+    const Operand X = grad_operand(P.gop, P.ldg, grad_nseg(grad_dtype));
+    const Operand Y = rowmajor_operand(nullptr, STIL_F32, dim, dim, P.proto_op, P.proto_nseg);
+    int rc = fill_gemm_store_mn(J, X, rows, Y, k, dim);
+    if (rc) return rc;
+    J.out = P.g;
+    J.ld_out = dim;
+    J.ksplit = (int)proto_bwd_slices(k);
+    J.slice_stride = rows * dim;
+    return STIL_OK;
+}
+// fused backward of the prototype CE when the shapes allow it (true: launched; d_feat still needs launch_proto_gradfinish)
+int proto_bwd_fused(GemmLaunch& GG, const ProtoPlan& P, int64_t rows, int64_t dim, int64_t k, int grad_dtype,
+                    cudaStream_t stream, bool* done) {
+    *done = false;
+    if (proto_bwd_slices(k) < 2) return STIL_OK;
+    GemmLaunch GS, GB;
+    std::memset(&GS, 0, sizeof(GS));
+    int rc = proto_store_job_split(GS.job[0], P, rows, dim, k, grad_dtype);
+    if (rc) return rc;
+    GS.njobs = 1;
+    gemm_job_tiles(GS);
+    if (!fuse_bwd(GB, GG, GS)) return STIL_OK;
+    if ((rc = launch_gemm(GB, stream))) return rc;
+    *done = true;
+    return STIL_OK;
+}
+int launch_proto_gradfinish(const ProtoPlan& P, int64_t rows, int64_t dim, int64_t k, void* d_feat, int grad_dtype,
+                            int64_t ld_grad, bool sliced, cudaStream_t stream) {
+    GradFinishLaunch GF;
+    std::memset(&GF, 0, sizeof(GF));
+    GradFinishJob& j = GF.job[0];
+    j.g = P.g; j.dx = d_feat; j.dx_dtype = grad_dtype; j.ld_dx = ld_grad;
+    j.rows = (int)rows; j.dim = (int)dim;
+    if (sliced) { j.nslices = (int)proto_bwd_slices(k); j.slice_stride = rows * dim; }
+    GF.njobs = 1;
+    GF.total_rows = (int)rows;
+    return launch_grad_finish(GF, stream);
+}
 // d_feat = G · prototypes (prototypes read in place, MN-major); cast to grad_dtype in the epilogue when possible
 int proto_store_job(GemmJob& J, const ProtoPlan& P, int64_t rows, int64_t dim, int64_t k, void* d_feat, int grad_dtype,
                     int64_t ld_grad, bool* fused) {
@@ -894,13 +964,17 @@ STIL_API int stil_proto_ce_bwd(const void* feat, int dtype, int64_t rows, int64_
         return rc;
     GL.njobs = 1;
     gemm_job_tiles(GL);
-    if ((rc = launch_gemm(GL, S(stream)))) return rc;
-    std::memset(&GL, 0, sizeof(GL));
+    bool done = false;
+    if ((rc = proto_bwd_fused(GL, P, rows, dim, k, grad_dtype, S(stream), &done))) return rc;
+    if (done) return launch_proto_gradfinish(P, rows, dim, k, d_feat, grad_dtype, ld_grad, true, S(stream));
+    GemmLaunch GS;
+    std::memset(&GS, 0, sizeof(GS));
     bool fused = false;
-    if ((rc = proto_store_job(GL.job[0], P, rows, dim, k, d_feat, grad_dtype, ld_grad, &fused))) return rc;
-    GL.njobs = 1;
-    gemm_job_tiles(GL);
+    if ((rc = proto_store_job(GS.job[0], P, rows, dim, k, d_feat, grad_dtype, ld_grad, &fused))) return rc;
+    GS.njobs = 1;
+    gemm_job_tiles(GS);
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    if ((rc = launch_gemm(GS, S(stream)))) return rc;
     if (!fused) {
         GradFinishLaunch GF;
         std::memset(&GF, 0, sizeof(GF));
@@ -1642,15 +1716,25 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         gemm_job_tiles(GL);
         set_early(GL, true, true);    // predecessor = cgpl_pgls: both operands were final two kernels ago ...
         GL.job[0].early_stats = 1;    // ... and so were the statistics of the student logits
-        if ((rc = launch_gemm(GL, st))) return rc;
-        if ((rc = mark(7, st))) return rc;
-        std::memset(&GL, 0, sizeof(GL));
-        if ((rc = proto_store_job(GL.job[0], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
-        GL.njobs = 1;
-        gemm_job_tiles(GL);
-        set_early(GL, false, true);   // predecessor = GRAD (writes X = G); Y = prototype operand
-        if ((rc = launch_gemm(GL, st))) return rc;
-        if ((rc = mark(8, st))) return rc;
+        GemmLaunch GS;
+        std::memset(&GS, 0, sizeof(GS));
+        bool done = false;
+        if ((rc = proto_bwd_fused(GL, P.pt, B, D, K, a->grad_dtype, st, &done))) return rc;   // recompute + dLogits + dX
+        if (done) {
+            if ((rc = mark(7, st))) return rc;
+            if ((rc = launch_proto_gradfinish(P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, true, st))) return rc;
+            if ((rc = mark(8, st))) return rc;
+            fused_pt = true;     // d_feat_m is written: nothing left to finish below
+        } else {
+            if ((rc = proto_store_job(GS.job[0], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
+            GS.njobs = 1;
+            gemm_job_tiles(GS);
+            if ((rc = launch_gemm(GL, st))) return rc;
+            if ((rc = mark(7, st))) return rc;
+            set_early(GS, false, true);   // predecessor = GRAD (writes X = G); Y = prototype operand
+            if ((rc = launch_gemm(GS, st))) return rc;
+            if ((rc = mark(8, st))) return rc;
+        }
         if (!fused_pt) {
             GradFinishLaunch GF;
             std::memset(&GF, 0, sizeof(GF));
@@ -1690,17 +1774,24 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         GL.njobs = 2;
         gemm_job_tiles(GL);
         set_early(GL, true, true);    // predecessor = STATS: operands were final two kernels ago
-        if ((rc = launch_gemm(GL, s_nce))) return rc;
-        if ((rc = mark(3, s_nce))) return rc;
-        std::memset(&GL, 0, sizeof(GL));
-        if ((rc = infonce_store_jobs(GL.job, P.nce, A, Bm, a->feat_i, a->feat_t, dt, B, B, D, D, 0, a->d_feat_i,
+        GemmLaunch GS, GB;
+        std::memset(&GS, 0, sizeof(GS));
+        if ((rc = infonce_store_jobs(GS.job, P.nce, A, Bm, a->feat_i, a->feat_t, dt, B, B, D, D, 0, a->d_feat_i,
                                      a->d_feat_t, a->grad_dtype, D, &fused)))
             return rc;
-        GL.njobs = 2;
-        gemm_job_tiles(GL);
-        set_early(GL, false, true);   // predecessor = GRAD (writes X = G)
-        if ((rc = launch_gemm(GL, s_nce))) return rc;
-        if ((rc = mark(4, s_nce))) return rc;
+        GS.njobs = 2;
+        gemm_job_tiles(GS);
+        if (fuse_bwd(GB, GL, GS)) {
+            if ((rc = launch_gemm(GB, s_nce))) return rc;
+            if ((rc = mark(3, s_nce))) return rc;
+            if ((rc = mark(4, s_nce))) return rc;
+        } else {
+            if ((rc = launch_gemm(GL, s_nce))) return rc;
+            if ((rc = mark(3, s_nce))) return rc;
+            set_early(GS, false, true);   // predecessor = GRAD (writes X = G)
+            if ((rc = launch_gemm(GS, s_nce))) return rc;
+            if ((rc = mark(4, s_nce))) return rc;
+        }
         if (!fused) {
             GradFinishLaunch GF;
             std::memset(&GF, 0, sizeof(GF));

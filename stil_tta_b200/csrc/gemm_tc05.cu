@@ -10,7 +10,9 @@
 // STiLModel.py:293, and both GEMMs of their backward passes (G = dLoss/dLogits is formed on chip from a
 // recomputed tile and written as bf16 hi/lo; dX = G·Y reads Y in place as an MN-major operand and applies
 // the backward of F.normalize in its epilogue).
+#include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 
 #include "internal.h"
@@ -601,6 +603,333 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
     }
 }
 
+// =====================================================================================================================
+// Fused backward: one CTA owns a 128-row block of dX and walks over its column tiles.  Per tile: TMA brings the Y rows
+// (X is loaded once), MMA 1 recomputes the logits into a TMEM buffer, the epilogue warps turn them into G = dLoss/dLogits
+// and write G as a swizzled K-major operand into shared memory, MMA 2 accumulates dX += G · Y with the SAME Y tile read
+// as an MN-major operand.  G never leaves the SM, and one launch replaces the GRAD + STORE pair (one kernel boundary and
+// one global round trip of G less on the critical chain of the step).  With two Y buffers the next tile's recompute runs
+// under this tile's epilogue (two logits buffers in TMEM).  Column tiles are dealt round-robin to `nsplit` CTAs per row
+// block for long rows (global batch); their partial dX tiles go to per-slice outputs that grad_finish_kernel adds.
+// =====================================================================================================================
+constexpr int kBwdEpiWarps = 16;
+constexpr int kBwdEpiThreads = 32 * kBwdEpiWarps;
+constexpr int kBwdThreads = 64 + kBwdEpiThreads;
+constexpr int kBoxBytes = kTileM * 128;          // one [128 rows x 64 bf16] swizzled box
+constexpr int kBwdMiscBytes = 2 * 2 * kTileN * 4 /*col scale, lse x2 buffers*/ + 4 * kTileM * 4 /*dot partials*/ + 256;
+constexpr uint32_t kBwdTmemCols = 512;           // logits x2 (256 columns) + dX (<= 128 columns)
+
+__global__ void __launch_bounds__(kBwdThreads, 1) gemm_bwd_kernel(const __grid_constant__ GemmLaunch L) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = tc05::smem_u32(smem_raw);
+    uint8_t* base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int jid = 0;
+#pragma unroll
+    for (int j = 1; j < kMaxGemmJobs; ++j)
+        if (j < L.njobs && (int)blockIdx.x >= L.job[j].tile_begin) jid = j;
+    const GemmJob& J = L.job[jid];
+    unsigned long long* trace = L.trace ? L.trace + (size_t)(L.trace_id % kTraceLaunches) * kTraceCtas * kTraceSlots : nullptr;
+    if (threadIdx.x == 0) { STIL_TRACE(0); if (trace && blockIdx.x < kTraceCtas) trace[blockIdx.x * kTraceSlots + 7] = GEMM_BWD; }
+    const int t_cta = blockIdx.x - J.tile_begin;
+    const int nsplit = J.nsplit > 1 ? J.nsplit : 1;
+    const int split = t_cta % nsplit, tm = t_cta / nsplit;
+    const int m0 = tm * kTileM;
+    const int ntile = (J.tiles_n - split + nsplit - 1) / nsplit;     // this CTA's column tiles: split, split+nsplit, ...
+    const int nbx = J.D / 64;                                        // 64-column boxes along the embedding dimension
+    const int nbuf = J.bw_nbuf;
+
+    uint8_t* xs = base;                                              // [bw_nx][nbx] boxes
+    uint8_t* ys = base + J.bw_y_off;                                 // [nbuf][bw_ny][nbx] boxes
+    uint8_t* gsm = base + J.bw_g_off;                                // [g_nseg][2] boxes (K-major A operand of MMA 2)
+    float* col_scale = reinterpret_cast<float*>(base + J.bw_misc_off);   // [2][128]
+    float* col_lse = col_scale + 2 * kTileN;                             // [2][128]
+    float* dot_part = col_lse + 2 * kTileN;                              // [4][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dot_part + 4 * kTileM);
+    uint64_t* x_full = bars;
+    uint64_t* y_full = bars + 1;      // [2]
+    uint64_t* y_empty = bars + 3;     // [2]
+    uint64_t* s_full = bars + 5;      // [2]
+    uint64_t* s_empty = bars + 7;     // [2]
+    uint64_t* g_full = bars + 9;
+    uint64_t* g_empty = bars + 10;
+    uint64_t* dx_full = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    if (warp == 0 && lane == 0) {
+        tc05::tma_prefetch_desc(&J.tmx);
+        tc05::tma_prefetch_desc(&J.tmy);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            tc05::mbar_init(x_full, 1);
+            for (int i = 0; i < 2; ++i) {
+                tc05::mbar_init(&y_full[i], 1);
+                tc05::mbar_init(&y_empty[i], 1);
+                tc05::mbar_init(&s_full[i], 1);
+                tc05::mbar_init(&s_empty[i], kBwdEpiWarps);
+            }
+            tc05::mbar_init(g_full, kBwdEpiWarps);
+            tc05::mbar_init(g_empty, 1);
+            tc05::mbar_init(dx_full, 1);
+            tc05::fence_mbar_init();
+        }
+        __syncwarp();
+        tc05::tmem_alloc(tmem_slot, kBwdTmemCols);
+        tc05::tmem_relinquish();
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t y_bytes = (uint32_t)(J.bw_ny * nbx * kBoxBytes);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            auto load_x = [&]() {
+                tc05::mbar_arrive_expect_tx(x_full, (uint32_t)(J.bw_nx * nbx * kBoxBytes));
+                for (int sg = 0; sg < J.bw_nx; ++sg)
+                    for (int b = 0; b < nbx; ++b)
+                        tc05::tma_load_3d(xs + (sg * nbx + b) * kBoxBytes, &J.tmx, x_full, b * 64, m0, sg);
+            };
+            auto load_y = [&](int i) {
+                const int yb = i % nbuf, n0 = (split + i * nsplit) * kTileN;
+                tc05::mbar_arrive_expect_tx(&y_full[yb], y_bytes);
+                for (int sg = 0; sg < J.bw_ny; ++sg)
+                    for (int b = 0; b < nbx; ++b)
+                        tc05::tma_load_3d(ys + yb * J.bw_y_stride + (sg * nbx + b) * kBoxBytes, &J.tmy, &y_full[yb], b * 64, n0,
+                                          sg);
+            };
+            const int first = min(ntile, nbuf);
+            const bool early = J.early_x && J.early_y;   // operands not written by the stream predecessor: before the wait
+            if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
+            load_x();
+            for (int i = 0; i < first; ++i) load_y(i);
+            for (int i = first; i < ntile; ++i) {
+                const int yb = i % nbuf;
+                tc05::mbar_wait(&y_empty[yb], ((i / nbuf) & 1) ^ 1);
+                load_y(i);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc1 = tc05::make_idesc_bf16_f32(kTileM, kTileN);
+            const uint32_t idesc2 = tc05::make_idesc_bf16_f32(kTileM, J.D) | (1u << 16);   // B = Y tile, MN-major
+            const uint32_t xs_a = tc05::smem_u32(xs), ys_a = tc05::smem_u32(ys), g_a = tc05::smem_u32(gsm);
+            auto mma1_ready = [&](int i) {
+                return tc05::mbar_test(&y_full[i % nbuf], (i / nbuf) & 1) && tc05::mbar_test(&s_empty[i & 1], ((i >> 1) & 1) ^ 1);
+            };
+            auto mma1 = [&](int i) {     // logits of tile i into TMEM buffer i & 1 (caller checked mma1_ready)
+                const int yb = i % nbuf, sb = i & 1;
+                tc05::fence_after_sync();
+                uint32_t acc = 0;
+                for (int p = 0; p < J.npair; ++p)
+                    for (int b = 0; b < nbx; ++b) {
+                        const uint64_t a_desc = tc05::make_kmajor_sw128_desc(xs_a + (J.xseg[p] * nbx + b) * kBoxBytes);
+                        const uint64_t b_desc =
+                            tc05::make_kmajor_sw128_desc(ys_a + yb * J.bw_y_stride + (J.yseg[p] * nbx + b) * kBoxBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            tc05::mma_f16_ss(tmem_base + sb * kTileN, a_desc + 2 * k, b_desc + 2 * k, idesc1, acc);
+                            acc = 1;
+                        }
+                    }
+                tc05::mma_commit(&s_full[sb]);
+            };
+            auto mma2 = [&](int i) {     // dX += G(tile i) · Y(tile i): contraction over the tile's 128 columns
+                const int yb = i % nbuf;   // (caller saw g_full complete its phase i)
+                tc05::fence_after_sync();
+                for (int p = 0; p < J.npair2; ++p) {
+                    const uint64_t b_base = tc05::make_mnmajor_sw128_desc(
+                        ys_a + yb * J.bw_y_stride + (J.yseg2[p] * nbx) * kBoxBytes, kBoxBytes);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t a_desc = tc05::make_kmajor_sw128_desc(g_a + (J.gseg2[p] * 2 + kb) * kBoxBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc05::mma_f16_ss(tmem_base + 2 * kTileN, a_desc + 2 * k, b_base + 128u * (kb * 4 + k), idesc2,
+                                             (i | p | kb | k) ? 1u : 0u);
+                    }
+                }
+                tc05::mma_commit(g_empty);           // G buffer free for the next tile
+                tc05::mma_commit(&y_empty[yb]);      // Y buffer free for the tile after next
+                if (i == ntile - 1) tc05::mma_commit(dx_full);
+            };
+            tc05::mbar_wait(x_full, 0);
+            // One thread serves both products: it issues whichever is ready (never parks on the Y tile of a later
+            // recompute while the current tile's G is waiting for its dX product).  A recompute may run at most two
+            // tiles ahead (two logits buffers).
+            int n1 = 0, n2 = 0;
+            unsigned long long spins = 0;
+            while (n2 < ntile) {
+                if (n1 < ntile && n1 < n2 + 2 && mma1_ready(n1)) { mma1(n1++); spins = 0; continue; }
+                if (n2 < n1 && tc05::mbar_test(g_full, n2 & 1)) { mma2(n2++); spins = 0; continue; }
+                if (++spins > (1ull << 28)) __trap();
+            }
+            if (ntile == 0) tc05::mbar_arrive(dx_full);
+        }
+    } else {
+        // ===================== epilogue: 16 warps, thread = row, one 32-column chunk per warp =====================
+        const int e = threadIdx.x - 64;
+        const int q = warp & 3;
+        const int c = (warp - 2) >> 2;                 // chunk 0..3 of the 128-column tile
+        const int r_in = q * 32 + lane;
+        const int row = m0 + r_in;
+        const bool row_ok = row < J.M;
+        const float alpha = J.alpha;
+        float lse_x_early = 0.f;
+        const bool pre_stats = J.early_stats && J.lse_x == nullptr && J.px_max != nullptr;
+        if (pre_stats && row_ok) lse_x_early = merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (e == 0) { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); STIL_TRACE(1); }
+        // ---- per-row quantities (as in gemm_tc05_kernel<GEMM_GRAD>)
+        const float rs = (row_ok && J.sx) ? J.sx[row] : 1.f;
+        float lse_x = 0.f, u = 0.f, d = 0.f, gs = 1.f;
+        int tgt = -1;
+        if (row_ok) {
+            lse_x = J.lse_x ? (J.lse_ll_tag ? ll_read(J.lse_x, row, J.lse_ll_tag) : J.lse_x[row])
+                    : pre_stats ? lse_x_early : merge_partials(J.px_max, J.px_sum, J.px_tiles, J.M, row);
+            tgt = J.tgt_vec ? J.tgt_vec[row] : row + J.tgt_offset;
+            if (J.w_z) {
+                const float p = expf(J.w_z[(long long)row * J.w_ldz + tgt] - lse_x);
+                u = (J.w_conf[row] ? J.w_coef : 0.f) * p / (p + 1e-7f);
+                d = u;
+            } else {
+                u = J.u_vec ? J.u_vec[row] : J.u_scalar;
+                d = J.u_vec ? u : J.d_scalar;
+            }
+            gs = J.gscale ? *J.gscale : 1.f;
+        }
+        const float v = (J.lse_y || J.py_max) ? J.v_scalar : 0.f;
+        const bool want_lo = J.g_nseg > 1;
+        // normalise-backward inputs of the final epilogue (this thread's 32 columns of x)
+        const bool fused_fin = J.fin_dx != nullptr;
+        const float fsx = (fused_fin && row_ok && J.fin_sx) ? J.fin_sx[row] : 0.f;
+        const int dcols = max(0, min(32, J.D - c * 32));
+        float xrow[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xrow[j] = 0.f;
+        if (fused_fin && J.fin_sx && row_ok && dcols > 0)
+            load32_as_float(J.fin_x, J.fin_x_dtype, (long long)row * J.fin_ldx + c * 32, dcols, xrow);
+        // column scale / LSE of a tile, fetched one tile ahead by the first 128 epilogue threads
+        auto col_vals = [&](int i, float& cs, float& cl) {
+            cs = 0.f; cl = 0.f;
+            const int col = (split + i * nsplit) * kTileN + e;
+            if (i < ntile && col < J.N) {
+                cs = alpha * (J.sy ? __ldcg(J.sy + col) : 1.f);
+                if (J.lse_y) cl = J.lse_ll_tag ? ll_read(J.lse_y, col, J.lse_ll_tag) : __ldcg(J.lse_y + col);
+                else if (J.py_max) cl = merge_partials(J.py_max, J.py_sum, J.py_tiles, J.N, col);
+            }
+        };
+        float ncs = 0.f, ncl = 0.f;
+        if (e < kTileN) col_vals(0, ncs, ncl);
+        if (e == 0) STIL_TRACE(2);      // row / column quantities loaded
+
+        for (int i = 0; i < ntile; ++i) {
+            const int sb = i & 1, n0 = (split + i * nsplit) * kTileN;
+            if (e < kTileN) {
+                col_scale[sb * kTileN + e] = ncs;
+                col_lse[sb * kTileN + e] = ncl;
+                col_vals(i + 1, ncs, ncl);            // next tile's values travel while this tile is processed
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kBwdEpiThreads) : "memory");
+            tc05::mbar_wait(&s_full[sb], (i >> 1) & 1);
+            tc05::fence_after_sync();
+            uint32_t acc[32];
+            tc05::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sb * kTileN + c * 32, acc);
+            tc05::tmem_ld_wait();
+            tc05::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(&s_empty[sb]);      // this warp is done with the logits buffer
+            const float* csc = col_scale + sb * kTileN + c * 32;
+            const float* cls_ = col_lse + sb * kTileN + c * 32;
+            uint32_t hi_pk[16], lo_pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                float g2[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int jj = j + h;
+                    const float l = __uint_as_float(acc[jj]) * rs * csc[jj];
+                    float g = u * fast_exp2((l - lse_x) * kLog2e);
+                    if (v != 0.f) g += v * fast_exp2((l - cls_[jj]) * kLog2e);
+                    if (n0 + c * 32 + jj == tgt) g -= d;
+                    g2[h] = row_ok ? g * csc[jj] * gs : 0.f;
+                }
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(g2[0], g2[1]);
+                const float2 hf = __bfloat1622float2(hh);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(g2[0] - hf.x, g2[1] - hf.y);
+                hi_pk[j / 2] = *reinterpret_cast<const uint32_t*>(&hh);
+                lo_pk[j / 2] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            if (i > 0) tc05::mbar_wait(g_empty, (i - 1) & 1);    // MMA 2 of the previous tile has read G
+            {
+                const int box = c >> 1, k0 = (c & 1) * 4;
+                uint8_t* hi_box = gsm + box * kBoxBytes + r_in * 128;
+                uint8_t* lo_box = hi_box + 2 * kBoxBytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int off = ((k0 + k) ^ (r_in & 7)) * 16;
+                    *reinterpret_cast<uint4*>(hi_box + off) = make_uint4(hi_pk[4 * k], hi_pk[4 * k + 1], hi_pk[4 * k + 2], hi_pk[4 * k + 3]);
+                    if (want_lo)
+                        *reinterpret_cast<uint4*>(lo_box + off) = make_uint4(lo_pk[4 * k], lo_pk[4 * k + 1], lo_pk[4 * k + 2], lo_pk[4 * k + 3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> MMA (async proxy) reads
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(g_full);
+            if (e == 0 && i == 0) STIL_TRACE(3);   // first G tile in shared memory
+            if (e == 0 && i == ntile - 1) STIL_TRACE(4);   // last G tile in shared memory
+        }
+
+        // ---- final epilogue: dX tile out of TMEM
+        tc05::mbar_wait(dx_full, 0);
+        tc05::fence_after_sync();
+        if (e == 0) STIL_TRACE(5);      // dX accumulator complete
+        float l[32];
+        if (dcols > 0 && ntile > 0) {
+            uint32_t acc[32];
+            tc05::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 2 * kTileN + c * 32, acc);
+            tc05::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) l[j] = __uint_as_float(acc[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) l[j] = 0.f;
+        }
+        if (fused_fin) {
+            if (J.fin_sx) {
+                float part_dot = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) part_dot += xrow[j] * l[j];
+                dot_part[c * kTileM + r_in] = part_dot * fsx;
+                asm volatile("bar.sync 1, %0;" ::"n"(kBwdEpiThreads) : "memory");
+                const float fin_dot = dot_part[r_in] + dot_part[kTileM + r_in] + dot_part[2 * kTileM + r_in] + dot_part[3 * kTileM + r_in];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xrow[j] * fin_dot);
+            }
+            if (row_ok && dcols > 0) store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + c * 32, dcols, l);
+        } else if (row_ok && dcols > 0) {
+            // partial (or plain fp32) dX: slice `split` of the output, added by grad_finish_kernel in index order
+            float* dst = J.out + (long long)split * J.slice_stride + (long long)row * J.ld_out + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j + 3 < dcols) *reinterpret_cast<float4*>(dst + j) = make_float4(l[j], l[j + 1], l[j + 2], l[j + 3]);
+        }
+    }
+
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) STIL_TRACE(6);
+    if (warp == 1) {
+        tc05::fence_after_sync();
+        tc05::tmem_dealloc(tmem_base, kBwdTmemCols);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -648,7 +977,8 @@ void gemm_job_tiles(GemmLaunch& L) {
         J.tiles_m = (int)ceil_div(J.M, kTileM);
         J.tiles_n = (int)ceil_div(J.N, kTileN);
         J.tile_begin = begin;
-        begin += J.tiles_m * J.tiles_n * (J.mode == GEMM_STORE && J.ksplit > 1 ? J.ksplit : 1);
+        begin += J.mode == GEMM_BWD ? J.tiles_m * std::max(1, J.nsplit)
+                                    : J.tiles_m * J.tiles_n * (J.mode == GEMM_STORE && J.ksplit > 1 ? J.ksplit : 1);
     }
     L.total_tiles = begin;
 }
@@ -672,6 +1002,72 @@ static int launch_gemm_mode(const GemmLaunch& L, cudaStream_t stream) {
     return STIL_OK;
 }
 
+// ---- fused backward: job construction and launch
+int bwd_nsplit(int64_t n_cols, int64_t row_blocks_total) {
+    // a CTA walks its column tiles one after the other (~1.5 us each): at most 4 per CTA, but no more CTAs than SMs
+    const int64_t tiles = ceil_div(n_cols, kTileN);
+    int64_t s = ceil_div(tiles, 4);
+    while (s > 1 && s * row_blocks_total > 148) --s;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(s, tiles));
+}
+
+bool make_bwd_job(GemmJob& out, const GemmJob& grad, const GemmJob& store, int nsplit) {
+    // EXPERIMENTAL, opt-in (STIL_FUSED_BWD=1).  Correct (tests/test_gpu_fused_bwd.py) but measured SLOWER than the
+    // GRAD + STORE pair at every size tried: one thread=row pass over a 128x128 logits tile costs ~3 us on one SM, and
+    // the fused kernel serialises those passes per row block (or pays a slice reduction kernel when the tiles are dealt
+    // to separate CTAs) — C2 step 34.3 vs 30.9 us, one rank's N=8 InfoNCE 42.9 vs 36.9 us (profiles/README.md).
+    static const bool on = [] { const char* e = getenv("STIL_FUSED_BWD"); return e && e[0] == '1'; }();
+    if (!on) return false;
+    if (grad.mode != GEMM_GRAD || store.mode != GEMM_STORE || !store.y_mn_major) return false;
+    if (grad.D != 64 && grad.D != 128) return false;                 // whole embedding rows as 64-column boxes
+    if (store.N != grad.D || store.D != grad.N || store.M != grad.M) return false;
+    out = grad;
+    out.mode = GEMM_BWD;
+    out.npair2 = store.npair;
+    int nx = 0, ny = 0;
+    for (int p = 0; p < grad.npair; ++p) { nx = std::max(nx, grad.xseg[p] + 1); ny = std::max(ny, grad.yseg[p] + 1); }
+    for (int p = 0; p < store.npair; ++p) {
+        out.gseg2[p] = store.xseg[p];
+        out.yseg2[p] = store.yseg[p];
+        ny = std::max(ny, store.yseg[p] + 1);
+        if (store.xseg[p] >= grad.g_nseg) return false;
+    }
+    out.bw_nx = nx; out.bw_ny = ny;
+    const int nbx = grad.D / 64;
+    const int x_bytes = nx * nbx * kBoxBytes, y_bytes = ny * nbx * kBoxBytes, g_bytes = grad.g_nseg * 2 * kBoxBytes;
+    const int limit = 227 * 1024 - 1024 /*alignment slack*/ - kBwdMiscBytes;
+    if (x_bytes + y_bytes + g_bytes > limit) return false;
+    out.bw_nbuf = (x_bytes + 2 * y_bytes + g_bytes <= limit) ? 2 : 1;
+    out.bw_y_off = x_bytes;
+    out.bw_y_stride = y_bytes;
+    out.bw_g_off = x_bytes + out.bw_nbuf * y_bytes;
+    out.bw_misc_off = out.bw_g_off + g_bytes;
+    out.nsplit = std::max(1, std::min(nsplit, (int)ceil_div(grad.N, kTileN)));
+    if (ceil_div(ceil_div(grad.N, kTileN), out.nsplit) > 8) return false;   // a CTA walks its tiles serially: keep it short
+    // outputs of the second product
+    out.fin_dx = store.fin_dx; out.fin_dx_dtype = store.fin_dx_dtype; out.fin_ld_dx = store.fin_ld_dx;
+    out.fin_x = store.fin_x; out.fin_x_dtype = store.fin_x_dtype; out.fin_ldx = store.fin_ldx; out.fin_sx = store.fin_sx;
+    out.out = store.out; out.ld_out = store.ld_out; out.slice_stride = store.slice_stride;
+    if (out.nsplit > 1 && (out.out == nullptr || out.slice_stride == 0)) return false;   // partial tiles need slices
+    if (out.nsplit == 1 && out.fin_dx == nullptr && out.out == nullptr) return false;
+    if (out.nsplit > 1) out.fin_dx = nullptr;
+    return true;
+}
+
+static int launch_gemm_bwd(const GemmLaunch& L, cudaStream_t stream) {
+    int smem = 0;
+    for (int j = 0; j < L.njobs; ++j) smem = std::max(smem, L.job[j].bw_misc_off + kBwdMiscBytes + 1024);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(gemm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess) prefer_max_shared(gemm_bwd_kernel);
+    });
+    STIL_CUDA(attr_err);
+    STIL_CUDA(launch_pdl(gemm_bwd_kernel, dim3(L.total_tiles), dim3(kBwdThreads), (size_t)smem, stream, L));
+    return STIL_OK;
+}
+
 // All jobs of one launch share the epilogue mode (the kernel is specialised per mode to keep it small).
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
     STIL_REQUIRE(L.njobs >= 1 && L.njobs <= kMaxGemmJobs, STIL_E_ARG, "gemm launch with %d jobs", L.njobs);
@@ -690,6 +1086,7 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
             if (rc) return rc;
         }
     }
+    if (mode == GEMM_BWD) return launch_gemm_bwd(L, stream);
     // more tiles than SMs: two CTAs per SM (3-deep rings) so epilogues overlap main loops
     const bool two = L.total_tiles > 148;
     if (mode == GEMM_STATS) return two ? launch_gemm_mode<GEMM_STATS, 2>(L, stream) : launch_gemm_mode<GEMM_STATS, 1>(L, stream);

@@ -13,7 +13,9 @@ namespace stil {
 enum GemmMode : int {
     GEMM_STATS = 0,  // per-row online (max, sum-exp) partial per column tile  [+ optional fp32 store]
     GEMM_STORE = 1,  // fp32 store of L
-    GEMM_GRAD = 2    // G = u_i e^{L-lse_x[i]} + v e^{L-lse_y[j]} - d_i [j == tgt_i], times cs_j, as bf16 hi/lo
+    GEMM_GRAD = 2,   // G = u_i e^{L-lse_x[i]} + v e^{L-lse_y[j]} - d_i [j == tgt_i], times cs_j, as bf16 hi/lo
+    GEMM_BWD = 3     // fused backward: per 128-row block, for each column tile: recompute L, form G in shared memory, and
+                     // accumulate dX += G · Y in TMEM (G never leaves the SM); see gemm_bwd_kernel
 };
 constexpr int kMaxGemmJobs = 4;
 constexpr int kMaxSegPairs = 6;
@@ -89,6 +91,14 @@ struct alignas(64) GemmJob {
     const unsigned long long* lse_ll_tag;
     // plain STORE post-op on the scaled value: 0 none, 1 exp, 2 diagonal (row == column) forced to 1
     int post_op;
+    // GEMM_BWD: second product dX += G · Y (segment pairs of G x Y), column tiles dealt round-robin to `nsplit` CTAs per row
+    // block (nsplit > 1: per-slice partial dX like ksplit slices), shared-memory plan (bytes from the 1024-aligned base)
+    int npair2;
+    int gseg2[kMaxSegPairs], yseg2[kMaxSegPairs];
+    int nsplit;
+    int bw_nx, bw_ny;          // X / Y segments resident in shared memory
+    int bw_nbuf;               // Y tile buffers (2 when they fit: next tile's recompute overlaps this tile's epilogue)
+    int bw_y_off, bw_y_stride, bw_g_off, bw_misc_off;
 };
 
 struct GemmLaunch {
@@ -104,6 +114,10 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t r
                      int64_t row_stride, int64_t seg_stride, int box_rows = 128);
 void gemm_job_tiles(GemmLaunch& L);  // fills tiles_m/tiles_n/tile_begin/total_tiles
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream);
+// Turn a GEMM_GRAD job + the GEMM_STORE job that would consume its G into one GEMM_BWD job (false: shapes / shared memory
+// do not allow the fused kernel — launch the two separately)
+bool make_bwd_job(GemmJob& out, const GemmJob& grad, const GemmJob& store, int nsplit);
+int bwd_nsplit(int64_t n_cols, int64_t row_blocks_total);
 int gemm_set_trace(void* buf);   // debug: device buffer of [64 launches][64 CTAs][8] u64 %globaltimer stamps, or nullptr
 
 // (max, sum) statistics partials of the two InfoNCE sides inside an stil_infonce workspace (api.cu; used by p2p.cu)
