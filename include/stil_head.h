@@ -250,6 +250,18 @@ STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, in
                                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * f-2 — CLUBMean mutual-information bound and its learning loss, from mu = p_mu(x_samples) on.  Replaces the tensor code
+ * of models/Disentangle/utils/club.py:107-121 (forward) and :125-130 (learning_loss), called STiLModel.py:327-330.
+ * The reference's B x B x D broadcast collapses to column sums (SURVEY f-2):
+ *   bound = sum_i mu_i.y_i / B - (sum_i mu_i).(sum_j y_j) / B^2;   est = sum_i ||mu_i - y_i||^2 / B
+ * colstats is 4*dim floats (kept for the backward).  bwd: g_bound / g_est are DEVICE scalars (NULL = 0);
+ * d_mu, d_y [rows, ld_grad] f32 receive g_bound * d bound + g_est * d est. */
+STIL_API int stil_club_fwd(const void* mu, const void* y, int dtype, int64_t rows, int64_t dim, int64_t ld, float* colstats,
+                           float* bound, float* est, void* stream);
+STIL_API int stil_club_bwd(const void* mu, const void* y, int dtype, int64_t rows, int64_t dim, int64_t ld, const float* colstats,
+                           const float* g_bound, const float* g_est, float* d_mu, float* d_y, int64_t ld_grad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * f-1 — masked soft-target CE of the three student heads on the unlabelled rows, forward and
  * gradient in one pass.  Replaces STiLModel.py:301-303.
  *   losses[3]  = (loss_m_u, loss_i_u, loss_t_u), each a mean over `rows`

@@ -121,3 +121,14 @@ def mmatch_block(pseudo_label_orig: Tensor, feat_m_u: Tensor, embed_queue: Tenso
     m = mask1.to(y_i_u.dtype)
     return dict(pseudo_label=pseudo, max_prob=max_prob, max_idx=max_idx, mask1=mask1,
                 loss_i_u=(ce(y_i_u) * m).mean(), loss_t_u=(ce(y_t_u) * m).mean())
+
+
+# --------------------------------------------------------------------------- f-2
+def club_mean(mu: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
+    """CLUBMean.forward and .learning_loss from mu = p_mu(x) on (models/Disentangle/utils/club.py:107-121, 125-130;
+    called STiLModel.py:327-330): the MI upper bound with its B x B x D broadcast, and the q(y|x) learning loss."""
+    positive = -(mu - y) ** 2 / 2.0
+    negative = -((y.unsqueeze(0) - mu.unsqueeze(1)) ** 2).mean(dim=1) / 2.0
+    bound = (positive.sum(dim=-1) - negative.sum(dim=-1)).mean()
+    est = -(-(mu - y) ** 2).sum(dim=1).mean(dim=0)
+    return bound, est

@@ -287,5 +287,39 @@ def main():
     mmatch_case("bank_mmatch_epoch0", MMatch, 3303, 4, 28, 2, 32, 96, ptr=0, da=True, epoch=0, th1=0.85)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--club" not in sys.argv:
     main()
+
+
+# ---------------------------------------------------------------------------------------------------- f-2
+def club_case(name, seed, b, d, hidden):
+    """models/Disentangle/utils/club.py CLUBMean (real module): forward (the MI upper bound, :107-121) and learning_loss
+    (:125-130) on planted samples; the fixture records mu = p_mu(x), so the GPU path is compared from mu on."""
+    club = importlib.import_module("models.Disentangle.utils.club")
+    torch.manual_seed(seed)
+    m = club.CLUBMean(d, d, hidden)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, d, generator=g)
+    y = (0.6 * x + 0.8 * torch.randn(b, d, generator=g)).requires_grad_(True)
+    mu = m.p_mu(x).detach().requires_grad_(True)
+    m.get_mu_logvar = lambda _x: (mu, 0)           # forward()/learning_loss() from the recorded mu on
+    bound = m.forward(x, y)
+    est = m.learning_loss(x, y)
+    gb = torch.autograd.grad(bound, (mu, y), retain_graph=True)
+    ge = torch.autograd.grad(est, (mu, y))
+    np.savez_compressed(OUT / f"{name}.npz", mu=to_np(mu), y=to_np(y), bound=to_np(bound), est=to_np(est),
+                        d_mu_bound=to_np(gb[0]), d_y_bound=to_np(gb[1]), d_mu_est=to_np(ge[0]), d_y_est=to_np(ge[1]))
+    print(f"{name}: bound {float(bound):.5f} est {float(est):.4f}")
+
+
+def main_club():
+    sys.path.insert(0, str(REF))
+    _stub_bank_modules()
+    OUT.mkdir(parents=True, exist_ok=True)
+    club_case("club_b64_d128", 3401, 64, 128, 64)
+    club_case("club_b56_d512", 3402, 56, 512, None)
+    club_case("club_b37_d24", 3403, 37, 24, 16)
+
+
+if __name__ == "__main__" and "--club" in sys.argv:
+    main_club()

@@ -115,6 +115,8 @@ SIGNATURES = {
     "stil_queue_enqueue": (i32, [vp, i32, i64, vp, i64, i64, vp, vp, i32, i64, i64, i64, vp, i64, i64, vp]),
     "stil_bank_update": (i32, [vp, i32, i64, vp, vp, i32, i64, vp, vp, i64, i64, vp]),
     "stil_da_apply_hist": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
+    "stil_club_fwd": (i32, [vp, vp, i32, i64, i64, i64, vp, vp, vp, vp]),
+    "stil_club_bwd": (i32, [vp, vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp]),
     "stil_masked_softce_workspace_bytes": (i64, [i64]),
     "stil_masked_softce": (i32, [vp, vp, vp, i32, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64,
                                  f32, vp, i64, vp]),

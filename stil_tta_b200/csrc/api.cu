@@ -1532,6 +1532,20 @@ STIL_API int stil_bank_update(void* bank, int b_dtype, int64_t ld_bank, int64_t*
     return launch_bank_update(bank, b_dtype, ld_bank, labels, k, k_dtype, ld_k, y, index, n, dim, S(stream));
 }
 
+STIL_API int stil_club_fwd(const void* mu, const void* y, int dtype, int64_t rows, int64_t dim, int64_t ld, float* colstats,
+                           float* bound, float* est, void* stream) {
+    STIL_REQUIRE(dtype == STIL_F32 || dtype == STIL_BF16, STIL_E_DTYPE, "club_fwd: bad dtype");
+    STIL_REQUIRE(mu && y && colstats && rows >= 1 && dim >= 1 && ld >= dim && (bound || est), STIL_E_ARG, "club_fwd: bad arguments");
+    return launch_club_fwd(mu, y, dtype, ld, rows, dim, colstats, bound, est, S(stream));
+}
+STIL_API int stil_club_bwd(const void* mu, const void* y, int dtype, int64_t rows, int64_t dim, int64_t ld, const float* colstats,
+                           const float* g_bound, const float* g_est, float* d_mu, float* d_y, int64_t ld_grad, void* stream) {
+    STIL_REQUIRE(dtype == STIL_F32 || dtype == STIL_BF16, STIL_E_DTYPE, "club_bwd: bad dtype");
+    STIL_REQUIRE(mu && y && colstats && d_mu && d_y && rows >= 1 && dim >= 1 && ld >= dim && ld_grad >= dim, STIL_E_ARG,
+                 "club_bwd: bad arguments");
+    return launch_club_bwd(mu, y, dtype, ld, rows, dim, colstats, g_bound, g_est, d_mu, d_y, ld_grad, S(stream));
+}
+
 STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* hist,
                                 int64_t hist_len, int64_t* count, float* qmean_scratch, float* out, int64_t ld_out,
                                 void* stream) {

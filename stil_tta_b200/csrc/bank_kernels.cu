@@ -2,6 +2,8 @@
 // a7-a9): bank softmax -> bf16 operand, smoothing mix + max/argmax/mask, CoMatch graph contrastive loss (forward +
 // gradient), embedding-graph gradient operand, single-head masked soft/hard CE, FIFO queue writes.
 // All HBM-bound; warp-shuffle / block reductions, coalesced row access.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace stil {
@@ -258,9 +260,94 @@ __global__ void __launch_bounds__(256) da_hist_update_kernel(const float* __rest
     if (threadIdx.x == 0) *count = cnt + 1;
 }
 
+// ---------------------------------------------------------------------------------------------------- f-2: CLUBMean
+// The reference forms a B x B x D broadcast ((y_j - mu_i)^2 averaged over j, club.py:113-118).  Algebraically
+//   bound = mean_i(positive_i - negative_i) = sum_i mu_i.y_i / B - (sum_i mu_i).(sum_j y_j) / B^2
+// (the ||y||^2 and ||mu||^2 terms cancel), so only column sums are needed: O(B D) work and no temporary.
+// stats[4][D] = (sum_i mu, sum_i y, sum_i mu*y, sum_i (mu-y)^2): 32 columns per block, rows split over 8 groups and
+// combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) club_colstats_kernel(const void* __restrict__ mu, const void* __restrict__ y, int dtype,
+                                                            long long ld, int rows, int dim, float* __restrict__ stats) {
+    __shared__ float part[8][4][33];
+    pdl_wait();
+    pdl_launch_dependents();
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int grp = threadIdx.x >> 5;
+    float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+    if (col < dim)
+        for (int r = grp; r < rows; r += 8) {
+            const float m = ld_as_float(mu, dtype, (long long)r * ld + col), v = ld_as_float(y, dtype, (long long)r * ld + col);
+            a += m; b += v; c += m * v; d += (m - v) * (m - v);
+        }
+    part[grp][0][threadIdx.x & 31] = a; part[grp][1][threadIdx.x & 31] = b;
+    part[grp][2][threadIdx.x & 31] = c; part[grp][3][threadIdx.x & 31] = d;
+    __syncthreads();
+    if (grp < 4 && col < dim) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += part[g][grp][threadIdx.x & 31];
+        stats[(long long)grp * dim + col] = t;
+    }
+}
+// bound (club.py:107-121) and learning loss (:125-130) from the column statistics; one block
+__global__ void __launch_bounds__(256) club_losses_kernel(const float* __restrict__ stats, int rows, int dim, float* bound,
+                                                          float* est) {
+    __shared__ float red[kBlk / 32];
+    pdl_wait();
+    pdl_launch_dependents();
+    float p = 0.f, ms = 0.f, q = 0.f;
+    for (int c = threadIdx.x; c < dim; c += 256) {
+        p += stats[2LL * dim + c];
+        ms += stats[c] * stats[(long long)dim + c];
+        q += stats[3LL * dim + c];
+    }
+    p = blk_reduce(p, red, false);
+    ms = blk_reduce(ms, red, false);
+    q = blk_reduce(q, red, false);
+    if (threadIdx.x == 0) {
+        const float b = (float)rows;
+        if (bound) *bound = p / b - ms / (b * b);
+        if (est) *est = q / b;
+    }
+}
+// d bound / d mu_i = y_i/B - s/B^2, d bound / d y_j = mu_j/B - m/B^2;  d est / d mu = 2(mu - y)/B = -d est / d y
+__global__ void __launch_bounds__(256) club_grad_kernel(const void* __restrict__ mu, const void* __restrict__ y, int dtype,
+                                                        long long ld, int rows, int dim, const float* __restrict__ stats,
+                                                        const float* g_bound, const float* g_est, float* d_mu, float* d_y,
+                                                        long long ld_g) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const float gb = g_bound ? *g_bound : 0.f, ge = g_est ? *g_est : 0.f;
+    const float ib = 1.0f / (float)rows;
+    const long long total = (long long)rows * dim;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / dim), c = (int)(idx % dim);
+        const float m = ld_as_float(mu, dtype, (long long)r * ld + c), v = ld_as_float(y, dtype, (long long)r * ld + c);
+        const float e2 = ge * 2.f * (m - v) * ib;
+        d_mu[(long long)r * ld_g + c] = gb * (v * ib - stats[(long long)dim + c] * ib * ib) + e2;
+        d_y[(long long)r * ld_g + c] = gb * (m * ib - stats[c] * ib * ib) - e2;
+    }
+}
+
 inline int warp_rows_block(int64_t rows) { return rows <= 4096 ? 64 : kBlk; }
 
 }  // namespace
+
+int launch_club_fwd(const void* mu, const void* y, int dtype, int64_t ld, int64_t rows, int64_t dim, float* stats, float* bound,
+                    float* est, cudaStream_t stream) {
+    STIL_CUDA(launch_pdl(club_colstats_kernel, dim3((unsigned)ceil_div(dim, 32)), dim3(256), 0, stream, mu, y, dtype,
+                         (long long)ld, (int)rows, (int)dim, stats));
+    STIL_CUDA(launch_pdl(club_losses_kernel, dim3(1), dim3(256), 0, stream, static_cast<const float*>(stats), (int)rows,
+                         (int)dim, bound, est));
+    return STIL_OK;
+}
+int launch_club_bwd(const void* mu, const void* y, int dtype, int64_t ld, int64_t rows, int64_t dim, const float* stats,
+                    const float* g_bound, const float* g_est, float* d_mu, float* d_y, int64_t ld_g, cudaStream_t stream) {
+    const int blocks = (int)std::min<int64_t>(ceil_div(rows * dim, 256), 148 * 8);
+    STIL_CUDA(launch_pdl(club_grad_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, mu, y, dtype, (long long)ld, (int)rows,
+                         (int)dim, stats, g_bound, g_est, d_mu, d_y, (long long)ld_g));
+    return STIL_OK;
+}
 
 int launch_bank_softmax_rows(const float* z, int64_t ldz, int64_t rows, int64_t k_q, float temperature,
                              __nv_bfloat16* gop, int64_t ldg, int nseg, cudaStream_t stream) {

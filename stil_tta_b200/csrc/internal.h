@@ -279,6 +279,10 @@ int launch_bank_update(void* bank, int b_dtype, int64_t ld_b, int64_t* labels, c
                        const int64_t* y, const int64_t* index, int64_t n, int64_t dim, cudaStream_t stream);
 int launch_da_hist_update(const float* batch_mean, float* hist, int64_t hist_len, int64_t k, int64_t* count, float* qmean,
                           cudaStream_t stream);
+int launch_club_fwd(const void* mu, const void* y, int dtype, int64_t ld, int64_t rows, int64_t dim, float* stats, float* bound,
+                    float* est, cudaStream_t stream);
+int launch_club_bwd(const void* mu, const void* y, int dtype, int64_t ld, int64_t rows, int64_t dim, const float* stats,
+                    const float* g_bound, const float* g_est, float* d_mu, float* d_y, int64_t ld_g, cudaStream_t stream);
 // probs / qmean with rows renormalised (the second half of launch_da_apply)
 int launch_da_rows(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* qmean, float* out, int64_t ld_out,
                    cudaStream_t stream);

@@ -258,3 +258,40 @@ def test_queue_enqueue_wraps_like_the_reference(S, BO):
         S.queue_enqueue(q, p, ptr, dev(z), dev(t))
         assert int(ptr) == int(ptr_ref)
         assert torch.equal(q.cpu(), q_ref) and torch.equal(p.cpu(), p_ref)
+
+
+# ------------------------------------------------------------------------------------------ f-2 CLUBMean
+from test_oracle_banks import CLUB_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", CLUB_CASES)
+def test_club_matches_reference_fixture(S, name):
+    z = load(name)
+    mu, y = dev(z["mu"]).requires_grad_(True), dev(z["y"]).requires_grad_(True)
+    bound, est = S.club_both(mu, y)
+    assert abs(float(bound) - float(z["bound"])) <= REL * abs(float(z["bound"])) + 2e-5
+    assert_rel(est, z["est"], REL, "learning_loss")
+    gb = torch.autograd.grad(bound, (mu, y), retain_graph=True)
+    ge = torch.autograd.grad(est, (mu, y))
+    assert_rel(gb[0], z["d_mu_bound"], REL, "d_mu bound"); assert_rel(gb[1], z["d_y_bound"], REL, "d_y bound")
+    assert_rel(ge[0], z["d_mu_est"], REL, "d_mu est"); assert_rel(ge[1], z["d_y_est"], REL, "d_y est")
+
+
+def test_club_module_matches_oracle_at_full_size(S, BO):
+    """B = D = 512 (the reference's broadcast temporary would be 512 MB): the drop-in module against the closed form in
+    fp64 and, through autograd, the parameter gradients of p_mu."""
+    torch.manual_seed(5)
+    m = S.CLUBMean(512, 512, 512).cuda()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(512, 512, generator=g).cuda()
+    y = (0.5 * x.cpu() + torch.randn(512, 512, generator=g)).cuda().requires_grad_(True)
+    loss = m(x, y) + m.learning_loss(x, y)
+    loss.backward()
+    mu64 = m.p_mu(x).detach().double().cpu().requires_grad_(True)
+    y64 = y.detach().double().cpu().requires_grad_(True)
+    b = 512
+    ref = (mu64 * y64).sum() / b - (mu64.sum(0) * y64.sum(0)).sum() / b ** 2 + ((mu64 - y64) ** 2).sum() / b
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= REL * abs(float(ref))
+    assert_rel(y.grad, y64.grad, REL, "d_y")
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())

@@ -113,3 +113,24 @@ def test_mmatch_oracle_matches_reference(name):
     BO.queue_enqueue(q, pq, pp, feat_m, torch.cat([onehot, o["pseudo_label"]]))
     close(q, z["embed_queue_out"]); close(pq, z["probs_queue_out"])
     assert int(pp) == int(z["embed_queue_ptr_out"])
+
+
+CLUB_CASES = ["club_b64_d128", "club_b56_d512", "club_b37_d24"]
+
+
+@pytest.mark.parametrize("name", CLUB_CASES)
+def test_club_oracle_matches_reference(name):
+    z = load(name)
+    torch.set_num_threads(1)
+    mu, y = z["mu"].clone().requires_grad_(True), z["y"].clone().requires_grad_(True)
+    bound, est = BO.club_mean(mu, y)
+    close(bound, z["bound"], rtol=1e-4, atol=1e-5)
+    close(est, z["est"])
+    gb = torch.autograd.grad(bound, (mu, y), retain_graph=True)
+    ge = torch.autograd.grad(est, (mu, y))
+    close(gb[0], z["d_mu_bound"], rtol=1e-4); close(gb[1], z["d_y_bound"], rtol=1e-4)
+    close(ge[0], z["d_mu_est"]); close(ge[1], z["d_y_est"])
+    # the closed form the CUDA path uses (SURVEY f-2): bound = sum_i mu_i.y_i / B - (sum_i mu_i).(sum_j y_j) / B^2
+    b = mu.shape[0]
+    closed = (mu * y).sum() / b - (mu.sum(0) * y.sum(0)).sum() / b ** 2
+    close(closed, z["bound"], rtol=1e-4, atol=2e-5)
