@@ -316,7 +316,12 @@ class DistributedSTiLHead(STiLHead):
             self._packed = torch.zeros(4 + 2 * n, dtype=torch.float32, device=dev)
             self._lse = self._packed[4:].view(2, W, B)
         # + cat, exchanges / collectives, infonce fwd (prep, gemm, finish), bwd (prep, gemm, gemm), add, loss
-        self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 3 + 3 + 3 + 2
+        if self.transport == "fused":
+            # row-local step (+ the class-partial push inside it), push_embeddings, stats GEMM, push_lse, loss finish,
+            # grad GEMM, dX GEMM (+ slice reduction for a split contraction), waiting proto_add
+            self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 6 + (1 if n >= 1024 else 0) + 1
+        else:
+            self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 3 + 3 + 3 + 2
 
     # ------------------------------------------------------------------------------------------
     def capture(self) -> None:
