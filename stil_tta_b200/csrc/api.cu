@@ -2,6 +2,7 @@
 // plans the caller-provided workspace, builds TMA descriptors and job tables, enqueues kernels.
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -329,7 +330,8 @@ int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const
 // when the loop is long and the grid small.
 int infonce_dx_ksplit(int64_t m, int64_t n, int64_t dim) {
     const int64_t kblocks = ceil_div(n, kTileK), tiles = 2 * ceil_div(m, kTileM) * ceil_div(dim, kTileN);
-    if (kblocks < 16 || tiles * 2 > 148) return 1;
+    static const int64_t min_kblocks = [] { const char* e = getenv("STIL_DX_SPLIT_MIN_KBLOCKS"); return e ? atoll(e) : 32ll; }();
+    if (kblocks < min_kblocks || tiles * 2 > 148) return 1;
     return (int)std::max<int64_t>(1, std::min<int64_t>(kblocks / 8, 148 / tiles));
 }
 

@@ -169,33 +169,82 @@ __device__ __forceinline__ void store_row(float* base, long long ld, int row, in
     }
 }
 
+// Reductions over the LPR lanes of a row.  LPR <= 32: shuffles inside the warp.  LPR > 32 (one row per BLOCK of LPR
+// threads, used for small batches where the per-row dependency chain — not bandwidth — bounds the kernel): warp shuffles,
+// then the warps' values through shared memory; every thread of the block takes part (control flow is row-uniform).
+template <int LPR>
+__device__ __forceinline__ float row_max(float v) {
+    if constexpr (LPR <= 32) {
+        return group_max<LPR>(v);
+    } else {
+        __shared__ float sh[LPR / 32];
+        v = warp_max(v);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        float r = sh[0];
+#pragma unroll
+        for (int w = 1; w < LPR / 32; ++w) r = fmaxf(r, sh[w]);
+        __syncthreads();
+        return r;
+    }
+}
+template <int LPR>
+__device__ __forceinline__ float row_sum(float v) {
+    if constexpr (LPR <= 32) {
+        return group_sum<LPR>(v);
+    } else {
+        __shared__ float sh[LPR / 32];
+        v = warp_sum(v);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        float r = sh[0];
+#pragma unroll
+        for (int w = 1; w < LPR / 32; ++w) r += sh[w];      // fixed order: deterministic
+        __syncthreads();
+        return r;
+    }
+}
+
 // in: logits a (−inf padded). out: e = exp(a − max) in place; returns the row sum (all lanes of the group).
 template <int LPR, int NV>
 __device__ __forceinline__ float softmax_exp(float (&a)[2 * NV]) {
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 2 * NV; ++j) m = fmaxf(m, a[j]);
-    m = group_max<LPR>(m);
+    m = row_max<LPR>(m);
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 2 * NV; ++j) {
         a[j] = expf(a[j] - m);
         s += a[j];
     }
-    return group_sum<LPR>(s);
+    return row_sum<LPR>(s);
 }
 
 // first-index argmax across the LPR lanes of a row group
 template <int LPR>
 __device__ __forceinline__ void group_argmax(float& v, int& idx) {
+    constexpr int W = LPR < 32 ? LPR : 32;
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
+    for (int o = W / 2; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, v, o);
         const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
         if (ov > v || (ov == v && oi < idx)) {
             v = ov;
             idx = oi;
         }
+    }
+    if constexpr (LPR > 32) {
+        __shared__ float shv[LPR / 32];
+        __shared__ int shi[LPR / 32];
+        if ((threadIdx.x & 31) == 0) { shv[threadIdx.x >> 5] = v; shi[threadIdx.x >> 5] = idx; }
+        __syncthreads();
+        v = shv[0];
+        idx = shi[0];
+#pragma unroll
+        for (int w = 1; w < LPR / 32; ++w)
+            if (shv[w] > v || (shv[w] == v && shi[w] < idx)) { v = shv[w]; idx = shi[w]; }
+        __syncthreads();
     }
 }
 
@@ -224,7 +273,7 @@ __device__ __forceinline__ int argmax_logits(const float (&y)[2 * NV], int sub, 
 
 template <int LPR, int NV>
 __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) {
-    constexpr int RPW = 32 / LPR;
+    constexpr int RPW = LPR <= 32 ? 32 / LPR : 0;
     pdl_wait();                 // predecessor complete and visible ...
     pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.b_l; i += gridDim.x * blockDim.x) {
@@ -233,8 +282,9 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
     }
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const int sub = lane % LPR;
-    const int row = warp_global * RPW + lane / LPR;
+    const int sub = LPR <= 32 ? lane % LPR : (int)threadIdx.x;                       // LPR > 32: one row per block of
+    const int row = LPR <= 32 ? warp_global * RPW + lane / (LPR <= 32 ? LPR : 1)      // LPR threads
+                              : (int)blockIdx.x;
     // rows beyond the end keep running with a clamped index so that the full-warp shuffles stay converged
     const bool row_ok = row < A.rows;
     const int r = row_ok ? row : A.rows - 1;
@@ -1037,8 +1087,8 @@ __global__ void zero_u32_kernel(unsigned int* p, int n) {
 
 template <int LPR, int NV>
 int launch_cgpl_t(const CgplArgs& A, cudaStream_t stream) {
-    const int threads = row_block_threads(ceil_div(A.rows, 32 / LPR));
-    const int rows_per_block = (threads / 32) * (32 / LPR);
+    const int threads = LPR > 32 ? LPR : row_block_threads(ceil_div(A.rows, LPR > 32 ? 1 : 32 / LPR));
+    const int rows_per_block = LPR > 32 ? 1 : (threads / 32) * (32 / (LPR > 32 ? 32 : LPR));
     const int blocks = (int)ceil_div(A.rows, rows_per_block);
     static const bool once = (prefer_max_shared(cgpl_pgls_kernel<LPR, NV>), true);
     (void)once;
@@ -1130,6 +1180,9 @@ int launch_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logi
     A.vec_t = (ld_t % 2 == 0) && al(teacher_logits, 8);
     A.vec_pl = (ld_pl % 2 == 0) && al(pseudo_label, 8);
     A.vec_pred = prediction ? ((ld_pred % 2 == 0) && al(prediction, 8)) : 0;
+    // small batches are bound by each row's dependency chain (5 softmaxes): spread a row over 4 warps
+    if (rows <= 2048 && k > 128 && k <= 512) return launch_cgpl_t<128, 2>(A, stream);
+    if (rows <= 2048 && k > 512) return launch_cgpl_t<128, 4>(A, stream);
     if (k <= 2) return launch_cgpl_t<1, 1>(A, stream);
     if (k <= 16) return launch_cgpl_t<4, 2>(A, stream);
     if (k <= 64) return launch_cgpl_t<8, 4>(A, stream);
