@@ -266,7 +266,10 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
     // overlaps the predecessor's execution and only the epilogue depends on it.
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The first pass over the ring is issued LANE-PARALLEL: lane s fills stage s.  A bulk-tensor instruction costs
+        // ~0.1 us of issue time; one thread issuing the 12-18 loads of a three-segment operand back to back spent 1.2-1.7 us
+        // on the critical path of the first kernel of the step.
+        {
             const bool mn = MODE == GEMM_STORE && J.y_mn_major != 0;
             auto load_x = [&](int kb, int s) {
                 const int p = kb / kper, kk = kk0 + kb - p * kper;
@@ -283,40 +286,43 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                     tc05::tma_load_3d(b_dst + 64 * kTileK * 2, &J.tmy, &full_bar[s], n0 + 64, kk * kTileK, J.yseg[p]);
                 }
             };
-            // first pass over the ring: operands that do not depend on the predecessor go out before the wait
+            // operands that do not depend on the predecessor go out before the wait
             const int first = min(nkb, kStages);
             const bool ex = J.early_x != 0, ey = J.early_y != 0;
-            if (ex || ey) {
-                for (int kb = 0; kb < first; ++kb) {
-                    tc05::mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
-                    if (ex) load_x(kb, kb);
-                    if (ey) load_y(kb, kb);
-                }
+            const bool mine = lane < first;
+            if ((ex || ey) && mine) {
+                tc05::mbar_arrive_expect_tx(&full_bar[lane], kStageBytes);
+                if (ex) load_x(lane, lane);
+                if (ey) load_y(lane, lane);
             }
             if (!(ex && ey)) {
                 asm volatile("griddepcontrol.wait;" ::: "memory");
                 if (J.wait_flags && J.wait_y) {
-                    // the Y rows of this tile were stored by their owner rank(s): wait for exactly those arrivals, then
-                    // order the acquire before the TMA (async proxy) reads
-                    wait_peer_rows(J.wait_flags, J.wait_seq, J.wait_rows_per_peer, n0, min(n0 + kTileN, J.N) - 1);
+                    // the Y rows of this tile were stored by their owner rank(s): wait for exactly those arrivals (one lane,
+                    // the warp barrier passes the acquire on), then order it before the TMA (async proxy) reads
+                    if (lane == 0) wait_peer_rows(J.wait_flags, J.wait_seq, J.wait_rows_per_peer, n0, min(n0 + kTileN, J.N) - 1);
+                    __syncwarp();
                     asm volatile("fence.proxy.async.global;" ::: "memory");
                 }
-                for (int kb = 0; kb < first; ++kb) {
-                    if (!(ex || ey)) tc05::mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
-                    if (!ex) load_x(kb, kb);
-                    if (!ey) load_y(kb, kb);
+                if (mine) {
+                    if (!(ex || ey)) tc05::mbar_arrive_expect_tx(&full_bar[lane], kStageBytes);
+                    if (!ex) load_x(lane, lane);
+                    if (!ey) load_y(lane, lane);
                 }
             }
-            int s = 0;
-            uint32_t ph = 1;            // second pass over the ring waits for the first release of each slot
-            for (int kb = first; kb < nkb; ++kb) {
-                tc05::mbar_wait(&empty_bar[s], ph ^ 1);
-                tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                load_x(kb, s);
-                load_y(kb, s);
-                if (++s == kStages) { s = 0; ph ^= 1; }
+            __syncwarp();
+            if (lane == 0) {
+                int s = 0;
+                uint32_t ph = 1;            // second pass over the ring waits for the first release of each slot
+                for (int kb = first; kb < nkb; ++kb) {
+                    tc05::mbar_wait(&empty_bar[s], ph ^ 1);
+                    tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                    load_x(kb, s);
+                    load_y(kb, s);
+                    if (++s == kStages) { s = 0; ph ^= 1; }
+                }
+                STIL_TRACE(2);
             }
-            STIL_TRACE(2);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
