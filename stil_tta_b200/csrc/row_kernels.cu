@@ -852,51 +852,60 @@ struct SoftCeArgs {
     int vec_y, vec_pl, vec_g;
 };
 
-template <int NV>
+// LPR lanes per row (32 / LPR rows per warp for small K, like cgpl_pgls_kernel), NV float2 items per lane
+template <int LPR, int NV>
 __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeArgs A) {
+    constexpr int RPW = 32 / LPR;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane % LPR;
     float lossv[3] = {0.f, 0.f, 0.f};
-    // grid-stride over rows: the grid is capped so that the final (serial, deterministic) reduction stays short
-    for (int row = blockIdx.x * (blockDim.x >> 5) + warp; row < A.rows; row += gridDim.x * (blockDim.x >> 5)) {
-        const int k = A.k;
+    const int k = A.k;
+    const float inv_rows = 1.0f / (float)A.rows;
+    // grid-stride over row groups: the grid is capped so that the final (serial, deterministic) reduction stays short
+    const int wpb = blockDim.x >> 5;
+    for (int row0 = (blockIdx.x * wpb + warp) * RPW; row0 < A.rows; row0 += gridDim.x * wpb * RPW) {
+        const int row = row0 + lane / LPR;
+        const bool ok = row < A.rows;
+        const int r = ok ? row : A.rows - 1;      // lanes past the end keep running on a clamped row (full-warp shuffles)
         // all four rows of this sample in flight together
         float pl[2 * NV], y[3][2 * NV];
-        load_row<32, NV>(A.pl, STIL_F32, A.ld_pl, row, k, lane, A.vec_pl, pl);
+        load_row<LPR, NV>(A.pl, STIL_F32, A.ld_pl, r, k, sub, A.vec_pl, pl);
 #pragma unroll
-        for (int h = 0; h < 3; ++h) load_row<32, NV>(A.y[h], A.logit_dtype, A.ld_y, row, k, lane, A.vec_y, y[h]);
-        const float m1 = A.mask1[row] ? 1.f : 0.f;
-        const float c1 = A.case1[row] ? 1.f : 0.f, c2i = A.case2_i[row] ? 1.f : 0.f;
-        const float c2t = A.case2_t[row] ? 1.f : 0.f, c3 = A.case3[row] ? 1.f : 0.f;
-        const float mr = A.mask_random[row] ? 1.f : 0.f;
+        for (int h = 0; h < 3; ++h) load_row<LPR, NV>(A.y[h], A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, y[h]);
+        const float m1 = (ok && A.mask1[r]) ? 1.f : 0.f;
+        const float c1 = A.case1[r] ? 1.f : 0.f, c2i = A.case2_i[r] ? 1.f : 0.f;
+        const float c2t = A.case2_t[r] ? 1.f : 0.f, c3 = A.case3[r] ? 1.f : 0.f;
+        const float mr = A.mask_random[r] ? 1.f : 0.f;
         const float wgt[3] = {m1 * c1, m1 * (c1 + c2t + c3 * mr), m1 * (c1 + c2i + c3 * (1.f - mr))};
         float spl = 0.f;
 #pragma unroll
         for (int it = 0; it < NV; ++it)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                if (2 * (lane + 32 * it) + h >= k) pl[2 * it + h] = 0.f;   // padding was -inf
+                if (2 * (sub + LPR * it) + h >= k) pl[2 * it + h] = 0.f;   // padding was -inf
                 spl += pl[2 * it + h];
             }
-        spl = warp_sum(spl);
-        const float inv_rows = 1.0f / (float)A.rows;
+        spl = group_sum<LPR>(spl);
 #pragma unroll
         for (int h = 0; h < 3; ++h) {
+            // one warp = one row (LPR == 32): a zero weight skips the softmax (warp-uniform branch); several rows per warp:
+            // no branch, a zero weight zeroes the loss term and the gradient
             float dy[2 * NV];
-            if (wgt[h] != 0.f) {   // warp-uniform
+            if (LPR < 32 || wgt[h] != 0.f) {
                 float m = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 2 * NV; ++j) m = fmaxf(m, y[h][j]);
-                m = warp_max(m);
+                m = group_max<LPR>(m);
                 float s = 0.f, py = 0.f;
 #pragma unroll
                 for (int j = 0; j < 2 * NV; ++j) {
                     s += expf(y[h][j] - m);                       // exp(-inf) = 0 for the padding
                     if (pl[j] != 0.f) py += pl[j] * y[h][j];
                 }
-                s = warp_sum(s);
-                py = warp_sum(py);
+                s = group_sum<LPR>(s);
+                py = group_sum<LPR>(py);
                 const float lse = m + logf(s);
-                lossv[h] += (lse * spl - py) * wgt[h];            // -sum_k pl_k log_softmax(y)_k, times the row weight
+                if (sub == 0 && wgt[h] != 0.f) lossv[h] += (lse * spl - py) * wgt[h];   // -sum_k pl_k log_softmax(y)_k, weighted
                 const float gs = A.grad_scale * wgt[h] * inv_rows;
 #pragma unroll
                 for (int j = 0; j < 2 * NV; ++j) dy[j] = gs * (expf(y[h][j] - lse) * spl - pl[j]);
@@ -904,9 +913,11 @@ __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeAr
 #pragma unroll
                 for (int j = 0; j < 2 * NV; ++j) dy[j] = 0.f;
             }
-            if (A.dy[h]) store_row<32, NV>(A.dy[h], A.ld_g, row, k, lane, A.vec_g, dy);
+            if (A.dy[h] && ok) store_row<LPR, NV>(A.dy[h], A.ld_g, row, k, sub, A.vec_g, dy);
         }
     }
+#pragma unroll
+    for (int h = 0; h < 3; ++h) lossv[h] = warp_sum(lossv[h]);     // the row leaders' terms of this warp
     __shared__ float sred[3][kRowBlock / 32];
     __shared__ bool is_last;
     if (lane == 0)
@@ -1323,15 +1334,25 @@ int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int 
     A.vec_y = (ld_y % 2 == 0) && al(y_m, 2 * esz) && al(y_i, 2 * esz) && al(y_t, 2 * esz);
     A.vec_pl = (ld_pl % 2 == 0) && al(pseudo_label, 8);
     A.vec_g = (ld_g % 2 == 0) && al(d_y_m, 8) && al(d_y_i, 8) && al(d_y_t, 8);
-    const int blocks = (int)masked_softce_blocks(rows, k);
-    static const bool once = (prefer_max_shared(masked_softce_kernel<1>), prefer_max_shared(masked_softce_kernel<5>),
-                              prefer_max_shared(masked_softce_kernel<8>), prefer_max_shared(masked_softce_kernel<16>), true);
+    static const bool once = (prefer_max_shared(masked_softce_kernel<1, 1>), prefer_max_shared(masked_softce_kernel<4, 2>),
+                              prefer_max_shared(masked_softce_kernel<8, 4>), prefer_max_shared(masked_softce_kernel<32, 2>),
+                              prefer_max_shared(masked_softce_kernel<32, 5>), prefer_max_shared(masked_softce_kernel<32, 8>),
+                              prefer_max_shared(masked_softce_kernel<32, 16>), true);
     (void)once;
     const int threads = row_block_threads(rows);
-    if (k <= 64) masked_softce_kernel<1><<<blocks, threads, 0, stream>>>(A);
-    else if (k <= 320) masked_softce_kernel<5><<<blocks, threads, 0, stream>>>(A);
-    else if (k <= 512) masked_softce_kernel<8><<<blocks, threads, 0, stream>>>(A);
-    else masked_softce_kernel<16><<<blocks, threads, 0, stream>>>(A);
+    auto go = [&](auto kernel, int lpr) {
+        const int64_t rows_per_block = (threads / 32) * (32 / lpr);
+        // never more blocks than masked_softce_blocks() sized the partials for
+        const int blocks = (int)std::min<int64_t>(ceil_div(rows, rows_per_block), masked_softce_blocks(rows, k));
+        kernel<<<blocks, threads, 0, stream>>>(A);
+    };
+    if (k <= 2) go(masked_softce_kernel<1, 1>, 1);
+    else if (k <= 16) go(masked_softce_kernel<4, 2>, 4);
+    else if (k <= 64) go(masked_softce_kernel<8, 4>, 8);
+    else if (k <= 128) go(masked_softce_kernel<32, 2>, 32);
+    else if (k <= 320) go(masked_softce_kernel<32, 5>, 32);
+    else if (k <= 512) go(masked_softce_kernel<32, 8>, 32);
+    else go(masked_softce_kernel<32, 16>, 32);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }
