@@ -50,6 +50,8 @@ typedef enum {
 } stil_status_t;
 
 STIL_API int stil_version(void);
+/* sizeof(stil_head_step_args) (which = 0) / sizeof(stil_p2p_channel) (1): lets a binding check its struct mirror */
+STIL_API int64_t stil_abi_struct_bytes(int which);
 STIL_API const char* stil_last_error(void);
 /* Debug aid: install (or clear with NULL) a device buffer of [64 launches][64 CTAs][8] uint64 into which the GEMM
  * kernel's CTAs store %globaltimer stamps of their phases (scripts/gemm_timeline.py).  Not for production use. */

@@ -57,6 +57,7 @@ class HeadStepArgs(C.Structure):
 # name -> (restype, argtypes); every symbol of include/stil_head.h
 SIGNATURES = {
     "stil_version": (i32, []),
+    "stil_abi_struct_bytes": (i64, [i32]),
     "stil_last_error": (C.c_char_p, []),
     "stil_check_device": (i32, []),
     "stil_debug_trace": (i32, [vp]),

@@ -423,6 +423,9 @@ using namespace stil;
 extern "C" {
 
 STIL_API int stil_version(void) { return STIL_VERSION; }
+STIL_API int64_t stil_abi_struct_bytes(int which) {
+    return which == 0 ? (int64_t)sizeof(stil_head_step_args) : which == 1 ? (int64_t)sizeof(stil_p2p_channel) : -1;
+}
 STIL_API const char* stil_last_error(void) { return stil::last_error(); }
 
 STIL_API int stil_debug_trace(void* buffer) { return gemm_set_trace(buffer); }

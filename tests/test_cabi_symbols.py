@@ -68,3 +68,42 @@ def test_ops_refuse_cpu_tensors():
         S.CLIPLoss(0.1)(torch.randn(8, 8), torch.randn(8, 8))
     with pytest.raises(ValueError):
         S.CLIPLoss(0.1, lambda_0=-0.1)
+
+
+def test_struct_mirrors_match_the_header(lib):
+    """The ctypes mirrors of the two ABI structs have the C compiler's sizes (field order / padding drift would corrupt
+    every argument after the first mismatch)."""
+    import ctypes
+    from stil_tta_b200 import _lib
+    assert lib.stil_abi_struct_bytes(0) == ctypes.sizeof(_lib.HeadStepArgs)
+    assert lib.stil_abi_struct_bytes(1) == ctypes.sizeof(_lib.P2PChannel)
+    assert lib.stil_abi_struct_bytes(7) == -1
+
+
+def test_new_entry_points_validate_arguments_without_gpu(lib):
+    buf = ctypes.create_string_buffer(8192)
+    p = (ctypes.addressof(buf) + 15) // 16 * 16
+    # bank smoothing: misaligned queue leading dimension (fp32 needs a multiple of 4)
+    rc = lib.stil_bank_smooth(p, 16, 4, 16, p, 0, 8, 8, p, 6, p, 8, 6, 0.1, 0.9, 0.1, p, 16, 0.9, None, None, None, p, 8192,
+                              None)
+    assert rc == -3
+    # bank smoothing without a bank (epoch gate) needs no workspace and no features
+    assert lib.stil_bank_smooth_workspace_bytes(448, 640, 128, 286, 0) > 0
+    # single-head CE: exactly one kind of target
+    rc = lib.stil_weighted_softce(p, 0, 8, p, 8, p, None, 4, 8, p, None, 8, 1.0, p, 8192, None)
+    assert rc == -6
+    rc = lib.stil_weighted_softce(p, 5, 8, p, 8, None, None, 4, 8, p, None, 8, 1.0, p, 8192, None)
+    assert rc == -2
+    # CoMatch graphs: output leading dimension must hold rows + k_q columns
+    rc = lib.stil_comatch_graphs_fwd(p, 16, 4, 16, p, 8, p, p, 0, 8, 8, p, 8, 8, 0.1, p, p, 8, p, 8192, None)
+    assert rc == -6
+    # CLUB: bad dtype / missing outputs
+    assert lib.stil_club_fwd(p, p, 9, 4, 8, 8, p, p, p, None) == -2
+    assert lib.stil_club_fwd(p, p, 0, 4, 8, 8, p, None, None, None) == -6
+    # gathered InfoNCE is bf16-only
+    rc = lib.stil_infonce_stats_gathered(p, p, p, p, 0, 8, 8, 8, 8, 0, 0.1, None, None, 0, p, 8192, None)
+    assert rc == -2
+    # peer exchange: world / rank / channel range
+    bases = (ctypes.c_void_p * 8)(*([p] * 8))
+    assert lib.stil_p2p_wait(bases, 9, 0, 0, 512, 0, None) == -6
+    assert lib.stil_p2p_wait(bases, 2, 0, 0, 512, 8, None) == -6
