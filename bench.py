@@ -32,6 +32,9 @@ UNIT = "samples/s"
 L2_BYTES = 126 * 2 ** 20
 
 
+PREWARM_STEPS = 6000   # untimed steps before the W warm-up steps of every timed region (~0.2-0.4 s of GPU work)
+
+
 def peaks():
     f = REPO / "MEASURED_PEAKS.json"
     if f.exists():
@@ -172,8 +175,14 @@ def run_reference_arm(args):
 def timed_region(fn_step, steps, warmup, dist_on, dev):
     """warm-up, barrier+sync, K steps between CUDA events on the current stream, barrier+sync; ms total."""
     import torch.distributed as dist
-    for i in range(warmup):
+    # untimed pre-warm before the W warm-up steps: a fixed NUMBER of steps (the same on every rank — the data-parallel
+    # step is collective) worth ~0.3 s, so that a short timed region (small K) is not measured on clocks still ramping up
+    # from the idle state the clock sampler's start-up sleep leaves the GPU in
+    pre = PREWARM_STEPS
+    for i in range(pre):
         fn_step(i)
+    for i in range(warmup):
+        fn_step(pre + i)
     torch.cuda.synchronize(dev)
     if dist_on:
         dist.barrier()
@@ -181,7 +190,7 @@ def timed_region(fn_step, steps, warmup, dist_on, dev):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        fn_step(warmup + i)
+        fn_step(pre + warmup + i)
     e1.record()
     torch.cuda.synchronize(dev)
     if dist_on:
@@ -359,7 +368,8 @@ def run_gpu_arm(args):
                           f"stream, inside the timed region, one step ahead) from a pool of {npool} distinct batches = "
                           f"{npool * in_bytes / 2**20:.0f} MiB in HBM"
                           if npool * in_bytes > L2_BYTES else f"EXPERIMENT: pool of {npool} batches fits in L2"),
-                   "parallelism": f"dp{world}", "cuda_graph": True},
+                   "parallelism": f"dp{world}", "cuda_graph": True,
+                   "prewarm": f"{PREWARM_STEPS} untimed steps before the W warm-up steps of each timed region (clock ramp)"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": heads[0].h2d_bytes,
                 "d2h_bytes_per_step": heads[0].d2h_bytes},
         "gpu_launches": heads[0].launches_per_step * args.steps,   # + one D2D input copy per step (not ours)
@@ -418,6 +428,30 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = {"value": cfg.batch / (ms_cpu * 1e-3), "unit": UNIT, "cores": n, "kind": "port",
                                     "sample": f"{done} head steps (fwd+bwd) of the oracle port on the host, "
                                               f"{ms_cpu:.2f} ms/step, best thread count of 1..{len(os.sched_getaffinity(0))} = {n}"}
+        if args.torch_gpu_baseline:
+            # "beat the library" bar: the same oracle port, eager PyTorch on THIS GPU (fp32, fwd+bwd); the
+            # oracle is the thing measured here only as a baseline, like the cpu_baseline leg
+            try:
+                from oracle import stil_head_oracle as O
+                gb = [{k: v.to(dev) for k, v in synth.make_batch(cfg, seed=100 + i).items()} for i in range(4)]
+                st = {"prototypes_sum": torch.zeros(cfg.num_classes, cfg.proj_dim, device=dev),
+                      "prototypes_count_sum": torch.zeros(cfg.num_classes, 1, device=dev)}
+                for i in range(5):
+                    O.head_step(gb[i % 4], cfg, state=st)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nstep = 100
+                e0.record()
+                for i in range(nstep):
+                    O.head_step(gb[i % 4], cfg, state=st)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms_t = e0.elapsed_time(e1) / nstep
+                line["torch_gpu_baseline"] = {"value": cfg.batch / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t,
+                                              "kind": "oracle port, eager torch CUDA fp32 on the same B200 (launch-bound)",
+                                              "sample": f"{nstep} head steps (fwd+bwd)"}
+            except Exception as ex:   # a baseline must never take the bench line down
+                line["torch_gpu_baseline"] = {"error": repr(ex)[:200]}
         print(json.dumps(line), flush=True)
     if dist_on:
         # graphs that captured NCCL work must die before the communicator; then leave without the (slow, and with
@@ -440,6 +474,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-CPU leg (profiling runs)")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the oracle port as eager PyTorch on the GPU (N=1; reported beside cpu_baseline)")
     ap.add_argument("--transport", default="fused", choices=["fused", "p2p", "nccl"],
                     help="N>1 exchange: fused peer-memory schedule, blocking peer-memory all-gathers, or NCCL")
     ap.add_argument("--nbuf", type=int, default=0, help="experiments: override the number of rotating batches")
