@@ -3,9 +3,9 @@
 //   L[i,j] = alpha * sx[i] * sy[j] * sum_{(p,q) in pairs} <X[i,p,:], Y[j,q,:]>
 //
 // One CTA per 128x128 tile.  Warp 0 streams 128x64 bf16 operand boxes with TMA (128-byte swizzle)
-// through a 3-stage mbarrier ring, warp 1 issues tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32 in
-// TMEM), warps 2-5 drain the accumulator with tcgen05.ld (thread = row) and run one of three
-// epilogues (see GemmMode in internal.h).  Used for: the InfoNCE logits of utils/clip_loss.py:33 and
+// through an mbarrier ring (6 stages with one CTA per SM, 3 with two), warp 1 issues tcgen05.mma (M=128,
+// N=128, K=16, bf16 -> fp32 in TMEM), the remaining 16 (or 8) warps drain the accumulator with tcgen05.ld
+// (thread = row, one or two 32-column chunks per warp) and run one of three epilogues (see GemmMode in internal.h).  Used for: the InfoNCE logits of utils/clip_loss.py:33 and
 // their row/column log-sum-exp (:36-37), the prototype logits of utils/prototype_loss.py:26 and
 // STiLModel.py:293, and both GEMMs of their backward passes (G = dLoss/dLogits is formed on chip from a
 // recomputed tile and written as bf16 hi/lo; dX = G·Y reads Y in place as an MN-major operand and applies
@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
             STIL_TRACE(3);
         }
     } else {
-        // ===================== epilogue: 8 warps, thread = accumulator row, two warps per lane quarter
-        // (one per 64-column half of the tile) =====================
+        // ===================== epilogue: kEpiWarps warps, thread = accumulator row, kParts warps per TMEM lane
+        // quarter (each owns kCPW 32-column chunks of the tile) =====================
         const int e = threadIdx.x - 64;      // 0..kEpiThreads-1
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const int part = (warp - 2) >> 2;    // which kCPW*32 columns
