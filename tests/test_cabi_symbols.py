@@ -107,3 +107,20 @@ def test_new_entry_points_validate_arguments_without_gpu(lib):
     bases = (ctypes.c_void_p * 8)(*([p] * 8))
     assert lib.stil_p2p_wait(bases, 9, 0, 0, 512, 0, None) == -6
     assert lib.stil_p2p_wait(bases, 2, 0, 0, 512, 8, None) == -6
+
+
+def test_bank_and_club_dropins_refuse_cpu_tensors():
+    import torch
+    import stil_tta_b200 as S
+    p = torch.softmax(torch.randn(4, 10), 1)
+    f, q, qp = torch.randn(4, 8), torch.randn(8, 16), torch.rand(10, 16)
+    for call in (lambda: S.bank_smooth(p, f, q, qp, 0.1, 0.9, 0.1, 0.9),
+                 lambda: S.mmatch_pseudo_label(p, f, q, qp, 0.1, 0.9),
+                 lambda: S.comatch_graphs(p, qp, f, f, q, 0.1),
+                 lambda: S.graph_contrast_loss(torch.rand(4, 20), torch.rand(4, 20), 0.8),
+                 lambda: S.masked_ce(torch.randn(4, 10), p, torch.ones(4, dtype=torch.bool)),
+                 lambda: S.queue_enqueue(q, qp, torch.zeros(1, dtype=torch.int64), f, p),
+                 lambda: S.club_bound(torch.randn(4, 8), torch.randn(4, 8)),
+                 lambda: S.CLUBMean(8, 8, 16)(torch.randn(4, 8), torch.randn(4, 8))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
