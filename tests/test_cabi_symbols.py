@@ -124,3 +124,15 @@ def test_bank_and_club_dropins_refuse_cpu_tensors():
                  lambda: S.CLUBMean(8, 8, 16)(torch.randn(4, 8), torch.randn(4, 8))):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             call()
+
+
+def test_header_is_plain_c():
+    """include/stil_head.h is the drop-in boundary: it must compile as C99 (no C++ in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not found")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", str(REPO / "include" / "stil_head.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
