@@ -319,7 +319,7 @@ class DistributedSTiLHead(STiLHead):
         if self.transport == "fused":
             # row-local step (+ the class-partial push inside it), push_embeddings, stats GEMM, push_lse, loss finish,
             # grad GEMM, dX GEMM (+ slice reduction for a split contraction), waiting proto_add
-            self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 6 + (1 if n >= 1024 else 0) + 1
+            self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 6 + (1 if n >= 2048 else 0) + 1
         else:
             self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 3 + 3 + 3 + 2
 
