@@ -105,6 +105,9 @@ STIL_API int stil_proto_logits(const void* feat, int dtype, int64_t rows, int64_
  * Replaces the inline block STiLModel.py:262-298 (sharpen_predictions :195-196 with T=1).
  *   y_m,y_i,y_t      teacher logits [rows, k] (logit_dtype, leading dim ld_y)
  *   teacher_logits   fp32 [rows, k] from stil_proto_logits (divided by `temperature` here, :294)
+ *   prediction_in    optional fp32 [rows, k] (leading dim ld_pin): the `prediction` of :276-277 when the caller has
+ *                    distribution-aligned softmax(y_m) (DA == True, stil_da_apply); NULL = softmax(y_m), :279.
+ *                    It replaces the thresholded distribution only — cases and pseudo label come from the logits.
  * Outputs (any may be NULL except pseudo_label/max_idx/mask1):
  *   pseudo_label [rows,k] f32 (:295), prediction [rows,k] f32 (:296), max_prob f32, max_idx i64 (:297),
  *   mask1 u8 (:298), case1/case2_i/case2_t/case3 u8 (:264-267), top1 i64 [3, rows] (:263, order m,i,t),
@@ -113,7 +116,8 @@ STIL_API int stil_proto_logits(const void* feat, int dtype, int64_t rows, int64_
  * Index/mask outputs follow torch semantics: first index among equal maxima, >= on fp32. */
 STIL_API int stil_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
                    const float* teacher_logits, int64_t ld_t, int64_t rows, int64_t k, float temperature,
-                   float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
+                   float rate_pseudo, float th1, int past_start_epoch, const float* prediction_in, int64_t ld_pin,
+                   float* pseudo_label, int64_t ld_pl,
                    float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
                    uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
                    int32_t* cls, uint8_t* conf, void* stream);
@@ -163,6 +167,9 @@ STIL_API int stil_proto_finalize(float* prototypes, float* psum, float* pcount, 
  *   stil_da_apply      : DA_queue[ptr] = mean; ptr = (ptr+1) % da_len; out = probs / DA_queue.mean(0), rows
  *                        renormalised (:176-179).  da_ptr is the reference's int64 [1] buffer ON THE DEVICE (no
  *                        host sync, unlike `int(self.DA_ptr)`); qmean_scratch is k floats of scratch. */
+/* out = torch.softmax(logits, dim=1) in fp32 — the argument of distribution_alignment at STiLModel.py:277. */
+STIL_API int stil_softmax_rows(const void* logits, int dtype, int64_t ld, int64_t rows, int64_t k, float* out, int64_t ld_out,
+                               void* stream);
 STIL_API int stil_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, void* stream);
 STIL_API int stil_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* da_queue,
                   int64_t da_len, int64_t* da_ptr, float* qmean_scratch, float* out, int64_t ld_out, void* stream);
@@ -173,7 +180,10 @@ STIL_API int stil_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t
  *   labels  [k_bank] int64 (:70);  prob_ku_orig [rows, num_classes] f32 (after the optional DA, :264-266)
  * fwd writes prob_ku [rows, num_classes] (:280) and loss_in [rows] (:286, per row — the caller takes .mean(),
  * SimMatch.py:92) and leaves dLoss/dLogits (bf16) in the workspace; bwd turns grad_loss_in [rows] into
- * d_feat_qu [rows, dim] (only the student feature gets a gradient).  The workspace must be the same, untouched,
+ * d_feat_qu [rows, dim] (only the student feature gets a gradient).  grad_loss_in == NULL means a unit upstream
+ * gradient: d_feat_qu[i, :] = d loss_in[i] / d feat_qu[i, :].  The reference overwrites the bank right after this block
+ * and before loss.backward() (simmatch_model.py:291, protected there by bank.clone(), :237), so a binding should run
+ * bwd with NULL inside its forward and scale the rows by grad_loss_in later — the bank is then never read again.  The workspace must be the same, untouched,
  * buffer for the forward and its backward (it holds the [rows, k_bank] teacher/student logits, fp32). */
 STIL_API int64_t stil_simmatch_workspace_bytes(int64_t rows, int64_t k_bank, int64_t dim, int dtype);
 STIL_API int stil_simmatch_fwd(const void* feat_ku, const void* feat_qu, int dtype, int64_t rows, int64_t dim, int64_t ld,
@@ -409,6 +419,9 @@ typedef struct stil_head_step_args {
      * rank's buffer on this channel (stil_p2p_push); the consumer is stil_proto_add_gathered_wait */
     const stil_p2p_channel* partials_push;
     int64_t partials_dst_offset;
+    /* optional [b_u, k] f32 (ld = k): distribution-aligned softmax(y_m_ue) of STiLModel.py:276-277 (DA == True);
+     * NULL = the kernel's own softmax(y_m_ue), :279 */
+    const float* prediction_in;
 } stil_head_step_args;
 STIL_API int64_t stil_head_step_workspace_bytes(int64_t batch, int64_t b_l, int64_t k, int64_t dim, int embed_dtype);
 STIL_API int stil_head_step(const stil_head_step_args* args);

@@ -84,7 +84,18 @@ class _Capture:
         return self._local
 
 
-def run_reference_step(STiLModel, CLIPLoss, PrototypeLoss, batch, cfg, prototypes_sum, prototypes_count_sum):
+def _ensure_process_group():
+    """STiLModel.distribution_alignment calls torch.distributed.all_reduce unguarded (STiLModel.py:174): a
+    one-rank gloo group makes it the identity."""
+    import tempfile
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        f = tempfile.NamedTemporaryFile(delete=False)
+        dist.init_process_group("gloo", store=dist.FileStore(f.name, 1), rank=0, world_size=1)
+
+
+def run_reference_step(STiLModel, CLIPLoss, PrototypeLoss, batch, cfg, prototypes_sum, prototypes_count_sum,
+                       da_state=None):
     """Execute the real training_step on planted tensors; return its locals + grads."""
     f32 = lambda t: t.to(torch.float32)
     B_l, P = cfg.b_l, cfg.proj_dim
@@ -143,6 +154,12 @@ def run_reference_step(STiLModel, CLIPLoss, PrototypeLoss, batch, cfg, prototype
     me.sharpen_predictions = lambda logits, temperature: STiLModel.sharpen_predictions(me, logits, temperature)
     me.cal_prototypes = lambda label, feat: STiLModel.cal_prototypes(me, label, feat)
     me.cal_prototypes_separate = lambda label, feat, bl: STiLModel.cal_prototypes_separate(me, label, feat, bl)
+    if da_state is not None:
+        # hparams.DA == True: the real distribution_alignment (STiLModel.py:171-180) on the real buffers (:98-100)
+        _ensure_process_group()
+        me.hparams.DA = True
+        me.DA_queue, me.DA_ptr, me.DA_len = da_state["DA_queue"], da_state["DA_ptr"], da_state["DA_queue"].shape[0]
+        me.distribution_alignment = lambda probs: STiLModel.distribution_alignment(me, probs)
 
     B = cfg.batch
     ident_l, ident_u = torch.ones(B_l), torch.zeros(B - B_l)
@@ -180,11 +197,20 @@ def to_np(t):
     return np.asarray(t)
 
 
-def save_case(name, cfg, seed, STiLModel, CLIPLoss, PrototypeLoss, **mk):
+def save_case(name, cfg, seed, STiLModel, CLIPLoss, PrototypeLoss, da=False, **mk):
     batch = synth.make_batch(cfg, seed=seed, **mk)
     K, P = cfg.num_classes, cfg.proj_dim
     psum, pcnt = torch.zeros(K, P), torch.zeros(K, 1)
-    loc, grads, me = run_reference_step(STiLModel, CLIPLoss, PrototypeLoss, batch, cfg, psum, pcnt)
+    da_state, da_in = None, {}
+    if da:
+        # a ring buffer that already holds a few batch means and is about to wrap (ptr = len - 1)
+        g = torch.Generator().manual_seed(seed + 1)
+        q = torch.zeros(256, K)
+        q[250:] = torch.softmax(torch.randn(6, K, generator=g), dim=1)
+        q[:3] = torch.softmax(torch.randn(3, K, generator=g) * 0.5, dim=1)
+        da_state = {"DA_queue": q, "DA_ptr": torch.tensor([255], dtype=torch.int64)}
+        da_in = {"in_DA_queue": to_np(q.clone()), "in_DA_ptr": to_np(da_state["DA_ptr"].clone())}
+    loc, grads, me = run_reference_step(STiLModel, CLIPLoss, PrototypeLoss, batch, cfg, psum, pcnt, da_state)
     # class partials as the reference computed them this step (accumulators started at zero)
     rec = {
         "meta_seed": seed, "meta_batch": cfg.batch, "meta_K": K, "meta_P": P,
@@ -206,6 +232,10 @@ def save_case(name, cfg, seed, STiLModel, CLIPLoss, PrototypeLoss, **mk):
     # only when that holds, otherwise record the count of empty classes)
     empty = int((me.prototypes_count_sum < 1).sum())
     rec["ref_empty_classes"] = empty
+    if da:
+        rec.update(da_in)
+        rec["ref_DA_queue"], rec["ref_DA_ptr"] = to_np(da_state["DA_queue"]), to_np(da_state["DA_ptr"])
+        rec["meta_da"] = 1
     for k, v in batch.items():
         rec["in_" + k] = to_np(v)
     OUT.mkdir(parents=True, exist_ok=True)
@@ -270,6 +300,9 @@ def main():
     save_case("step_cardiac_b64_ragged", S.cardiac_config(72, unlabelled_ratio=5), 2027, *args)
     save_case("step_dvm_b200_k10", S.dvm_config(200, num_classes=10, proj_dim=64, unlabelled_ratio=3,
                                                  embed_dtype="f32", th1=0.6), 2028, *args)
+    # hparams.DA == True (STiLModel.py:276-277): prediction = distribution_alignment(softmax(y_hat_m_ue))
+    save_case("step_dvm_b64_da", S.dvm_config(64, embed_dtype="f32"), 2029, *args, da=True)
+    save_case("step_cardiac_b128_da", S.cardiac_config(128), 2030, *args, da=True)
 
 
 if __name__ == "__main__":

@@ -67,10 +67,11 @@ def clip_loss_global(out0_parts, out1_parts, temperature: float, lambda_0: float
 
 
 # --------------------------------------------------------------------------- a2
-def cgpl(y_m: Tensor, y_i: Tensor, y_t: Tensor) -> Dict[str, Tensor]:
+def cgpl(y_m: Tensor, y_i: Tensor, y_t: Tensor, prediction_override: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """Consensus pseudo-labelling. Follows STiLModel.py:262-279 (+ :195-196, T=1).
 
-    Inputs are the *teacher* logits of the unlabelled rows, [B_u, K]."""
+    Inputs are the *teacher* logits of the unlabelled rows, [B_u, K].  `prediction_override` is the
+    distribution-aligned softmax(y_m) of :276-277 (hparams.DA == True)."""
     p_m, p_i, p_t = (torch.softmax(y, dim=1) for y in (y_m, y_i, y_t))            # :262
     top_m, top_i, top_t = (p.argmax(dim=1) for p in (p_m, p_i, p_t))              # :263 (on probs)
     mi, mt = top_m == top_i, top_m == top_t
@@ -85,6 +86,8 @@ def cgpl(y_m: Tensor, y_i: Tensor, y_t: Tensor) -> Dict[str, Tensor]:
     f = lambda m: m[:, None].to(y_m.dtype)
     pl_orig = f(case1) * avg3 + f(case2_i) * avg_mi + f(case2_t) * avg_mt + f(case3) * only_m   # :274
     prediction = torch.softmax(y_m, dim=1)                                        # :279 (DA False)
+    if prediction_override is not None:
+        prediction = prediction_override                                          # :276-277 (DA True)
     return dict(pseudo_label_orig=pl_orig, prediction=prediction,
                 case1=case1, case2_i=case2_i, case2_t=case2_t, case3=case3,
                 top1_m=top_m, top1_i=top_i, top1_t=top_t)
@@ -104,9 +107,10 @@ def pgls(feat_m_ue: Tensor, prototypes: Tensor, pseudo_label_orig: Tensor, predi
                 prediction=prediction, max_prob=max_prob, max_idx=max_idx, mask1=mask1)
 
 
-def cgpl_pgls(y_m, y_i, y_t, feat_m_ue, prototypes, *, T, rate_pseudo, th1) -> Dict[str, Tensor]:
+def cgpl_pgls(y_m, y_i, y_t, feat_m_ue, prototypes, *, T, rate_pseudo, th1, prediction_override=None
+              ) -> Dict[str, Tensor]:
     """a2 followed by a3 — the inline block STiLModel.py:262-298."""
-    a = cgpl(y_m, y_i, y_t)
+    a = cgpl(y_m, y_i, y_t, prediction_override)
     b = pgls(feat_m_ue, prototypes, a["pseudo_label_orig"], a["prediction"], T, rate_pseudo, th1)
     out = dict(a)
     out.update(b)
@@ -235,10 +239,12 @@ def mmatch_bank(prob: Tensor, feat_u: Tensor, embed_rows: Tensor, probs_rows: Te
 
 # ----------------------------------------------------------------- whole step
 def head_step(batch: Dict[str, Tensor], cfg, *, dtype=torch.float32, with_grads: bool = True,
-              state: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+              state: Optional[Dict[str, Tensor]] = None, da_state: Optional[Dict[str, Tensor]] = None
+              ) -> Dict[str, Tensor]:
     """The full hot path of STiLModel.training_step (lines 262-303, 317-322, 339, 374-381)
     on one synthetic batch (see stil_tta_b200/synth.py).  Embeddings stored in bf16 are
-    upcast — the oracle computes on the *same values* in `dtype`."""
+    upcast — the oracle computes on the *same values* in `dtype`.  `da_state` = {"DA_queue", "DA_ptr"}
+    switches hparams.DA on (:276-277): the buffers are updated in place like the reference's."""
     up = lambda t: t.to(dtype)
     B_l = cfg.b_l
     feat_i = up(batch["feat_i"]).clone().requires_grad_(with_grads)
@@ -248,8 +254,12 @@ def head_step(batch: Dict[str, Tensor], cfg, *, dtype=torch.float32, with_grads:
     feat_m_e = up(batch["feat_m_e"])
     protos = up(batch["prototypes"])
     with torch.no_grad():
+        pred_da = None
+        if da_state is not None:
+            pred_da = distribution_alignment(torch.softmax(up(batch["y_m_ue"]), dim=1), da_state["DA_queue"],
+                                             da_state["DA_ptr"])
         pl = cgpl_pgls(up(batch["y_m_ue"]), up(batch["y_i_ue"]), up(batch["y_t_ue"]), feat_m_e[B_l:], protos,
-                       T=cfg.temperature, rate_pseudo=cfg.rate_pseudo, th1=cfg.th1)
+                       T=cfg.temperature, rate_pseudo=cfg.rate_pseudo, th1=cfg.th1, prediction_override=pred_da)
         label_all = pseudo_label_all(batch["y_l"], cfg.num_classes, pl["prediction"], cfg.past_start_epoch)
     l_m, l_i, l_t = masked_soft_ce(y_s[0][B_l:], y_s[1][B_l:], y_s[2][B_l:], pl["pseudo_label"], pl["mask1"],
                                    pl["case1"], pl["case2_i"], pl["case2_t"], pl["case3"], batch["mask_random"])
@@ -272,11 +282,13 @@ def head_step(batch: Dict[str, Tensor], cfg, *, dtype=torch.float32, with_grads:
     return out
 
 
-def ambiguous_rows(batch: Dict[str, Tensor], cfg, tol: float = 1e-5) -> Tensor:
+def ambiguous_rows(batch: Dict[str, Tensor], cfg, tol: float = 1e-5, da_state=None) -> Tensor:
     """Rows whose index/mask decisions are not determined at fp32 resolution:
     |max_prob - th1| < tol, or a top-2 gap < tol in any of the four argmaxes.  Evaluated in fp64.
     Exact ties (gap == 0) are NOT ambiguous: the first-index rule decides them."""
-    o = head_step(batch, cfg, dtype=torch.float64, with_grads=False)
+    if da_state is not None:
+        da_state = {"DA_queue": da_state["DA_queue"].to(torch.float64), "DA_ptr": da_state["DA_ptr"].clone()}
+    o = head_step(batch, cfg, dtype=torch.float64, with_grads=False, da_state=da_state)
     up = lambda t: t.to(torch.float64)
 
     def near_tie(p):

@@ -45,7 +45,7 @@ def rows_sweep():
 
         def cg():
             _lib.check(lib.stil_cgpl_pgls(ptr(ys[0]), ptr(ys[1]), ptr(ys[2]), 0, k, ptr(tl), k, rows, k, 0.1, 0.9, 0.9, 1,
-                                          ptr(pl), k, None, 0, ptr(mp), ptr(mi), ptr(fl[0]), ptr(fl[1]), ptr(fl[2]),
+                                          None, 0, ptr(pl), k, None, 0, ptr(mp), ptr(mi), ptr(fl[0]), ptr(fl[1]), ptr(fl[2]),
                                           ptr(fl[3]), ptr(fl[4]), None, None, None, _lib.stream_ptr(dev)))
         t = time_fn(cg)
         b = 5 * rows * k * 4 + rows * 17

@@ -51,6 +51,7 @@ class HeadStepArgs(C.Structure):
         ("workspace", vp), ("workspace_bytes", i64), ("stream", vp),
         ("timing_events", vp), ("n_timing_events", i32), ("skip_infonce", i32), ("prototypes_prepared", i32),
         ("partials_push", C.POINTER(P2PChannel)), ("partials_dst_offset", i64),
+        ("prediction_in", vp),
     ]
 
 
@@ -69,8 +70,8 @@ SIGNATURES = {
                                          vp, i64, vp]),
     "stil_proto_logits_workspace_bytes": (i64, [i64, i64, i64, i32]),
     "stil_proto_logits": (i32, [vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]),
-    "stil_cgpl_pgls": (i32, [vp, vp, vp, i32, i64, vp, i64, i64, i64, f32, f32, f32, i32, vp, i64, vp, i64, vp, vp, vp,
-                             vp, vp, vp, vp, vp, vp, vp, vp]),
+    "stil_cgpl_pgls": (i32, [vp, vp, vp, i32, i64, vp, i64, i64, i64, f32, f32, f32, i32, vp, i64, vp, i64, vp, i64, vp,
+                             vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "stil_label_argmax": (i32, [vp, i64, i64, i64, f32, vp, vp, vp, vp]),
     "stil_proto_ce_workspace_bytes": (i64, [i64, i64, i64, i32]),
     "stil_proto_ce_fwd": (i32, [vp, i32, i64, i64, i64, vp, i64, vp, vp, f32, vp, vp, vp, vp, i64, vp]),
@@ -96,6 +97,7 @@ SIGNATURES = {
     "stil_proto_add_gathered_wait": (i32, [vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "stil_infonce_bwd_gathered": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, vp,
                                         vp, i32, i64, vp, i64, vp]),
+    "stil_softmax_rows": (i32, [vp, i32, i64, i64, i64, vp, i64, vp]),
     "stil_da_batch_mean": (i32, [vp, i64, i64, i64, vp, vp]),
     "stil_da_apply": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
     "stil_simmatch_workspace_bytes": (i64, [i64, i64, i64, i32]),

@@ -45,29 +45,32 @@ class _SimMatchFn(torch.autograd.Function):
         ws = torch.empty(lib.stil_simmatch_workspace_bytes(rows, kb, d, code), dtype=torch.uint8, device=dev)
         prob_ku = torch.empty(rows, c, dtype=torch.float32, device=dev)
         loss_in = torch.empty(rows, dtype=torch.float32, device=dev)
-        gcode = dtype_code(fq)
+        gcode = _lib.STIL_F32            # dLoss/dLogits kept as a bf16 hi+lo pair, fp32 gradient
         with torch.cuda.device(dev):
             check(lib.stil_simmatch_fwd(ptr(fk), ptr(fq), code, rows, d, d, ptr(bank), bank.stride(0), ptr(lab), kb, ptr(p), c,
                                         float(tt), float(st), float(c_smooth), ptr(prob_ku), ptr(loss_in), gcode, ptr(ws),
                                         ws.numel(), _lib.stream_ptr(dev)))
-        ctx.save_for_backward(fq, bank, ws)
-        ctx.meta = (feat_qu.dtype, gcode)
+        # d loss_in[i] / d feat_qu[i, :] is computed HERE, while the bank still holds what the forward saw: the reference
+        # overwrites bank columns right after this block and before loss.backward() (simmatch_model.py:291; it protects
+        # itself with bank.clone(), :237).  In-place writes through raw kernels do not move torch's version counter, so
+        # reading the live bank in backward would silently use the new columns.
+        jac = None
+        if ctx.needs_input_grad[1]:
+            jac = torch.empty(rows, d, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                check(lib.stil_simmatch_bwd(ptr(fq), code, rows, d, ptr(bank), bank.stride(0), kb, None, ptr(jac),
+                                            _lib.STIL_F32, d, ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        ctx.jac = jac
+        ctx.in_dtype = feat_qu.dtype
         ctx.mark_non_differentiable(prob_ku)
         return prob_ku, loss_in
 
     @staticmethod
     def backward(ctx, _g_prob, g_loss):
-        fq, bank, ws = ctx.saved_tensors
-        in_dtype, gcode = ctx.meta
-        dev = fq.device
-        rows, d = fq.shape
-        kb = bank.shape[1]
-        g = g_loss.detach().to(torch.float32).contiguous()
-        d_fq = torch.empty_like(fq)
-        with torch.cuda.device(dev):
-            check(_lib.load().stil_simmatch_bwd(ptr(fq), dtype_code(fq), rows, d, ptr(bank), bank.stride(0), kb, ptr(g),
-                                                ptr(d_fq), gcode, d, ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
-        return None, d_fq.to(in_dtype), None, None, None, None, None, None
+        if ctx.jac is None:
+            return (None,) * 8
+        d_fq = g_loss.detach().to(torch.float32)[:, None] * ctx.jac
+        return None, d_fq.to(ctx.in_dtype), None, None, None, None, None, None
 
 
 def simmatch_bank(feat_ku: torch.Tensor, feat_qu: torch.Tensor, prob_ku_orig: torch.Tensor, bank: torch.Tensor,

@@ -114,7 +114,10 @@ class _GraphsFn(torch.autograd.Function):
             check(lib.stil_comatch_graphs_fwd(ptr(p), c, rows, c, ptr(pu), pu.stride(0), ptr(f0), ptr(f1), code, d, d, ptr(q_s),
                                               q_s.stride(0), kq, float(temperature), ptr(Q), ptr(sim), ld, ptr(ws),
                                               ws.numel(), _lib.stream_ptr(dev)))
-        ctx.save_for_backward(sim, f1, q_s)
+        # snapshot of queue_s: queue_enqueue overwrites it in place (raw kernel, torch's version counter does not move)
+        # between this forward and loss.backward() — the reference passes self.queue_s.clone().detach() for the same
+        # reason (comatch_model.py:310)
+        ctx.save_for_backward(sim, f1, q_s.clone())
         ctx.meta = (float(temperature), feat_s0.dtype, ld)
         ctx.mark_non_differentiable(Q)
         return Q, sim
@@ -133,11 +136,12 @@ class _GraphsFn(torch.autograd.Function):
             g = gp
         lib = _lib.load()
         code = dtype_code(f1)
-        d_f0 = torch.empty(rows, d, dtype=f1.dtype, device=dev)
+        d_f0 = torch.empty(rows, d, dtype=torch.float32, device=dev)
         ws = _lib.workspace(dev, "comatch_sim_bwd", lib.stil_comatch_sim_bwd_workspace_bytes(rows, kq, d, code))
         with torch.cuda.device(dev):
             check(lib.stil_comatch_sim_bwd(ptr(g), ptr(sim), ld, rows, kq, ptr(f1), code, d, d, ptr(q_s), q_s.stride(0),
-                                           temperature, ptr(d_f0), code, d, ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+                                           temperature, ptr(d_f0), _lib.STIL_F32, d, ptr(ws), ws.numel(),
+                                           _lib.stream_ptr(dev)))
         return None, None, d_f0.to(in_dtype), None, None, None
 
 

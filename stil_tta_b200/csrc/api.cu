@@ -761,18 +761,21 @@ STIL_API int stil_proto_logits(const void* feat, int dtype, int64_t rows, int64_
 // =============================================================================================== a2+a3
 STIL_API int stil_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
                    const float* teacher_logits, int64_t ld_t, int64_t rows, int64_t k, float temperature,
-                   float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
+                   float rate_pseudo, float th1, int past_start_epoch, const float* prediction_in, int64_t ld_pin,
+                   float* pseudo_label, int64_t ld_pl,
                    float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
                    uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
                    int32_t* cls, uint8_t* conf, void* stream) {
     STIL_REQUIRE(logit_dtype == STIL_F32 || logit_dtype == STIL_BF16, STIL_E_DTYPE, "cgpl_pgls: bad logit dtype");
+    STIL_REQUIRE(!prediction_in || ld_pin >= k, STIL_E_SHAPE, "cgpl_pgls: prediction_in leading dimension smaller than k");
     STIL_REQUIRE(rows == 0 || (y_m && y_i && y_t && teacher_logits && pseudo_label && max_idx && mask1), STIL_E_ARG,
                  "cgpl_pgls: null pointer");
     STIL_REQUIRE(ld_y >= k && ld_t >= k && ld_pl >= k && (!prediction || ld_pred >= k), STIL_E_SHAPE,
                  "cgpl_pgls: leading dimension smaller than k");
     return launch_cgpl_pgls(y_m, y_i, y_t, logit_dtype, ld_y, teacher_logits, ld_t, rows, k, temperature, rate_pseudo,
-                            th1, past_start_epoch, pseudo_label, ld_pl, prediction, ld_pred, max_prob, max_idx, mask1,
-                            case1, case2_i, case2_t, case3, top1, cls, conf, nullptr, 0, nullptr, nullptr, S(stream));
+                            th1, past_start_epoch, prediction_in, ld_pin, pseudo_label, ld_pl, prediction, ld_pred, max_prob,
+                            max_idx, mask1, case1, case2_i, case2_t, case3, top1, cls, conf, nullptr, 0, nullptr, nullptr,
+                            S(stream));
 }
 
 STIL_API int stil_label_argmax(const float* label, int64_t ld, int64_t rows, int64_t k, float threshold, int32_t* cls,
@@ -1038,6 +1041,13 @@ STIL_API int stil_proto_finalize(float* prototypes, float* psum, float* pcount, 
 }
 
 // =============================================================================================== a6
+STIL_API int stil_softmax_rows(const void* logits, int dtype, int64_t ld, int64_t rows, int64_t k, float* out, int64_t ld_out,
+                               void* stream) {
+    STIL_REQUIRE(dtype == STIL_F32 || dtype == STIL_BF16, STIL_E_DTYPE, "softmax_rows: bad dtype");
+    STIL_REQUIRE(rows == 0 || (logits && out && k >= 1 && ld >= k && ld_out >= k), STIL_E_ARG, "softmax_rows: bad arguments");
+    return launch_softmax_rows(logits, dtype, ld, rows, k, out, ld_out, S(stream));
+}
+
 STIL_API int stil_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, void* stream) {
     STIL_REQUIRE(probs && mean && rows >= 1 && ld >= k, STIL_E_ARG, "da_batch_mean: bad arguments");
     return launch_da_batch_mean(probs, ld, rows, k, mean, S(stream));
@@ -1150,7 +1160,10 @@ STIL_API int stil_simmatch_bwd(const void* feat_qu, int dtype, int64_t rows, int
                       int64_t k_bank, const float* grad_loss_in, void* d_feat_qu, int grad_dtype, int64_t ld_grad,
                       void* workspace, int64_t workspace_bytes, void* stream) {
     (void)feat_qu;
-    STIL_REQUIRE(grad_loss_in && d_feat_qu && bank, STIL_E_ARG, "simmatch_bwd: null pointer");
+    // grad_loss_in == NULL: unit upstream gradient, i.e. the per-row Jacobian d loss_in[i] / d feat_qu[i, :] — what the
+    // Python drop-in computes inside its forward so that the bank may be overwritten (simmatch_model.py:291 runs
+    // _update_bank right after this block, before loss.backward()) without touching the gradient
+    STIL_REQUIRE(d_feat_qu && bank, STIL_E_ARG, "simmatch_bwd: null pointer");
     STIL_REQUIRE(grad_dtype == STIL_F32 || grad_dtype == STIL_BF16, STIL_E_DTYPE, "bad grad dtype");
     SimPlan P = plan_sim(workspace, workspace_bytes, rows, k_bank, dim, dtype);
     STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "simmatch workspace too small");
@@ -1717,8 +1730,8 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
 
     // 3. main stream: CGPL + PGLS on the unlabelled rows, (cls, conf) of every row ...
     if ((rc = launch_cgpl_pgls(a->y_m_ue, a->y_i_ue, a->y_t_ue, a->logit_dtype, K, P.teacher_logits, P.ldk, B_u, K,
-                               a->temperature, a->rate_pseudo, a->th1, a->past_start_epoch, a->pseudo_label, K, nullptr,
-                               0, a->max_prob, a->max_idx, a->mask1, a->case1, a->case2_i, a->case2_t, a->case3,
+                               a->temperature, a->rate_pseudo, a->th1, a->past_start_epoch, a->prediction_in, K,
+                               a->pseudo_label, K, nullptr, 0, a->max_prob, a->max_idx, a->mask1, a->case1, a->case2_i, a->case2_t, a->case3,
                                nullptr, P.cls + B_l, P.conf + B_l, a->y_l, B_l, P.cls, P.conf, st)))
         return rc;
     if ((rc = mark(6, st))) return rc;

@@ -220,7 +220,8 @@ int launch_grad_finish(const GradFinishLaunch& L, cudaStream_t stream);
 
 int launch_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
                      const float* teacher_logits, int64_t ld_t, int64_t rows, int64_t k, float temperature,
-                     float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
+                     float rate_pseudo, float th1, int past_start_epoch, const float* prediction_in, int64_t ld_pin,
+                     float* pseudo_label, int64_t ld_pl,
                      float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
                      uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
                      int32_t* cls, uint8_t* conf, const int64_t* y_l, int64_t b_l, int32_t* cls_l, uint8_t* conf_l,
@@ -253,6 +254,8 @@ int launch_zero_u32(unsigned int* p, int n, cudaStream_t stream);
 int launch_simmatch_rows(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_bank,
                          const float* p_orig, int num_classes, float tt, float st, float c_smooth, float* p_out,
                          float* loss_in, __nv_bfloat16* gop, long long ld_g, int g_nseg, cudaStream_t stream);
+int launch_softmax_rows(const void* y, int dtype, int64_t ld, int64_t rows, int64_t k, float* out, int64_t ld_out,
+                        cudaStream_t stream);
 int launch_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, cudaStream_t stream);
 int launch_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* da_queue,
                     int64_t da_len, int64_t* da_ptr, float* qmean, float* out, int64_t ld_out, cudaStream_t stream);

@@ -126,6 +126,11 @@ struct CgplArgs {
     int b_l;
     int* cls_l;
     unsigned char* conf_l;
+    // optional replacement of softmax(y_m) as the thresholded `prediction` — the distribution-aligned probabilities of
+    // STiLModel.py:276-277 (DA == True); the agreement cases and the pseudo label still come from the logits
+    const float* pred_in;
+    long long ld_pin;
+    int vec_pin;
 };
 
 template <int LPR, int NV>
@@ -356,6 +361,13 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
         const float rs = __frcp_rn(softmax_exp<LPR, NV>(tp));
 #pragma unroll
         for (int j = 0; j < 2 * NV; ++j) tp[j] = __fmul_rn(tp[j], rs);
+    }
+    // ---- :276-277 `prediction` given by the caller (distribution alignment) instead of softmax(y_m)
+    if (A.pred_in) {
+        load_row<LPR, NV>(A.pred_in, STIL_F32, A.ld_pin, r, k, sub, A.vec_pin, pm);
+#pragma unroll
+        for (int j = 0; j < 2 * NV; ++j)
+            if (pm[j] == -INFINITY) pm[j] = 0.f;     // padding slots beyond k
     }
     // ---- :295-298 smoothing mix, max/argmax, threshold
     float bv = -1.f;
@@ -1009,6 +1021,25 @@ __global__ void __launch_bounds__(kRowBlock) da_apply_kernel(const float* __rest
         out[(long long)row * ld_out + c] = __fdiv_rn(__fdiv_rn(probs[(long long)row * ld + c], qmean[c]), s);
 }
 
+// torch.softmax(y, dim=1) of the teacher logits feeding distribution alignment (STiLModel.py:277): one warp per row, the
+// row stays in registers for k <= 1024 (re-read otherwise); IEEE exp and division
+__global__ void __launch_bounds__(kRowBlock) softmax_rows_kernel(const void* __restrict__ y, int dtype, long long ld, int rows,
+                                                                 int k, float* __restrict__ out, long long ld_out) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float m = -INFINITY;
+    for (int c = lane; c < k; c += 32) m = fmaxf(m, ld_as_float(y, dtype, (long long)row * ld + c));
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < k; c += 32) s += expf(ld_as_float(y, dtype, (long long)row * ld + c) - m);
+    s = warp_sum(s);
+    for (int c = lane; c < k; c += 32)
+        out[(long long)row * ld_out + c] = __fdiv_rn(expf(ld_as_float(y, dtype, (long long)row * ld + c) - m), s);
+}
+
 // =====================================================================================
 // SimMatch bank block on materialised logits (simmatch_model.py:268-286): one block per unlabelled row
 // =====================================================================================
@@ -1160,7 +1191,8 @@ int launch_grad_finish(const GradFinishLaunch& L, cudaStream_t stream) {
 
 int launch_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,
                      const float* teacher_logits, int64_t ld_t, int64_t rows, int64_t k, float temperature,
-                     float rate_pseudo, float th1, int past_start_epoch, float* pseudo_label, int64_t ld_pl,
+                     float rate_pseudo, float th1, int past_start_epoch, const float* prediction_in, int64_t ld_pin,
+                     float* pseudo_label, int64_t ld_pl,
                      float* prediction, int64_t ld_pred, float* max_prob, int64_t* max_idx, uint8_t* mask1,
                      uint8_t* case1, uint8_t* case2_i, uint8_t* case2_t, uint8_t* case3, int64_t* top1,
                      int32_t* cls, uint8_t* conf, const int64_t* y_l, int64_t b_l, int32_t* cls_l, uint8_t* conf_l,
@@ -1192,6 +1224,8 @@ int launch_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logi
     A.vec_t = (ld_t % 2 == 0) && al(teacher_logits, 8);
     A.vec_pl = (ld_pl % 2 == 0) && al(pseudo_label, 8);
     A.vec_pred = prediction ? ((ld_pred % 2 == 0) && al(prediction, 8)) : 0;
+    A.pred_in = prediction_in; A.ld_pin = ld_pin;
+    A.vec_pin = prediction_in ? ((ld_pin % 2 == 0) && al(prediction_in, 8)) : 0;
     // small batches are bound by each row's dependency chain (5 softmaxes): spread a row over 4 warps
     // (four warps per row measured best: eight warps per row was 2.4 us slower per C2 step)
     if (rows <= 2048 && k > 128 && k <= 512) return launch_cgpl_t<128, 2>(A, stream);
@@ -1281,6 +1315,14 @@ int launch_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, con
                                             qmean);
     STIL_LAUNCH_CHECK();
     return launch_da_rows(probs, ld, rows, k, qmean, out, ld_out, stream);
+}
+int launch_softmax_rows(const void* y, int dtype, int64_t ld, int64_t rows, int64_t k, float* out, int64_t ld_out,
+                        cudaStream_t stream) {
+    if (rows == 0) return STIL_OK;
+    const int threads = row_block_threads(rows);
+    STIL_CUDA(launch_pdl(softmax_rows_kernel, dim3((unsigned)ceil_div(rows, threads / 32)), dim3((unsigned)threads), 0, stream,
+                         y, dtype, (long long)ld, (int)rows, (int)k, out, (long long)ld_out));
+    return STIL_OK;
 }
 int launch_da_rows(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* qmean, float* out, int64_t ld_out,
                    cudaStream_t stream) {

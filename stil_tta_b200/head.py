@@ -25,7 +25,13 @@ _IN_STUDENT = ("y_m", "y_i", "y_t")
 
 class STiLHead:
     def __init__(self, cfg: HeadConfig, device="cuda", student_ce: bool = True, use_graph: bool = True,
-                 rate_uce: float = 1.0, logit_dtype: torch.dtype = torch.float32) -> None:
+                 rate_uce: float = 1.0, logit_dtype: torch.dtype = torch.float32,
+                 grad_dtype: torch.dtype = torch.float32, da: bool = False, da_len: int = 256) -> None:
+        """``grad_dtype``: dtype of ``d_feat_i/t/m``.  The default fp32 keeps dLoss/dLogits as a bf16 hi+lo pair and
+        writes fp32 gradients, so bf16 *embeddings* (C2) still give gradients within 1e-3 of the fp32 reference;
+        ``torch.bfloat16`` rounds both (2^-9) like autograd returning a bf16 ``.grad``.
+        ``da``: ``hparams.DA == True`` (``STiLModel.py:276-277``) — ``prediction`` is the distribution-aligned
+        ``softmax(y_m_ue)``; the ring buffer lives in ``DA_queue`` / ``DA_ptr`` (reference names, ``:98-100``)."""
         self.cfg = cfg
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
@@ -55,16 +61,27 @@ class STiLHead:
         self.prototypes = z(K, P)
         self.prototypes_sum = z(K, P)
         self.prototypes_count_sum = z(K, 1)
-        self.out: Dict[str, torch.Tensor] = {
-            "losses": z(5),                      # itc, pt, m_u, i_u, t_u
-            "d_feat_i": z(B, P, dtype=edt), "d_feat_t": z(B, P, dtype=edt), "d_feat_m": z(B, P, dtype=edt),
-            "pseudo_label": z(B_u, K), "max_prob": z(B_u), "max_idx": z(B_u, dtype=torch.int64),
-            "mask1": z(B_u, dtype=torch.bool), "case1": z(B_u, dtype=torch.bool), "case2_i": z(B_u, dtype=torch.bool),
-            "case2_t": z(B_u, dtype=torch.bool), "case3": z(B_u, dtype=torch.bool),
-            "class_sum": z(K, P), "class_count": z(K, 1),
-        }
+        # ... and so does every per-batch output (one device allocation, one pinned host mirror): a caller that wants the
+        # gradients, pseudo labels and masks on the host gets them with a single device->host copy (step_host_full)
+        ospec = [("losses", (5,), torch.float32),                      # itc, pt, m_u, i_u, t_u
+                 ("d_feat_i", (B, P), grad_dtype), ("d_feat_t", (B, P), grad_dtype), ("d_feat_m", (B, P), grad_dtype),
+                 ("pseudo_label", (B_u, K), torch.float32), ("max_prob", (B_u,), torch.float32),
+                 ("max_idx", (B_u,), torch.int64)]
+        ospec += [(k, (B_u,), torch.bool) for k in ("mask1", "case1", "case2_i", "case2_t", "case3")]
         if student_ce:
-            self.out.update({"d_y_m": z(B, K), "d_y_i": z(B, K), "d_y_t": z(B, K)})
+            ospec += [(k, (B, K), torch.float32) for k in ("d_y_m", "d_y_i", "d_y_t")]
+        self._out_layout, off = [], 0
+        for name, shape, dtype in ospec:
+            nbytes = int(torch.tensor([], dtype=dtype).element_size()) * int(torch.Size(shape).numel())
+            self._out_layout.append((name, shape, dtype, off, nbytes))
+            off += (nbytes + 255) // 256 * 256
+        self._packed_out = torch.zeros(max(off, 256), dtype=torch.uint8, device=dev)
+        self.out: Dict[str, torch.Tensor] = self._views(self._packed_out, self._out_layout)
+        self.out.update({"class_sum": z(K, P), "class_count": z(K, 1)})
+        self.da = bool(da)
+        if self.da:
+            self.DA_queue, self.DA_ptr = z(da_len, K), z(1, dtype=torch.int64)
+            self._da = {"probs": z(B_u, K), "mean": z(K), "qmean": z(K), "aligned": z(B_u, K)}
         lib = _lib.load()
         code = _lib.STIL_BF16 if edt == torch.bfloat16 else _lib.STIL_F32
         self._ws = torch.zeros(lib.stil_head_step_workspace_bytes(B, B_l, K, P, code), dtype=torch.uint8, device=dev)
@@ -74,14 +91,16 @@ class STiLHead:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._pinned: Optional[Dict[str, torch.Tensor]] = None
         self._losses_host = torch.zeros(5, dtype=torch.float32).pin_memory()
+        self._out_host: Optional[torch.Tensor] = None
         self.h2d_bytes = self._packed_in.numel()
         self.d2h_bytes = self._losses_host.numel() * 4
+        self.d2h_bytes_full = self._packed_out.numel()
 
     # ------------------------------------------------------------------------------------------
-    def _views(self, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """Typed views of a packed input buffer (device or pinned host) following self._layout."""
+    def _views(self, buf: torch.Tensor, layout=None) -> Dict[str, torch.Tensor]:
+        """Typed views of a packed input / output buffer (device or pinned host) following self._layout."""
         out = {}
-        for name, shape, dtype, off, nbytes in self._layout:
+        for name, shape, dtype, off, nbytes in (self._layout if layout is None else layout):
             out[name] = buf[off:off + nbytes].view(dtype).view(shape) if nbytes else torch.empty(shape, dtype=dtype,
                                                                                                  device=buf.device)
         return out
@@ -91,7 +110,7 @@ class STiLHead:
         p = lambda t: t.data_ptr()
         a = HeadStepArgs()
         a.batch, a.b_l, a.k, a.dim = c.batch, c.b_l, c.num_classes, c.proj_dim
-        a.embed_dtype, a.logit_dtype, a.grad_dtype = embed_code, logit_code, embed_code
+        a.embed_dtype, a.logit_dtype, a.grad_dtype = embed_code, logit_code, _lib.dtype_code(o["d_feat_i"])
         a.temperature, a.lambda0, a.th1 = c.temperature, c.lambda_0, c.th1
         a.rate_pseudo, a.repeat_ratio = c.rate_pseudo, c.repeat_ratio
         a.past_start_epoch = int(c.past_start_epoch)
@@ -110,7 +129,33 @@ class STiLHead:
         a.prototypes_sum, a.prototypes_count_sum = p(self.prototypes_sum), p(self.prototypes_count_sum)
         a.rate_uce_scale = self.rate_uce
         a.workspace, a.workspace_bytes = p(self._ws), self._ws.numel()
+        if self.da:
+            a.prediction_in = p(self._da["aligned"])
         return a
+
+    def set_hparams(self, **kw) -> None:
+        """Change step hyper-parameters after construction — ``past_start_epoch`` (the reference flips the gate of
+        ``STiLModel.py:317-320`` when ``current_epoch > start_epoch``), ``th1``, ``rate_pseudo``, ``temperature``,
+        ``lambda_0``, ``repeat_ratio``, ``rate_uce``.  They are kernel parameters baked into the captured CUDA graph,
+        so the graph is dropped and re-captured on the next ``run()`` (in the data-parallel head every rank must make
+        the same call before its next step: capture is collective)."""
+        names = {"past_start_epoch", "th1", "rate_pseudo", "temperature", "lambda_0", "repeat_ratio"}
+        for k, v in kw.items():
+            if k == "rate_uce":
+                self.rate_uce = float(v)
+            elif k in names:
+                setattr(self.cfg, k, v)
+            else:
+                raise ValueError(f"unknown head hyper-parameter {k!r}")
+        a, c = self._args, self.cfg
+        a.temperature, a.lambda0, a.th1 = c.temperature, c.lambda_0, c.th1
+        a.rate_pseudo, a.repeat_ratio = c.rate_pseudo, c.repeat_ratio
+        a.past_start_epoch = int(c.past_start_epoch)
+        a.rate_uce_scale = self.rate_uce
+        self._drop_graphs()
+
+    def _drop_graphs(self) -> None:
+        self._graph = None
 
     def load(self, batch: Dict[str, torch.Tensor]) -> None:
         """Copy one batch (CPU or CUDA tensors, keys as in synth.make_batch) into the static input buffers."""
@@ -130,28 +175,51 @@ class STiLHead:
             self._args.prototypes_prepared = 1
             self._proto_version = v
 
+    def _all_reduce_mean(self, mean: torch.Tensor) -> None:
+        """``torch.distributed.all_reduce(probs_bt_mean)`` / world size (``STiLModel.py:174-176``); one rank: no-op."""
+
+    def _enqueue_da(self, stream: int) -> None:
+        """``prediction = distribution_alignment(torch.softmax(y_hat_m_ue, dim=1))`` (``STiLModel.py:276-277``) into the
+        buffer ``stil_head_step`` reads as ``prediction_in``."""
+        lib, d, p = _lib.load(), self._da, (lambda t: t.data_ptr())
+        B_u, K = self.cfg.b_u, self.cfg.num_classes
+        y = self.inp["y_m_ue"]
+        check(lib.stil_softmax_rows(p(y), _lib.dtype_code(y), K, B_u, K, p(d["probs"]), K, stream))
+        check(lib.stil_da_batch_mean(p(d["probs"]), K, B_u, K, p(d["mean"]), stream))
+        self._all_reduce_mean(d["mean"])
+        check(lib.stil_da_apply(p(d["probs"]), K, B_u, K, p(d["mean"]), p(self.DA_queue), self.DA_queue.shape[0],
+                                p(self.DA_ptr), p(d["qmean"]), p(d["aligned"]), K, stream))
+
     def _enqueue(self) -> None:
         self._args.stream = torch.cuda.current_stream(self.dev).cuda_stream
+        if self.da:
+            self._enqueue_da(self._args.stream)
         check(_lib.load().stil_head_step(C.byref(self._args)))
 
     def capture(self) -> None:
         """Warm up once, then record the step into a CUDA graph (kernel params are baked in)."""
         with torch.cuda.device(self.dev):
             self._ensure_prototypes()
-            # the warm-up run must not leave a trace in the running accumulators (STiLModel.py:380-381)
-            keep = (self.prototypes_sum.clone(), self.prototypes_count_sum.clone())
+            # the warm-up run must not leave a trace in the running accumulators (STiLModel.py:380-381) or the DA ring
+            keep = [t.clone() for t in self._state_tensors()]
             s = torch.cuda.Stream(self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
                 self._enqueue()
             torch.cuda.current_stream(self.dev).wait_stream(s)
-            self.prototypes_sum.copy_(keep[0])
-            self.prototypes_count_sum.copy_(keep[1])
+            for t, k in zip(self._state_tensors(), keep):
+                t.copy_(k)
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._enqueue()
             self._graph = g
+
+    def _state_tensors(self):
+        st = [self.prototypes_sum, self.prototypes_count_sum]
+        if self.da:
+            st += [self.DA_queue, self.DA_ptr]
+        return st
 
     def timed_run(self, names=False):
         """One un-captured step with CUDA events recorded (on the launching streams) around the launches of the two
@@ -216,6 +284,23 @@ class STiLHead:
             self.run()
             self._losses_host.copy_(self.out["losses"], non_blocking=True)
         return self._losses_host
+
+    def copy_out_full(self) -> Dict[str, torch.Tensor]:
+        """Device -> host copy (current stream, ONE transfer) of every per-batch output — losses, the three embedding
+        gradients, the logit gradients, pseudo labels, max_prob / max_idx and the five masks — into a pinned host mirror;
+        returns typed host views (valid once the stream has synchronised)."""
+        if self._out_host is None:
+            self._out_host = torch.zeros(self._packed_out.numel(), dtype=torch.uint8).pin_memory()
+            self._out_host_views = self._views(self._out_host, self._out_layout)
+        self._out_host.copy_(self._packed_out, non_blocking=True)
+        return self._out_host_views
+
+    def step_host_full(self, pinned: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """step_host, but EVERYTHING the step produces per batch goes back to the host (one D2H copy)."""
+        with torch.cuda.device(self.dev):
+            self.copy_in(pinned)
+            self.run()
+            return self.copy_out_full()
 
     def finalize_prototypes(self) -> torch.Tensor:
         """Epoch end (STiLModel.py:408-415)."""
@@ -324,12 +409,21 @@ class DistributedSTiLHead(STiLHead):
             self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 3 + 3 + 3 + 2
 
     # ------------------------------------------------------------------------------------------
+    def _drop_graphs(self) -> None:
+        self._graph = None
+        self._graphs = [None, None]
+
+    def _all_reduce_mean(self, mean: torch.Tensor) -> None:
+        if self.world > 1:
+            self.dist.all_reduce(mean, group=self.group)
+            mean.div_(self.world)
+
     def capture(self) -> None:
         """Record kernels AND exchanges of one step into CUDA graphs (every rank must call this and later replay
         in lockstep).  The p2p transport alternates destination halves, hence one graph per parity."""
         with torch.cuda.device(self.dev):
             self._ensure_prototypes()
-            keep = (self.prototypes_sum.clone(), self.prototypes_count_sum.clone())
+            keep = [t.clone() for t in self._state_tensors()]
             s = torch.cuda.Stream(self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
@@ -343,8 +437,8 @@ class DistributedSTiLHead(STiLHead):
                 with torch.cuda.graph(g):
                     self._run_eager(parity)
                 self._graphs[parity] = g
-            self.prototypes_sum.copy_(keep[0])
-            self.prototypes_count_sum.copy_(keep[1])
+            for t, k in zip(self._state_tensors(), keep):
+                t.copy_(k)
             torch.cuda.synchronize(self.dev)
             self.dist.barrier(group=self.group)
             self._graph = self._graphs[0]

@@ -75,7 +75,9 @@ class _InfoNCEFn(torch.autograd.Function):
         ws_bytes = lib.stil_infonce_workspace_bytes(m, n, d, dtype_code(a))
         ws = _lib.workspace(dev, "infonce", ws_bytes)
         g = grad_loss.detach().to(torch.float32).contiguous()
-        d_a, d_b = torch.empty_like(a), torch.empty_like(b)
+        # gradients are formed and written in fp32 whatever the embedding dtype (dLoss/dLogits travels as a bf16 hi+lo
+        # pair); autograd's contract then rounds them ONCE to the dtype of the inputs
+        d_a, d_b = torch.empty_like(a, dtype=torch.float32), torch.empty_like(b, dtype=torch.float32)
         with torch.cuda.device(dev):
             check(lib.stil_infonce_bwd(ptr(a), ptr(b), ptr(a_all), ptr(b_all), dtype_code(a), m, n, d, d, off,
                                        temperature, lambda_0, ptr(lse_row_all), ptr(lse_col_all), ptr(g), ptr(d_a),
@@ -166,7 +168,7 @@ class _ProtoCEFn(torch.autograd.Function):
         lib = _lib.load()
         ws = _lib.workspace(dev, "proto", lib.stil_proto_ce_workspace_bytes(rows, k, d, dtype_code(f)))
         g = grad_loss.detach().to(torch.float32).contiguous()
-        d_f = torch.empty_like(f)
+        d_f = torch.empty_like(f, dtype=torch.float32)      # fp32 gradient, rounded once to the input dtype below
         with torch.cuda.device(dev):
             check(lib.stil_proto_ce_bwd(ptr(f), dtype_code(f), rows, d, d, ptr(protos), k, ptr(cls), ptr(lse), ptr(w),
                                         temperature, ptr(g), ptr(d_f), dtype_code(d_f), d, ptr(ws), ws.numel(),

@@ -52,13 +52,18 @@ def prototype_logits(feat: torch.Tensor, prototypes: torch.Tensor) -> torch.Tens
 @torch.no_grad()
 def cgpl_pgls(y_m: torch.Tensor, y_i: torch.Tensor, y_t: torch.Tensor, feat_m_ue: torch.Tensor,
               prototypes: torch.Tensor, *, T: float, rate_pseudo: float, th1: float,
-              return_prediction: bool = True, teacher_logits: Optional[torch.Tensor] = None) -> PseudoLabels:
+              return_prediction: bool = True, teacher_logits: Optional[torch.Tensor] = None,
+              prediction_override: Optional[torch.Tensor] = None) -> PseudoLabels:
     """Fused CGPL (3x softmax/argmax, 4 agreement cases, case-averaged pseudo label) and PGLS (teacher
     prototype probabilities, smoothing mix, max/argmax, confidence mask).
 
     ``y_*`` are the TEACHER logits of the unlabelled rows [B_u, K]; ``feat_m_ue`` the teacher multimodal
     feature [B_u, P]; ``prototypes`` the (un-normalised) bank [K, P].  Index / mask outputs are bit-exact
     with torch semantics (first index among equal maxima, ``>=`` on fp32).
+
+    ``prediction_override`` [B_u, K]: the ``prediction`` of ``STiLModel.py:276-277`` when ``DA == True`` —
+    ``distribution_alignment(torch.softmax(y_hat_m_ue, dim=1))`` — which then replaces ``softmax(y_m)`` in the
+    smoothing mix and the threshold (``:296-298``); cases and ``pseudo_label`` are unaffected (``:263-274, :295``).
     """
     ys = [y.detach() for y in (y_m, y_i, y_t)]
     if any(y.dtype not in (torch.float32, torch.bfloat16) for y in ys) or len({y.dtype for y in ys}) != 1:
@@ -72,6 +77,14 @@ def cgpl_pgls(y_m: torch.Tensor, y_i: torch.Tensor, y_t: torch.Tensor, feat_m_ue
     tl = teacher_logits
     if tl.dtype != torch.float32 or tl.stride(1) != 1:
         tl = tl.float().contiguous()
+    pin = prediction_override
+    if pin is not None:
+        pin = pin.detach()
+        if pin.dtype != torch.float32 or pin.stride(-1) != 1:
+            pin = pin.float().contiguous()
+        if pin.shape != (rows, k):
+            raise ValueError(f"prediction_override must be [{rows}, {k}], got {tuple(pin.shape)}")
+        _lib.require_cuda(pin, ys[0])
     f32 = dict(dtype=torch.float32, device=dev)
     pl = torch.empty(rows, k, **f32)
     pred = torch.empty(rows, k, **f32) if return_prediction else None
@@ -82,7 +95,8 @@ def cgpl_pgls(y_m: torch.Tensor, y_i: torch.Tensor, y_t: torch.Tensor, feat_m_ue
     with torch.cuda.device(dev):
         check(_lib.load().stil_cgpl_pgls(ptr(ys[0]), ptr(ys[1]), ptr(ys[2]), dtype_code(ys[0]), k, ptr(tl),
                                          tl.stride(0) if rows > 0 else k, rows, k, float(T), float(rate_pseudo),
-                                         float(th1), 1, ptr(pl), k, ptr(pred), k, ptr(max_prob), ptr(max_idx),
+                                         float(th1), 1, ptr(pin), pin.stride(0) if pin is not None and rows > 0 else k,
+                                         ptr(pl), k, ptr(pred), k, ptr(max_prob), ptr(max_idx),
                                          ptr(flags[0]), ptr(flags[1]), ptr(flags[2]), ptr(flags[3]), ptr(flags[4]),
                                          ptr(top1), None, None, _lib.stream_ptr(dev)))
     return PseudoLabels(pl, pred, max_prob, max_idx, flags[0], flags[1], flags[2], flags[3], flags[4], top1, tl)

@@ -53,7 +53,7 @@ def test_argument_validation_without_gpu(lib):
     rc = lib.stil_infonce_fwd(p, p, p, p, 7, 8, 8, 8, 8, 0, 0.1, 0.5, p, p, p, None, 0, p, 4096, None)
     assert rc == -2
     # too many classes for the row kernel
-    rc = lib.stil_cgpl_pgls(p, p, p, 0, 4096, p, 4096, 4, 4096, 0.1, 0.9, 0.9, 1, p, 4096, None, 0, p, p, p, p, p, p,
+    rc = lib.stil_cgpl_pgls(p, p, p, 0, 4096, p, 4096, 4, 4096, 0.1, 0.9, 0.9, 1, None, 0, p, 4096, None, 0, p, p, p, p, p, p,
                             p, None, None, None, None)
     assert rc == -1
     # workspace too small

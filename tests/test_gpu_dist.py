@@ -43,7 +43,7 @@ def _worker(rank, world, port, batch, use_graph, transport):
         assert abs(got - float(loss)) <= 1e-3 * float(loss), (got, float(loss))
         for name, ref in (("d_feat_i", ga), ("d_feat_t", gb)):
             err = float((head.out[name].float().cpu() - ref).abs().max() / ref.abs().max())
-            assert err <= 1e-2, (name, err)
+            assert err <= 1e-3, (name, err)      # fp32 gradients of bf16 embeddings (the head's default)
         # row-local outputs == single-rank oracle; prototype partials == sum over ranks
         os_ = [O.head_step(b, cfg, with_grads=False) for b in batches]
         for k in ("max_idx", "mask1", "case1", "case3"):

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, STEP_CASES, cfg_for, load_golden
+from conftest import DA_CASES, GOLDEN, STEP_CASES, cfg_for, da_state_of, load_golden
 from oracle import stil_head_oracle as O
 
 RTOL = 2e-5
@@ -14,7 +14,7 @@ def close(a, b, rtol=RTOL, atol=1e-6):
     torch.testing.assert_close(a.to(torch.float32), b.to(torch.float32), rtol=rtol, atol=atol)
 
 
-@pytest.mark.parametrize("name", STEP_CASES)
+@pytest.mark.parametrize("name", STEP_CASES + DA_CASES)
 def test_step_matches_reference(name):
     ins, ref, meta = load_golden(name)
     cfg = cfg_for(name, meta)
@@ -22,7 +22,12 @@ def test_step_matches_reference(name):
     # mask_random is drawn by torch's RNG inside the reference (STiLModel.py:299); it is an INPUT of
     # the head, so replay the very mask the reference drew.
     ins["mask_random"] = ref["mask_random"]
-    o = O.head_step(ins, cfg)
+    da = da_state_of(ins) if name in DA_CASES else None
+    o = O.head_step(ins, cfg, da_state=da)
+    if da is not None:
+        # the ring buffer is updated like the reference's (STiLModel.py:175-177), wrap-around included
+        assert torch.equal(da["DA_ptr"], ref["DA_ptr"])
+        close(da["DA_queue"], ref["DA_queue"], atol=1e-8)
     # decisions: bit-exact
     for k in ("max_idx", "mask1", "case1", "case2_i", "case2_t", "case3", "top1_m", "top1_i", "top1_t"):
         assert torch.equal(o[k], ref[k]), k
@@ -43,12 +48,13 @@ def test_step_matches_reference(name):
     close(o["pseudo_label"].sum(1), torch.ones(cfg.b_u), atol=1e-5)
 
 
-@pytest.mark.parametrize("name", STEP_CASES)
+@pytest.mark.parametrize("name", STEP_CASES + DA_CASES)
 def test_fixture_has_no_ambiguous_rows(name):
     """Bit-exact comparison of masks/indices is only meaningful if no row sits within fp32 noise of a
     decision boundary; the committed fixtures are checked to have none."""
     ins, ref, meta = load_golden(name)
-    assert int(O.ambiguous_rows(ins, cfg_for(name, meta)).sum()) == 0
+    da = da_state_of(ins) if name in DA_CASES else None
+    assert int(O.ambiguous_rows(ins, cfg_for(name, meta), da_state=da).sum()) == 0
 
 
 def test_modules_match_reference():
