@@ -194,6 +194,28 @@ STIL_API int stil_simmatch_bwd(const void* feat_qu, int dtype, int64_t rows, int
                       int64_t k_bank, const float* grad_loss_in, void* d_feat_qu, int grad_dtype, int64_t ld_grad,
                       void* workspace, int64_t workspace_bytes, void* stream);
 
+/* a7, bank column-sharded over the ranks of one node (BASELINE config C5: 65536 x 512 over 8 GPUs).  Every rank
+ * holds bank[:, shard] (reference layout, [dim, k_shard]) with its labels and sweeps it for the GATHERED rows of all ranks:
+ *   stil_simmatch_shard_stats : teacher / student logits against the shard, then per row, with the FIXED shift
+ *       e = exp((z - 1)/T) (unit features and bank columns, simmatch_model.py:68-69: z <= 1), the additive statistics
+ *       stats[row, 0:3+C] = [ sum e_t | sum e_s | sum e_t p[y_j] z_s/st | A_c = sum_{j in class c} e_t ]
+ *   (caller: SUM stats over ranks — one all-reduce of [rows, 3+C] floats)
+ *   stil_simmatch_shard_finish: totals -> prob_ku (:280), loss_in (:286) and norms[row] = {1/sum e_s, 1/den} for the gradient
+ *   stil_simmatch_shard_grad  : G = (S - T')/st on the shard's columns (bf16 hi+lo) from the logits left in the workspace
+ *       by _stats, and d_feat_partial [rows, dim] f32 = G · bank_shard^T — the caller reduce-scatters the partials so
+ *       that every rank ends up with d loss_in[i] / d feat_qu[i, :] of its own rows.
+ * Workspace: stil_simmatch_workspace_bytes(rows, k_shard, dim, dtype), the same untouched buffer for _stats and _grad. */
+STIL_API int stil_simmatch_shard_stats(const void* feat_ku, const void* feat_qu, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                                       const void* bank, int64_t ld_bank, const int64_t* labels, int64_t k_shard,
+                                       const float* prob_ku_orig, int64_t num_classes, float tt, float st, float* stats,
+                                       void* workspace, int64_t workspace_bytes, void* stream);
+STIL_API int stil_simmatch_shard_finish(const float* stats_total, const float* prob_ku_orig, int64_t rows, int64_t num_classes,
+                                        float st, float c_smooth, float* prob_ku, float* loss_in, float* norms, void* stream);
+STIL_API int stil_simmatch_shard_grad(int dtype, int64_t rows, int64_t dim, const void* bank, int64_t ld_bank,
+                                      const int64_t* labels, int64_t k_shard, const float* prob_ku_orig, int64_t num_classes,
+                                      float tt, float st, const float* norms, float* d_feat_partial, int64_t ld_grad,
+                                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a8 / a9 — memory-bank smoothing of a pseudo-label distribution.  Replaces comatch_model.py:288-293 (c_keep = alpha,
  * c_bank = 1 - alpha) and MMatch.py:222-227 (the literals 0.9 / 0.1), followed by the max / argmax / threshold of

@@ -132,3 +132,33 @@ def club_mean(mu: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
     bound = (positive.sum(dim=-1) - negative.sum(dim=-1)).mean()
     est = -(-(mu - y) ** 2).sum(dim=1).mean(dim=0)
     return bound, est
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Column-sharded SimMatch bank: torch restatement of the three shard kernels (include/stil_head.h,
+# stil_simmatch_shard_stats / _finish / _grad).  The REFERENCE of the sharded sweep is stil_head_oracle.simmatch_bank on
+# the whole bank; these functions only let tests run the sharding SCHEDULE (additive fixed-shift statistics, all-reduce,
+# reduce-scatter) on CPU ranks over gloo.
+# ----------------------------------------------------------------------------------------------------------------------
+def simmatch_shard_stats(fk: Tensor, fq: Tensor, p: Tensor, bank_shard: Tensor, labels: Tensor, tt: float, st: float) -> Tensor:
+    """bank_shard [dim, k_shard].  stats[row] = [sum e_t | sum e_s | sum e_t p[y_j] z_s/st | A_c], e = exp((z - 1)/T)."""
+    zt, zs = fk @ bank_shard, fq @ bank_shard
+    et, es = torch.exp((zt - 1) / tt), torch.exp((zs - 1) / st)
+    f = p[:, labels]
+    agg = torch.zeros_like(p).index_add_(1, labels, et)
+    return torch.cat((et.sum(1, keepdim=True), es.sum(1, keepdim=True), (et * f * zs / st).sum(1, keepdim=True), agg), dim=1)
+
+
+def simmatch_shard_finish(stats: Tensor, p: Tensor, st: float, c_smooth: float):
+    sum_t, sum_s, num, agg = stats[:, 0], stats[:, 1], stats[:, 2], stats[:, 3:]
+    den = (p * agg).sum(1)
+    prob_ku = c_smooth * p + (1 - c_smooth) * agg / sum_t[:, None] if c_smooth < 1 else p.clone()
+    loss_in = 1.0 / st + torch.log(sum_s) - num / den
+    return prob_ku, loss_in, torch.stack((1 / sum_s, 1 / den), dim=1)
+
+
+def simmatch_shard_grad(fk: Tensor, fq: Tensor, p: Tensor, bank_shard: Tensor, labels: Tensor, tt: float, st: float,
+                        norms: Tensor) -> Tensor:
+    zt, zs = fk @ bank_shard, fq @ bank_shard
+    g = (torch.exp((zs - 1) / st) * norms[:, :1] - torch.exp((zt - 1) / tt) * p[:, labels] * norms[:, 1:]) / st
+    return g @ bank_shard.t()

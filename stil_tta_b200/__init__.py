@@ -12,7 +12,7 @@ _LAZY = {
     "CLIPLoss": "losses", "PrototypeLoss": "losses", "masked_soft_ce": "losses", "label_argmax": "losses",
     "cgpl_pgls": "pseudo_label", "distribution_alignment": "pseudo_label", "prototype_logits": "pseudo_label", "PseudoLabels": "pseudo_label",
     "cal_prototypes": "prototypes", "cal_prototypes_separate": "prototypes", "PrototypeBank": "prototypes",
-    "simmatch_bank": "bank", "alloc_bank": "bank",
+    "simmatch_bank": "bank", "alloc_bank": "bank", "ShardedSimMatchBank": "bank",
     "bank_smooth": "bank_blocks", "mmatch_pseudo_label": "bank_blocks", "comatch_smooth": "bank_blocks",
     "comatch_graphs": "bank_blocks", "graph_contrast_loss": "bank_blocks", "masked_ce": "bank_blocks",
     "queue_enqueue": "bank_blocks", "update_bank": "bank_blocks", "HistAlignment": "bank_blocks",

@@ -104,6 +104,9 @@ SIGNATURES = {
     "stil_simmatch_fwd": (i32, [vp, vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, f32, f32, f32, vp, vp, i32, vp,
                                 i64, vp]),
     "stil_simmatch_bwd": (i32, [vp, i32, i64, i64, vp, i64, i64, vp, vp, i32, i64, vp, i64, vp]),
+    "stil_simmatch_shard_stats": (i32, [vp, vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, f32, f32, vp, vp, i64, vp]),
+    "stil_simmatch_shard_finish": (i32, [vp, vp, i64, i64, f32, f32, vp, vp, vp, vp]),
+    "stil_simmatch_shard_grad": (i32, [i32, i64, i64, vp, i64, vp, i64, vp, i64, f32, f32, vp, vp, i64, vp, i64, vp]),
     "stil_bank_smooth_workspace_bytes": (i64, [i64, i64, i64, i64, i32]),
     "stil_bank_smooth": (i32, [vp, i64, i64, i64, vp, i32, i64, i64, vp, i64, vp, i64, i64, f32, f32, f32, vp, i64, f32,
                                vp, vp, vp, vp, i64, vp]),

@@ -79,3 +79,182 @@ def simmatch_bank(feat_ku: torch.Tensor, feat_qu: torch.Tensor, prob_ku_orig: to
     probabilities of the bank labels, class-aggregated smoothing of the pseudo label, and the instance-similarity loss
     (per row; only ``feat_qu`` receives a gradient)."""
     return _SimMatchFn.apply(feat_ku, feat_qu, prob_ku_orig, bank, labels, tt, st, c_smooth)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Column-sharded bank over the GPUs of one node (SURVEY §8e a7; BASELINE config C5: 65536 x 512 over 8 B200)
+# ----------------------------------------------------------------------------------------------------------------------
+class _ShardedSimMatchFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat_ku, feat_qu, prob_ku_orig, owner, tt, st, c_smooth):
+        prob_ku, loss_in, jac = owner._sweep(feat_ku, feat_qu, prob_ku_orig, tt, st, c_smooth, ctx.needs_input_grad[1])
+        ctx.jac = jac
+        ctx.in_dtype = feat_qu.dtype
+        ctx.mark_non_differentiable(prob_ku)
+        return prob_ku, loss_in
+
+    @staticmethod
+    def backward(ctx, _g_prob, g_loss):
+        if ctx.jac is None:
+            return (None,) * 7
+        return None, (g_loss.detach().to(torch.float32)[:, None] * ctx.jac).to(ctx.in_dtype), None, None, None, None, None
+
+
+class ShardedSimMatchBank:
+    """The SimMatch memory bank (``simmatch_model.py:68-70``) column-sharded over the ranks of ``group``: rank ``r`` holds
+    ``bank[:, r*K/W : (r+1)*K/W]`` (reference layout ``[dim, K/W]``) and the matching ``labels`` slice.
+
+    The reference instead REPLICATES the bank on every GPU and all-gathers the updates (``_update_bank``, ``:141-147``); at
+    C5 sizes (65536 x 512) that is 64 MiB of bank swept by every GPU for its 448 rows.  Sharded, every rank sweeps
+    ``K/W`` columns for the gathered rows of all ranks — the same tensor work per GPU, 1/W of the bank bytes per GPU, and
+    the bank grows with the node.  One step (``__call__``, the block ``simmatch_model.py:268-286``):
+
+      1. all-gather ``feat_ku``, ``feat_qu``, ``prob_ku_orig`` over ranks (rows of all ranks, rank-major)
+      2. ``stil_simmatch_shard_stats``: logits against the local shard, per-row statistics with a FIXED shift
+         (unit vectors: ``e = exp((z - 1)/T)``), so that they are ADDITIVE over shards
+      3. all-reduce(SUM) of the ``[W*rows, 3 + C]`` statistics
+      4. ``stil_simmatch_shard_finish``: ``prob_ku`` (``:280``), ``loss_in`` (``:286``) and the normalisers
+      5. (when ``feat_qu`` needs a gradient) ``stil_simmatch_shard_grad``: ``G = (S - T')/st`` on the shard's columns and
+         the partial ``G · bank_shardᵀ``; reduce-scatter(SUM) gives every rank ``d loss_in / d feat_qu`` of its own rows.
+         It is computed in the forward, while the bank still holds what the forward saw (the reference overwrites bank
+         columns before ``loss.backward()``, ``:291``).
+
+    ``emulate_shards=S`` (tests, one process): the bank is split into ``S`` shards swept one after the other on this GPU
+    and the collectives become sums — the same kernels, offsets and additive statistics as ``S`` ranks.
+    """
+
+    def __init__(self, dim: int, k_bank: int, num_classes: int, dtype=torch.bfloat16, device="cuda", group=None,
+                 emulate_shards: int = 1) -> None:
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.dev = torch.device(device)
+        self._check_device()
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.nshards = emulate_shards if self.world == 1 else 1
+        parts = self.world * self.nshards
+        if k_bank % parts:
+            raise ValueError(f"k_bank {k_bank} must be divisible by the number of shards {parts}")
+        self.dim, self.k_bank, self.num_classes, self.dtype = dim, k_bank, num_classes, dtype
+        self.k_shard = k_bank // parts
+        # reference buffer names (simmatch_model.py:68-70); one (bank, labels) pair per local shard
+        self.bank = [alloc_bank(dim, self.k_shard, dtype, self.dev) for _ in range(self.nshards)]
+        self.labels = [torch.zeros(self.k_shard, dtype=torch.int64, device=self.dev) for _ in range(self.nshards)]
+        self._ws = None
+        # gather x2 (+p), GEMM, stats, all-reduce, finish, grad, memset, split-K GEMM, grad_finish, reduce-scatter
+        self.launches_per_step = self.nshards * 7 + 1
+
+    def _check_device(self) -> None:
+        if self.dev.type != "cuda":
+            raise RuntimeError("ShardedSimMatchBank runs on a CUDA device (sm_100a) only; there is no CPU fallback")
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
+        _lib.ensure_device(self.dev)
+
+    # ------------------------------------------------------------------------------------------
+    def load_shard(self, bank_rows: torch.Tensor, labels: torch.Tensor, shard: int = 0) -> None:
+        """Fill local shard ``shard`` from ``bank_rows [k_shard, dim]`` (row-major, unit rows) and its labels."""
+        self.bank[shard].copy_(bank_rows.to(self.dev).t())
+        self.labels[shard].copy_(labels.to(self.dev))
+
+    def load(self, bank_rows: torch.Tensor, labels: torch.Tensor) -> None:
+        """Fill every local shard from the WHOLE bank ``[k_bank, dim]`` (each rank keeps only its columns)."""
+        for s in range(self.nshards):
+            g = (self.rank * self.nshards + s) * self.k_shard
+            self.load_shard(bank_rows[g:g + self.k_shard], labels[g:g + self.k_shard], s)
+
+    def update(self, k: torch.Tensor, y: torch.Tensor, index: torch.Tensor) -> None:
+        """``_update_bank`` (``simmatch_model.py:141-147``) with GLOBAL column indices: ``k``/``y``/``index`` are gathered
+        over ranks like the reference does, then every rank writes the columns it owns."""
+        if self.world > 1:
+            k, y, index = self._gather(k.contiguous()), self._gather(y.contiguous()), self._gather(index.contiguous())
+        for s in range(self.nshards):
+            g = (self.rank * self.nshards + s) * self.k_shard
+            mine = (index >= g) & (index < g + self.k_shard)
+            if bool(mine.any()):
+                self._k_update(s, k[mine], y[mine], index[mine] - g)
+
+    def _k_update(self, s, k, y, index_local) -> None:
+        from .bank_blocks import update_bank
+        update_bank(self.bank[s], self.labels[s], k, y, index_local)
+
+    def _gather(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return t
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t, group=self.group)
+        return out
+
+    # ---- the three kernels of one sweep (tests/test_dist_gloo.py overrides them with the torch restatement of
+    # oracle/bank_oracle.py to run the SCHEDULE below on CPU ranks over gloo)
+    def _k_stats(self, s, fk, fq, p, tt, st, out):
+        lib, bank = _lib.load(), self.bank[s]
+        rows_all, d = fq.shape
+        check(lib.stil_simmatch_shard_stats(ptr(fk), ptr(fq), dtype_code(fq), rows_all, d, d, ptr(bank), bank.stride(0),
+                                            ptr(self.labels[s]), self.k_shard, ptr(p), p.shape[1], float(tt), float(st), ptr(out),
+                                            ptr(self._ws[s]), self._ws[s].numel(), _lib.stream_ptr(self.dev)))
+
+    def _k_finish(self, stats, p, st, c_smooth, prob_all, loss_all, norms):
+        check(_lib.load().stil_simmatch_shard_finish(ptr(stats), ptr(p), p.shape[0], p.shape[1], float(st), float(c_smooth),
+                                                     ptr(prob_all), ptr(loss_all), ptr(norms), _lib.stream_ptr(self.dev)))
+
+    def _k_grad(self, s, fk, fq, p, tt, st, norms, out):
+        lib, bank = _lib.load(), self.bank[s]
+        rows_all, d = fq.shape
+        check(lib.stil_simmatch_shard_grad(dtype_code(fq), rows_all, d, ptr(bank), bank.stride(0), ptr(self.labels[s]),
+                                           self.k_shard, ptr(p), p.shape[1], float(tt), float(st), ptr(norms), ptr(out), d,
+                                           ptr(self._ws[s]), self._ws[s].numel(), _lib.stream_ptr(self.dev)))
+
+    def _alloc_ws(self, rows_all, d, code):
+        nbytes = _lib.load().stil_simmatch_workspace_bytes(rows_all, self.k_shard, d, code)
+        if self._ws is None or self._ws[0].numel() < nbytes:
+            self._ws = [torch.empty(nbytes, dtype=torch.uint8, device=self.dev) for _ in range(self.nshards)]
+
+    def _sweep(self, feat_ku, feat_qu, prob_ku_orig, tt, st, c_smooth, need_grad):
+        dev, W = self.dev, self.world
+        fk = self._gather(feat_ku.detach().to(self.dtype).contiguous())
+        fq = self._gather(feat_qu.detach().to(self.dtype).contiguous())
+        p = self._gather(prob_ku_orig.detach().to(torch.float32).contiguous())
+        rows_all, d = fq.shape
+        rows = rows_all // W
+        c = p.shape[1]
+        if d != self.dim or c != self.num_classes:
+            raise ValueError("feature / probability shapes do not match the bank")
+        self._alloc_ws(rows_all, d, dtype_code(fq))
+        f32 = dict(dtype=torch.float32, device=dev)
+        stats = torch.zeros(rows_all, 3 + c, **f32)
+        part = torch.empty(rows_all, 3 + c, **f32) if self.nshards > 1 else stats
+        with self._device_guard():
+            for s in range(self.nshards):
+                self._k_stats(s, fk, fq, p, tt, st, part)
+                if self.nshards > 1:
+                    stats += part
+            if W > 1:
+                self.dist.all_reduce(stats, group=self.group)
+            prob_all, loss_all, norms = torch.empty(rows_all, c, **f32), torch.empty(rows_all, **f32), torch.empty(rows_all, 2, **f32)
+            self._k_finish(stats, p, st, c_smooth, prob_all, loss_all, norms)
+            jac = None
+            if need_grad:
+                jall = torch.zeros(rows_all, d, **f32) if self.nshards > 1 else None
+                jp = torch.empty(rows_all, d, **f32)
+                for s in range(self.nshards):
+                    self._k_grad(s, fk, fq, p, tt, st, norms, jp)
+                    if self.nshards > 1:
+                        jall += jp
+                jall = jp if jall is None else jall
+                if W > 1:
+                    jac = torch.empty(rows, d, **f32)
+                    self.dist.reduce_scatter_tensor(jac, jall, group=self.group)
+                else:
+                    jac = jall
+        lo = self.rank * rows
+        return prob_all[lo:lo + rows], loss_all[lo:lo + rows], jac
+
+    def _device_guard(self):
+        return torch.cuda.device(self.dev)
+
+    def __call__(self, feat_ku, feat_qu, prob_ku_orig, tt: float, st: float, c_smooth: float):
+        """``(prob_ku, loss_in)`` of ``simmatch_model.py:268-286`` for this rank's rows against the WHOLE (sharded) bank."""
+        return _ShardedSimMatchFn.apply(feat_ku, feat_qu, prob_ku_orig, self, tt, st, c_smooth)

@@ -1199,6 +1199,85 @@ STIL_API int stil_simmatch_bwd(const void* feat_qu, int dtype, int64_t rows, int
     return launch_grad_finish(GF, S(stream));
 }
 
+// ---- a7, column-sharded: every rank sweeps ITS bank shard for the gathered rows of all ranks with a fixed
+// shift, the per-row statistics are summed over ranks by the caller (all-reduce), and the gradient partials reduce-scattered.
+namespace {
+int sim_shard_checks(const void* bank, int dtype, int64_t k_shard, int64_t ld_bank, const char* what) {
+    const int per16 = dtype == STIL_BF16 ? 8 : 4;
+    STIL_REQUIRE(dtype == STIL_F32 || dtype == STIL_BF16, STIL_E_DTYPE, "%s: bad dtype", what);
+    STIL_REQUIRE(bank && k_shard >= 1 && ld_bank >= k_shard && ld_bank % per16 == 0 && (reinterpret_cast<uintptr_t>(bank) & 15) == 0,
+                 STIL_E_ALIGN, "%s: bank shard [dim, k_shard] needs ld %% %d == 0 and a 16-byte aligned base", what, per16);
+    return STIL_OK;
+}
+}  // namespace
+
+STIL_API int stil_simmatch_shard_stats(const void* feat_ku, const void* feat_qu, int dtype, int64_t rows, int64_t dim, int64_t ld,
+                                       const void* bank, int64_t ld_bank, const int64_t* labels, int64_t k_shard,
+                                       const float* prob_ku_orig, int64_t num_classes, float tt, float st, float* stats,
+                                       void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_embed(feat_ku, dtype, rows, dim, ld, "simmatch_shard feat_ku");
+    if (rc) return rc;
+    if ((rc = check_embed(feat_qu, dtype, rows, dim, ld, "simmatch_shard feat_qu"))) return rc;
+    if ((rc = sim_shard_checks(bank, dtype, k_shard, ld_bank, "simmatch_shard_stats"))) return rc;
+    STIL_REQUIRE(labels && prob_ku_orig && stats && tt > 0.f && st > 0.f && num_classes >= 1, STIL_E_ARG,
+                 "simmatch_shard_stats: bad arguments");
+    SimPlan P = plan_sim(workspace, workspace_bytes, rows, k_shard, dim, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "simmatch workspace too small: need %lld",
+                 (long long)P.bytes);
+    if (rows == 0) return STIL_OK;
+    if (dtype != STIL_BF16) {
+        PrepLaunch PL;
+        std::memset(&PL, 0, sizeof(PL));
+        prep_add(PL, prep_job(feat_ku, dtype, rows, dim, ld, 3, P.fk_op, nullptr, 0, 0, nullptr));
+        prep_add(PL, prep_job(feat_qu, dtype, rows, dim, ld, 3, P.fq_op, nullptr, 0, 0, nullptr));
+        if ((rc = launch_prep(PL, S(stream)))) return rc;
+        STIL_REQUIRE(k_shard % 32 == 0, STIL_E_ALIGN, "simmatch: an fp32 bank needs k_shard %% 32 == 0 (got %lld)", (long long)k_shard);
+        std::memset(&PL, 0, sizeof(PL));
+        prep_add(PL, prep_job(bank, dtype, dim, k_shard, ld_bank, 3, P.bank_op, nullptr, 0, 0, nullptr));
+        if ((rc = launch_prep(PL, S(stream)))) return rc;
+    }
+    const Operand Bk = bank_operand(bank, dtype, k_shard, ld_bank, P.bank_op, P.ldg);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    for (int s = 0; s < 2; ++s) {
+        const Operand X = rowmajor_operand(s == 0 ? feat_ku : feat_qu, dtype, dim, ld, s == 0 ? P.fk_op : P.fq_op, 3);
+        if ((rc = fill_gemm_store_mn(GL.job[s], X, rows, Bk, dim, k_shard))) return rc;
+        GL.job[s].npair = seg_pairs(X.nseg, Bk.nseg, 2, GL.job[s].xseg, GL.job[s].yseg);
+        GL.job[s].out = s == 0 ? P.zt : P.zs;
+        GL.job[s].ld_out = P.ldz;
+    }
+    GL.njobs = 2;
+    gemm_job_tiles(GL);
+    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    return launch_simmatch_shard_stats(P.zt, P.zs, P.ldz, reinterpret_cast<const long long*>(labels), (int)rows, (int)k_shard,
+                                       prob_ku_orig, (int)num_classes, tt, st, stats, S(stream));
+}
+
+STIL_API int stil_simmatch_shard_finish(const float* stats_total, const float* prob_ku_orig, int64_t rows, int64_t num_classes,
+                                        float st, float c_smooth, float* prob_ku, float* loss_in, float* norms, void* stream) {
+    STIL_REQUIRE(stats_total && prob_ku_orig && norms && st > 0.f, STIL_E_ARG, "simmatch_shard_finish: bad arguments");
+    return launch_simmatch_shard_finish(stats_total, prob_ku_orig, (int)rows, (int)num_classes, st, c_smooth, prob_ku, loss_in, norms,
+                                        S(stream));
+}
+
+STIL_API int stil_simmatch_shard_grad(int dtype, int64_t rows, int64_t dim, const void* bank, int64_t ld_bank,
+                                      const int64_t* labels, int64_t k_shard, const float* prob_ku_orig, int64_t num_classes,
+                                      float tt, float st, const float* norms, float* d_feat_partial, int64_t ld_grad,
+                                      void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = sim_shard_checks(bank, dtype, k_shard, ld_bank, "simmatch_shard_grad");
+    if (rc) return rc;
+    STIL_REQUIRE(labels && prob_ku_orig && norms && d_feat_partial, STIL_E_ARG, "simmatch_shard_grad: null pointer");
+    SimPlan P = plan_sim(workspace, workspace_bytes, rows, k_shard, dim, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "simmatch workspace too small");
+    if (rows == 0) return STIL_OK;
+    // G (bf16 hi+lo) from the logits the statistics pass left in the workspace, then dX_partial = G · bank_shardᵀ
+    if ((rc = launch_simmatch_shard_grad(P.zt, P.zs, P.ldz, reinterpret_cast<const long long*>(labels), (int)rows, (int)k_shard,
+                                         prob_ku_orig, (int)num_classes, tt, st, norms, P.gop, P.ldg, 2, S(stream))))
+        return rc;
+    return stil_simmatch_bwd(nullptr, dtype, rows, dim, bank, ld_bank, k_shard, nullptr, d_feat_partial, STIL_F32, ld_grad,
+                             workspace, workspace_bytes, stream);
+}
+
 // =============================================================================================== f-1
 STIL_API int64_t stil_masked_softce_workspace_bytes(int64_t rows) {
     Workspace W(nullptr, 0);

@@ -81,6 +81,27 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 // ---- device helpers
+// Waits on a PEER rank (arrival flags, LL words of the peer-memory exchanges) are bounded by WALL-CLOCK time, not by a spin
+// count: skew between ranks at the head step is not bounded by any earlier collective (a data-loader stall at an epoch
+// boundary, a checkpoint written by rank 0, a lazy graph capture on one rank), so the default is minutes — NCCL would simply
+// wait; a peer that is really gone still becomes a CUDA error instead of a hung GPU.  Override at build time with
+// -DSTIL_PEER_TIMEOUT_S=<seconds> (0 = wait for ever).
+#ifndef STIL_PEER_TIMEOUT_S
+#define STIL_PEER_TIMEOUT_S 600
+#endif
+__device__ __forceinline__ unsigned long long peer_wait_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// call once per spin with the iteration count; reads the clock every 4096 spins only
+__device__ __forceinline__ void peer_wait_check(unsigned long long& spins, unsigned long long& t0) {
+    if ((++spins & 4095ull) != 0) return;
+    if (STIL_PEER_TIMEOUT_S == 0) return;
+    const unsigned long long now = peer_wait_now();
+    if (t0 == 0) { t0 = now; return; }
+    if (now - t0 > (unsigned long long)STIL_PEER_TIMEOUT_S * 1000000000ull) __trap();
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

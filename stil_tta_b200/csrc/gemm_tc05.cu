@@ -151,18 +151,18 @@ __device__ __forceinline__ unsigned long long gtime() {
     } while (0)
 
 // Arrival flags of the peer-memory all-gathers (csrc/p2p.cu): a consumer tile waits only for the peers whose rows it reads,
-// so the transfer overlaps the tiles that need local data.  Bounded spin: a lost peer is a CUDA error, not a hang.
+// so the transfer overlaps the tiles that need local data.  Wall-clock-bounded wait (common.cuh, STIL_PEER_TIMEOUT_S).
 __device__ __forceinline__ void wait_peer_rows(const unsigned long long* flags, const unsigned long long* seq_ptr, int rpp,
                                                int r0, int r1) {
     unsigned long long seq;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seq) : "l"(seq_ptr) : "memory");
     // acquire loads, polled by ONE thread per role (a trailing fence.sys instead costs microseconds: measured)
     for (int p = r0 / rpp; p <= r1 / rpp; ++p) {
-        unsigned long long v, spins = 0;
+        unsigned long long v, spins = 0, t0 = 0;
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
             if (v >= seq) break;
-            if (++spins > (1ull << 24)) __trap();
+            peer_wait_check(spins, t0);
             __nanosleep(20);
         }
     }
@@ -175,11 +175,11 @@ __device__ __forceinline__ float ll_read(const float* base, long long idx, const
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(tag) : "l"(tag_ptr) : "memory");
     const unsigned int want = (unsigned int)tag;
     const unsigned long long* w = reinterpret_cast<const unsigned long long*>(base) + idx;
-    unsigned long long v, spins = 0;
+    unsigned long long v, spins = 0, t0 = 0;
     for (;;) {
         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
         if ((unsigned int)(v >> 32) == want) break;
-        if (++spins > (1ull << 24)) __trap();
+        peer_wait_check(spins, t0);
         __nanosleep(32);
     }
     return __uint_as_float((unsigned int)v);

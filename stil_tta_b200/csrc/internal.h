@@ -254,6 +254,13 @@ int launch_zero_u32(unsigned int* p, int n, cudaStream_t stream);
 int launch_simmatch_rows(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_bank,
                          const float* p_orig, int num_classes, float tt, float st, float c_smooth, float* p_out,
                          float* loss_in, __nv_bfloat16* gop, long long ld_g, int g_nseg, cudaStream_t stream);
+int launch_simmatch_shard_stats(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
+                                const float* p_all, int num_classes, float tt, float st, float* stats, cudaStream_t stream);
+int launch_simmatch_shard_finish(const float* stats, const float* p_all, int rows, int num_classes, float st, float c_smooth,
+                                 float* p_out, float* loss_in, float* norms, cudaStream_t stream);
+int launch_simmatch_shard_grad(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
+                               const float* p_all, int num_classes, float tt, float st, const float* norms, __nv_bfloat16* gop,
+                               long long ld_g, int g_nseg, cudaStream_t stream);
 int launch_softmax_rows(const void* y, int dtype, int64_t ld, int64_t rows, int64_t k, float* out, int64_t ld_out,
                         cudaStream_t stream);
 int launch_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, cudaStream_t stream);

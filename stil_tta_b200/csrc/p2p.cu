@@ -77,10 +77,8 @@ __global__ void p2p_wait_kernel(const P2PChannel C) {
     if ((int)threadIdx.x < C.world) {
         const unsigned long long* my_flag =
             reinterpret_cast<const unsigned long long*>(self + C.flags_offset) + C.channel * kMaxWorld + threadIdx.x;
-        unsigned long long spins = 0;
-        while (ld_acquire_sys(my_flag) < seq) {
-            if (++spins > (1ull << 26)) __trap();
-        }
+        unsigned long long spins = 0, t0 = 0;
+        while (ld_acquire_sys(my_flag) < seq) peer_wait_check(spins, t0);
     }
 }
 
@@ -227,10 +225,8 @@ __global__ void __launch_bounds__(kP2PBlock) p2p_exchange_kernel(const P2PExchan
         if (X.wait) {
             const unsigned long long* my_flag =
                 reinterpret_cast<const unsigned long long*>(self + X.flags_offset) + X.channel * kMaxWorld + p;
-            unsigned long long spins = 0;
-            while (ld_acquire_sys(my_flag) < seq) {
-                if (++spins > (1ull << 26)) __trap();   // a lost peer becomes a CUDA error, not a hung GPU
-            }
+            unsigned long long spins = 0, t0 = 0;   // wall-clock bound (common.cuh): a lost peer becomes a CUDA error
+            while (ld_acquire_sys(my_flag) < seq) peer_wait_check(spins, t0);
         }
     }
     __syncthreads();

@@ -274,7 +274,7 @@ __device__ __forceinline__ int argmax_logits(const float (&y)[2 * NV], int sub, 
         }
     }
     group_argmax<LPR>(bv, bi);
-    return bi;
+    return bi < k ? bi : 0;      // a row of NaNs compares false everywhere: keep the index in range
 }
 
 template <int LPR, int NV>
@@ -283,8 +283,12 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
     pdl_wait();                 // predecessor complete and visible ...
     pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.b_l; i += gridDim.x * blockDim.x) {
-        A.cls_l[i] = (int)A.y_l[i];
-        A.conf_l[i] = 1.0f >= A.th1;
+        // a label outside [0, k) (F.one_hot raises on it in the reference) must not become a row index downstream: the row
+        // is kept in range and marked not confident, so it contributes nothing
+        const long long y = A.y_l[i];
+        const bool ok = y >= 0 && y < A.k;
+        A.cls_l[i] = ok ? (int)y : 0;
+        A.conf_l[i] = ok && (1.0f >= A.th1);
     }
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -308,24 +312,10 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
     for (int j = 0; j < 2 * NV; ++j) pm[j] = ym[j];
     const float sm = softmax_exp<LPR, NV>(pm);
     const float rsm = __frcp_rn(sm);   // p = e * (1/s): within 1 ulp of torch's e / s (same class as exp differences)
-    int top_m;
-    {
-        float bv = -1.f;
-        int bi = 0x7fffffff;
 #pragma unroll
-        for (int it = 0; it < NV; ++it)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int idx = 2 * (sub + LPR * it) + h;
-                pm[2 * it + h] = __fmul_rn(pm[2 * it + h], rsm);
-                if (idx < k && pm[2 * it + h] > bv) {
-                    bv = pm[2 * it + h];
-                    bi = idx;
-                }
-            }
-        group_argmax<LPR>(bv, bi);
-        top_m = bi;
-    }
+    for (int j = 0; j < 2 * NV; ++j) pm[j] = __fmul_rn(pm[j], rsm);
+    // the same rule for the three heads: first index of the largest logit (see argmax_logits)
+    const int top_m = argmax_logits<LPR, NV>(ym, sub, k);
     const int top_i = argmax_logits<LPR, NV>(yi, sub, k);
     const int top_t = argmax_logits<LPR, NV>(yt, sub, k);
     // ---- :264-267 agreement cases
@@ -387,6 +377,7 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
             }
         }
     group_argmax<LPR>(bv, bi);
+    if (bi >= k) { bi = 0; bv = __int_as_float(0x7fc00000); }   // NaN row: index stays in range, max_prob = NaN, mask1 = false
     const bool m1 = bv >= A.th1;
 
     if (!row_ok) return;
@@ -464,6 +455,31 @@ __global__ void labelled_cls_kernel(const long long* y_l, int b_l, float th, int
     }
 }
 
+// four consecutive elements of an f32 / bf16 row as floats (16- / 8-byte load; the caller guarantees alignment)
+__device__ __forceinline__ void ld4f(const void* base, int dtype, long long off, float (&x)[4]) {
+    if (dtype == STIL_BF16) {
+        const uint2 v = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(base) + off);
+        x[0] = __uint_as_float(v.x << 16); x[1] = __uint_as_float(v.x & 0xffff0000u);
+        x[2] = __uint_as_float(v.y << 16); x[3] = __uint_as_float(v.y & 0xffff0000u);
+    } else {
+        const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(base) + off);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+}
+__device__ __forceinline__ void st4f(void* base, int dtype, long long off, const float (&x)[4]) {
+    if (dtype == STIL_BF16) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(base) + off) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    } else {
+        *reinterpret_cast<float4*>(static_cast<float*>(base) + off) = make_float4(x[0], x[1], x[2], x[3]);
+    }
+}
+__device__ __forceinline__ bool rows_vec4(const void* base, int dtype, long long ld) {
+    const int esz = dtype == STIL_BF16 ? 2 : 4;
+    return (reinterpret_cast<uintptr_t>(base) % (4 * esz)) == 0 && (ld % 4) == 0;
+}
+
 // =====================================================================================
 // merge GEMM_STATS partials -> LSE, diagonal / picked logit, loss terms (deterministic reduction)
 // =====================================================================================
@@ -522,8 +538,32 @@ __global__ void __launch_bounds__(kRowBlock) finish_kernel(const __grid_constant
         const float lse = m + logf(s);
         // dot product with the partner row
         float dot = xv[0] * yv[0] + xv[1] * yv[1] + xv[2] * yv[2] + xv[3] * yv[3];
-        for (int d = lane + 128; d < J.dim; d += 32)
-            dot += ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d) * ld_as_float(J.y, J.y_dtype, yrow * J.ldy + d);
+        if (J.dim > 128) {
+            // wide rows (D = 512 / 2048): 4-element vector loads, four independent pairs in flight per lane
+            if ((J.dim & 3) == 0 && rows_vec4(J.x, J.x_dtype, J.ldx) && rows_vec4(J.y, J.y_dtype, J.ldy)) {
+                for (int d0 = 128 + 4 * lane; d0 < J.dim; d0 += 512) {
+                    float a[4][4], b[4][4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int d = d0 + 128 * u;
+                        if (d < J.dim) {
+                            ld4f(J.x, J.x_dtype, (long long)i * J.ldx + d, a[u]);
+                            ld4f(J.y, J.y_dtype, yrow * J.ldy + d, b[u]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) a[u][q] = b[u][q] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dot += a[u][q] * b[u][q];
+                }
+            } else {
+                for (int d = lane + 128; d < J.dim; d += 32)
+                    dot += ld_as_float(J.x, J.x_dtype, (long long)i * J.ldx + d) * ld_as_float(J.y, J.y_dtype, yrow * J.ldy + d);
+            }
+        }
         dot = warp_sum(dot);
         const float z = dot * J.alpha * sxv * syv;
         if (lane == 0) {
@@ -618,6 +658,66 @@ __global__ void __launch_bounds__(kRowBlock) grad_finish_kernel(const __grid_con
         }
         return v;
     };
+    // wide rows (D = 512 / 2048; one warp per row): 4-element vector loads with four independent chunks in flight per lane —
+    // the scalar form below serialises one memory round trip per 32 elements (215 us for 2 x 4096 x 2048, 28 % of a CLIPLoss
+    // forward + backward at that shape)
+    const bool wide = J.dim > 128 && (J.dim & 3) == 0 && (reinterpret_cast<uintptr_t>(J.g) & 15) == 0 && (J.slice_stride & 3) == 0 &&
+                      rows_vec4(J.dx, J.dx_dtype, J.ld_dx) && (!J.sx || rows_vec4(J.x, J.x_dtype, J.ldx));
+    if (wide) {
+        auto gsum4 = [&](int d, float (&v)[4]) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(g0 + d));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            for (int k = 1; k < ns; ++k) {
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(g0 + (long long)k * J.slice_stride + d));
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+            }
+        };
+        const float sx = J.sx ? J.sx[i] : 0.f;
+        float dot = 0.f;
+        if (J.sx) {
+            for (int d0 = 4 * lane; d0 < J.dim; d0 += 512) {
+                float gv[4][4], xv[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int d = d0 + 128 * u;
+                    if (d < J.dim) {
+                        gsum4(d, gv[u]);
+                        ld4f(J.x, J.x_dtype, (long long)i * J.ldx + d, xv[u]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) gv[u][q] = xv[u][q] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dot += sx * xv[u][q] * gv[u][q];
+            }
+            dot = warp_sum(dot);
+        }
+        for (int d0 = 4 * lane; d0 < J.dim; d0 += 512) {
+            float gv[4][4], xv[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = d0 + 128 * u;
+                if (d < J.dim) {
+                    gsum4(d, gv[u]);
+                    if (J.sx) ld4f(J.x, J.x_dtype, (long long)i * J.ldx + d, xv[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int d = d0 + 128 * u;
+                if (d < J.dim) {
+                    float o[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) o[q] = J.sx ? sx * (gv[u][q] - sx * xv[u][q] * dot) : gv[u][q];
+                    st4f(J.dx, J.dx_dtype, (long long)i * J.ld_dx + d, o);
+                }
+            }
+        }
+        return;
+    }
     if (J.sx) {
         const float sx = J.sx[i];
         // dim <= 128: the row's gradient stays in registers between the dot product and the projection
@@ -788,11 +888,11 @@ __global__ void proto_add_gathered_kernel(const float* parts, int world, long lo
             // one polling thread per block, acquire loads with back-off
             const unsigned long long target = *wait_target;
             for (int w = 0; w < world; ++w) {
-                unsigned long long v, spins = 0;
+                unsigned long long v, spins = 0, t0 = 0;
                 for (;;) {
                     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + w) : "memory");
                     if (v >= target) break;
-                    if (++spins > (1ull << 24)) __trap();
+                    peer_wait_check(spins, t0);
                     __nanosleep(64);
                 }
             }
@@ -804,11 +904,11 @@ __global__ void proto_add_gathered_kernel(const float* parts, int world, long lo
         const unsigned int want = (unsigned int)(*loss_tag);
         float s = 0.f;
         for (int w = 0; w < world; ++w) {
-            unsigned long long v, spins = 0;
+            unsigned long long v, spins = 0, t0 = 0;
             for (;;) {
                 asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(loss_ll + w) : "memory");
                 if ((unsigned int)(v >> 32) == want) break;
-                if (++spins > (1ull << 24)) __trap();
+                peer_wait_check(spins, t0);
                 __nanosleep(64);
             }
             s += __uint_as_float((unsigned int)v);
@@ -1123,6 +1223,95 @@ __global__ void __launch_bounds__(kSimBlock) simmatch_rows_kernel(const float* _
     }
 }
 
+// ---- column-sharded bank: the same block with a FIXED shift instead of the row max, so that the
+// statistics of the shards are additive.  Features and bank columns are unit vectors (simmatch_model.py:68-69, :251-252),
+// hence z <= 1 and e = exp((z - 1)/T) lies in [e^{-2/T}, 1]: no overflow, and for the reference temperatures (0.1) no
+// underflow that matters (e^{-20} = 2e-9 against a row sum >= 1 entry of order 1... K_b entries of order e^{-10}).
+//   stats[row] = [ sum_j e_t | sum_j e_s | sum_j e_t p[y_j] z_s/st | A_c = sum_{j in c} e_t  (c < C) ]      one pass over j
+__device__ __forceinline__ float shifted_exp(float z, float inv_t) { return __expf(fminf((z - 1.f) * inv_t, 60.f)); }
+
+__global__ void __launch_bounds__(kSimBlock) simmatch_shard_stats_kernel(const float* __restrict__ zt, const float* __restrict__ zs,
+                                                                         long long ldz, const long long* __restrict__ labels,
+                                                                         int k_shard, const float* __restrict__ p_all, int C,
+                                                                         float inv_tt, float inv_st, float* __restrict__ stats) {
+    extern __shared__ float sm[];   // p[C] | A[C] | red[8]
+    float* sp = sm;
+    float* sA = sm + C;
+    float* red = sm + 2 * C;
+    const int row = blockIdx.x;
+    const float* rt = zt + (long long)row * ldz;
+    const float* rs = zs + (long long)row * ldz;
+    for (int c = threadIdx.x; c < C; c += kSimBlock) {
+        sp[c] = p_all[(long long)row * C + c];
+        sA[c] = 0.f;
+    }
+    __syncthreads();
+    float st_ = 0.f, ss_ = 0.f, num = 0.f;
+    for (int j = threadIdx.x; j < k_shard; j += kSimBlock) {
+        const float z_s = rs[j];
+        const float et = shifted_exp(rt[j], inv_tt);
+        const int y = (int)labels[j];
+        st_ += et;
+        ss_ += shifted_exp(z_s, inv_st);
+        num += et * sp[y] * (z_s * inv_st);
+        atomicAdd(&sA[y], et);
+    }
+    st_ = block_reduce(st_, red, false);
+    ss_ = block_reduce(ss_, red, false);
+    num = block_reduce(num, red, false);
+    float* out = stats + (long long)row * (3 + C);
+    if (threadIdx.x == 0) { out[0] = st_; out[1] = ss_; out[2] = num; }
+    for (int c = threadIdx.x; c < C; c += kSimBlock) out[3 + c] = sA[c];
+}
+
+// totals (summed over the shards) -> prob_ku (:280), loss_in (:286) and the two normalisers the gradient needs; warp per row
+__global__ void __launch_bounds__(kRowBlock) simmatch_shard_finish_kernel(const float* __restrict__ stats, const float* __restrict__ p_all,
+                                                                          int rows, int C, float inv_st, float c_smooth,
+                                                                          float* __restrict__ p_out, float* __restrict__ loss_in,
+                                                                          float* __restrict__ norms) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* st = stats + (long long)row * (3 + C);
+    const float sum_t = st[0], sum_s = st[1], num = st[2];
+    const float inv_sum_t = 1.f / sum_t;
+    float den = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float p = p_all[(long long)row * C + c], a = st[3 + c];
+        den += p * a;
+        if (p_out) p_out[(long long)row * C + c] = c_smooth < 1.f ? p * c_smooth + (a * inv_sum_t) * (1.f - c_smooth) : p;
+    }
+    den = warp_sum(den);
+    if (lane == 0) {
+        // log S_ij = z_ij/st - (1/st + log sum_s);  loss_in = lse_s - sum_j T'_ij z_ij/st
+        if (loss_in) loss_in[row] = inv_st + logf(sum_s) - num / den;
+        norms[2 * row] = 1.f / sum_s;
+        norms[2 * row + 1] = 1.f / den;
+    }
+}
+
+// G_ij = (S_ij - T'_ij)/st for the columns of this shard, as a bf16 hi/lo operand of the dX GEMM
+__global__ void __launch_bounds__(kSimBlock) simmatch_shard_grad_kernel(const float* __restrict__ zt, const float* __restrict__ zs,
+                                                                        long long ldz, const long long* __restrict__ labels,
+                                                                        int k_shard, const float* __restrict__ p_all, int C,
+                                                                        float inv_tt, float inv_st, const float* __restrict__ norms,
+                                                                        __nv_bfloat16* gop, long long ld_g, int g_nseg) {
+    extern __shared__ float sm[];   // p[C]
+    const int row = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += kSimBlock) sm[c] = p_all[(long long)row * C + c];
+    __syncthreads();
+    const float* rt = zt + (long long)row * ldz;
+    const float* rs = zs + (long long)row * ldz;
+    const float inv_sum_s = norms[2 * row], inv_den = norms[2 * row + 1];
+    __nv_bfloat16* gh = gop + (long long)row * g_nseg * ld_g;
+    for (int j = threadIdx.x; j < k_shard; j += kSimBlock) {
+        const float g = (shifted_exp(rs[j], inv_st) * inv_sum_s - shifted_exp(rt[j], inv_tt) * sm[(int)labels[j]] * inv_den) * inv_st;
+        const __nv_bfloat16 h = __float2bfloat16_rn(g);
+        gh[j] = h;
+        if (g_nseg > 1) gh[ld_g + j] = __float2bfloat16_rn(g - __bfloat162float(h));
+    }
+}
+
 __global__ void zero_u32_kernel(unsigned int* p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = 0u;
@@ -1348,6 +1537,36 @@ int launch_simmatch_rows(const float* zt, const float* zs, long long ldz, const 
 
 int64_t masked_softce_blocks(int64_t rows, int64_t) {
     return std::min<int64_t>(ceil_div(rows, row_block_threads(rows) / 32), 148 * 16);
+}
+
+int launch_simmatch_shard_stats(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
+                                const float* p_all, int num_classes, float tt, float st, float* stats, cudaStream_t stream) {
+    if (rows == 0) return STIL_OK;
+    const size_t smem = (2 * (size_t)num_classes + 8) * sizeof(float);
+    STIL_REQUIRE(smem <= 48 * 1024, STIL_E_SHAPE, "simmatch: too many classes (%d)", num_classes);
+    simmatch_shard_stats_kernel<<<rows, kSimBlock, smem, stream>>>(zt, zs, ldz, labels, k_shard, p_all, num_classes, 1.f / tt,
+                                                                   1.f / st, stats);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+int launch_simmatch_shard_finish(const float* stats, const float* p_all, int rows, int num_classes, float st, float c_smooth,
+                                 float* p_out, float* loss_in, float* norms, cudaStream_t stream) {
+    if (rows == 0) return STIL_OK;
+    simmatch_shard_finish_kernel<<<(unsigned)ceil_div(rows, kRowBlock / 32), kRowBlock, 0, stream>>>(stats, p_all, rows, num_classes,
+                                                                                                    1.f / st, c_smooth, p_out,
+                                                                                                    loss_in, norms);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+int launch_simmatch_shard_grad(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
+                               const float* p_all, int num_classes, float tt, float st, const float* norms, __nv_bfloat16* gop,
+                               long long ld_g, int g_nseg, cudaStream_t stream) {
+    if (rows == 0) return STIL_OK;
+    const size_t smem = (size_t)num_classes * sizeof(float);
+    simmatch_shard_grad_kernel<<<rows, kSimBlock, smem, stream>>>(zt, zs, ldz, labels, k_shard, p_all, num_classes, 1.f / tt,
+                                                                  1.f / st, norms, gop, ld_g, g_nseg);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
 }
 
 int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int logit_dtype, int64_t ld_y,

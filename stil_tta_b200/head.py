@@ -342,6 +342,16 @@ class DistributedSTiLHead(STiLHead):
         from .distributed import GlobalBatch
         self.dist, self.group, self.gb = dist, group, GlobalBatch(group)
         self.world, self.rank = self.gb.world_size, self.gb.rank
+        if self.world > 1:
+            # every rank must launch the same shapes: the arrival counters / LL tags of the peer-memory transports count
+            # pushes per step, so a rank with a different batch (a ragged last batch) would make its peers wait for ever
+            sig = torch.tensor([cfg.batch, cfg.b_l, cfg.num_classes, cfg.proj_dim, int(self.inp["feat_i"].dtype == torch.bfloat16),
+                                int(self.student_ce), int(self.da)], dtype=torch.int64, device=self.dev)
+            allsig = [torch.zeros_like(sig) for _ in range(self.world)]
+            dist.all_gather(allsig, sig, group=group)
+            if any(not torch.equal(s_, sig) for s_ in allsig):
+                raise ValueError("DistributedSTiLHead: every rank must use the same batch / class / dimension / dtype "
+                                 f"configuration (got {[s_.tolist() for s_ in allsig]}); pad or drop a ragged last batch")
         if transport == "fused" and self.inp["feat_i"].dtype != torch.bfloat16:
             transport = "p2p"           # the fused schedule reads bf16 rows in place; fp32 needs the operand split pass
         self.transport = transport if self.world > 1 else "nccl"

@@ -101,3 +101,82 @@ def _worker(rank, world, port, m, d, k):
 @pytest.mark.parametrize("world,m,d", [(2, 24, 16), (2, 7, 8)])
 def test_sharded_schedule_matches_single_process(world, m, d):
     mp.spawn(_worker, args=(world, _free_port(), m, d, 5), nprocs=world, join=True)
+
+
+# ----------------------------------------------------------------------------------------------- column-sharded bank (C5)
+def _bank_worker(rank, world, port, rows, kb, d, c):
+    """The schedule of stil_tta_b200.ShardedSimMatchBank (gather, additive fixed-shift statistics, all-reduce,
+    reduce-scatter of the gradient partials, bank writes to the owning shard) on CPU ranks, with the three shard kernels
+    replaced by their torch restatement — against the oracle on the WHOLE bank in one process."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import bank_oracle as BO
+        from stil_tta_b200.bank import ShardedSimMatchBank
+        import contextlib
+
+        class CpuSharded(ShardedSimMatchBank):
+            def _check_device(self):          # test double: CPU ranks, torch kernels
+                pass
+
+            def _device_guard(self):
+                return contextlib.nullcontext()
+
+            def _alloc_ws(self, *a):
+                pass
+
+            def _k_stats(self, s, fk, fq, p, tt, st, out):
+                out.copy_(BO.simmatch_shard_stats(fk, fq, p, self.bank[s], self.labels[s], tt, st))
+
+            def _k_finish(self, stats, p, st, c_smooth, prob_all, loss_all, norms):
+                a, b, n = BO.simmatch_shard_finish(stats, p, st, c_smooth)
+                prob_all.copy_(a); loss_all.copy_(b); norms.copy_(n)
+
+            def _k_grad(self, s, fk, fq, p, tt, st, norms, out):
+                out.copy_(BO.simmatch_shard_grad(fk, fq, p, self.bank[s], self.labels[s], tt, st, norms))
+
+            def _k_update(self, s, k, y, index_local):
+                BO.update_bank(self.bank[s], self.labels[s], k, y, index_local)
+
+        import stil_tta_b200.bank as bank_mod
+        bank_mod.alloc_bank = lambda dim, k, dtype, device: torch.zeros(dim, k, dtype=dtype)   # CPU buffers for the test double
+        g = torch.Generator().manual_seed(5)
+        unit = torch.nn.functional.normalize
+        bank_rows = unit(torch.randn(kb, d, generator=g))
+        labels = torch.randint(0, c, (kb,), generator=g)
+        fk_all = unit(bank_rows[torch.randint(0, kb, (world * rows,), generator=g)] + 0.3 * torch.randn(world * rows, d, generator=g))
+        fq_all = unit(fk_all + 0.2 * torch.randn(world * rows, d, generator=g))
+        p_all = torch.softmax(torch.randn(world * rows, c, generator=g) * 3, 1)
+        sb = CpuSharded(d, kb, c, dtype=torch.float32, device="cpu")
+        assert sb.world == world and sb.k_shard == kb // world
+        sb.load(bank_rows, labels)
+        loc = slice(rank * rows, (rank + 1) * rows)
+        fq = fq_all[loc].clone().requires_grad_(True)
+        prob_ku, loss_in = sb(fk_all[loc], fq, p_all[loc], 0.1, 0.1, 0.9)
+        # _update_bank between forward and backward (the reference order): bank writes go to the owning shard
+        idx = torch.arange(rank, kb, 7)[:8]
+        newk = unit(torch.randn(len(idx), d, generator=torch.Generator().manual_seed(rank)))
+        sb.update(newk, torch.full((len(idx),), 1, dtype=torch.int64), idx)
+        (gq,) = torch.autograd.grad(loss_in.mean(), fq)
+        fqr = fq_all.clone().requires_grad_(True)
+        ref = O.simmatch_bank(fk_all, fqr, p_all, bank_rows, labels, 0.1, 0.1, 0.9)
+        (g_ref,) = torch.autograd.grad(ref["loss_in"][loc].mean(), fqr)
+        torch.testing.assert_close(prob_ku, ref["prob_ku"][loc], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(loss_in, ref["loss_in"][loc].detach(), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(gq, g_ref[loc], rtol=1e-3, atol=1e-6)
+        # every rank's update landed in the shard that owns the column
+        full = torch.cat([t.clone() for t in [sb.bank[0]]], dim=1)
+        gathered = [torch.zeros_like(full) for _ in range(world)]
+        dist.all_gather(gathered, full)
+        whole = torch.cat(gathered, dim=1)
+        for r in range(world):
+            idx_r = torch.arange(r, kb, 7)[:8]
+            exp = unit(torch.randn(len(idx_r), d, generator=torch.Generator().manual_seed(r)))
+            torch.testing.assert_close(whole[:, idx_r], exp.t())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_bank_schedule_matches_whole_bank_oracle():
+    mp.spawn(_bank_worker, args=(2, _free_port(), 12, 256, 16, 5), nprocs=2, join=True)

@@ -338,3 +338,42 @@ def test_comatch_backward_after_queue_enqueue(S, BO):
     S.queue_enqueue(qs, pu, ptr_, dev(F.normalize(torch.randn(rows, d, generator=g))), dev(probs))   # overwrites columns 0..rows-1
     (gc,) = torch.autograd.grad(loss, f0c)
     assert_rel(gc, gr, REL, "d_feat_s0 after queue_enqueue")
+
+
+# ----------------------------------------------------------------------------------------------- column-sharded bank (e-C5)
+@pytest.mark.parametrize("rows,kb,d,c,dtype,shards", [
+    (96, 1024, 128, 10, torch.bfloat16, 1), (96, 1024, 128, 10, torch.bfloat16, 4), (64, 640, 64, 10, torch.float32, 2),
+    (448, 4096, 128, 286, torch.bfloat16, 8), (448, 65536, 512, 286, torch.bfloat16, 8),      # the last one is BASELINE config C5
+])
+def test_sharded_simmatch_bank_matches_whole_bank_oracle(S, rows, kb, d, c, dtype, shards):
+    """The column-sharded sweep (fixed-shift additive statistics; `shards` emulated one after the other on this GPU — the same
+    kernels, column offsets and sums as `shards` ranks) against the oracle on the WHOLE bank, incl. the C5 shape."""
+    from oracle import stil_head_oracle as O
+    g = torch.Generator().manual_seed(rows + kb + shards)
+    unit = F.normalize
+    bank_rows = unit(torch.randn(kb, d, generator=g)).to(dtype)
+    labels = torch.randint(0, c, (kb,), generator=g)
+    fk = unit(bank_rows.float()[torch.randint(0, kb, (rows,), generator=g)] + 0.3 * torch.randn(rows, d, generator=g)).to(dtype)
+    fq = unit(fk.float() + 0.2 * torch.randn(rows, d, generator=g)).to(dtype)
+    p = torch.softmax(torch.randn(rows, c, generator=g) * 3, 1)
+    fqr = fq.float().requires_grad_(True)
+    ref = O.simmatch_bank(fk.float(), fqr, p, bank_rows.float(), labels, 0.1, 0.1, 0.9)
+    (g_ref,) = torch.autograd.grad(ref["loss_in"].mean(), fqr)
+    sb = S.ShardedSimMatchBank(d, kb, c, dtype=dtype, device="cuda", emulate_shards=shards)
+    sb.load(bank_rows, labels)
+    fqc = dev(fq).requires_grad_(True)
+    prob_ku, loss_in = sb(dev(fk), fqc, dev(p), 0.1, 0.1, 0.9)
+    # the reference order: bank columns are overwritten before loss.backward() (simmatch_model.py:291)
+    idx = torch.randperm(kb, generator=g)[:64]
+    sb.update(dev(unit(torch.randn(64, d, generator=g))), dev(torch.randint(0, c, (64,), generator=g)), dev(idx))
+    (g_c,) = torch.autograd.grad(loss_in.mean(), fqc)
+    assert float((prob_ku.cpu() - ref["prob_ku"]).abs().max()) <= 2e-5
+    assert_rel(loss_in, ref["loss_in"].detach(), REL, "loss_in (sharded)")
+    assert_rel(g_c, g_ref, REL, "d_feat_qu (sharded)")
+    mp_ref = ref["prob_ku"].max(1).values
+    keep = (mp_ref - 0.95).abs() > 1e-4
+    assert torch.equal((prob_ku.cpu().max(1).values >= 0.95)[keep], (mp_ref >= 0.95)[keep])
+    # the update reached the owning shards: the next sweep sees the new columns
+    whole = torch.cat([b.float().cpu() for b in sb.bank], dim=1)
+    assert float((whole[:, idx].t().norm(dim=1) - 1).abs().max()) < 1e-2
+    assert not torch.equal(whole.t().to(dtype), bank_rows)

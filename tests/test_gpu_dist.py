@@ -73,3 +73,48 @@ def _worker(rank, world, port, batch, use_graph, transport):
 def test_distributed_head_two_ranks(use_graph, transport):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), 256, use_graph, transport), nprocs=2, join=True)
+
+
+def _bank_worker(rank, world, port):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ok = False
+    try:
+        import stil_tta_b200 as S
+        from oracle import stil_head_oracle as O
+        rows, kb, d, c = 96, 2048, 128, 10
+        g = torch.Generator().manual_seed(3)
+        unit = torch.nn.functional.normalize
+        bank_rows = unit(torch.randn(kb, d, generator=g)).to(torch.bfloat16)
+        labels = torch.randint(0, c, (kb,), generator=g)
+        fk_all = unit(bank_rows.float()[torch.randint(0, kb, (world * rows,), generator=g)] + 0.3 * torch.randn(world * rows, d, generator=g)).to(torch.bfloat16)
+        fq_all = unit(fk_all.float() + 0.2 * torch.randn(world * rows, d, generator=g)).to(torch.bfloat16)
+        p_all = torch.softmax(torch.randn(world * rows, c, generator=g) * 3, 1)
+        loc = slice(rank * rows, (rank + 1) * rows)
+        sb = S.ShardedSimMatchBank(d, kb, c, dtype=torch.bfloat16, device=f"cuda:{rank}")
+        assert sb.world == world
+        sb.load(bank_rows, labels)
+        fq = fq_all[loc].cuda().requires_grad_(True)
+        prob_ku, loss_in = sb(fk_all[loc].cuda(), fq, p_all[loc].cuda(), 0.1, 0.1, 0.9)
+        (gq,) = torch.autograd.grad(loss_in.mean(), fq)
+        fqr = fq_all.float().requires_grad_(True)
+        ref = O.simmatch_bank(fk_all.float(), fqr, p_all, bank_rows.float(), labels, 0.1, 0.1, 0.9)
+        (g_ref,) = torch.autograd.grad(ref["loss_in"][loc].mean(), fqr)
+        assert float((prob_ku.cpu() - ref["prob_ku"][loc]).abs().max()) <= 2e-5
+        e1 = float((loss_in.cpu() - ref["loss_in"][loc].detach()).abs().max() / ref["loss_in"][loc].abs().max())
+        e2 = float((gq.float().cpu() - g_ref[loc]).abs().max() / g_ref[loc].abs().max())
+        assert e1 <= 1e-3 and e2 <= 4e-3, (e1, e2)       # gq is bf16 (input dtype): 2^-9 output rounding on top of 1e-3
+        ok = True
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+    os._exit(0 if ok else 1)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_simmatch_bank_two_ranks():
+    import torch.multiprocessing as mp
+    mp.spawn(_bank_worker, args=(2, _free_port()), nprocs=2, join=True)
