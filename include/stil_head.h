@@ -50,7 +50,7 @@ typedef enum {
 } stil_status_t;
 
 STIL_API int stil_version(void);
-/* sizeof(stil_head_step_args) (which = 0) / sizeof(stil_p2p_channel) (1): lets a binding check its struct mirror */
+/* sizeof(stil_head_step_args) (which = 0) / stil_p2p_channel (1) / stil_ema_entry (2): lets a binding check its struct mirror */
 STIL_API int64_t stil_abi_struct_bytes(int which);
 STIL_API const char* stil_last_error(void);
 /* Debug aid: install (or clear with NULL) a device buffer of [64 launches][64 CTAs][8] uint64 into which the GEMM
@@ -282,6 +282,25 @@ STIL_API int stil_bank_update(void* bank, int b_dtype, int64_t ld_bank, int64_t*
 STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* hist,
                                 int64_t hist_len, int64_t* count, float* qmean_scratch, float* out, int64_t ld_out,
                                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * f-4 — EMA teacher update.  Replaces STiLModel.momentum_update_ema (STiLModel.py:154-168), a per-tensor Python loop of
+ * mul_ / add_ / copy_ over the whole state dict every step, by ONE launch over a device-resident table:
+ *   kind 0: ema = ema * momentum + (1 - momentum) * main   (dtype STIL_F32 / STIL_BF16; each product and the sum rounded like
+ *           the eager ops, so fp32 results are bit-identical to the reference)
+ *   kind 1: ema = main, byte copy (`num_batches_tracked`, :163-164); numel counts BYTES
+ * `table` is a DEVICE array of n_entries stil_ema_entry; the tensors are cut into chunks of chunk_elems elements (bytes for
+ * kind 1): chunk c covers elements [chunk_start[c], chunk_start[c] + chunk_elems) of entry chunk_entry[c] (both DEVICE arrays,
+ * built once per model by the binding).  One block per chunk. */
+typedef struct stil_ema_entry {
+    void* ema;
+    const void* main;
+    int64_t numel;
+    int32_t dtype; /* stil_dtype_t (kind 0) */
+    int32_t kind;
+} stil_ema_entry;
+STIL_API int stil_ema_update(const stil_ema_entry* table, int64_t n_entries, const int32_t* chunk_entry,
+                             const int64_t* chunk_start, int64_t n_chunks, int64_t chunk_elems, float momentum, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * f-2 — CLUBMean mutual-information bound and its learning loss, from mu = p_mu(x_samples) on.  Replaces the tensor code

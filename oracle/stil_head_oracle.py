@@ -303,3 +303,19 @@ def ambiguous_rows(batch: Dict[str, Tensor], cfg, tol: float = 1e-5, da_state=No
     for k in ("y_m_ue", "y_i_ue", "y_t_ue"):
         amb |= near_tie(torch.softmax(up(batch[k]), dim=1))
     return amb
+
+
+# ---------------------------------------------------------------------- f-4
+def momentum_update_ema(main_state: Dict[str, Tensor], ema_state: Dict[str, Tensor], momentum: float, eman: bool,
+                        param_names=None) -> None:
+    """EMA teacher update, in place on `ema_state`. Follows STiLModel.py:154-168: with `eman` every state-dict
+    entry (``num_batches_tracked`` copied, :163-164); otherwise only the parameters (`param_names`, :167-168)."""
+    for k, v_main in main_state.items():
+        v_ema = ema_state[k]
+        if eman:
+            if "num_batches_tracked" in k:
+                v_ema.copy_(v_main)                                                    # :164
+            else:
+                v_ema.mul_(momentum).add_((1.0 - momentum) * v_main)                  # :166
+        elif param_names is None or k in param_names:
+            v_ema.mul_(momentum).add_((1.0 - momentum) * v_main)                      # :168

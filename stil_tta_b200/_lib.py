@@ -28,6 +28,11 @@ class P2PChannel(C.Structure):
                 ("channel", i32)]
 
 
+class EmaEntry(C.Structure):
+    """Mirror of `stil_ema_entry` (include/stil_head.h)."""
+    _fields_ = [("ema", vp), ("main", vp), ("numel", i64), ("dtype", i32), ("kind", i32)]
+
+
 class HeadStepArgs(C.Structure):
     """Mirror of `stil_head_step_args` (include/stil_head.h) — field order must match."""
     _fields_ = [
@@ -121,6 +126,7 @@ SIGNATURES = {
     "stil_queue_enqueue": (i32, [vp, i32, i64, vp, i64, i64, vp, vp, i32, i64, i64, i64, vp, i64, i64, vp]),
     "stil_bank_update": (i32, [vp, i32, i64, vp, vp, i32, i64, vp, vp, i64, i64, vp]),
     "stil_da_apply_hist": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
+    "stil_ema_update": (i32, [vp, i64, vp, vp, i64, i64, f32, vp]),
     "stil_club_fwd": (i32, [vp, vp, i32, i64, i64, i64, vp, vp, vp, vp]),
     "stil_club_bwd": (i32, [vp, vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp]),
     "stil_masked_softce_workspace_bytes": (i64, [i64]),

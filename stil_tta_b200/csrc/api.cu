@@ -424,7 +424,8 @@ extern "C" {
 
 STIL_API int stil_version(void) { return STIL_VERSION; }
 STIL_API int64_t stil_abi_struct_bytes(int which) {
-    return which == 0 ? (int64_t)sizeof(stil_head_step_args) : which == 1 ? (int64_t)sizeof(stil_p2p_channel) : -1;
+    return which == 0 ? (int64_t)sizeof(stil_head_step_args) : which == 1 ? (int64_t)sizeof(stil_p2p_channel)
+           : which == 2 ? (int64_t)sizeof(stil_ema_entry) : -1;
 }
 STIL_API const char* stil_last_error(void) { return stil::last_error(); }
 
@@ -1651,6 +1652,15 @@ STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, in
     int rc = launch_da_hist_update(batch_mean, hist, hist_len, k, count, qmean_scratch, S(stream));
     if (rc) return rc;
     return launch_da_rows(probs, ld, rows, k, qmean_scratch, out, ld_out, S(stream));
+}
+
+// =============================================================================================== f-4
+STIL_API int stil_ema_update(const stil_ema_entry* table, int64_t n_entries, const int32_t* chunk_entry,
+                             const int64_t* chunk_start, int64_t n_chunks, int64_t chunk_elems, float momentum, void* stream) {
+    STIL_REQUIRE(n_chunks == 0 || (table && chunk_entry && chunk_start && n_entries >= 1), STIL_E_ARG, "ema_update: null pointer");
+    STIL_REQUIRE(chunk_elems >= 1 && chunk_elems % 16 == 0, STIL_E_ARG, "ema_update: chunk_elems must be a positive multiple of 16");
+    STIL_REQUIRE(n_chunks < (1LL << 31), STIL_E_SHAPE, "ema_update: too many chunks");
+    return launch_ema_update(table, chunk_entry, chunk_start, n_chunks, chunk_elems, momentum, S(stream));
 }
 
 // =============================================================================================== whole step

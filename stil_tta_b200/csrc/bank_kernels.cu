@@ -424,6 +424,73 @@ int launch_bank_update(void* bank, int b_dtype, int64_t ld_b, int64_t* labels, c
     return STIL_OK;
 }
 
+// =====================================================================================================================
+// f-4 — EMA teacher update (STiLModel.momentum_update_ema, STiLModel.py:154-168): the reference walks the state dict in
+// Python and issues mul_ / add_ (or copy_) per tensor, every step.  Here: ONE launch over a device table of tensors cut into
+// fixed-size chunks (a block per chunk).  Rounding mirrors the eager ops: ema*m, (1-m)*main and their sum are each rounded to
+// the tensor's dtype (no FMA contraction), so fp32 results are bit-identical to the reference's.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) ema_update_kernel(const stil_ema_entry* __restrict__ table, const int* __restrict__ chunk_entry,
+                                                         const long long* __restrict__ chunk_start, long long chunk_elems, float m,
+                                                         float om) {
+    const stil_ema_entry e = table[chunk_entry[blockIdx.x]];
+    const long long i0 = chunk_start[blockIdx.x];
+    const long long i1 = min((long long)e.numel, i0 + chunk_elems);
+    if (e.kind == 1) {
+        // plain copy (`num_batches_tracked`, :163-164): numel counts BYTES
+        const unsigned char* src = static_cast<const unsigned char*>(e.main);
+        unsigned char* dst = static_cast<unsigned char*>(e.ema);
+        if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)i0) & 15) == 0) {
+            long long i = i0 + 16LL * threadIdx.x;
+            for (; i + 16 <= i1; i += 16LL * blockDim.x) *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+            for (long long j = i0 + ((i1 - i0) / 16) * 16 + threadIdx.x; j < i1; j += blockDim.x) dst[j] = src[j];
+        } else {
+            for (long long j = i0 + threadIdx.x; j < i1; j += blockDim.x) dst[j] = src[j];
+        }
+        return;
+    }
+    if (e.dtype == STIL_F32) {
+        float* dst = static_cast<float*>(e.ema);
+        const float* src = static_cast<const float*>(e.main);
+        if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && (i0 & 3) == 0) {
+            long long i = i0 + 4LL * threadIdx.x;
+            for (; i + 4 <= i1; i += 4LL * blockDim.x) {
+                float4 a = *reinterpret_cast<const float4*>(dst + i);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(src + i));
+                a.x = __fadd_rn(__fmul_rn(a.x, m), __fmul_rn(om, b.x));
+                a.y = __fadd_rn(__fmul_rn(a.y, m), __fmul_rn(om, b.y));
+                a.z = __fadd_rn(__fmul_rn(a.z, m), __fmul_rn(om, b.z));
+                a.w = __fadd_rn(__fmul_rn(a.w, m), __fmul_rn(om, b.w));
+                *reinterpret_cast<float4*>(dst + i) = a;
+            }
+            for (long long j = i0 + ((i1 - i0) / 4) * 4 + threadIdx.x; j < i1; j += blockDim.x)
+                dst[j] = __fadd_rn(__fmul_rn(dst[j], m), __fmul_rn(om, src[j]));
+        } else {
+            for (long long j = i0 + threadIdx.x; j < i1; j += blockDim.x)
+                dst[j] = __fadd_rn(__fmul_rn(dst[j], m), __fmul_rn(om, src[j]));
+        }
+    } else {
+        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(e.ema);
+        const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(e.main);
+        for (long long j = i0 + threadIdx.x; j < i1; j += blockDim.x) {
+            const float a = __bfloat162float(__float2bfloat16_rn(__fmul_rn(__bfloat162float(dst[j]), m)));
+            const float b = __bfloat162float(__float2bfloat16_rn(__fmul_rn(om, __bfloat162float(src[j]))));
+            dst[j] = __float2bfloat16_rn(__fadd_rn(a, b));
+        }
+    }
+}
+
+int launch_ema_update(const stil_ema_entry* table, const int32_t* chunk_entry, const int64_t* chunk_start, int64_t n_chunks,
+                      int64_t chunk_elems, float momentum, cudaStream_t stream) {
+    if (n_chunks == 0) return STIL_OK;
+    // `(1. - self.momentum) * v_main`: the Python double is rounded to the tensor's computation type (fp32)
+    const float om = (float)(1.0 - (double)momentum);
+    ema_update_kernel<<<(unsigned)n_chunks, 256, 0, stream>>>(table, chunk_entry, reinterpret_cast<const long long*>(chunk_start),
+                                                              (long long)chunk_elems, momentum, om);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
 int launch_da_hist_update(const float* batch_mean, float* hist, int64_t hist_len, int64_t k, int64_t* count, float* qmean,
                           cudaStream_t stream) {
     da_hist_update_kernel<<<1, 256, 0, stream>>>(batch_mean, hist, (int)hist_len, (int)k, reinterpret_cast<long long*>(count),

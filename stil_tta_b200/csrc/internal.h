@@ -287,6 +287,8 @@ int launch_queue_enqueue(void* queue, int q_dtype, int64_t ld_q, float* qprobs, 
                          int64_t num_classes, cudaStream_t stream);
 int launch_bank_update(void* bank, int b_dtype, int64_t ld_b, int64_t* labels, const void* k, int k_dtype, int64_t ld_k,
                        const int64_t* y, const int64_t* index, int64_t n, int64_t dim, cudaStream_t stream);
+int launch_ema_update(const stil_ema_entry* table, const int32_t* chunk_entry, const int64_t* chunk_start, int64_t n_chunks,
+                      int64_t chunk_elems, float momentum, cudaStream_t stream);
 int launch_da_hist_update(const float* batch_mean, float* hist, int64_t hist_len, int64_t k, int64_t* count, float* qmean,
                           cudaStream_t stream);
 int launch_club_fwd(const void* mu, const void* y, int dtype, int64_t ld, int64_t rows, int64_t dim, float* stats, float* bound,
