@@ -56,6 +56,9 @@ STIL_API const char* stil_last_error(void);
 /* Debug aid: install (or clear with NULL) a device buffer of [64 launches][64 CTAs][8] uint64 into which the GEMM
  * kernel's CTAs store %globaltimer stamps of their phases (scripts/gemm_timeline.py).  Not for production use. */
 STIL_API int stil_debug_trace(void* buffer);
+/* Debug / measurement aid: 0 launches every kernel with plain stream serialisation instead of programmatic dependent launch
+ * (a profiler's per-kernel duration then excludes the dependent's wait for its predecessor); 1 restores the default. */
+STIL_API int stil_debug_pdl(int enable);
 /* 0 if the current device can run the kernels (compute capability 10.x), STIL_E_ARCH otherwise. */
 STIL_API int stil_check_device(void);
 
@@ -289,6 +292,7 @@ STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, in
  *   kind 0: ema = ema * momentum + (1 - momentum) * main   (dtype STIL_F32 / STIL_BF16; each product and the sum rounded like
  *           the eager ops, so fp32 results are bit-identical to the reference)
  *   kind 1: ema = main, byte copy (`num_batches_tracked`, :163-164); numel counts BYTES
+ * `momentum` is the Python double of the reference: m = (float)momentum and (float)(1.0 - momentum) are what the eager ops use.
  * `table` is a DEVICE array of n_entries stil_ema_entry; the tensors are cut into chunks of chunk_elems elements (bytes for
  * kind 1): chunk c covers elements [chunk_start[c], chunk_start[c] + chunk_elems) of entry chunk_entry[c] (both DEVICE arrays,
  * built once per model by the binding).  One block per chunk. */
@@ -300,7 +304,7 @@ typedef struct stil_ema_entry {
     int32_t kind;
 } stil_ema_entry;
 STIL_API int stil_ema_update(const stil_ema_entry* table, int64_t n_entries, const int32_t* chunk_entry,
-                             const int64_t* chunk_start, int64_t n_chunks, int64_t chunk_elems, float momentum, void* stream);
+                             const int64_t* chunk_start, int64_t n_chunks, int64_t chunk_elems, double momentum, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * f-2 — CLUBMean mutual-information bound and its learning loss, from mu = p_mu(x_samples) on.  Replaces the tensor code

@@ -67,6 +67,7 @@ SIGNATURES = {
     "stil_last_error": (C.c_char_p, []),
     "stil_check_device": (i32, []),
     "stil_debug_trace": (i32, [vp]),
+    "stil_debug_pdl": (i32, [i32]),
     "stil_infonce_workspace_bytes": (i64, [i64, i64, i64, i32]),
     "stil_infonce_fwd": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, i64, vp, i64, vp]),
     "stil_infonce_bwd": (i32, [vp, vp, vp, vp, i32, i64, i64, i64, i64, i64, f32, f32, vp, vp, vp, vp, vp, i32, i64,
@@ -126,7 +127,7 @@ SIGNATURES = {
     "stil_queue_enqueue": (i32, [vp, i32, i64, vp, i64, i64, vp, vp, i32, i64, i64, i64, vp, i64, i64, vp]),
     "stil_bank_update": (i32, [vp, i32, i64, vp, vp, i32, i64, vp, vp, i64, i64, vp]),
     "stil_da_apply_hist": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
-    "stil_ema_update": (i32, [vp, i64, vp, vp, i64, i64, f32, vp]),
+    "stil_ema_update": (i32, [vp, i64, vp, vp, i64, i64, C.c_double, vp]),
     "stil_club_fwd": (i32, [vp, vp, i32, i64, i64, i64, vp, vp, vp, vp]),
     "stil_club_bwd": (i32, [vp, vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp]),
     "stil_masked_softce_workspace_bytes": (i64, [i64]),

@@ -335,13 +335,30 @@ int infonce_dx_ksplit(int64_t m, int64_t n, int64_t dim) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(kblocks / 8, 148 / tiles));
 }
 
+// Cluster split-K of a dX GEMM whose tiles span `dim` (<= 128 columns, fused epilogue): `tiles` CTAs would each walk
+// `kblocks` operand stages at L2 -> shared-memory bandwidth; 2 / 4 / 8 CTAs per tile share the walk and the leader adds the
+// partial accumulators through distributed shared memory (gemm_tc05.cu).  1 = not worth it / not possible.
+int dx_cluster_k(int64_t tiles, int64_t kblocks) {
+    static const int forced = [] { const char* e = getenv("STIL_DX_CLUSTER"); return e ? atoi(e) : -1; }();
+    if (forced >= 0) return forced <= 1 ? 1 : forced;
+    int ck = 1;
+    while (ck < 8 && tiles * ck * 2 <= 148 && kblocks / (ck * 2) >= 2) ck *= 2;
+    return ck;
+}
+
 // d(x̂_i) = sum_j G'_ij y_j, then the backward of F.normalize in the epilogue when one tile spans `dim`
 int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const Operand& B, const void* a_all,
                        const void* b_all, int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t off,
-                       void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, bool* fused) {
+                       void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, bool* fused, int* cluster_k) {
     const int esz = dtype == STIL_BF16 ? 2 : 4;
-    const int ksplit = infonce_dx_ksplit(m, n, dim);
-    *fused = dim <= kTileN && ksplit == 1;
+    int ksplit = infonce_dx_ksplit(m, n, dim);
+    *cluster_k = 1;
+    if (dim <= kTileN) {
+        // one tile spans the embedding: split the contraction over a CLUSTER and keep the fused epilogue
+        const int ck = dx_cluster_k(2 * ceil_div(m, kTileM), ceil_div(n, kTileK) * grad_nseg(grad_dtype) * B.nseg);
+        ksplit = *cluster_k = (int)std::min<int64_t>(ck, ceil_div(n, kTileK));
+    }
+    *fused = dim <= kTileN;
     for (int s = 0; s < 2; ++s) {
         const Operand X = grad_operand(P.gop[s], P.ldg, grad_nseg(grad_dtype));
         const Operand& Y = s == 0 ? B : A;
@@ -416,6 +433,8 @@ int get_side_streams(SideStreams** out) {
 }
 
 }  // namespace
+bool g_pdl_enabled = true;
+bool pdl_enabled() { return g_pdl_enabled; }
 }  // namespace stil
 
 using namespace stil;
@@ -430,6 +449,11 @@ STIL_API int64_t stil_abi_struct_bytes(int which) {
 STIL_API const char* stil_last_error(void) { return stil::last_error(); }
 
 STIL_API int stil_debug_trace(void* buffer) { return gemm_set_trace(buffer); }
+
+STIL_API int stil_debug_pdl(int enable) {
+    stil::g_pdl_enabled = enable != 0;
+    return STIL_OK;
+}
 
 STIL_API int stil_check_device(void) {
     int dev = 0;
@@ -528,10 +552,12 @@ int infonce_bwd_impl(const void* a_all, const void* b_all, int dtype,
     GemmLaunch GS, GB;
     std::memset(&GS, 0, sizeof(GS));
     bool fused = false;
+    int dx_ck = 1;
     if ((rc = infonce_store_jobs(GS.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
-                                 ld_grad, &fused)))
+                                 ld_grad, &fused, &dx_ck)))
         return rc;
     GS.njobs = 2;
+    GS.cluster_k = dx_ck;
     gemm_job_tiles(GS);
     if (fuse_bwd(GB, GL, GS)) {
         if ((rc = launch_gemm(GB, S(stream)))) return rc;       // recompute + dLogits + dX in one kernel
@@ -704,10 +730,12 @@ STIL_API int stil_infonce_bwd_gathered(const void* a_all, const void* b_all, con
     GemmLaunch GS, GB;
     std::memset(&GS, 0, sizeof(GS));
     bool fused = false;
+    int dx_ck = 1;
     if ((rc = infonce_store_jobs(GS.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
-                                 ld_grad, &fused)))
+                                 ld_grad, &fused, &dx_ck)))
         return rc;
     GS.njobs = 2;
+    GS.cluster_k = dx_ck;
     gemm_job_tiles(GS);
     if (fuse_bwd(GB, GL, GS)) {
         if ((rc = launch_gemm(GB, S(stream)))) return rc;
@@ -897,6 +925,10 @@ int proto_store_job(GemmJob& J, const ProtoPlan& P, int64_t rows, int64_t dim, i
     if (rc) return rc;
     *fused = dim <= kTileN;
     if (*fused) {
+        // the contraction over the classes is split over a cluster (see dx_cluster_k); the caller copies J.ksplit into
+        // GemmLaunch::cluster_k
+        const int ck = dx_cluster_k(ceil_div(rows, kTileM), ceil_div(k, kTileK) * J.npair);
+        J.ksplit = (int)std::min<int64_t>(ck, ceil_div(k, kTileK));
         J.fin_dx = d_feat;
         J.fin_dx_dtype = grad_dtype;
         J.fin_ld_dx = ld_grad;
@@ -981,6 +1013,7 @@ STIL_API int stil_proto_ce_bwd(const void* feat, int dtype, int64_t rows, int64_
     bool fused = false;
     if ((rc = proto_store_job(GS.job[0], P, rows, dim, k, d_feat, grad_dtype, ld_grad, &fused))) return rc;
     GS.njobs = 1;
+    GS.cluster_k = fused ? GS.job[0].ksplit : 1;
     gemm_job_tiles(GS);
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
     if ((rc = launch_gemm(GS, S(stream)))) return rc;
@@ -1656,7 +1689,7 @@ STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, in
 
 // =============================================================================================== f-4
 STIL_API int stil_ema_update(const stil_ema_entry* table, int64_t n_entries, const int32_t* chunk_entry,
-                             const int64_t* chunk_start, int64_t n_chunks, int64_t chunk_elems, float momentum, void* stream) {
+                             const int64_t* chunk_start, int64_t n_chunks, int64_t chunk_elems, double momentum, void* stream) {
     STIL_REQUIRE(n_chunks == 0 || (table && chunk_entry && chunk_start && n_entries >= 1), STIL_E_ARG, "ema_update: null pointer");
     STIL_REQUIRE(chunk_elems >= 1 && chunk_elems % 16 == 0, STIL_E_ARG, "ema_update: chunk_elems must be a positive multiple of 16");
     STIL_REQUIRE(n_chunks < (1LL << 31), STIL_E_SHAPE, "ema_update: too many chunks");
@@ -1849,6 +1882,7 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         } else {
             if ((rc = proto_store_job(GS.job[0], P.pt, B, D, K, a->d_feat_m, a->grad_dtype, D, &fused_pt))) return rc;
             GS.njobs = 1;
+            GS.cluster_k = fused_pt ? GS.job[0].ksplit : 1;
             gemm_job_tiles(GS);
             if ((rc = launch_gemm(GL, st))) return rc;
             if ((rc = mark(7, st))) return rc;
@@ -1897,10 +1931,12 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         set_early(GL, true, true);    // predecessor = STATS: operands were final two kernels ago
         GemmLaunch GS, GB;
         std::memset(&GS, 0, sizeof(GS));
+        int dx_ck = 1;
         if ((rc = infonce_store_jobs(GS.job, P.nce, A, Bm, a->feat_i, a->feat_t, dt, B, B, D, D, 0, a->d_feat_i,
-                                     a->d_feat_t, a->grad_dtype, D, &fused)))
+                                     a->d_feat_t, a->grad_dtype, D, &fused, &dx_ck)))
             return rc;
         GS.njobs = 2;
+        GS.cluster_k = dx_ck;
         gemm_job_tiles(GS);
         if (fuse_bwd(GB, GL, GS)) {
             if ((rc = launch_gemm(GB, s_nce))) return rc;

@@ -481,12 +481,12 @@ __global__ void __launch_bounds__(256) ema_update_kernel(const stil_ema_entry* _
 }
 
 int launch_ema_update(const stil_ema_entry* table, const int32_t* chunk_entry, const int64_t* chunk_start, int64_t n_chunks,
-                      int64_t chunk_elems, float momentum, cudaStream_t stream) {
+                      int64_t chunk_elems, double momentum, cudaStream_t stream) {
     if (n_chunks == 0) return STIL_OK;
     // `(1. - self.momentum) * v_main`: the Python double is rounded to the tensor's computation type (fp32)
-    const float om = (float)(1.0 - (double)momentum);
+    const float om = (float)(1.0 - momentum);
     ema_update_kernel<<<(unsigned)n_chunks, 256, 0, stream>>>(table, chunk_entry, reinterpret_cast<const long long*>(chunk_start),
-                                                              (long long)chunk_elems, momentum, om);
+                                                              (long long)chunk_elems, (float)momentum, om);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }

@@ -62,6 +62,35 @@ inline void prefer_max_shared(K kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+bool pdl_enabled();            // api.cu (stil_debug_pdl)
+
+// cluster_x > 1: the grid is launched as thread-block clusters of cluster_x consecutive blocks (gridDim.x % cluster_x == 0)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+    static const bool no_pdl = [] { const char* e = getenv("STIL_NO_PDL"); return e && e[0] == '1'; }();
+    if (!no_pdl && pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args&&... args) {
@@ -74,9 +103,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    // STIL_NO_PDL=1 (debug / measurement): plain stream serialisation for every launch
+    // STIL_NO_PDL=1 / stil_debug_pdl(0) (debug / measurement): plain stream serialisation for every launch, so that a
+    // profiler's per-kernel duration is the kernel's own time (with PDL a dependent's duration includes its wait)
     static const bool no_pdl = [] { const char* e = getenv("STIL_NO_PDL"); return e && e[0] == '1'; }();
-    cfg.numAttrs = no_pdl ? 0 : 1;
+    cfg.numAttrs = (no_pdl || !pdl_enabled()) ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
     const GemmJob& J = L.job[jid];
     int t = blockIdx.x - J.tile_begin;
     const int ksplit = (MODE == GEMM_STORE && J.ksplit > 1) ? J.ksplit : 1;
+    // cluster split-K (see GemmLaunch::cluster_k): the ksplit CTAs of a tile are consecutive blocks = one cluster
+    const bool clustered = MODE == GEMM_STORE && L.cluster_k > 1;
     const int ks = t % ksplit;
     t /= ksplit;
     const int tm = t / J.tiles_n, tn = t % J.tiles_n;
@@ -324,6 +326,10 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                 STIL_TRACE(2);
             }
         }
+        if (clustered) {   // the two cluster barriers of the split-K reduction (every thread of the cluster takes part)
+            tc05::cluster_arrive(); tc05::cluster_wait();
+            tc05::cluster_arrive(); tc05::cluster_wait();
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
@@ -351,6 +357,10 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
             if (nkb > 0) tc05::mma_commit(tmem_full_bar);
             else tc05::mbar_arrive(tmem_full_bar);   // empty slice of a split contraction: nothing to wait for
             STIL_TRACE(3);
+        }
+        if (clustered) {
+            tc05::cluster_arrive(); tc05::cluster_wait();
+            tc05::cluster_arrive(); tc05::cluster_wait();
         }
     } else {
         // ===================== epilogue: kEpiWarps warps, thread = accumulator row, kParts warps per TMEM lane
@@ -437,8 +447,67 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int c_begin = part * kCPW, c_end = c_begin + kCPW;   // this warp's 32-column chunks
 
+        bool cluster_follower = false;
+        if (MODE == GEMM_STORE && clustered) {
+            // Partial tile [128 x 128] fp32 in this CTA's (now idle) operand ring: row r holds 32 16-byte slots, slot s of row r
+            // is stored at s ^ (r & 31), so that the 32 rows of a warp hit 32 different slots (no bank conflicts on either
+            // side).  The raw accumulator travels: scales are linear and applied once, by the leader.
+            const int r_in = q * 32 + lane;
+            if (ks != 0) {
+                cluster_follower = true;
+                float4* mine = reinterpret_cast<float4*>(tiles) + r_in * 32;
+#pragma unroll 1
+                for (int c = c_begin; c < c_end; ++c) {
+                    uint32_t acc[32];
+                    if (nkb > 0) {
+                        tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
+                        tc05::tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = 0u;     // empty slice: the accumulator was never written
+                    }
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; ++s8)
+                        mine[(c * 8 + s8) ^ (r_in & 31)] = make_float4(__uint_as_float(acc[4 * s8]), __uint_as_float(acc[4 * s8 + 1]),
+                                                                       __uint_as_float(acc[4 * s8 + 2]), __uint_as_float(acc[4 * s8 + 3]));
+                }
+                tc05::cluster_arrive(); tc05::cluster_wait();     // partial published
+                tc05::cluster_arrive(); tc05::cluster_wait();     // the leader has read it: the CTA may retire
+            } else {
+                tc05::cluster_arrive(); tc05::cluster_wait();     // every follower's partial is in its shared memory
+                const uint32_t local = tc05::smem_u32(reinterpret_cast<float4*>(tiles) + r_in * 32);
+#pragma unroll 1
+                for (int c = c_begin; c < c_end; ++c) {
+                    uint32_t acc[32];
+                    if (nkb > 0) {
+                        tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
+                        tc05::tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = 0u;
+                    }
+                    for (int peer = 1; peer < ksplit; ++peer) {       // fixed order: deterministic
+                        const uint32_t remote = tc05::map_to_cta(local, (uint32_t)peer);
+                        float4 v[8];
+#pragma unroll
+                        for (int s8 = 0; s8 < 8; ++s8) v[s8] = tc05::ld_dsmem_f4(remote + (((c * 8 + s8) ^ (r_in & 31)) << 4));
+#pragma unroll
+                        for (int s8 = 0; s8 < 8; ++s8) {
+                            acc[4 * s8] = __float_as_uint(__uint_as_float(acc[4 * s8]) + v[s8].x);
+                            acc[4 * s8 + 1] = __float_as_uint(__uint_as_float(acc[4 * s8 + 1]) + v[s8].y);
+                            acc[4 * s8 + 2] = __float_as_uint(__uint_as_float(acc[4 * s8 + 2]) + v[s8].z);
+                            acc[4 * s8 + 3] = __float_as_uint(__uint_as_float(acc[4 * s8 + 3]) + v[s8].w);
+                        }
+                    }
+                    tc05::tmem_st_32x32b_x32(taddr + c * 32, acc);   // the summed tile replaces this CTA's accumulator
+                }
+                tc05::tmem_st_wait();
+                tc05::cluster_arrive();                               // followers may retire (waited for at the very end)
+            }
+        }
+
         float fin_dot = 0.f;
-        if (MODE == GEMM_STORE && fused_fin && J.fin_sx) {
+        if (MODE == GEMM_STORE && fused_fin && J.fin_sx && !cluster_follower) {
             // pass 1 of the normalise-backward: <xh, g> over the whole row (the tile spans all of N)
             float part_dot = 0.f;
 #pragma unroll
@@ -459,7 +528,7 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
         }
 
 #pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
+        for (int c = c_begin; c < (cluster_follower ? c_begin : c_end); ++c) {
             float run_max = -INFINITY, run_sum = 0.f;
             if (c * 32 >= ncols) {   // warp-uniform: an empty chunk contributes the neutral statistics (-inf, 0)
                 if (MODE == GEMM_STATS && row_ok) {
@@ -504,7 +573,7 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                     }
                 }
                 if (row_ok) store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + n0 + c * 32, nv, l);
-            } else if (MODE == GEMM_STORE && ksplit > 1 && J.slice_stride == 0) {
+            } else if (MODE == GEMM_STORE && ksplit > 1 && J.slice_stride == 0 && !clustered) {
                 // split contraction: add this CTA's partial tile (an empty slice adds nothing)
                 if (row_ok && nkb > 0) {
                     float* dst = J.out + (long long)row * J.ld_out + n0 + c * 32;
@@ -532,13 +601,13 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                 float* stg = reinterpret_cast<float*>(tiles) + (warp - 2) * kStageFloats;
                 // split contraction with per-slice outputs (deterministic: the consumer adds the slices in order);
                 // an empty slice stores zeros (its accumulator was never written)
-                const bool empty_slice = MODE == GEMM_STORE && ksplit > 1 && nkb == 0;
+                const bool empty_slice = MODE == GEMM_STORE && ksplit > 1 && nkb == 0 && !clustered;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = empty_slice ? 0.f : l[j];
                 __syncwarp();
                 {
                     const int rbase = m0 + q * 32;
-                    float* obase = J.out + (MODE == GEMM_STORE ? (long long)ks * J.slice_stride : 0ll) +
+                    float* obase = J.out + ((MODE == GEMM_STORE && !clustered) ? (long long)ks * J.slice_stride : 0ll) +
                                    (long long)rbase * J.ld_out + n0 + c * 32 + lane;
                     const int rmax = min(32, J.M - rbase);
                     if (lane < nv) {
@@ -600,6 +669,7 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
     }
 
     // ---- teardown: all TMEM reads done before dealloc
+    if (MODE == GEMM_STORE && clustered && warp >= 2 && ks == 0) tc05::cluster_wait();   // second cluster barrier (leader side)
     tc05::fence_before_sync();
     __syncthreads();
     if (threadIdx.x == 0) STIL_TRACE(6);
@@ -1004,6 +1074,11 @@ static int launch_gemm_mode(const GemmLaunch& L, cudaStream_t stream) {
         if (attr_err == cudaSuccess) prefer_max_shared(gemm_tc05_kernel<MODE, OCC>);
     });
     STIL_CUDA(attr_err);
+    if (MODE == GEMM_STORE && L.cluster_k > 1) {
+        STIL_CUDA(launch_pdl_cluster(gemm_tc05_kernel<MODE, OCC>, dim3(L.total_tiles), dim3(threads_for(OCC)), smem, stream,
+                                     L.cluster_k, L));
+        return STIL_OK;
+    }
     STIL_CUDA(launch_pdl(gemm_tc05_kernel<MODE, OCC>, dim3(L.total_tiles), dim3(threads_for(OCC)), smem, stream, L));
     return STIL_OK;
 }
@@ -1091,6 +1166,12 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
             int rc = make_operand_map(&J.tmg, J.gop, J.ld_g, J.M, J.g_nseg, (int64_t)J.g_nseg * J.ld_g, J.ld_g, kTileM);
             if (rc) return rc;
         }
+    }
+    if (L.cluster_k > 1) {
+        STIL_REQUIRE(mode == GEMM_STORE && L.cluster_k <= 8, STIL_E_ARG, "cluster split-K needs GEMM_STORE and cluster_k <= 8");
+        for (int j = 0; j < L.njobs; ++j)
+            STIL_REQUIRE(L.job[j].ksplit == L.cluster_k && L.job[j].slice_stride == 0, STIL_E_ARG,
+                         "cluster split-K: every job's ksplit must equal cluster_k (no slice outputs)");
     }
     if (mode == GEMM_BWD) return launch_gemm_bwd(L, stream);
     // more tiles than SMs: two CTAs per SM (3-deep rings) so epilogues overlap main loops

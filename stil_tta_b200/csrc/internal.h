@@ -105,6 +105,11 @@ struct GemmLaunch {
     GemmJob job[kMaxGemmJobs];
     int njobs;
     int total_tiles;
+    // GEMM_STORE with a split contraction reduced ON CHIP: the `cluster_k` CTAs that share a tile (every job's ksplit must
+    // equal cluster_k, 2..8) are launched as one thread-block cluster; the non-leaders publish their raw partial accumulator
+    // in their own shared memory, the leader adds them through distributed shared memory into its TMEM accumulator and runs the
+    // normal epilogue (fused normalise-backward included) — no partial tiles in global memory, no reduction kernel.  0/1 = off.
+    int cluster_k;
     unsigned int trace_id;   // launch ordinal for the optional timeline trace
     unsigned long long* trace;   // nullptr unless stil_debug_trace installed a buffer
 };
@@ -288,7 +293,7 @@ int launch_queue_enqueue(void* queue, int q_dtype, int64_t ld_q, float* qprobs, 
 int launch_bank_update(void* bank, int b_dtype, int64_t ld_b, int64_t* labels, const void* k, int k_dtype, int64_t ld_k,
                        const int64_t* y, const int64_t* index, int64_t n, int64_t dim, cudaStream_t stream);
 int launch_ema_update(const stil_ema_entry* table, const int32_t* chunk_entry, const int64_t* chunk_start, int64_t n_chunks,
-                      int64_t chunk_elems, float momentum, cudaStream_t stream);
+                      int64_t chunk_elems, double momentum, cudaStream_t stream);
 int launch_da_hist_update(const float* batch_mean, float* hist, int64_t hist_len, int64_t k, int64_t* count, float* qmean,
                           cudaStream_t stream);
 int launch_club_fwd(const void* mu, const void* y, int dtype, int64_t ld, int64_t rows, int64_t dim, float* stats, float* bound,
