@@ -341,8 +341,13 @@ int infonce_dx_ksplit(int64_t m, int64_t n, int64_t dim) {
 int dx_cluster_k(int64_t tiles, int64_t kblocks) {
     static const int forced = [] { const char* e = getenv("STIL_DX_CLUSTER"); return e ? atoi(e) : -1; }();
     if (forced >= 0) return forced <= 1 ? 1 : forced;
+    // Measured on the C2 step (512 x 512 x 128, 16 stages per CTA): clusters of 4-8 made the dX GEMMs 2-3x SLOWER (27.6 us
+    // against 9.0 us in the captured step): a cluster needs all its SMs free in ONE GPC at the same time, which the other
+    // chains' one-CTA-per-SM kernels rarely leave, and the barrier + distributed-shared-memory round trips cost more than the
+    // 2-3 us of operand streaming they save.  So: only long walks (>= 16 stages left per CTA: the global batch of 2+ ranks),
+    // and at most 4 CTAs per tile.
     int ck = 1;
-    while (ck < 8 && tiles * ck * 2 <= 148 && kblocks / (ck * 2) >= 2) ck *= 2;
+    while (ck < 4 && tiles * ck * 2 <= 148 && kblocks / (ck * 2) >= 16) ck *= 2;
     return ck;
 }
 
