@@ -287,6 +287,25 @@ STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, in
                                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * f-3 — the Linear layers either side of the head: projector_imaging / projector_tabular = nn.Linear(512, 128) followed
+ * by F.normalize (STiLModel.py:56-63, project_3features :182-192) and the classifier Linears that produce y_hat_m/i/t
+ * (models/Disentangle/utils/STiLModel_backbone.py:66-68, 153-155).
+ *   fwd: y = x · weightᵀ + bias  (weight [out_dim, in_dim] f32, bias [out_dim] f32 or NULL), fp32-accurate on the tensor
+ *        cores (3 x bf16 split); with `normalize` (out_dim <= 128) the rows are L2-normalised in the GEMM epilogue like
+ *        F.normalize (eps 1e-12): y receives the unit rows, y_raw [rows, out_dim] the biased product and inv_norm [rows]
+ *        1 / max(||row||, eps) — both needed by bwd.
+ *   bwd: d_y [rows, out_dim] f32 -> d_x [rows, in_dim] (grad_dtype; NULL to skip), d_weight [out_dim, in_dim] f32,
+ *        d_bias [out_dim] f32 (each NULL to skip); y_raw / inv_norm from fwd when it normalised, NULL otherwise. */
+STIL_API int64_t stil_linear_workspace_bytes(int64_t rows, int64_t in_dim, int64_t out_dim, int dtype);
+STIL_API int stil_linear_fwd(const void* x, int dtype, int64_t rows, int64_t in_dim, int64_t ld_x, const float* weight,
+                             const float* bias, int64_t out_dim, int normalize, float* y, int64_t ld_y, float* y_raw,
+                             float* inv_norm, void* workspace, int64_t workspace_bytes, void* stream);
+STIL_API int stil_linear_bwd(const void* x, int dtype, int64_t rows, int64_t in_dim, int64_t ld_x, const float* weight,
+                             int64_t out_dim, const float* y_raw, const float* inv_norm, const float* d_y, int64_t ld_dy,
+                             void* d_x, int grad_dtype, int64_t ld_dx, float* d_weight, float* d_bias, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * f-4 — EMA teacher update.  Replaces STiLModel.momentum_update_ema (STiLModel.py:154-168), a per-tensor Python loop of
  * mul_ / add_ / copy_ over the whole state dict every step, by ONE launch over a device-resident table:
  *   kind 0: ema = ema * momentum + (1 - momentum) * main   (dtype STIL_F32 / STIL_BF16; each product and the sum rounded like

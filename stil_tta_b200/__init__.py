@@ -17,6 +17,7 @@ _LAZY = {
     "comatch_graphs": "bank_blocks", "graph_contrast_loss": "bank_blocks", "masked_ce": "bank_blocks",
     "queue_enqueue": "bank_blocks", "update_bank": "bank_blocks", "HistAlignment": "bank_blocks",
     "SmoothedLabels": "bank_blocks",
+    "Linear": "linear", "linear": "linear",
     "EmaTeacher": "ema", "momentum_update_ema": "ema",
     "CLUBMean": "club", "club_bound": "club", "club_learning_loss": "club", "club_both": "club", "STiLHead": "head", "DistributedSTiLHead": "head", "GlobalBatch": "distributed", "P2PBuffer": "distributed", "all_reduce_prototype_partials": "distributed",
 }

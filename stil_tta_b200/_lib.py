@@ -127,6 +127,9 @@ SIGNATURES = {
     "stil_queue_enqueue": (i32, [vp, i32, i64, vp, i64, i64, vp, vp, i32, i64, i64, i64, vp, i64, i64, vp]),
     "stil_bank_update": (i32, [vp, i32, i64, vp, vp, i32, i64, vp, vp, i64, i64, vp]),
     "stil_da_apply_hist": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
+    "stil_linear_workspace_bytes": (i64, [i64, i64, i64, i32]),
+    "stil_linear_fwd": (i32, [vp, i32, i64, i64, i64, vp, vp, i64, i32, vp, i64, vp, vp, vp, i64, vp]),
+    "stil_linear_bwd": (i32, [vp, i32, i64, i64, i64, vp, i64, vp, vp, vp, i64, vp, i32, i64, vp, vp, vp, i64, vp]),
     "stil_ema_update": (i32, [vp, i64, vp, vp, i64, i64, C.c_double, vp]),
     "stil_club_fwd": (i32, [vp, vp, i32, i64, i64, i64, vp, vp, vp, vp]),
     "stil_club_bwd": (i32, [vp, vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp]),

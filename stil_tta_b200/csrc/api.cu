@@ -1692,6 +1692,153 @@ STIL_API int stil_da_apply_hist(const float* probs, int64_t ld, int64_t rows, in
     return launch_da_rows(probs, ld, rows, k, qmean_scratch, out, ld_out, S(stream));
 }
 
+// =============================================================================================== f-3
+// Linear (+ bias) (+ F.normalize) feeding the head: projector_imaging / projector_tabular = nn.Linear(512, 128) followed by
+// F.normalize (STiLModel.py:56-63, 182-192) and the three classifier Linears (STiLModel_backbone.py:66-68, 153-155).
+namespace {
+struct LinearPlan {
+    __nv_bfloat16 *x_op, *w_op, *g_op;   // [rows,3,in] (fp32 x only) | [out,3,in] | [rows,3,out]
+    float* g;                            // [rows, out] gradient w.r.t. the pre-normalisation output
+    int64_t bytes;
+};
+LinearPlan plan_linear(void* ws, int64_t ws_bytes, int64_t rows, int64_t in_dim, int64_t out_dim, int dtype) {
+    LinearPlan P;
+    Workspace W(ws, ws_bytes);
+    P.x_op = dtype == STIL_BF16 ? nullptr : W.take<__nv_bfloat16>(rows * 3 * in_dim);
+    P.w_op = W.take<__nv_bfloat16>(out_dim * 3 * in_dim);
+    P.g_op = W.take<__nv_bfloat16>(rows * 3 * round_up(out_dim, 8));   // rows padded to 16-byte granularity
+    P.g = W.take<float>(rows * out_dim);
+    P.bytes = W.off;
+    return P;
+}
+int linear_checks(const void* x, int dtype, int64_t rows, int64_t in_dim, int64_t ld_x, const float* weight, int64_t out_dim,
+                  const char* what) {
+    int rc = check_embed(x, dtype, rows, in_dim, ld_x, what);
+    if (rc) return rc;
+    if ((rc = check_embed(weight, STIL_F32, out_dim, in_dim, in_dim, "linear weight"))) return rc;
+    STIL_REQUIRE(out_dim >= 1 && out_dim <= 16384, STIL_E_SHAPE, "%s: out_dim %lld out of range", what, (long long)out_dim);
+    return STIL_OK;
+}
+}  // namespace
+
+STIL_API int64_t stil_linear_workspace_bytes(int64_t rows, int64_t in_dim, int64_t out_dim, int dtype) {
+    return plan_linear(nullptr, 0, rows, in_dim, out_dim, dtype).bytes;
+}
+
+STIL_API int stil_linear_fwd(const void* x, int dtype, int64_t rows, int64_t in_dim, int64_t ld_x, const float* weight,
+                             const float* bias, int64_t out_dim, int normalize, float* y, int64_t ld_y, float* y_raw,
+                             float* inv_norm, void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = linear_checks(x, dtype, rows, in_dim, ld_x, weight, out_dim, "linear_fwd x");
+    if (rc) return rc;
+    STIL_REQUIRE(y && ld_y >= out_dim, STIL_E_ARG, "linear_fwd: bad output");
+    STIL_REQUIRE(!normalize || (out_dim <= kTileN && y_raw && inv_norm), STIL_E_SHAPE,
+                 "linear_fwd: the fused F.normalize needs out_dim <= %d and the y_raw / inv_norm outputs", kTileN);
+    LinearPlan P = plan_linear(workspace, workspace_bytes, rows, in_dim, out_dim, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "linear workspace too small: need %lld", (long long)P.bytes);
+    if (rows == 0) return STIL_OK;
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    if (dtype != STIL_BF16) prep_add(PL, prep_job(x, dtype, rows, in_dim, ld_x, 3, P.x_op, nullptr, 0, 0, nullptr));
+    prep_add(PL, prep_job(weight, STIL_F32, out_dim, in_dim, in_dim, 3, P.w_op, nullptr, 0, 0, nullptr));
+    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    const Operand X = rowmajor_operand(x, dtype, in_dim, ld_x, P.x_op, 3);
+    const Operand Wt = rowmajor_operand(nullptr, STIL_F32, in_dim, in_dim, P.w_op, 3);
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    if ((rc = fill_gemm_common(GL.job[0], X, 0, rows, Wt, out_dim, in_dim))) return rc;      // y = x · Wᵀ, fp32-accurate pairs
+    GemmJob& J = GL.job[0];
+    J.mode = GEMM_STORE;
+    J.out = y; J.ld_out = ld_y;
+    J.col_bias = bias;
+    J.fwd_norm = normalize ? 1 : 0;
+    J.fwd_inv_norm = inv_norm;
+    J.fwd_raw = y_raw; J.fwd_ld_raw = out_dim;
+    GL.njobs = 1;
+    gemm_job_tiles(GL);
+    return launch_gemm(GL, S(stream));
+}
+
+STIL_API int stil_linear_bwd(const void* x, int dtype, int64_t rows, int64_t in_dim, int64_t ld_x, const float* weight,
+                             int64_t out_dim, const float* y_raw, const float* inv_norm, const float* d_y, int64_t ld_dy,
+                             void* d_x, int grad_dtype, int64_t ld_dx, float* d_weight, float* d_bias, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+    int rc = linear_checks(x, dtype, rows, in_dim, ld_x, weight, out_dim, "linear_bwd x");
+    if (rc) return rc;
+    STIL_REQUIRE(d_y && ld_dy >= out_dim && (d_x || d_weight || d_bias), STIL_E_ARG, "linear_bwd: bad arguments");
+    STIL_REQUIRE((inv_norm == nullptr) == (y_raw == nullptr), STIL_E_ARG, "linear_bwd: y_raw and inv_norm go together");
+    STIL_REQUIRE(grad_dtype == STIL_F32 || grad_dtype == STIL_BF16, STIL_E_DTYPE, "bad grad dtype");
+    LinearPlan P = plan_linear(workspace, workspace_bytes, rows, in_dim, out_dim, dtype);
+    STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "linear workspace too small");
+    if (rows == 0) {
+        if (d_weight) STIL_CUDA(cudaMemsetAsync(d_weight, 0, out_dim * in_dim * sizeof(float), S(stream)));
+        if (d_bias) STIL_CUDA(cudaMemsetAsync(d_bias, 0, out_dim * sizeof(float), S(stream)));
+        return STIL_OK;
+    }
+    // 1. g = backward of F.normalize applied to d_y (or d_y itself): [rows, out] f32
+    const float* g = d_y;
+    int64_t ld_g = ld_dy;
+    if (inv_norm) {
+        GradFinishLaunch GF;
+        std::memset(&GF, 0, sizeof(GF));
+        GradFinishJob& j = GF.job[0];
+        STIL_REQUIRE(ld_dy == out_dim, STIL_E_SHAPE, "linear_bwd: d_y must be contiguous when the output was normalised");
+        j.g = d_y; j.x = y_raw; j.x_dtype = STIL_F32; j.ldx = out_dim; j.sx = inv_norm;
+        j.dx = P.g; j.dx_dtype = STIL_F32; j.ld_dx = out_dim;
+        j.rows = (int)rows; j.dim = (int)out_dim;
+        GF.njobs = 1;
+        GF.total_rows = (int)rows;
+        if ((rc = launch_grad_finish(GF, S(stream)))) return rc;
+        g = P.g;
+        ld_g = out_dim;
+    }
+    if (d_bias && (rc = launch_col_sum(g, ld_g, rows, out_dim, d_bias, S(stream)))) return rc;
+    // 2. operands: g as three bf16 segments [rows, 3, out]; the weight (and an fp32 x) likewise
+    PrepLaunch PL;
+    std::memset(&PL, 0, sizeof(PL));
+    const int64_t og = round_up(out_dim, 8);
+    {
+        PrepJob pj = prep_job(g, STIL_F32, rows, out_dim, ld_g, 3, P.g_op, nullptr, 0, 0, nullptr);
+        pj.op_dim = (int)og;          // zero-filled beyond out_dim
+        prep_add(PL, pj);
+    }
+    if (d_x) prep_add(PL, prep_job(weight, STIL_F32, out_dim, in_dim, in_dim, 3, P.w_op, nullptr, 0, 0, nullptr));
+    if (d_weight && dtype != STIL_BF16) prep_add(PL, prep_job(x, dtype, rows, in_dim, ld_x, 3, P.x_op, nullptr, 0, 0, nullptr));
+    if ((rc = launch_prep(PL, S(stream)))) return rc;
+    Operand G;
+    G.base = P.g_op; G.nseg = 3; G.row_stride = 3 * og; G.seg_stride = og;
+    GemmLaunch GL;
+    std::memset(&GL, 0, sizeof(GL));
+    int nj = 0;
+    if (d_x) {
+        // d_x = g · W: contraction over out; W [out, 3, in] read as an MN-major operand (in contiguous)
+        Operand Wm;
+        Wm.base = P.w_op; Wm.nseg = 3; Wm.row_stride = 3 * in_dim; Wm.seg_stride = in_dim;
+        GemmJob& J = GL.job[nj++];
+        if ((rc = fill_gemm_store_mn(J, G, rows, Wm, out_dim, in_dim))) return rc;
+        J.npair = seg_pairs(G.nseg, Wm.nseg, 2, J.xseg, J.yseg);
+        J.fin_dx = d_x; J.fin_dx_dtype = grad_dtype; J.fin_ld_dx = ld_dx;       // plain cast / store epilogue
+    }
+    if (d_weight) {
+        // d_W = gᵀ · x: contraction over the ROWS of both row-major matrices (X and Y MN-major)
+        Operand Xm;
+        if (dtype == STIL_BF16) { Xm.base = static_cast<const __nv_bfloat16*>(x); Xm.nseg = 1; Xm.row_stride = ld_x; Xm.seg_stride = in_dim; }
+        else { Xm.base = P.x_op; Xm.nseg = 3; Xm.row_stride = 3 * in_dim; Xm.seg_stride = in_dim; }
+        GemmJob& J = GL.job[nj++];
+        std::memset(&J, 0, sizeof(J));
+        if ((rc = make_operand_map(&J.tmx, G.base, out_dim, rows, G.nseg, G.row_stride, G.seg_stride, 64))) return rc;
+        if ((rc = make_operand_map(&J.tmy, Xm.base, in_dim, rows, Xm.nseg, Xm.row_stride, Xm.seg_stride, 64))) return rc;
+        J.M = (int)out_dim; J.N = (int)in_dim; J.D = (int)rows;
+        J.npair = seg_pairs(G.nseg, Xm.nseg, 2, J.xseg, J.yseg);
+        J.alpha = 1.f;
+        J.mode = GEMM_STORE;
+        J.x_mn_major = 1; J.y_mn_major = 1;
+        J.out = d_weight; J.ld_out = in_dim;
+    }
+    GL.njobs = nj;
+    gemm_job_tiles(GL);
+    return launch_gemm(GL, S(stream));
+}
+
 // =============================================================================================== f-4
 STIL_API int stil_ema_update(const stil_ema_entry* table, int64_t n_entries, const int32_t* chunk_entry,
                              const int64_t* chunk_start, int64_t n_chunks, int64_t chunk_elems, double momentum, void* stream) {

@@ -273,9 +273,17 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
         // on the critical path of the first kernel of the step.
         {
             const bool mn = MODE == GEMM_STORE && J.y_mn_major != 0;
+            const bool xmn = MODE == GEMM_STORE && J.x_mn_major != 0;
             auto load_x = [&](int kb, int s) {
                 const int p = kb / kper, kk = kk0 + kb - p * kper;
-                tc05::tma_load_3d(tiles + s * kStageBytes, &J.tmx, &full_bar[s], kk * kTileK, m0, J.xseg[p]);
+                uint8_t* a_dst = tiles + s * kStageBytes;
+                if (!xmn) {
+                    tc05::tma_load_3d(a_dst, &J.tmx, &full_bar[s], kk * kTileK, m0, J.xseg[p]);
+                } else {
+                    // X tile [64 contraction rows x 128 M] as two 64x64 boxes (M chunks 8 KiB apart), like the MN-major Y tile
+                    tc05::tma_load_3d(a_dst, &J.tmx, &full_bar[s], m0, kk * kTileK, J.xseg[p]);
+                    tc05::tma_load_3d(a_dst + 64 * kTileK * 2, &J.tmx, &full_bar[s], m0 + 64, kk * kTileK, J.xseg[p]);
+                }
             };
             auto load_y = [&](int kb, int s) {
                 const int p = kb / kper, kk = kk0 + kb - p * kper;
@@ -334,7 +342,9 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const bool mn = MODE == GEMM_STORE && J.y_mn_major != 0;
-            const uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, kTileN) | (mn ? (1u << 16) : 0u);
+            const bool xmn = MODE == GEMM_STORE && J.x_mn_major != 0;
+            // bits 15 / 16: A / B given MN-major
+            const uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, kTileN) | (mn ? (1u << 16) : 0u) | (xmn ? (1u << 15) : 0u);
             int s = 0;
             uint32_t ph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -342,15 +352,17 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                 tc05::fence_after_sync();
                 const uint32_t a_addr = tc05::smem_u32(tiles + s * kStageBytes);
                 const uint32_t b_addr = a_addr + kTileM * kTileK * 2;
-                const uint64_t a_desc = tc05::make_kmajor_sw128_desc(a_addr);
+                const uint64_t a_desc = xmn ? tc05::make_mnmajor_sw128_desc(a_addr, 64 * kTileK * 2)
+                                            : tc05::make_kmajor_sw128_desc(a_addr);
                 const uint64_t b_desc = mn ? tc05::make_mnmajor_sw128_desc(b_addr, 64 * kTileK * 2)
                                            : tc05::make_kmajor_sw128_desc(b_addr);
                 // K-major: 16 bf16 = 32 B inside the swizzle atom (+2 in the >>4 address field);
                 // MN-major: 16 contraction rows = 2 KiB (+128)
+                const uint32_t a_step = xmn ? 128u : 2u;
                 const uint32_t b_step = mn ? 128u : 2u;
 #pragma unroll
                 for (int k = 0; k < kTileK / 16; ++k)
-                    tc05::mma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + b_step * k, idesc, (kb | k) ? 1u : 0u);
+                    tc05::mma_f16_ss(tmem_base, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) ? 1u : 0u);
                 tc05::mma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
                 if (++s == kStages) { s = 0; ph ^= 1; }
             }
@@ -398,6 +410,7 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                     else if (J.py_max) cl = merge_partials(J.py_max, J.py_sum, J.py_tiles, J.N, col);
                 }
             }
+            if (MODE == GEMM_STORE) cl = (J.col_bias && col < J.N) ? __ldg(J.col_bias + col) : 0.f;   // Linear bias (f-3)
             col_scale[e] = cs;
             col_lse[e] = cl;
         }
@@ -506,6 +519,34 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
             }
         }
 
+        // forward of Linear + F.normalize (STiLModel.py:182-192): pass 1 = squared norm of the biased row (tile spans N)
+        float fwd_inv = 1.f;
+        if (MODE == GEMM_STORE && J.fwd_norm && !cluster_follower) {
+            float part_ss = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < kCPW; ++cc) {
+                const int c = c_begin + cc;
+                if (c * 32 < ncols) {   // warp-uniform
+                    uint32_t acc[32];
+                    tc05::tmem_ld_32x32b_x32(taddr + c * 32, acc);
+                    tc05::tmem_ld_wait();
+                    const int nv = min(32, ncols - c * 32);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(acc[j]) * rs * col_scale[c * 32 + j] + col_lse[c * 32 + j];
+                        if (j < nv) part_ss += v * v;
+                    }
+                }
+            }
+            dot_part[part * kTileM + q * 32 + lane] = part_ss;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            float ss = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < kParts; ++pp) ss += dot_part[pp * kTileM + q * 32 + lane];
+            fwd_inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);       // F.normalize eps
+            if (part == 0 && row_ok && J.fwd_inv_norm) J.fwd_inv_norm[row] = fwd_inv;
+        }
+
         float fin_dot = 0.f;
         if (MODE == GEMM_STORE && fused_fin && J.fin_sx && !cluster_follower) {
             // pass 1 of the normalise-backward: <xh, g> over the whole row (the tile spans all of N)
@@ -544,6 +585,21 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
             float l[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) l[j] = __uint_as_float(acc[j]) * rs * col_scale[c * 32 + j];
+
+            if (MODE == GEMM_STORE && (J.col_bias || J.fwd_norm)) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) l[j] += col_lse[c * 32 + j];
+                if (J.fwd_norm) {
+                    if (J.fwd_raw && row_ok) {
+                        float* rw = J.fwd_raw + (long long)row * J.fwd_ld_raw + n0 + c * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nv) rw[j] = l[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) l[j] *= fwd_inv;
+                }
+            }
 
             if (MODE == GEMM_STATS) {
                 float cmax = -INFINITY;

@@ -66,6 +66,16 @@ struct alignas(64) GemmJob {
     long long slice_stride;
     // STORE with Y given MN-major ([contraction rows, N contiguous]) — the backward's dX = G · Y
     int y_mn_major;
+    // STORE with X given MN-major ([contraction rows, M contiguous]): out = Xᵀ · Y, the contraction runs over the ROWS of both
+    // row-major matrices (a Linear layer's dW = gᵀ · x, STiLModel.py:56-63; tmx then has inner = M, box 64 x 64)
+    int x_mn_major;
+    // STORE epilogue extras of the forward of a Linear layer (f-3): + col_bias[j]; fwd_norm: rows L2-normalised like
+    // F.normalize (needs tiles_n == 1), 1 / max(||row||, 1e-12) written to fwd_inv_norm and the un-normalised row to fwd_raw
+    const float* col_bias;
+    int fwd_norm;
+    float* fwd_inv_norm;
+    float* fwd_raw;
+    long long fwd_ld_raw;
     // STORE with the normalise-backward / cast fused in (needs tiles_n == 1):
     //   dx = fin_sx ? sx*(g - xh*(xh·g)), xh = sx*x : g      written in fin_dx_dtype
     void* fin_dx;            // nullptr -> plain fp32 store to `out`
@@ -268,6 +278,7 @@ int launch_simmatch_shard_grad(const float* zt, const float* zs, long long ldz, 
                                long long ld_g, int g_nseg, cudaStream_t stream);
 int launch_softmax_rows(const void* y, int dtype, int64_t ld, int64_t rows, int64_t k, float* out, int64_t ld_out,
                         cudaStream_t stream);
+int launch_col_sum(const float* x, int64_t ld, int64_t rows, int64_t k, float* out, cudaStream_t stream);
 int launch_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, cudaStream_t stream);
 int launch_da_apply(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* batch_mean, float* da_queue,
                     int64_t da_len, int64_t* da_ptr, float* qmean, float* out, int64_t ld_out, cudaStream_t stream);

@@ -1094,6 +1094,23 @@ __global__ void __launch_bounds__(256) da_batch_mean_kernel(const float* __restr
         mean[col] = t / (float)rows;                                   // probs.mean(0), :173
     }
 }
+// column sums of a [rows, k] f32 matrix (bias gradient of a Linear layer): same fixed-order reduction as the batch mean
+__global__ void __launch_bounds__(256) col_sum_kernel(const float* __restrict__ x, long long ld, int rows, int k, float* __restrict__ out) {
+    __shared__ float part[8][33];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int grp = threadIdx.x >> 5;
+    float s = 0.f;
+    if (col < k)
+        for (int r = grp; r < rows; r += 8) s += x[(long long)r * ld + col];
+    part[grp][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (grp == 0 && col < k) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += part[g][threadIdx.x];
+        out[col] = t;
+    }
+}
 // queue[ptr] = batch_mean (already averaged over ranks); ptr = (ptr+1) % len; qmean = queue.mean(0) over ALL rows
 __global__ void __launch_bounds__(256) da_update_kernel(const float* __restrict__ batch_mean, float* da_queue, int da_len,
                                                         int k, long long* da_ptr, float* qmean) {
@@ -1492,6 +1509,12 @@ int launch_proto_finalize(float* prototypes, float* psum, float* pcount, int64_t
     return STIL_OK;
 }
 
+int launch_col_sum(const float* x, int64_t ld, int64_t rows, int64_t k, float* out, cudaStream_t stream) {
+    if (k == 0) return STIL_OK;
+    col_sum_kernel<<<(unsigned)ceil_div(k, 32), 256, 0, stream>>>(x, (long long)ld, (int)rows, (int)k, out);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
 int launch_da_batch_mean(const float* probs, int64_t ld, int64_t rows, int64_t k, float* mean, cudaStream_t stream) {
     if (k == 0) return STIL_OK;
     da_batch_mean_kernel<<<(int)ceil_div(k, 32), 256, 0, stream>>>(probs, ld, (int)rows, (int)k, mean);
