@@ -33,6 +33,20 @@ constexpr int kPrepRows = kRowBlock / 32;  // one warp per row
 // chain start its prologue now, and wait for the previous one's results before touching global memory.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// exp(x) for x <= 0 as ONE multiply and ONE special-function instruction (ex2.approx: relative error <= 2^-22; the rounding
+// of x * log2(e) adds |x| * 2^-24).  libdevice expf costs ~14 instructions per call and made the row kernels
+// instruction-bound (ncu, profiles/r2_ncu_rows.txt: 65 % issue-slot utilisation at 38 % of the HBM peak); the softmax
+// probabilities differ from torch's by <= 2e-6, far inside the 1e-5 ambiguity band of DESIGN.md §2.
+__device__ __forceinline__ float exp_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+__device__ __forceinline__ float log_fast(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.6931471805599453f;
+}
 
 __global__ void __launch_bounds__(kRowBlock) prep_kernel(const __grid_constant__ PrepLaunch L) {
     pdl_wait();                 // predecessor complete and visible ...
@@ -109,6 +123,8 @@ struct CgplArgs {
     long long ld_t;
     int rows, k;
     float temperature, rate_pseudo, one_minus_rate, th1;
+    float inv_temperature, third;   // 1.0f / T and 1.0f / 3.0f: tensor / python-scalar is a multiply by the fp32 reciprocal in
+                                    // torch's CUDA eager kernels, which is where the reference trains
     int past_start;
     float* pseudo_label;
     long long ld_pl;
@@ -221,7 +237,7 @@ __device__ __forceinline__ float softmax_exp(float (&a)[2 * NV]) {
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < 2 * NV; ++j) {
-        a[j] = expf(a[j] - m);
+        a[j] = exp_fast(a[j] - m);     // padding slots hold -inf -> 0
         s += a[j];
     }
     return row_sum<LPR>(s);
@@ -260,25 +276,25 @@ __device__ __forceinline__ void group_argmax(float& v, int& idx) {
 // DESIGN.md §2 classifies as ambiguous.)
 template <int LPR, int NV>
 __device__ __forceinline__ int argmax_logits(const float (&y)[2 * NV], int sub, int k) {
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
+    // slots beyond k hold -inf (load_row), so they never win against a finite logit; ascending idx within a lane and the
+    // strict > keep the first maximum.  The lane's first slot is the initial candidate (a lane whose slots are all
+    // padding then offers (-inf, idx >= k), which loses every comparison in group_argmax).
+    float bv = y[0];
+    int bi = 2 * sub;
 #pragma unroll
-    for (int it = 0; it < NV; ++it) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int idx = 2 * (sub + LPR * it) + h;
-            if (idx < k && (y[2 * it + h] > bv || bi == 0x7fffffff)) {   // ascending idx within a lane: strict > keeps the first
-                bv = y[2 * it + h];
-                bi = idx;
-            }
+    for (int j = 1; j < 2 * NV; ++j) {
+        const int idx = 2 * (sub + LPR * (j >> 1)) + (j & 1);
+        if (y[j] > bv) {
+            bv = y[j];
+            bi = idx;
         }
     }
     group_argmax<LPR>(bv, bi);
-    return bi < k ? bi : 0;      // a row of NaNs compares false everywhere: keep the index in range
+    return bi < k ? bi : 0;      // a row of NaNs / -inf compares false everywhere: keep the index in range
 }
 
 template <int LPR, int NV>
-__global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) {
+__global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) cgpl_pgls_kernel(const CgplArgs A) {
     constexpr int RPW = LPR <= 32 ? 32 / LPR : 0;
     pdl_wait();                 // predecessor complete and visible ...
     pdl_launch_dependents();    // ... before the next kernel of the chain may start (see gemm_tc05.cu)
@@ -333,7 +349,7 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
         for (int j = 0; j < 2 * NV; ++j) {
             float a;
             if (c1)
-                a = __fdiv_rn(__fadd_rn(__fadd_rn(ym[j], yi[j]), yt[j]), 3.0f);
+                a = __fmul_rn(__fadd_rn(__fadd_rn(ym[j], yi[j]), yt[j]), A.third);
             else if (c2i)
                 a = __fmul_rn(__fadd_rn(ym[j], yi[j]), 0.5f);
             else
@@ -346,7 +362,7 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
     }
     // ---- :293-294 teacher prototype probabilities
 #pragma unroll
-    for (int j = 0; j < 2 * NV; ++j) tp[j] = __fdiv_rn(tp[j], A.temperature);
+    for (int j = 0; j < 2 * NV; ++j) tp[j] = __fmul_rn(tp[j], A.inv_temperature);
     {
         const float rs = __frcp_rn(softmax_exp<LPR, NV>(tp));
 #pragma unroll
@@ -360,22 +376,20 @@ __global__ void __launch_bounds__(kRowBlock) cgpl_pgls_kernel(const CgplArgs A) 
             if (pm[j] == -INFINITY) pm[j] = 0.f;     // padding slots beyond k
     }
     // ---- :295-298 smoothing mix, max/argmax, threshold
+    // padding slots carry probability 0 in pm, pl and tp, strictly below the row maximum (>= 1/k): no index test needed
     float bv = -1.f;
     int bi = 0x7fffffff;
 #pragma unroll
-    for (int it = 0; it < NV; ++it)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = 2 * it + h;
-            const int idx = 2 * (sub + LPR * it) + h;
-            const float t = __fmul_rn(A.one_minus_rate, tp[j]);
-            pl[j] = __fadd_rn(__fmul_rn(A.rate_pseudo, pl[j]), t);
-            pm[j] = __fadd_rn(__fmul_rn(A.rate_pseudo, pm[j]), t);
-            if (idx < k && pm[j] > bv) {
-                bv = pm[j];
-                bi = idx;
-            }
+    for (int j = 0; j < 2 * NV; ++j) {
+        const int idx = 2 * (sub + LPR * (j >> 1)) + (j & 1);
+        const float t = __fmul_rn(A.one_minus_rate, tp[j]);
+        pl[j] = __fadd_rn(__fmul_rn(A.rate_pseudo, pl[j]), t);
+        pm[j] = __fadd_rn(__fmul_rn(A.rate_pseudo, pm[j]), t);
+        if (pm[j] > bv) {
+            bv = pm[j];
+            bi = idx;
         }
+    }
     group_argmax<LPR>(bv, bi);
     if (bi >= k) { bi = 0; bv = __int_as_float(0x7fc00000); }   // NaN row: index stays in range, max_prob = NaN, mask1 = false
     const bool m1 = bv >= A.th1;
@@ -966,7 +980,7 @@ struct SoftCeArgs {
 
 // LPR lanes per row (32 / LPR rows per warp for small K, like cgpl_pgls_kernel), NV float2 items per lane
 template <int LPR, int NV>
-__global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeArgs A) {
+__global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) masked_softce_kernel(const SoftCeArgs A) {
     constexpr int RPW = 32 / LPR;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane % LPR;
@@ -1011,16 +1025,18 @@ __global__ void __launch_bounds__(kRowBlock) masked_softce_kernel(const SoftCeAr
                 float s = 0.f, py = 0.f;
 #pragma unroll
                 for (int j = 0; j < 2 * NV; ++j) {
-                    s += expf(y[h][j] - m);                       // exp(-inf) = 0 for the padding
                     if (pl[j] != 0.f) py += pl[j] * y[h][j];
+                    y[h][j] = exp_fast(y[h][j] - m);              // e = exp(y - max) replaces the logit; exp(-inf) = 0 for the padding
+                    s += y[h][j];
                 }
                 s = group_sum<LPR>(s);
                 py = group_sum<LPR>(py);
-                const float lse = m + logf(s);
+                const float lse = m + log_fast(s);
                 if (sub == 0 && wgt[h] != 0.f) lossv[h] += (lse * spl - py) * wgt[h];   // -sum_k pl_k log_softmax(y)_k, weighted
                 const float gs = A.grad_scale * wgt[h] * inv_rows;
+                const float ps = gs * spl * __frcp_rn(s);         // softmax = e / s
 #pragma unroll
-                for (int j = 0; j < 2 * NV; ++j) dy[j] = gs * (expf(y[h][j] - lse) * spl - pl[j]);
+                for (int j = 0; j < 2 * NV; ++j) dy[j] = fmaf(y[h][j], ps, -gs * pl[j]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 2 * NV; ++j) dy[j] = 0.f;
@@ -1413,6 +1429,8 @@ int launch_cgpl_pgls(const void* y_m, const void* y_i, const void* y_t, int logi
     A.tl = teacher_logits; A.ld_t = ld_t;
     A.rows = (int)rows; A.k = (int)k;
     A.temperature = temperature;
+    A.inv_temperature = 1.0f / temperature;
+    A.third = 1.0f / 3.0f;
     A.rate_pseudo = rate_pseudo;
     // `1 - rate_pseudo` is formed in Python double and then rounded to fp32 (STiLModel.py:295)
     A.one_minus_rate = (float)(1.0 - (double)rate_pseudo);
