@@ -38,7 +38,47 @@ WANT = ["Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.s
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "smsp__inst_executed.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
-        "lts__t_bytes.sum", "l1tex__t_bytes.sum"]
+        "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+        "smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_membar_per_warp_active.pct",
+        "smsp__warp_issue_stalled_sleeping_per_warp_active.pct", "smsp__warp_issue_stalled_selected_per_warp_active.pct",
+        "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct", "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct",
+        "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct", "smsp__warp_issue_stalled_tex_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_drain_per_warp_active.pct", "smsp__warp_issue_stalled_imc_miss_per_warp_active.pct"]
+
+
+def opcode_mix(rep, f):
+    """instruction mix per kernel from the source page (needs -lineinfo + --import-source on)"""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    cur, hdr, agg, samp = None, None, None, None
+
+    def flush():
+        if cur and agg:
+            tot, ts = sum(agg.values()), max(1, sum(samp.values()))
+            f.write(f"\n--- opcode mix (all captured launches): {cur[:100]}\n    total warp instructions {tot}\n")
+            for k, v in agg.most_common(14):
+                f.write(f"    {k:10s} {100 * v / tot:6.2f} % of instructions   {100 * samp[k] / ts:6.2f} % of stall samples\n")
+    for r in csv.reader(raw.splitlines()):
+        if r and r[0] == "Kernel Name":
+            flush()
+            cur, hdr, agg, samp = r[1], None, collections.Counter(), collections.Counter()
+        elif r and r[0] == "Address":
+            hdr = r
+        elif hdr and len(r) == len(hdr):
+            try:
+                toks = r[hdr.index("Source")].split()
+                op = (toks[1] if toks[0].startswith("@") else toks[0]).split(".")[0]
+                agg[op] += int(r[hdr.index("Instructions Executed")])
+                samp[op] += int(r[hdr.index("# Samples")])
+            except (ValueError, IndexError):
+                pass
+    flush()
 
 
 def full(rep, out, title):
@@ -53,6 +93,7 @@ def full(rep, out, title):
                 if w in hdr:
                     i = hdr.index(w)
                     f.write(f"    {w:72s} {r[i]:>16s} {units[i]}\n")
+        opcode_mix(rep, f)
 
 
 if __name__ == "__main__":

@@ -42,6 +42,12 @@ __device__ __forceinline__ float exp_fast(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
     return y;
 }
+// exp(x - m) with m * log2(e) formed once per row: one FFMA + one ex2 per element
+__device__ __forceinline__ float exp_fast_shift(float x, float m_log2e) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(x, 1.4426950408889634f, -m_log2e)));
+    return y;
+}
 __device__ __forceinline__ float log_fast(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -191,6 +197,31 @@ __device__ __forceinline__ void store_row(float* base, long long ld, int row, in
     }
 }
 
+// FAST path of the row kernels (fp32 rows, even k, 8-byte aligned rows — every reference shape): one float2 per slot, ONE
+// predicate per slot and a 32-bit offset from a row pointer formed once; the generic load_row above costs two bounds tests,
+// a dtype test and a 64-bit address per element (ncu, profiles/r2_ncu_rows_before.txt: ISETP + IMAD + BRA = 22 % of the
+// instructions of an instruction-bound kernel)
+template <int LPR, int NV>
+__device__ __forceinline__ void load_row_fast(const float* base, long long ld, int row, int khalf, int sub, float (&a)[2 * NV]) {
+    const float2* p = reinterpret_cast<const float2*>(base + (long long)row * ld);
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+        const int i2 = sub + LPR * it;
+        const float2 v = i2 < khalf ? p[i2] : make_float2(-INFINITY, -INFINITY);
+        a[2 * it] = v.x;
+        a[2 * it + 1] = v.y;
+    }
+}
+template <int LPR, int NV>
+__device__ __forceinline__ void store_row_fast(float* base, long long ld, int row, int khalf, int sub, const float (&a)[2 * NV]) {
+    float2* p = reinterpret_cast<float2*>(base + (long long)row * ld);
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+        const int i2 = sub + LPR * it;
+        if (i2 < khalf) p[i2] = make_float2(a[2 * it], a[2 * it + 1]);
+    }
+}
+
 // Reductions over the LPR lanes of a row.  LPR <= 32: shuffles inside the warp.  LPR > 32 (one row per BLOCK of LPR
 // threads, used for small batches where the per-row dependency chain — not bandwidth — bounds the kernel): warp shuffles,
 // then the warps' values through shared memory; every thread of the block takes part (control flow is row-uniform).
@@ -235,9 +266,10 @@ __device__ __forceinline__ float softmax_exp(float (&a)[2 * NV]) {
     for (int j = 0; j < 2 * NV; ++j) m = fmaxf(m, a[j]);
     m = row_max<LPR>(m);
     float s = 0.f;
+    const float ml = m * 1.4426950408889634f;
 #pragma unroll
     for (int j = 0; j < 2 * NV; ++j) {
-        a[j] = exp_fast(a[j] - m);     // padding slots hold -inf -> 0
+        a[j] = exp_fast_shift(a[j], ml);     // padding slots hold -inf -> 0
         s += a[j];
     }
     return row_sum<LPR>(s);
@@ -293,7 +325,7 @@ __device__ __forceinline__ int argmax_logits(const float (&y)[2 * NV], int sub, 
     return bi < k ? bi : 0;      // a row of NaNs / -inf compares false everywhere: keep the index in range
 }
 
-template <int LPR, int NV>
+template <int LPR, int NV, bool FAST>
 __global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) cgpl_pgls_kernel(const CgplArgs A) {
     constexpr int RPW = LPR <= 32 ? 32 / LPR : 0;
     pdl_wait();                 // predecessor complete and visible ...
@@ -317,10 +349,17 @@ __global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) cgpl_pgls_kernel
     const int k = A.k;
 
     float ym[2 * NV], yi[2 * NV], yt[2 * NV], tp[2 * NV];
-    load_row<LPR, NV>(A.y_m, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, ym);
-    load_row<LPR, NV>(A.y_i, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, yi);
-    load_row<LPR, NV>(A.y_t, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, yt);
-    load_row<LPR, NV>(A.tl, STIL_F32, A.ld_t, r, k, sub, A.vec_t, tp);   // all four rows in flight together
+    if constexpr (FAST) {
+        load_row_fast<LPR, NV>(static_cast<const float*>(A.y_m), A.ld_y, r, k >> 1, sub, ym);
+        load_row_fast<LPR, NV>(static_cast<const float*>(A.y_i), A.ld_y, r, k >> 1, sub, yi);
+        load_row_fast<LPR, NV>(static_cast<const float*>(A.y_t), A.ld_y, r, k >> 1, sub, yt);
+        load_row_fast<LPR, NV>(A.tl, A.ld_t, r, k >> 1, sub, tp);
+    } else {
+        load_row<LPR, NV>(A.y_m, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, ym);
+        load_row<LPR, NV>(A.y_i, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, yi);
+        load_row<LPR, NV>(A.y_t, A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, yt);
+        load_row<LPR, NV>(A.tl, STIL_F32, A.ld_t, r, k, sub, A.vec_t, tp);   // all four rows in flight together
+    }
 
     // ---- :262-263  top-1 of the three softmaxes
     float pm[2 * NV];  // becomes softmax(y_m) = `prediction` (:279) and the case-3 pseudo label (:273)
@@ -395,8 +434,13 @@ __global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) cgpl_pgls_kernel
     const bool m1 = bv >= A.th1;
 
     if (!row_ok) return;
-    store_row<LPR, NV>(A.pseudo_label, A.ld_pl, row, k, sub, A.vec_pl, pl);
-    if (A.prediction) store_row<LPR, NV>(A.prediction, A.ld_pred, row, k, sub, A.vec_pred, pm);
+    if constexpr (FAST) {
+        store_row_fast<LPR, NV>(A.pseudo_label, A.ld_pl, row, k >> 1, sub, pl);
+        if (A.prediction) store_row_fast<LPR, NV>(A.prediction, A.ld_pred, row, k >> 1, sub, pm);
+    } else {
+        store_row<LPR, NV>(A.pseudo_label, A.ld_pl, row, k, sub, A.vec_pl, pl);
+        if (A.prediction) store_row<LPR, NV>(A.prediction, A.ld_pred, row, k, sub, A.vec_pred, pm);
+    }
     if (sub == 0) {
         if (A.max_prob) A.max_prob[row] = bv;
         A.max_idx[row] = bi;
@@ -979,7 +1023,7 @@ struct SoftCeArgs {
 };
 
 // LPR lanes per row (32 / LPR rows per warp for small K, like cgpl_pgls_kernel), NV float2 items per lane
-template <int LPR, int NV>
+template <int LPR, int NV, bool FAST>
 __global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) masked_softce_kernel(const SoftCeArgs A) {
     constexpr int RPW = 32 / LPR;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -995,9 +1039,15 @@ __global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) masked_softce_ke
         const int r = ok ? row : A.rows - 1;      // lanes past the end keep running on a clamped row (full-warp shuffles)
         // all four rows of this sample in flight together
         float pl[2 * NV], y[3][2 * NV];
-        load_row<LPR, NV>(A.pl, STIL_F32, A.ld_pl, r, k, sub, A.vec_pl, pl);
+        if constexpr (FAST) {
+            load_row_fast<LPR, NV>(A.pl, A.ld_pl, r, k >> 1, sub, pl);
 #pragma unroll
-        for (int h = 0; h < 3; ++h) load_row<LPR, NV>(A.y[h], A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, y[h]);
+            for (int h = 0; h < 3; ++h) load_row_fast<LPR, NV>(static_cast<const float*>(A.y[h]), A.ld_y, r, k >> 1, sub, y[h]);
+        } else {
+            load_row<LPR, NV>(A.pl, STIL_F32, A.ld_pl, r, k, sub, A.vec_pl, pl);
+#pragma unroll
+            for (int h = 0; h < 3; ++h) load_row<LPR, NV>(A.y[h], A.logit_dtype, A.ld_y, r, k, sub, A.vec_y, y[h]);
+        }
         const float m1 = (ok && A.mask1[r]) ? 1.f : 0.f;
         const float c1 = A.case1[r] ? 1.f : 0.f, c2i = A.case2_i[r] ? 1.f : 0.f;
         const float c2t = A.case2_t[r] ? 1.f : 0.f, c3 = A.case3[r] ? 1.f : 0.f;
@@ -1023,10 +1073,11 @@ __global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) masked_softce_ke
                 for (int j = 0; j < 2 * NV; ++j) m = fmaxf(m, y[h][j]);
                 m = group_max<LPR>(m);
                 float s = 0.f, py = 0.f;
+                const float ml = m * 1.4426950408889634f;
 #pragma unroll
                 for (int j = 0; j < 2 * NV; ++j) {
                     if (pl[j] != 0.f) py += pl[j] * y[h][j];
-                    y[h][j] = exp_fast(y[h][j] - m);              // e = exp(y - max) replaces the logit; exp(-inf) = 0 for the padding
+                    y[h][j] = exp_fast_shift(y[h][j], ml);        // e = exp(y - max) replaces the logit; exp(-inf) = 0 for the padding
                     s += y[h][j];
                 }
                 s = group_sum<LPR>(s);
@@ -1041,7 +1092,10 @@ __global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) masked_softce_ke
 #pragma unroll
                 for (int j = 0; j < 2 * NV; ++j) dy[j] = 0.f;
             }
-            if (A.dy[h] && ok) store_row<LPR, NV>(A.dy[h], A.ld_g, row, k, sub, A.vec_g, dy);
+            if (A.dy[h] && ok) {
+                if constexpr (FAST) store_row_fast<LPR, NV>(A.dy[h], A.ld_g, row, k >> 1, sub, dy);
+                else store_row<LPR, NV>(A.dy[h], A.ld_g, row, k, sub, A.vec_g, dy);
+            }
         }
     }
 #pragma unroll
@@ -1355,9 +1409,13 @@ int launch_cgpl_t(const CgplArgs& A, cudaStream_t stream) {
     const int threads = LPR > 32 ? LPR : row_block_threads(ceil_div(A.rows, LPR > 32 ? 1 : 32 / LPR));
     const int rows_per_block = LPR > 32 ? 1 : (threads / 32) * (32 / (LPR > 32 ? 32 : LPR));
     const int blocks = (int)ceil_div(A.rows, rows_per_block);
-    static const bool once = (prefer_max_shared(cgpl_pgls_kernel<LPR, NV>), true);
+    static const bool once = (prefer_max_shared(cgpl_pgls_kernel<LPR, NV, false>), prefer_max_shared(cgpl_pgls_kernel<LPR, NV, true>), true);
     (void)once;
-    STIL_CUDA(launch_pdl(cgpl_pgls_kernel<LPR, NV>, dim3(blocks), dim3(threads), 0, stream, A));
+    // fp32 rows, even k, every row 8-byte aligned: the one-predicate float2 path
+    const bool fast = A.logit_dtype == STIL_F32 && (A.k & 1) == 0 && A.vec_y && A.vec_t && A.vec_pl && (!A.prediction || A.vec_pred) &&
+                      (!A.pred_in || A.vec_pin);
+    if (fast) STIL_CUDA(launch_pdl(cgpl_pgls_kernel<LPR, NV, true>, dim3(blocks), dim3(threads), 0, stream, A));
+    else STIL_CUDA(launch_pdl(cgpl_pgls_kernel<LPR, NV, false>, dim3(blocks), dim3(threads), 0, stream, A));
     return STIL_OK;
 }
 
@@ -1636,25 +1694,25 @@ int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int 
     A.vec_y = (ld_y % 2 == 0) && al(y_m, 2 * esz) && al(y_i, 2 * esz) && al(y_t, 2 * esz);
     A.vec_pl = (ld_pl % 2 == 0) && al(pseudo_label, 8);
     A.vec_g = (ld_g % 2 == 0) && al(d_y_m, 8) && al(d_y_i, 8) && al(d_y_t, 8);
-    static const bool once = (prefer_max_shared(masked_softce_kernel<1, 1>), prefer_max_shared(masked_softce_kernel<4, 2>),
-                              prefer_max_shared(masked_softce_kernel<8, 4>), prefer_max_shared(masked_softce_kernel<32, 2>),
-                              prefer_max_shared(masked_softce_kernel<32, 5>), prefer_max_shared(masked_softce_kernel<32, 8>),
-                              prefer_max_shared(masked_softce_kernel<32, 16>), true);
-    (void)once;
     const int threads = row_block_threads(rows);
-    auto go = [&](auto kernel, int lpr) {
+    // fp32 rows, even k, 8-byte aligned rows, all three gradients wanted: the one-predicate float2 path
+    const bool fast = logit_dtype == STIL_F32 && (k & 1) == 0 && A.vec_y && A.vec_pl && A.vec_g;
+    auto go = [&](auto kernel_fast, auto kernel_gen, int lpr) {
         const int64_t rows_per_block = (threads / 32) * (32 / lpr);
         // never more blocks than masked_softce_blocks() sized the partials for
         const int blocks = (int)std::min<int64_t>(ceil_div(rows, rows_per_block), masked_softce_blocks(rows, k));
-        kernel<<<blocks, threads, 0, stream>>>(A);
+        if (fast) kernel_fast<<<blocks, threads, 0, stream>>>(A);
+        else kernel_gen<<<blocks, threads, 0, stream>>>(A);
     };
-    if (k <= 2) go(masked_softce_kernel<1, 1>, 1);
-    else if (k <= 16) go(masked_softce_kernel<4, 2>, 4);
-    else if (k <= 64) go(masked_softce_kernel<8, 4>, 8);
-    else if (k <= 128) go(masked_softce_kernel<32, 2>, 32);
-    else if (k <= 320) go(masked_softce_kernel<32, 5>, 32);
-    else if (k <= 512) go(masked_softce_kernel<32, 8>, 32);
-    else go(masked_softce_kernel<32, 16>, 32);
+#define STIL_SOFTCE(LPR, NV) go(masked_softce_kernel<LPR, NV, true>, masked_softce_kernel<LPR, NV, false>, LPR)
+    if (k <= 2) STIL_SOFTCE(1, 1);
+    else if (k <= 16) STIL_SOFTCE(4, 2);
+    else if (k <= 64) STIL_SOFTCE(8, 4);
+    else if (k <= 128) STIL_SOFTCE(32, 2);
+    else if (k <= 320) STIL_SOFTCE(32, 5);
+    else if (k <= 512) STIL_SOFTCE(32, 8);
+    else STIL_SOFTCE(32, 16);
+#undef STIL_SOFTCE
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }
