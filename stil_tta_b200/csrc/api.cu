@@ -1288,8 +1288,11 @@ STIL_API int stil_simmatch_shard_stats(const void* feat_ku, const void* feat_qu,
     GL.njobs = 2;
     gemm_job_tiles(GL);
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    // per-chunk partial statistics live in the G buffer of the workspace (not written before _shard_grad)
+    STIL_REQUIRE((int64_t)simmatch_shard_chunks(rows, k_shard) * rows * (3 + num_classes) * 4 <= rows * 2 * P.ldg * 2, STIL_E_SHAPE,
+                 "simmatch_shard_stats: %lld classes do not fit the chunk scratch", (long long)num_classes);
     return launch_simmatch_shard_stats(P.zt, P.zs, P.ldz, reinterpret_cast<const long long*>(labels), (int)rows, (int)k_shard,
-                                       prob_ku_orig, (int)num_classes, tt, st, stats, S(stream));
+                                       prob_ku_orig, (int)num_classes, tt, st, stats, reinterpret_cast<float*>(P.gop), S(stream));
 }
 
 STIL_API int stil_simmatch_shard_finish(const float* stats_total, const float* prob_ku_orig, int64_t rows, int64_t num_classes,

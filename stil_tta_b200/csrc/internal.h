@@ -270,7 +270,9 @@ int launch_simmatch_rows(const float* zt, const float* zs, long long ldz, const 
                          const float* p_orig, int num_classes, float tt, float st, float c_smooth, float* p_out,
                          float* loss_in, __nv_bfloat16* gop, long long ld_g, int g_nseg, cudaStream_t stream);
 int launch_simmatch_shard_stats(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
-                                const float* p_all, int num_classes, float tt, float st, float* stats, cudaStream_t stream);
+                                const float* p_all, int num_classes, float tt, float st, float* stats, float* chunk_scratch,
+                                cudaStream_t stream);
+int simmatch_shard_chunks(int64_t rows, int64_t k_shard);
 int launch_simmatch_shard_finish(const float* stats, const float* p_all, int rows, int num_classes, float st, float c_smooth,
                                  float* p_out, float* loss_in, float* norms, cudaStream_t stream);
 int launch_simmatch_shard_grad(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,

@@ -1320,12 +1320,18 @@ __device__ __forceinline__ float shifted_exp(float z, float inv_t) { return __ex
 __global__ void __launch_bounds__(kSimBlock) simmatch_shard_stats_kernel(const float* __restrict__ zt, const float* __restrict__ zs,
                                                                          long long ldz, const long long* __restrict__ labels,
                                                                          int k_shard, const float* __restrict__ p_all, int C,
-                                                                         float inv_tt, float inv_st, float* __restrict__ stats) {
+                                                                         float inv_tt, float inv_st, float* __restrict__ stats,
+                                                                         long long chunk_stride) {
     extern __shared__ float sm[];   // p[C] | A[C] | red[8]
     float* sp = sm;
     float* sA = sm + C;
     float* red = sm + 2 * C;
     const int row = blockIdx.x;
+    // a row is cut into gridDim.y column chunks (one block each) so that a few hundred rows still fill the chip; chunk c
+    // writes its partial statistics to stats + c * chunk_stride, simmatch_shard_reduce_kernel adds the chunks in order
+    const int cw = (k_shard + gridDim.y - 1) / gridDim.y;
+    const int j0 = blockIdx.y * cw, j1 = min(k_shard, j0 + cw);
+    stats += (long long)blockIdx.y * chunk_stride;
     const float* rt = zt + (long long)row * ldz;
     const float* rs = zs + (long long)row * ldz;
     for (int c = threadIdx.x; c < C; c += kSimBlock) {
@@ -1334,7 +1340,7 @@ __global__ void __launch_bounds__(kSimBlock) simmatch_shard_stats_kernel(const f
     }
     __syncthreads();
     float st_ = 0.f, ss_ = 0.f, num = 0.f;
-    for (int j = threadIdx.x; j < k_shard; j += kSimBlock) {
+    for (int j = j0 + threadIdx.x; j < j1; j += kSimBlock) {
         const float z_s = rs[j];
         const float et = shifted_exp(rt[j], inv_tt);
         const int y = (int)labels[j];
@@ -1349,6 +1355,16 @@ __global__ void __launch_bounds__(kSimBlock) simmatch_shard_stats_kernel(const f
     float* out = stats + (long long)row * (3 + C);
     if (threadIdx.x == 0) { out[0] = st_; out[1] = ss_; out[2] = num; }
     for (int c = threadIdx.x; c < C; c += kSimBlock) out[3 + c] = sA[c];
+}
+
+// stats[i] = sum over chunks, in chunk order (deterministic)
+__global__ void __launch_bounds__(256) simmatch_shard_reduce_kernel(const float* __restrict__ parts, long long chunk_stride, int nchunk,
+                                                                    long long n, float* __restrict__ stats) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int c = 0; c < nchunk; ++c) s += parts[(long long)c * chunk_stride + i];
+    stats[i] = s;
 }
 
 // totals (summed over the shards) -> prob_ku (:280), loss_in (:286) and the two normalisers the gradient needs; warp per row
@@ -1391,7 +1407,9 @@ __global__ void __launch_bounds__(kSimBlock) simmatch_shard_grad_kernel(const fl
     const float* rs = zs + (long long)row * ldz;
     const float inv_sum_s = norms[2 * row], inv_den = norms[2 * row + 1];
     __nv_bfloat16* gh = gop + (long long)row * g_nseg * ld_g;
-    for (int j = threadIdx.x; j < k_shard; j += kSimBlock) {
+    const int cw = (k_shard + gridDim.y - 1) / gridDim.y;
+    const int j0 = blockIdx.y * cw, j1 = min(k_shard, j0 + cw);
+    for (int j = j0 + threadIdx.x; j < j1; j += kSimBlock) {
         const float g = (shifted_exp(rs[j], inv_st) * inv_sum_s - shifted_exp(rt[j], inv_tt) * sm[(int)labels[j]] * inv_den) * inv_st;
         const __nv_bfloat16 h = __float2bfloat16_rn(g);
         gh[j] = h;
@@ -1638,14 +1656,26 @@ int64_t masked_softce_blocks(int64_t rows, int64_t) {
     return std::min<int64_t>(ceil_div(rows, row_block_threads(rows) / 32), 148 * 16);
 }
 
+int simmatch_shard_chunks(int64_t rows, int64_t k_shard) {
+    // ~2048 blocks in flight, at least 1024 columns per block
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div(2048, std::max<int64_t>(rows, 1)), 32), k_shard / 1024));
+}
 int launch_simmatch_shard_stats(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
-                                const float* p_all, int num_classes, float tt, float st, float* stats, cudaStream_t stream) {
+                                const float* p_all, int num_classes, float tt, float st, float* stats, float* chunk_scratch,
+                                cudaStream_t stream) {
     if (rows == 0) return STIL_OK;
     const size_t smem = (2 * (size_t)num_classes + 8) * sizeof(float);
     STIL_REQUIRE(smem <= 48 * 1024, STIL_E_SHAPE, "simmatch: too many classes (%d)", num_classes);
-    simmatch_shard_stats_kernel<<<rows, kSimBlock, smem, stream>>>(zt, zs, ldz, labels, k_shard, p_all, num_classes, 1.f / tt,
-                                                                   1.f / st, stats);
+    const int nchunk = simmatch_shard_chunks(rows, k_shard);
+    const long long n = (long long)rows * (3 + num_classes);
+    float* dst = nchunk > 1 ? chunk_scratch : stats;
+    simmatch_shard_stats_kernel<<<dim3(rows, nchunk), kSimBlock, smem, stream>>>(zt, zs, ldz, labels, k_shard, p_all, num_classes,
+                                                                                 1.f / tt, 1.f / st, dst, n);
     STIL_LAUNCH_CHECK();
+    if (nchunk > 1) {
+        simmatch_shard_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(chunk_scratch, n, nchunk, n, stats);
+        STIL_LAUNCH_CHECK();
+    }
     return STIL_OK;
 }
 int launch_simmatch_shard_finish(const float* stats, const float* p_all, int rows, int num_classes, float st, float c_smooth,
@@ -1662,8 +1692,8 @@ int launch_simmatch_shard_grad(const float* zt, const float* zs, long long ldz, 
                                long long ld_g, int g_nseg, cudaStream_t stream) {
     if (rows == 0) return STIL_OK;
     const size_t smem = (size_t)num_classes * sizeof(float);
-    simmatch_shard_grad_kernel<<<rows, kSimBlock, smem, stream>>>(zt, zs, ldz, labels, k_shard, p_all, num_classes, 1.f / tt,
-                                                                  1.f / st, norms, gop, ld_g, g_nseg);
+    simmatch_shard_grad_kernel<<<dim3(rows, simmatch_shard_chunks(rows, k_shard)), kSimBlock, smem, stream>>>(
+        zt, zs, ldz, labels, k_shard, p_all, num_classes, 1.f / tt, 1.f / st, norms, gop, ld_g, g_nseg);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }
