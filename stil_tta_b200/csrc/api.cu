@@ -241,8 +241,35 @@ int infonce_args_check(const void* a_all, const void* b_all, int dtype, int64_t 
 }
 
 // jobs shared by the op-level entry points and stil_head_step --------------------------------------
+// The local InfoNCE (every row sees every column: m == n) is computed in a SINGLE pass over a·bᵀ: each tile emits row AND
+// column statistics (the columns' statistics are the rows' statistics of b·aᵀ), the backward forms dLoss/dLogits once and
+// feeds both dA = G·B and dB = Gᵀ·A from it (the second with G read as an MN-major A operand).  Executed tensor work: 2 + 2
+// + 2x2 products of n^2 d instead of 4 + 4 + 2x2.  The fixed shift needs |logit| <= 1/T to stay in fp32 range: T >= 1/40.
+// The data-parallel head (m < n) keeps the two-sided form: each rank owns the ROWS of both sides, so nothing is reduced
+// across ranks.  STIL_NCE_TWO_SIDED=1 forces the two-sided form (A/B measurements).
+bool infonce_single_pass(int64_t m, int64_t n, int64_t off, float inv_t) {
+    static const bool two_sided = [] { const char* e = getenv("STIL_NCE_TWO_SIDED"); return e && e[0] == '1'; }();
+    return !two_sided && m == n && off == 0 && inv_t <= 40.f;
+}
+
+// returns the number of jobs (1: single pass, 2: one per side) through *njobs
 int infonce_stats_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const Operand& B, int64_t m, int64_t n,
-                       int64_t dim, int64_t off, float inv_t, float* logits, int64_t ld_logits) {
+                       int64_t dim, int64_t off, float inv_t, float* logits, int64_t ld_logits, int* njobs) {
+    *njobs = 2;
+    if (infonce_single_pass(m, n, off, inv_t)) {
+        int rc = fill_gemm_common(J2[0], A, 0, m, B, n, dim);
+        if (rc) return rc;
+        GemmJob& J = J2[0];
+        J.mode = GEMM_STATS;
+        J.alpha = inv_t;
+        J.sx = P.ra; J.sy = P.rb;
+        J.part_max = P.pmax[0]; J.part_sum = P.psum[0];
+        J.cpart_max = P.pmax[1]; J.cpart_sum = P.psum[1];      // same [4 * tiles, n] layout as side 1's row partials
+        J.sym_shift = inv_t;
+        if (logits) { J.out = logits; J.ld_out = ld_logits; }
+        *njobs = 1;
+        return STIL_OK;
+    }
     for (int s = 0; s < 2; ++s) {
         const Operand& X = s == 0 ? A : B;
         const Operand& Y = s == 0 ? B : A;
@@ -292,8 +319,9 @@ void infonce_finish_jobs(FinishJob* F2, const InfoncePlan& P, const void* a_all,
 
 int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const Operand& B, int64_t m, int64_t n,
                       int64_t dim, int64_t off, float inv_t, float lambda0, const float* lse_row_all,
-                      const float* lse_col_all, const float* grad_loss, int grad_dtype) {
-    for (int s = 0; s < 2; ++s) {
+                      const float* lse_col_all, const float* grad_loss, int grad_dtype, int* njobs) {
+    *njobs = infonce_single_pass(m, n, off, inv_t) ? 1 : 2;
+    for (int s = 0; s < *njobs; ++s) {
         const Operand& X = s == 0 ? A : B;
         const Operand& Y = s == 0 ? B : A;
         int rc = fill_gemm_common(J2[s], X, off, m, Y, n, dim);
@@ -321,6 +349,8 @@ int infonce_grad_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const
         J.gop = P.gop[s];
         J.ld_g = P.ldg;
         J.g_nseg = grad_nseg(grad_dtype);
+        // single pass: ONE G = dLoss/dLogits * alpha * sx_i * sy_j serves both products; each undoes "its" scale in the epilogue
+        J.g_row_scale = *njobs == 1 ? 1 : 0;
     }
     return STIL_OK;
 }
@@ -354,7 +384,7 @@ int dx_cluster_k(int64_t tiles, int64_t kblocks) {
 // d(x̂_i) = sum_j G'_ij y_j, then the backward of F.normalize in the epilogue when one tile spans `dim`
 int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, const Operand& B, const void* a_all,
                        const void* b_all, int dtype, int64_t m, int64_t n, int64_t dim, int64_t ld, int64_t off,
-                       void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, bool* fused, int* cluster_k) {
+                       void* d_a, void* d_b, int grad_dtype, int64_t ld_grad, float inv_t, bool* fused, int* cluster_k) {
     const int esz = dtype == STIL_BF16 ? 2 : 4;
     int ksplit = infonce_dx_ksplit(m, n, dim);
     *cluster_k = 1;
@@ -364,11 +394,22 @@ int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, cons
         ksplit = *cluster_k = (int)std::min<int64_t>(ck, ceil_div(n, kTileK));
     }
     *fused = dim <= kTileN;
+    const bool single = infonce_single_pass(m, n, off, inv_t);
     for (int s = 0; s < 2; ++s) {
-        const Operand X = grad_operand(P.gop[s], P.ldg, grad_nseg(grad_dtype));
+        const Operand X = grad_operand(P.gop[single ? 0 : s], P.ldg, grad_nseg(grad_dtype));
         const Operand& Y = s == 0 ? B : A;
         int rc = fill_gemm_store_mn(J2[s], X, m, Y, n, dim);
         if (rc) return rc;
+        if (single) {
+            // G carries alpha * sx_i * sy_j: dA_i = (1/sx_i) sum_j G_ij b_j, dB_j = (1/sy_j) sum_i G_ij a_i — the second reads
+            // the SAME G as an MN-major A operand (contraction over its rows)
+            J2[s].sx = s == 0 ? P.ra : P.rb;
+            J2[s].sx_recip = 1;
+            if (s == 1) {
+                if ((rc = make_operand_map(&J2[s].tmx, X.base, n, m, X.nseg, X.row_stride, X.seg_stride, 64))) return rc;
+                J2[s].x_mn_major = 1;
+            }
+        }
         J2[s].ksplit = ksplit;
         if (*fused) {
             J2[s].fin_dx = s == 0 ? d_a : d_b;
@@ -501,8 +542,7 @@ STIL_API int stil_infonce_fwd(const void* a_loc, const void* b_loc, const void* 
     const Operand B = rowmajor_operand(b_all, dtype, dim, ld, P.b_op, P.nseg);
     GemmLaunch GL;
     std::memset(&GL, 0, sizeof(GL));
-    if ((rc = infonce_stats_jobs(GL.job, P, A, B, m, n, dim, row_offset, inv_t, logits, ld_logits))) return rc;
-    GL.njobs = 2;
+    if ((rc = infonce_stats_jobs(GL.job, P, A, B, m, n, dim, row_offset, inv_t, logits, ld_logits, &GL.njobs))) return rc;
     gemm_job_tiles(GL);
     set_early(GL, dtype == STIL_BF16, dtype == STIL_BF16);   // predecessor = prep: bf16 operands are the caller's inputs
     if ((rc = launch_gemm(GL, S(stream)))) return rc;
@@ -548,9 +588,8 @@ int infonce_bwd_impl(const void* a_all, const void* b_all, int dtype,
     GemmLaunch GL;
     std::memset(&GL, 0, sizeof(GL));
     if ((rc = infonce_grad_jobs(GL.job, P, A, B, m, n, dim, row_offset, inv_t, lambda0, lse_row_all, lse_col_all,
-                                grad_loss, grad_dtype)))
+                                grad_loss, grad_dtype, &GL.njobs)))
         return rc;
-    GL.njobs = 2;
     gemm_job_tiles(GL);
     // predecessor = this call's prep: bf16 operands are the caller's inputs (after_fwd: the predecessor is the caller's)
     if (!after_fwd) set_early(GL, dtype == STIL_BF16, dtype == STIL_BF16);
@@ -559,7 +598,7 @@ int infonce_bwd_impl(const void* a_all, const void* b_all, int dtype,
     bool fused = false;
     int dx_ck = 1;
     if ((rc = infonce_store_jobs(GS.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
-                                 ld_grad, &fused, &dx_ck)))
+                                 ld_grad, inv_t, &fused, &dx_ck)))
         return rc;
     GS.njobs = 2;
     GS.cluster_k = dx_ck;
@@ -651,8 +690,7 @@ STIL_API int stil_infonce_stats_gathered(const void* a_all, const void* b_all, c
     const Operand B = rowmajor_operand(b_all, dtype, dim, ld, nullptr, 1);
     GemmLaunch GL;
     std::memset(&GL, 0, sizeof(GL));
-    if ((rc = infonce_stats_jobs(GL.job, P, A, B, m, n, dim, row_offset, 1.0f / temperature, nullptr, 0))) return rc;
-    GL.njobs = 2;
+    if ((rc = infonce_stats_jobs(GL.job, P, A, B, m, n, dim, row_offset, 1.0f / temperature, nullptr, 0, &GL.njobs))) return rc;
     gemm_job_tiles(GL);
     set_wait(GL, wait_flags, wait_seq, rows_per_peer, 1);
     return launch_gemm(GL, S(stream));
@@ -720,9 +758,8 @@ STIL_API int stil_infonce_bwd_gathered(const void* a_all, const void* b_all, con
     GemmLaunch GL;
     std::memset(&GL, 0, sizeof(GL));
     if ((rc = infonce_grad_jobs(GL.job, P, A, B, m, n, dim, row_offset, 1.0f / temperature, lambda0, lse_row_all, lse_col_all,
-                                grad_loss, grad_dtype)))
+                                grad_loss, grad_dtype, &GL.njobs)))
         return rc;
-    GL.njobs = 2;
     gemm_job_tiles(GL);
     // every embedding row landed before the statistics GEMM finished (it waited for each peer): the operands stream
     // before the wait; only the epilogue needs the peers' LSEs
@@ -737,7 +774,7 @@ STIL_API int stil_infonce_bwd_gathered(const void* a_all, const void* b_all, con
     bool fused = false;
     int dx_ck = 1;
     if ((rc = infonce_store_jobs(GS.job, P, A, B, a_all, b_all, dtype, m, n, dim, ld, row_offset, d_a, d_b, grad_dtype,
-                                 ld_grad, &fused, &dx_ck)))
+                                 ld_grad, 1.0f / temperature, &fused, &dx_ck)))
         return rc;
     GS.njobs = 2;
     GS.cluster_k = dx_ck;
@@ -2068,8 +2105,7 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         if ((rc = mark(9, s_nce))) return rc;
         if ((rc = launch_prep(PL, s_nce))) return rc;
         std::memset(&GL, 0, sizeof(GL));
-        if ((rc = infonce_stats_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, nullptr, 0))) return rc;
-        GL.njobs = 2;
+        if ((rc = infonce_stats_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, nullptr, 0, &GL.njobs))) return rc;
         gemm_job_tiles(GL);
         set_early(GL, dt == STIL_BF16, dt == STIL_BF16);   // predecessor = prep: bf16 operands are the caller's inputs
         if ((rc = mark(10, s_nce))) return rc;
@@ -2079,16 +2115,15 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
         bool fused = true;
         std::memset(&GL, 0, sizeof(GL));
         if ((rc = infonce_grad_jobs(GL.job, P.nce, A, Bm, B, B, D, 0, inv_t, a->lambda0, nullptr, nullptr, nullptr,
-                                    a->grad_dtype)))
+                                    a->grad_dtype, &GL.njobs)))
             return rc;
-        GL.njobs = 2;
         gemm_job_tiles(GL);
         set_early(GL, true, true);    // predecessor = STATS: operands were final two kernels ago
         GemmLaunch GS, GB;
         std::memset(&GS, 0, sizeof(GS));
         int dx_ck = 1;
         if ((rc = infonce_store_jobs(GS.job, P.nce, A, Bm, a->feat_i, a->feat_t, dt, B, B, D, D, 0, a->d_feat_i,
-                                     a->d_feat_t, a->grad_dtype, D, &fused, &dx_ck)))
+                                     a->d_feat_t, a->grad_dtype, D, inv_t, &fused, &dx_ck)))
             return rc;
         GS.njobs = 2;
         GS.cluster_k = dx_ck;

@@ -414,7 +414,8 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
             col_scale[e] = cs;
             col_lse[e] = cl;
         }
-        const float rs = (row_ok && J.sx) ? J.sx[row] : 1.f;
+        float rs = (row_ok && J.sx) ? J.sx[row] : 1.f;
+        if (MODE == GEMM_STORE && J.sx_recip) rs = 1.0f / rs;
         float lse_x = 0.f, u = 0.f, d = 0.f, gs = 1.f;
         int tgt = -1;
         if (MODE == GEMM_GRAD && row_ok) {
@@ -431,6 +432,7 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                 d = J.u_vec ? u : J.d_scalar;
             }
             gs = J.gscale ? *J.gscale : 1.f;
+            if (J.g_row_scale) gs *= rs;
         }
         const float v = (MODE == GEMM_GRAD && (J.lse_y || J.py_max)) ? J.v_scalar : 0.f;
         const bool fused_fin = MODE == GEMM_STORE && J.fin_dx != nullptr;
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                     for (int j = 0; j < 32; ++j) part_dot += xrow[cc][j] * __uint_as_float(acc[j]);
                 }
             }
-            dot_part[part * kTileM + q * 32 + lane] = part_dot * fsx * alpha;
+            dot_part[part * kTileM + q * 32 + lane] = part_dot * fsx * alpha * rs;
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 #pragma unroll
             for (int pp = 0; pp < kParts; ++pp) fin_dot += dot_part[pp * kTileM + q * 32 + lane];
@@ -601,7 +603,38 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                 }
             }
 
-            if (MODE == GEMM_STATS) {
+            if (MODE == GEMM_STATS && J.cpart_sum != nullptr) {
+                // single pass over the symmetric problem: e = exp(L - shift) once per element, row sum in the thread,
+                // column sums over this warp's 32 rows by a shuffle transpose-reduce (31 shuffles per 32 x 32 block)
+                const float shift_l2 = J.sym_shift * kLog2e;
+                float ev[32];
+                float rsum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    ev[j] = (row_ok && j < nv) ? fast_exp2(fmaf(l[j], kLog2e, -shift_l2)) : 0.f;
+                    rsum += ev[j];
+                }
+                if (row_ok) {
+                    J.part_max[(long long)(tn * 4 + c) * J.M + row] = J.sym_shift;
+                    J.part_sum[(long long)(tn * 4 + c) * J.M + row] = rsum;
+                }
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) {
+                    const bool up = (lane & o) != 0;
+#pragma unroll
+                    for (int i = 0; i < o; ++i) {
+                        const float send = up ? ev[i] : ev[i + o];
+                        const float keep = up ? ev[i + o] : ev[i];
+                        ev[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    }
+                }
+                // lane j now holds the sum of column c*32 + j over the 32 rows of this TMEM lane quarter
+                if (lane < nv) {
+                    const long long slot = (long long)(tm * 4 + q) * J.N + n0 + c * 32 + lane;
+                    J.cpart_max[slot] = J.sym_shift;
+                    J.cpart_sum[slot] = ev[0];
+                }
+            } else if (MODE == GEMM_STATS) {
                 float cmax = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)

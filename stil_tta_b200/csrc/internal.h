@@ -35,6 +35,18 @@ struct alignas(64) GemmJob {
     // STATS
     float* part_max;  // [tiles_n, M]
     float* part_sum;
+    // STATS, single pass over a SYMMETRIC problem (the InfoNCE's a·bᵀ: the columns' statistics are the rows' statistics of
+    // b·aᵀ): besides the row partials the tile also emits COLUMN partials [4 * tiles_m, N] — the sum of e^{L - sym_shift}
+    // over each 32-row quarter of the tile (warp-shuffle transpose-reduce), so b·aᵀ is never computed.  All partials of such
+    // a job use the FIXED shift sym_shift >= max L (unit rows: |L| <= alpha) instead of a running maximum, which makes them
+    // plain sums; the max arrays receive the constant so that every consumer's merge code stays as it is.
+    float* cpart_max;
+    float* cpart_sum;
+    float sym_shift;
+    // GRAD: G additionally carries the row scale sx[i] (one G for both dX products of the symmetric problem);
+    // STORE: the row scale is 1 / sx[i] (undoes it)
+    int g_row_scale;
+    int sx_recip;
     // STORE / STATS(optional)
     float* out;
     long long ld_out;
