@@ -25,7 +25,9 @@ for W in worlds:
     ws = torch.empty(lib.stil_infonce_workspace_bytes(m, n, P, 1), dtype=torch.uint8, device=dev)
     loss = torch.zeros(4, device=dev)
     lse = torch.zeros(2, n, device=dev)
-    d_a = torch.empty(m, P, dtype=torch.bfloat16, device=dev)
+    import os
+    gf32 = os.environ.get("GRAD_F32", "1") == "1"          # the head's default: fp32 gradients (G as bf16 hi+lo)
+    d_a = torch.empty(m, P, dtype=torch.float32 if gf32 else torch.bfloat16, device=dev)
     d_b = torch.empty_like(d_a)
     s = torch.cuda.Stream()
 
@@ -33,7 +35,7 @@ for W in worlds:
         check(lib.stil_infonce_fwd(a_loc, b_loc, a_all, b_all, 1, m, n, P, 2 * P, off, 0.1, 0.5, loss.data_ptr(),
                                    lse[0, off:].data_ptr(), lse[1, off:].data_ptr(), None, 0, ws.data_ptr(), ws.numel(), st))
         check(lib.stil_infonce_bwd_after_fwd(a_all, b_all, 1, m, n, P, 2 * P, off, 0.1, 0.5, lse[0].data_ptr(),
-                                             lse[1].data_ptr(), None, d_a.data_ptr(), d_b.data_ptr(), 1, P, ws.data_ptr(),
+                                             lse[1].data_ptr(), None, d_a.data_ptr(), d_b.data_ptr(), 0 if gf32 else 1, P, ws.data_ptr(),
                                              ws.numel(), st))
 
     with torch.cuda.stream(s):

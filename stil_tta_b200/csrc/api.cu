@@ -369,15 +369,16 @@ int infonce_dx_ksplit(int64_t m, int64_t n, int64_t dim) {
 // `kblocks` operand stages at L2 -> shared-memory bandwidth; 2 / 4 / 8 CTAs per tile share the walk and the leader adds the
 // partial accumulators through distributed shared memory (gemm_tc05.cu).  1 = not worth it / not possible.
 int dx_cluster_k(int64_t tiles, int64_t kblocks) {
+    // STIL_DX_CLUSTER=0/1: never (long contractions fall back to slice outputs + the reduction kernel), 2/4/8: always
     static const int forced = [] { const char* e = getenv("STIL_DX_CLUSTER"); return e ? atoi(e) : -1; }();
     if (forced >= 0) return forced <= 1 ? 1 : forced;
-    // Measured on the C2 step (512 x 512 x 128, 16 stages per CTA): clusters of 4-8 made the dX GEMMs 2-3x SLOWER (27.6 us
-    // against 9.0 us in the captured step): a cluster needs all its SMs free in ONE GPC at the same time, which the other
-    // chains' one-CTA-per-SM kernels rarely leave, and the barrier + distributed-shared-memory round trips cost more than the
-    // 2-3 us of operand streaming they save.  So: only long walks (>= 16 stages left per CTA: the global batch of 2+ ranks),
-    // and at most 4 CTAs per tile.
+    // Measured (profiles/r2_cluster_splitk.txt): reading a 64 KB partial tile through distributed shared memory costs ~1.5 us
+    // per peer even with a coalesced (column-major) layout, and a cluster needs all its SMs free in ONE GPC at the same time.
+    // On the C2 step clusters of 4-8 made the dX GEMMs 2-3x slower; on one rank's global-batch backward (512 x 4096 x 128)
+    // slice outputs + the reduction kernel (43 us) beat clusters of 4 / 8 (49 us).  A PAIR wins only in the narrow band where
+    // the walk is long enough to share (>= 32 stages per tile) but too short for the slice path (n = 1024: 34.6 vs 36.6 us).
     int ck = 1;
-    while (ck < 4 && tiles * ck * 2 <= 148 && kblocks / (ck * 2) >= 16) ck *= 2;
+    if (tiles * 4 <= 148 && kblocks >= 32) ck = 2;
     return ck;
 }
 
@@ -390,10 +391,11 @@ int infonce_store_jobs(GemmJob* J2, const InfoncePlan& P, const Operand& A, cons
     *cluster_k = 1;
     if (dim <= kTileN) {
         // one tile spans the embedding: split the contraction over a CLUSTER and keep the fused epilogue
-        const int ck = dx_cluster_k(2 * ceil_div(m, kTileM), ceil_div(n, kTileK) * grad_nseg(grad_dtype) * B.nseg);
-        ksplit = *cluster_k = (int)std::min<int64_t>(ck, ceil_div(n, kTileK));
+        // ... unless the contraction is long enough for the slice path (ksplit > 1 above)
+        const int ck = ksplit > 1 ? 1 : dx_cluster_k(2 * ceil_div(m, kTileM), ceil_div(n, kTileK) * grad_nseg(grad_dtype) * B.nseg);
+        if (ck > 1) ksplit = *cluster_k = (int)std::min<int64_t>(ck, ceil_div(n, kTileK));
     }
-    *fused = dim <= kTileN;
+    *fused = dim <= kTileN && (ksplit == 1 || *cluster_k > 1);
     const bool single = infonce_single_pass(m, n, off, inv_t);
     for (int s = 0; s < 2; ++s) {
         const Operand X = grad_operand(P.gop[single ? 0 : s], P.ldg, grad_nseg(grad_dtype));

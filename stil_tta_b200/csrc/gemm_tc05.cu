@@ -464,13 +464,15 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
 
         bool cluster_follower = false;
         if (MODE == GEMM_STORE && clustered) {
-            // Partial tile [128 x 128] fp32 in this CTA's (now idle) operand ring: row r holds 32 16-byte slots, slot s of row r
-            // is stored at s ^ (r & 31), so that the 32 rows of a warp hit 32 different slots (no bank conflicts on either
-            // side).  The raw accumulator travels: scales are linear and applied once, by the leader.
+            // Partial tile [128 x 128] fp32 in this CTA's (now idle) operand ring, stored COLUMN-major ([col][row]): the 32
+            // threads of a warp (consecutive rows) then touch 32 consecutive words, on the writing side (conflict-free shared
+            // stores) and, more importantly, on the reading side — distributed shared memory behaves like global memory: a
+            // row-major tile read thread = row (512-byte stride between lanes) moved 17 GB/s and took 11 us per leader
+            // (profiles/r2_cluster_splitk.txt).  The raw accumulator travels: scales are linear, applied once by the leader.
             const int r_in = q * 32 + lane;
             if (ks != 0) {
                 cluster_follower = true;
-                float4* mine = reinterpret_cast<float4*>(tiles) + r_in * 32;
+                float* mine = reinterpret_cast<float*>(tiles);
 #pragma unroll 1
                 for (int c = c_begin; c < c_end; ++c) {
                     uint32_t acc[32];
@@ -482,15 +484,13 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                         for (int j = 0; j < 32; ++j) acc[j] = 0u;     // empty slice: the accumulator was never written
                     }
 #pragma unroll
-                    for (int s8 = 0; s8 < 8; ++s8)
-                        mine[(c * 8 + s8) ^ (r_in & 31)] = make_float4(__uint_as_float(acc[4 * s8]), __uint_as_float(acc[4 * s8 + 1]),
-                                                                       __uint_as_float(acc[4 * s8 + 2]), __uint_as_float(acc[4 * s8 + 3]));
+                    for (int j = 0; j < 32; ++j) mine[(c * 32 + j) * kTileM + r_in] = __uint_as_float(acc[j]);
                 }
                 tc05::cluster_arrive(); tc05::cluster_wait();     // partial published
                 tc05::cluster_arrive(); tc05::cluster_wait();     // the leader has read it: the CTA may retire
             } else {
                 tc05::cluster_arrive(); tc05::cluster_wait();     // every follower's partial is in its shared memory
-                const uint32_t local = tc05::smem_u32(reinterpret_cast<float4*>(tiles) + r_in * 32);
+                const uint32_t local = tc05::smem_u32(reinterpret_cast<float*>(tiles) + r_in);
 #pragma unroll 1
                 for (int c = c_begin; c < c_end; ++c) {
                     uint32_t acc[32];
@@ -502,17 +502,12 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                         for (int j = 0; j < 32; ++j) acc[j] = 0u;
                     }
                     for (int peer = 1; peer < ksplit; ++peer) {       // fixed order: deterministic
-                        const uint32_t remote = tc05::map_to_cta(local, (uint32_t)peer);
-                        float4 v[8];
+                        const uint32_t remote = tc05::map_to_cta(local, (uint32_t)peer) + (uint32_t)(c * 32 * kTileM * 4);
+                        float v[32];
 #pragma unroll
-                        for (int s8 = 0; s8 < 8; ++s8) v[s8] = tc05::ld_dsmem_f4(remote + (((c * 8 + s8) ^ (r_in & 31)) << 4));
+                        for (int j = 0; j < 32; ++j) v[j] = tc05::ld_dsmem_f32(remote + (uint32_t)(j * kTileM * 4));
 #pragma unroll
-                        for (int s8 = 0; s8 < 8; ++s8) {
-                            acc[4 * s8] = __float_as_uint(__uint_as_float(acc[4 * s8]) + v[s8].x);
-                            acc[4 * s8 + 1] = __float_as_uint(__uint_as_float(acc[4 * s8 + 1]) + v[s8].y);
-                            acc[4 * s8 + 2] = __float_as_uint(__uint_as_float(acc[4 * s8 + 2]) + v[s8].z);
-                            acc[4 * s8 + 3] = __float_as_uint(__uint_as_float(acc[4 * s8 + 3]) + v[s8].w);
-                        }
+                        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + v[j]);
                     }
                     tc05::tmem_st_32x32b_x32(taddr + c * 32, acc);   // the summed tile replaces this CTA's accumulator
                 }

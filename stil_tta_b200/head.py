@@ -413,9 +413,8 @@ class DistributedSTiLHead(STiLHead):
         # + cat, exchanges / collectives, infonce fwd (prep, gemm, finish), bwd (prep, gemm, gemm), add, loss
         if self.transport == "fused":
             # row-local step (+ the class-partial push inside it), push_embeddings, stats GEMM, push_lse, loss finish,
-            # grad GEMM, dX GEMM (contraction split over a CTA cluster, reduced on chip; + a normalise-backward kernel only when
-            # the embedding is wider than one tile), waiting proto_add
-            self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 6 + (1 if P > 128 else 0) + 1
+            # grad GEMM, dX GEMM (+ slice reduction for a long split contraction), waiting proto_add
+            self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 6 + (1 if (n >= 2048 or P > 128) else 0) + 1
         else:
             self.launches_per_step = lib.stil_head_step_launches(C.byref(a)) + 1 + 3 + 3 + 3 + 2
 
