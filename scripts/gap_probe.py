@@ -20,20 +20,30 @@ torch.cuda.synchronize()
 
 
 def timed(fn, n=3000):
+    """us per call of fn, timed on the device: the side streams are joined into the current stream around the region"""
+    c = torch.cuda.current_stream(dev)
     for i in range(300):
         fn(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(c)
+    for s_ in _side:
+        s_.wait_event(e0)
     for i in range(n):
         fn(i)
-    e1.record()
+    for s_ in _side:
+        c.wait_stream(s_)
+    e1.record(c)
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 
 
+_side = []
+
+
 print(f"one stream, alternating heads        : {timed(lambda i: heads[i & 1].run()):6.2f} us/step")
 streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+_side.extend(streams)
 evs = [torch.cuda.Event(), torch.cuda.Event()]
 cur = torch.cuda.current_stream(dev)
 for e in evs:
@@ -52,3 +62,35 @@ def two_streams(i):
 t = timed(two_streams)
 cur.wait_event(evs[0]); cur.wait_event(evs[1])
 print(f"two streams chained by events        : {t:6.2f} us/step")
+
+# --- is the chained version really serial?  (1) the same head on both streams: a replay overwrites what the previous one wrote;
+# (2) a 200 us spin kernel in front of every replay: serial steps must then take >= 200 us each
+def two_streams_same_head(i):
+    j = i & 1
+    s = streams[j]
+    s.wait_event(evs[1 - j])
+    with torch.cuda.stream(s):
+        heads[0].run()
+        evs[j].record(s)
+
+
+t = timed(two_streams_same_head)
+cur.wait_event(evs[0]); cur.wait_event(evs[1])
+print(f"two streams, SAME head               : {t:6.2f} us/step")
+
+
+def two_streams_sleep(i):
+    j = i & 1
+    s = streams[j]
+    s.wait_event(evs[1 - j])
+    with torch.cuda.stream(s):
+        torch.cuda._sleep(400_000)       # ~200 us at 1.9 GHz
+        heads[j].run()
+        evs[j].record(s)
+
+
+t = timed(two_streams_sleep, 300)
+cur.wait_event(evs[0]); cur.wait_event(evs[1])
+print(f"two streams + 200 us spin per step   : {t:6.2f} us/step (serial if >= 200)")
+t = timed(lambda i: (torch.cuda._sleep(400_000), heads[i & 1].run()), 300)
+print(f"one stream  + 200 us spin per step   : {t:6.2f} us/step")

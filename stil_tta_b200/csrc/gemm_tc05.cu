@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
     if (warp == 0 && lane == 0) {
         tc05::tma_prefetch_desc(&J.tmx);
         tc05::tma_prefetch_desc(&J.tmy);
-        if (MODE == GEMM_GRAD) tc05::tma_prefetch_desc(&J.tmg);
+        if (MODE == GEMM_GRAD || J.out_tma) tc05::tma_prefetch_desc(&J.tmg);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -679,6 +679,21 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
 #pragma unroll
                     for (int j = 0; j < 32; ++j) l[j] = store_post(l[j], J.post_op, row, n0 + c * 32 + j);
                 }
+                if (J.out_tma) {
+                    // fp32 tile -> 128-byte-swizzled [128 rows x 32 floats] boxes in the (idle) operand ring -> ONE bulk tensor
+                    // store per box after the loop: the per-lane path below needed 32 store instructions per 32 x 32 block and
+                    // made the epilogue the long pole of the bank logits (202 us for 2 x 448 x 65536, profiles/r2_c5_kernels.txt)
+                    const bool empty = MODE == GEMM_STORE && ksplit > 1 && nkb == 0 && !clustered;
+                    const int r_in = q * 32 + lane;
+                    uint8_t* box = tiles + c * (kTileM * 128) + r_in * 128;
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const int off = (k4 ^ (r_in & 7)) * 16;
+                        *reinterpret_cast<float4*>(box + off) = empty ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                                                      : make_float4(l[4 * k4], l[4 * k4 + 1], l[4 * k4 + 2], l[4 * k4 + 3]);
+                    }
+                    continue;
+                }
                 // coalesced store through a per-warp staging tile (the operand ring is idle once the accumulator is
                 // complete): registers (thread = row) -> smem [32][33] -> 32 rows of up to 128 contiguous bytes; no
                 // alignment or leading-dimension requirement on `out`
@@ -737,6 +752,17 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                     if (want_lo)
                         *reinterpret_cast<uint4*>(lo_box + off) = make_uint4(lo_pk[4 * k], lo_pk[4 * k + 1], lo_pk[4 * k + 2], lo_pk[4 * k + 3]);
                 }
+            }
+        }
+        if ((MODE == GEMM_STATS || MODE == GEMM_STORE) && J.out && J.out_tma && !cluster_follower &&
+            !(MODE == GEMM_STORE && J.fin_dx != nullptr)) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy (TMA)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (e == 0) {
+                const int slice = (MODE == GEMM_STORE && !clustered && J.slice_stride > 0) ? ks : 0;
+                for (int c = 0; c < 4; ++c)
+                    if (c * 32 < ncols) tc05::tma_store_3d(&J.tmg, tiles + c * (kTileM * 128), n0 + c * 32, m0, slice);
+                tc05::tma_store_commit_and_wait();
             }
         }
         if (MODE == GEMM_GRAD) {
@@ -1130,6 +1156,18 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t r
     return STIL_OK;
 }
 
+// fp32 output map [cols, rows, slices]: 32 x 128 x 1 boxes (128 bytes wide), 128-byte swizzle; false = `out` not eligible
+static bool make_out_map(CUtensorMap* tm, float* base, int64_t cols, int64_t rows, int64_t ld, int64_t slices, int64_t slice_stride) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0 || (slices > 1 && (slice_stride & 3) != 0)) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)std::max<int64_t>(slices, 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(slices > 1 ? slice_stride : ld * rows) * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)kTileM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 void gemm_job_tiles(GemmLaunch& L) {
     int begin = 0;
     for (int j = 0; j < L.njobs; ++j) {
@@ -1256,6 +1294,18 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
         for (int j = 0; j < L.njobs; ++j)
             STIL_REQUIRE(L.job[j].ksplit == L.cluster_k && L.job[j].slice_stride == 0, STIL_E_ARG,
                          "cluster split-K: every job's ksplit must equal cluster_k (no slice outputs)");
+    }
+    if (mode == GEMM_STATS || mode == GEMM_STORE) {
+        static const bool no_tma_out = [] { const char* e = getenv("STIL_NO_TMA_OUT"); return e && e[0] == '1'; }();
+        for (int j = 0; j < L.njobs; ++j) {
+            GemmJob& J = const_cast<GemmLaunch&>(L).job[j];
+            J.out_tma = 0;
+            // plain fp32 outputs only (not the fused dX epilogue, not red.global accumulation into `out`)
+            const bool sliced = mode == GEMM_STORE && J.ksplit > 1 && J.slice_stride > 0 && L.cluster_k <= 1;
+            const bool accum = mode == GEMM_STORE && J.ksplit > 1 && J.slice_stride == 0 && L.cluster_k <= 1;
+            if (no_tma_out || !J.out || J.fin_dx || accum || J.fwd_norm) continue;
+            if (make_out_map(&J.tmg, J.out, J.N, J.M, J.ld_out, sliced ? J.ksplit : 1, J.slice_stride)) J.out_tma = 1;
+        }
     }
     if (mode == GEMM_BWD) return launch_gemm_bwd(L, stream);
     // more tiles than SMs: two CTAs per SM (3-deep rings) so epilogues overlap main loops

@@ -50,6 +50,10 @@ struct alignas(64) GemmJob {
     // STORE / STATS(optional)
     float* out;
     long long ld_out;
+    // set by launch_gemm when `out` allows it (16-byte aligned base, ld_out % 4 == 0): the fp32 tile leaves through shared
+    // memory and TMA bulk tensor stores (tmg = map of out [N, M, slices], 32 x 128 boxes, 128-byte swizzle) instead of
+    // per-lane 4-byte stores
+    int out_tma;
     // GRAD
     const float* lse_x;      // [M]
     const float* lse_y;      // [N] or nullptr (v ignored)
