@@ -1303,7 +1303,9 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
             // plain fp32 outputs only (not the fused dX epilogue, not red.global accumulation into `out`)
             const bool sliced = mode == GEMM_STORE && J.ksplit > 1 && J.slice_stride > 0 && L.cluster_k <= 1;
             const bool accum = mode == GEMM_STORE && J.ksplit > 1 && J.slice_stride == 0 && L.cluster_k <= 1;
-            if (no_tma_out || !J.out || J.fin_dx || accum || J.fwd_norm) continue;
+            // N % 4: a bulk tensor store clips out-of-range columns in 16-byte granules — with N = 130 it overwrote columns
+            // 130-131, which belong to the neighbouring block of the CoMatch graphs (found by tests/test_gpu_banks.py)
+            if (no_tma_out || !J.out || J.fin_dx || accum || J.fwd_norm || (J.N & 3) != 0) continue;
             if (make_out_map(&J.tmg, J.out, J.N, J.M, J.ld_out, sliced ? J.ksplit : 1, J.slice_stride)) J.out_tma = 1;
         }
     }
