@@ -1022,6 +1022,118 @@ struct SoftCeArgs {
     int vec_y, vec_pl, vec_g;
 };
 
+// block partial of the three losses, then the last block adds the partials in order (deterministic)
+__device__ __forceinline__ void softce_block_finish(float (&lossv)[3], const SoftCeArgs& A) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int h = 0; h < 3; ++h) lossv[h] = warp_sum(lossv[h]);     // the row leaders' terms of this warp
+    __shared__ float sred[3][kRowBlock / 32];
+    __shared__ bool is_last;
+    if (lane == 0)
+        for (int h = 0; h < 3; ++h) sred[h][warp] = lossv[h];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int h = 0; h < 3; ++h) {
+            float a = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sred[h][w];
+            A.block_partials[3 * blockIdx.x + h] = a;
+        }
+        __threadfence();
+        is_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && warp == 0) {
+        // deterministic: lane-strided partial sums in block order, then a fixed shuffle tree, per loss
+        __threadfence();
+        const float* bp = A.block_partials;
+        float sum3[3] = {0.f, 0.f, 0.f};
+        for (unsigned int b0 = 0; b0 < gridDim.x; b0 += 128) {      // four independent L2 loads per lane and loss per batch
+            float v[4][3];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned int b = b0 + lane + 32 * q;
+#pragma unroll
+                for (int h = 0; h < 3; ++h) v[q][h] = b < gridDim.x ? __ldcg(bp + 3 * b + h) : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int h = 0; h < 3; ++h) sum3[h] += v[q][h];
+        }
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            const float sum = warp_sum(sum3[h]);
+            if (lane == 0) A.losses[h] = sum / (float)A.rows;   // .mean() over B_u
+        }
+        if (lane == 0) *A.ticket = 0u;
+    }
+}
+
+// K = 2 (cardiac: binary CAD / infarction): a row is 8 bytes, so one thread takes TWO rows with 16-byte loads / stores and
+// 2-byte flag loads — the generic one-thread-per-row form issues 13 memory instructions for 62 bytes and is LSU / issue bound
+// (ncu, profiles/r2_ncu_rows2_before.txt: 17 % of the DRAM peak at 64 % issue utilisation)
+__global__ void __launch_bounds__(kRowBlock) masked_softce_k2_kernel(const SoftCeArgs A) {
+    float lossv[3] = {0.f, 0.f, 0.f};
+    const float inv_rows = 1.0f / (float)A.rows;
+    const int pairs = A.rows >> 1;
+    const float4* pl4 = reinterpret_cast<const float4*>(A.pl);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += gridDim.x * blockDim.x) {
+        const float4 pl = pl4[p];
+        float4 y[3];
+#pragma unroll
+        for (int h = 0; h < 3; ++h) y[h] = reinterpret_cast<const float4*>(A.y[h])[p];
+        const uchar2 m1 = reinterpret_cast<const uchar2*>(A.mask1)[p], c1 = reinterpret_cast<const uchar2*>(A.case1)[p];
+        const uchar2 c2i = reinterpret_cast<const uchar2*>(A.case2_i)[p], c2t = reinterpret_cast<const uchar2*>(A.case2_t)[p];
+        const uchar2 c3 = reinterpret_cast<const uchar2*>(A.case3)[p], mr = reinterpret_cast<const uchar2*>(A.mask_random)[p];
+        float4 dy[3];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float p0 = r ? pl.z : pl.x, p1 = r ? pl.w : pl.y;
+            const float fm1 = (r ? m1.y : m1.x) ? 1.f : 0.f, fc1 = (r ? c1.y : c1.x) ? 1.f : 0.f;
+            const float fc2i = (r ? c2i.y : c2i.x) ? 1.f : 0.f, fc2t = (r ? c2t.y : c2t.x) ? 1.f : 0.f;
+            const float fc3 = (r ? c3.y : c3.x) ? 1.f : 0.f, fmr = (r ? mr.y : mr.x) ? 1.f : 0.f;
+            const float wgt[3] = {fm1 * fc1, fm1 * (fc1 + fc2t + fc3 * fmr), fm1 * (fc1 + fc2i + fc3 * (1.f - fmr))};
+            const float spl = p0 + p1;
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                const float y0 = r ? y[h].z : y[h].x, y1 = r ? y[h].w : y[h].y;
+                const float m = fmaxf(y0, y1);
+                const float ml = m * 1.4426950408889634f;
+                const float e0 = exp_fast_shift(y0, ml), e1 = exp_fast_shift(y1, ml);
+                const float s = e0 + e1;
+                const float lse = m + log_fast(s);
+                lossv[h] += (lse * spl - (p0 * y0 + p1 * y1)) * wgt[h];
+                const float gs = A.grad_scale * wgt[h] * inv_rows;
+                const float ps = gs * spl * __frcp_rn(s);
+                const float d0 = fmaf(e0, ps, -gs * p0), d1 = fmaf(e1, ps, -gs * p1);
+                if (r) { dy[h].z = d0; dy[h].w = d1; } else { dy[h].x = d0; dy[h].y = d1; }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 3; ++h)
+            if (A.dy[h]) reinterpret_cast<float4*>(A.dy[h])[p] = dy[h];
+    }
+    // odd row count: the last row alone
+    if ((A.rows & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int row = A.rows - 1;
+        const float p0 = A.pl[2 * row], p1 = A.pl[2 * row + 1];
+        const float fm1 = A.mask1[row] ? 1.f : 0.f, fc1 = A.case1[row] ? 1.f : 0.f, fc2i = A.case2_i[row] ? 1.f : 0.f;
+        const float fc2t = A.case2_t[row] ? 1.f : 0.f, fc3 = A.case3[row] ? 1.f : 0.f, fmr = A.mask_random[row] ? 1.f : 0.f;
+        const float wgt[3] = {fm1 * fc1, fm1 * (fc1 + fc2t + fc3 * fmr), fm1 * (fc1 + fc2i + fc3 * (1.f - fmr))};
+        const float spl = p0 + p1;
+        for (int h = 0; h < 3; ++h) {
+            const float* yy = static_cast<const float*>(A.y[h]) + 2 * row;
+            const float m = fmaxf(yy[0], yy[1]), ml = m * 1.4426950408889634f;
+            const float e0 = exp_fast_shift(yy[0], ml), e1 = exp_fast_shift(yy[1], ml), s = e0 + e1;
+            const float lse = m + log_fast(s);
+            lossv[h] += (lse * spl - (p0 * yy[0] + p1 * yy[1])) * wgt[h];
+            const float gs = A.grad_scale * wgt[h] * inv_rows, ps = gs * spl * __frcp_rn(s);
+            if (A.dy[h]) { A.dy[h][2 * row] = fmaf(e0, ps, -gs * p0); A.dy[h][2 * row + 1] = fmaf(e1, ps, -gs * p1); }
+        }
+    }
+    softce_block_finish(lossv, A);
+}
+
 // LPR lanes per row (32 / LPR rows per warp for small K, like cgpl_pgls_kernel), NV float2 items per lane
 template <int LPR, int NV, bool FAST>
 __global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) masked_softce_kernel(const SoftCeArgs A) {
@@ -1098,48 +1210,7 @@ __global__ void __launch_bounds__(kRowBlock, (NV <= 5 ? 3 : 1)) masked_softce_ke
             }
         }
     }
-#pragma unroll
-    for (int h = 0; h < 3; ++h) lossv[h] = warp_sum(lossv[h]);     // the row leaders' terms of this warp
-    __shared__ float sred[3][kRowBlock / 32];
-    __shared__ bool is_last;
-    if (lane == 0)
-        for (int h = 0; h < 3; ++h) sred[h][warp] = lossv[h];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int h = 0; h < 3; ++h) {
-            float a = 0.f;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sred[h][w];
-            A.block_partials[3 * blockIdx.x + h] = a;
-        }
-        __threadfence();
-        is_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (is_last && warp == 0) {
-        // deterministic: lane-strided partial sums in block order, then a fixed shuffle tree, per loss
-        __threadfence();
-        const float* bp = A.block_partials;
-        float sum3[3] = {0.f, 0.f, 0.f};
-        for (unsigned int b0 = 0; b0 < gridDim.x; b0 += 128) {      // four independent L2 loads per lane and loss per batch
-            float v[4][3];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned int b = b0 + lane + 32 * q;
-#pragma unroll
-                for (int h = 0; h < 3; ++h) v[q][h] = b < gridDim.x ? __ldcg(bp + 3 * b + h) : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int h = 0; h < 3; ++h) sum3[h] += v[q][h];
-        }
-#pragma unroll
-        for (int h = 0; h < 3; ++h) {
-            const float sum = warp_sum(sum3[h]);
-            if (lane == 0) A.losses[h] = sum / (float)A.rows;   // .mean() over B_u
-        }
-        if (lane == 0) *A.ticket = 0u;
-    }
+    softce_block_finish(lossv, A);
 }
 
 // =====================================================================================
@@ -1735,7 +1806,15 @@ int launch_masked_softce(const void* y_m, const void* y_i, const void* y_t, int 
         else kernel_gen<<<blocks, threads, 0, stream>>>(A);
     };
 #define STIL_SOFTCE(LPR, NV) go(masked_softce_kernel<LPR, NV, true>, masked_softce_kernel<LPR, NV, false>, LPR)
-    if (k <= 2) STIL_SOFTCE(1, 1);
+    auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool k2 = k == 2 && logit_dtype == STIL_F32 && ld_y == 2 && ld_pl == 2 && ld_g == 2 && al16(y_m) && al16(y_i) && al16(y_t) &&
+                    al16(pseudo_label) && al16(d_y_m) && al16(d_y_i) && al16(d_y_t) &&
+                    ((reinterpret_cast<uintptr_t>(mask1) | reinterpret_cast<uintptr_t>(case1) | reinterpret_cast<uintptr_t>(case2_i) |
+                      reinterpret_cast<uintptr_t>(case2_t) | reinterpret_cast<uintptr_t>(case3) | reinterpret_cast<uintptr_t>(mask_random)) & 1) == 0;
+    if (k2) {
+        const int blocks = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(rows / 2, threads), 1), masked_softce_blocks(rows, k));
+        masked_softce_k2_kernel<<<blocks, threads, 0, stream>>>(A);
+    } else if (k <= 2) STIL_SOFTCE(1, 1);
     else if (k <= 16) STIL_SOFTCE(4, 2);
     else if (k <= 64) STIL_SOFTCE(8, 4);
     else if (k <= 128) STIL_SOFTCE(32, 2);

@@ -530,3 +530,23 @@ def test_head_set_hparams_recaptures(S, O):
     assert torch.equal(head.out["mask1"].cpu()[keep], o1["mask1"][keep])
     with pytest.raises(ValueError):
         head.set_hparams(no_such_parameter=1)
+
+
+@pytest.mark.parametrize("rows", [33, 64, 1])
+def test_masked_soft_ce_binary_two_rows_per_thread(S, O, rows):
+    """K = 2 takes the two-rows-per-thread kernel (16-byte loads); odd row counts end in a single-row tail."""
+    g = torch.Generator().manual_seed(rows)
+    ys = [torch.randn(rows, 2, generator=g) * 3 for _ in range(3)]
+    pl = torch.softmax(torch.randn(rows, 2, generator=g) * 2, 1)
+    flags = [torch.rand(rows, generator=g) > 0.4 for _ in range(6)]
+    yr = [y.clone().requires_grad_(True) for y in ys]
+    lr = O.masked_soft_ce(*yr, pl, *flags)
+    gr = torch.autograd.grad(lr[0] + 2 * lr[1] + 3 * lr[2], yr)
+    yc = [dev(y).requires_grad_(True) for y in ys]
+    lc = S.masked_soft_ce(*yc, dev(pl), *[dev(f) for f in flags])
+    gc = torch.autograd.grad(lc[0] + 2 * lc[1] + 3 * lc[2], yc)
+    for a, b in zip(lc, lr):
+        assert abs(float(a) - float(b)) <= REL * abs(float(b)) + 1e-7
+    for a, b, nm in zip(gc, gr, ("d_y_m", "d_y_i", "d_y_t")):
+        if float(b.abs().max()) > 0:
+            assert_rel(a, b, REL, nm + " (K=2)")
