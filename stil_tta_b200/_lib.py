@@ -206,8 +206,9 @@ _ws_cache: Dict[tuple, torch.Tensor] = {}
 
 
 def workspace(dev: torch.device, key: str, nbytes: int) -> torch.Tensor:
-    """Scratch owned by the Python side (the extension allocates nothing), cached per device/op."""
-    k = (dev.index, key)
+    """Scratch owned by the Python side (the extension allocates nothing), cached per device, op AND stream: two
+    streams (or threads with their own streams) driving the same op concurrently never share a buffer."""
+    k = (dev.index, key, torch.cuda.current_stream(dev).cuda_stream)
     buf = _ws_cache.get(k)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)

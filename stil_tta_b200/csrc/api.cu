@@ -1986,6 +1986,13 @@ STIL_API int stil_head_step(const stil_head_step_args* a) {
                  (long long)P.bytes);
     SideStreams* SS = nullptr;
     if ((rc = get_side_streams(&SS))) return rc;
+    // The side streams and their fork / join events are shared by every caller on this device: the whole enqueue (a few
+    // dozen microseconds of host time) is serialised, so two host threads or two heads driving the same device cannot
+    // interleave each other's event records and waits.  The caller still owns the workspace: one per concurrent step.
+    static std::mutex enqueue_mutex[64];
+    int dev_id = 0;
+    STIL_CUDA(cudaGetDevice(&dev_id));
+    std::lock_guard<std::mutex> enqueue_lock(enqueue_mutex[dev_id & 63]);
     cudaStream_t s_loss = SS->s[0], s_acc = SS->s[1], s_ce = SS->s[2], s_nce = SS->s[3];
     const float inv_t = 1.0f / a->temperature;
     const int esz = dt == STIL_BF16 ? 2 : 4;
