@@ -1228,7 +1228,10 @@ STIL_API int stil_simmatch_fwd(const void* feat_ku, const void* feat_qu, int dty
     }
     GL.njobs = 2;
     gemm_job_tiles(GL);
-    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    if (bank_logits_eligible(dtype, rows, dim, k_bank, P.ldz)) {
+        // short contraction, long bank axis: the persistent resident-rows kernel (bank_sweep.cu)
+        if ((rc = launch_bank_logits(feat_ku, feat_qu, rows, dim, ld, bank, ld_bank, k_bank, P.zt, P.zs, P.ldz, S(stream)))) return rc;
+    } else if ((rc = launch_gemm(GL, S(stream)))) return rc;
     return launch_simmatch_rows(P.zt, P.zs, P.ldz, reinterpret_cast<const long long*>(labels), (int)rows, (int)k_bank,
                                 prob_ku_orig, (int)num_classes, tt, st, c_smooth, prob_ku, loss_in, P.gop, P.ldg,
                                 grad_nseg(grad_dtype), S(stream));
@@ -1247,6 +1250,10 @@ STIL_API int stil_simmatch_bwd(const void* feat_qu, int dtype, int64_t rows, int
     STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "simmatch workspace too small");
     if (rows == 0) return STIL_OK;
     int rc;
+    if (grad_dtype == STIL_F32 && bank_dx_eligible(dtype, rows, dim, k_bank, static_cast<const float*>(d_feat_qu), ld_grad))
+        // long bank axis onto a small output: the whole [128 x dim] accumulator lives in tensor memory (bank_sweep.cu)
+        return launch_bank_dx(P.gop, P.ldg, grad_nseg(grad_dtype), rows, bank, ld_bank, dim, k_bank, grad_loss_in,
+                              static_cast<float*>(d_feat_qu), ld_grad, S(stream));
     // d_feat_q[i,:] = grad_i * sum_j G_ij bank[:, j]; G (bf16) was left in the workspace by the forward.
     // The contraction runs over k_bank: split it across CTAs so the whole chip works on it.
     const Operand X = grad_operand(P.gop, P.ldg, grad_nseg(grad_dtype));
@@ -1326,7 +1333,9 @@ STIL_API int stil_simmatch_shard_stats(const void* feat_ku, const void* feat_qu,
     }
     GL.njobs = 2;
     gemm_job_tiles(GL);
-    if ((rc = launch_gemm(GL, S(stream)))) return rc;
+    if (bank_logits_eligible(dtype, rows, dim, k_shard, P.ldz)) {
+        if ((rc = launch_bank_logits(feat_ku, feat_qu, rows, dim, ld, bank, ld_bank, k_shard, P.zt, P.zs, P.ldz, S(stream)))) return rc;
+    } else if ((rc = launch_gemm(GL, S(stream)))) return rc;
     // per-chunk partial statistics live in the G buffer of the workspace (not written before _shard_grad)
     STIL_REQUIRE((int64_t)simmatch_shard_chunks(rows, k_shard) * rows * (3 + num_classes) * 4 <= rows * 2 * P.ldg * 2, STIL_E_SHAPE,
                  "simmatch_shard_stats: %lld classes do not fit the chunk scratch", (long long)num_classes);

@@ -1,0 +1,459 @@
+// a7 bank sweep (SURVEY §8 a7 / e-C5; reference models/MatchModel/simmatch_model.py:268,281 — the two products
+// `feat_kw @ bank` and `feat_qu @ bank` against a [dim, K_b] memory bank): persistent tcgen05 kernels for the shapes
+// where the general tiled GEMM (gemm_tc05.cu) is bound by operand re-fetch instead of the tensor pipe.
+//
+// The products have a SHORT contraction (dim <= 512) and a LONG bank axis (65536 columns).  With one CTA per 128 x 128
+// output tile every tile re-loads its 128 x dim feature rows (128 KiB at dim 512) next to its 128 KiB of bank columns,
+// pays a CTA prologue (barrier init, TMEM allocation, tensor-map fetch, pipeline fill) per 1 us of tensor work and
+// cannot overlap its epilogue with anything: 180 us for 2 x 448 x 65536 x 512 (profiles/r2_bank_timeline_n1.txt).
+//
+// bank_logits_kernel: one CTA per SM.  A CTA owns a UNIT (teacher or student rows of one 128-row block, kept RESIDENT
+// in shared memory) and walks over a range of 128-column bank blocks:
+//   warp 0  streams bank blocks through a ring of 16 KiB stages (TMA, the bank read in place as an MN-major operand)
+//   warp 1  issues tcgen05.mma into one of TWO 128-column TMEM accumulators
+//   warps 2-5 drain the other accumulator: tcgen05.ld -> 128-byte-swizzled fp32 boxes in shared memory -> bulk tensor
+//           stores, so the epilogue of block i runs under the MMAs of block i + 1
+//   warp 6  (re)loads the resident feature rows when the CTA moves to its next unit
+// Chunks (unit x column range) are dealt so that CTAs running at the same time sweep the SAME bank columns for
+// different units: the bank streams from HBM once per sweep and is shared through L2.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "internal.h"
+#include "tc05.cuh"
+
+namespace stil {
+namespace {
+
+constexpr int kSweepEpiWarps = 4;
+constexpr int kSweepEpiThreads = 32 * kSweepEpiWarps;
+constexpr int kSweepThreads = 64 + kSweepEpiThreads + 32;   // TMA(bank) | MMA | 4 epilogue warps | TMA(features)
+constexpr int kBoxA = kTileM * 128;                // [128 rows x 64 bf16], 128-byte swizzle
+constexpr int kStageB = kTileK * kTileN * 2;       // [64 contraction rows x 128 columns] as two 64 x 64 boxes
+constexpr int kOutBox = kTileM * 128;              // [128 rows x 32 fp32], 128-byte swizzle
+constexpr int kOutBoxes = 2;                       // the epilogue leaves in two 64-column halves
+constexpr int kMaxStagesB = 8;
+constexpr int kSweepBarBytes = 256;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr uint32_t kSweepTmemCols = 256;
+
+struct alignas(64) BankSweepLaunch {
+    CUtensorMap tma[2];   // feat_ku / feat_qu [rows, dim], K-major boxes 64 x 128
+    CUtensorMap tmb;      // bank [dim, k_shard] in place, MN-major boxes 64 (columns) x 64 (contraction rows)
+    CUtensorMap tmo[2];   // zt / zs fp32 [rows, ldz], boxes 32 x 128
+    int k_shard, nbx, tiles_m, nblocks, ranges, stages, nchunks;
+};
+
+struct Chunk {
+    int job, m0, b0, b1;
+};
+__device__ __forceinline__ Chunk decode_chunk(const BankSweepLaunch& L, int c) {
+    const int units = 2 * L.tiles_m;
+    const int r = c / units, u = c - r * units;
+    Chunk k;
+    k.job = u & 1;
+    k.m0 = (u >> 1) * kTileM;
+    k.b0 = (int)(((long long)r * L.nblocks) / L.ranges);
+    k.b1 = (int)(((long long)(r + 1) * L.nblocks) / L.ranges);
+    return k;
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 1) bank_logits_kernel(const __grid_constant__ BankSweepLaunch L) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = tc05::smem_u32(smem_raw);
+    uint8_t* base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* as = base;                                   // [nbx] resident feature boxes
+    uint8_t* bs = as + L.nbx * kBoxA;                     // [stages] bank ring
+    uint8_t* os = bs + L.stages * kStageB;                // [kOutBoxes] output staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(os + kOutBoxes * kOutBox);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* b_full = bars + 2;                          // [kMaxStagesB]
+    uint64_t* b_empty = b_full + kMaxStagesB;             // [kMaxStagesB]
+    uint64_t* t_full = b_empty + kMaxStagesB;             // [2]
+    uint64_t* t_empty = t_full + 2;                       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc05::tma_prefetch_desc(&L.tmb);
+        tc05::tma_prefetch_desc(&L.tma[0]);
+        tc05::tma_prefetch_desc(&L.tma[1]);
+        tc05::tma_prefetch_desc(&L.tmo[0]);
+        tc05::tma_prefetch_desc(&L.tmo[1]);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            tc05::mbar_init(a_full, 1);
+            tc05::mbar_init(a_empty, 1);
+            for (int s = 0; s < kMaxStagesB; ++s) {
+                tc05::mbar_init(&b_full[s], 1);
+                tc05::mbar_init(&b_empty[s], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                tc05::mbar_init(&t_full[i], 1);
+                tc05::mbar_init(&t_empty[i], kSweepEpiWarps);
+            }
+            tc05::fence_mbar_init();
+        }
+        __syncwarp();
+        tc05::tmem_alloc(tmem_slot, kSweepTmemCols);
+        tc05::tmem_relinquish();
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nbx = L.nbx, stages = L.stages;
+
+    if (warp == 0) {
+        // ===================== bank producer: every (chunk, block, contraction box) in MMA order =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int c = blockIdx.x; c < L.nchunks; c += gridDim.x) {
+                const Chunk k = decode_chunk(L, c);
+                for (int nb = k.b0; nb < k.b1; ++nb)
+                    for (int kb = 0; kb < nbx; ++kb) {
+                        tc05::mbar_wait(&b_empty[s], ph ^ 1);
+                        tc05::mbar_arrive_expect_tx(&b_full[s], kStageB);
+                        uint8_t* dst = bs + s * kStageB;
+                        tc05::tma_load_3d(dst, &L.tmb, &b_full[s], nb * kTileN, kb * kTileK, 0);
+                        tc05::tma_load_3d(dst + 64 * kTileK * 2, &L.tmb, &b_full[s], nb * kTileN + 64, kb * kTileK, 0);
+                        if (++s == stages) { s = 0; ph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 6) {
+        // ===================== feature producer: the unit's rows, once per chunk =====================
+        if (lane == 0) {
+            int ci = 0;
+            for (int c = blockIdx.x; c < L.nchunks; c += gridDim.x, ++ci) {
+                const Chunk k = decode_chunk(L, c);
+                if (ci > 0) tc05::mbar_wait(a_empty, (ci - 1) & 1);     // the previous unit's MMAs have retired
+                tc05::mbar_arrive_expect_tx(a_full, (uint32_t)(nbx * kBoxA));
+                for (int b = 0; b < nbx; ++b) tc05::tma_load_3d(as + b * kBoxA, &L.tma[k.job], a_full, b * kTileK, k.m0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, kTileN) | (1u << 16);   // B MN-major
+            const uint32_t as_a = tc05::smem_u32(as), bs_a = tc05::smem_u32(bs);
+            int s = 0, ci = 0, ti = 0;
+            uint32_t ph = 0;
+            for (int c = blockIdx.x; c < L.nchunks; c += gridDim.x, ++ci) {
+                const Chunk k = decode_chunk(L, c);
+                tc05::mbar_wait(a_full, ci & 1);
+                for (int nb = k.b0; nb < k.b1; ++nb, ++ti) {
+                    const int sb = ti & 1;
+                    tc05::mbar_wait(&t_empty[sb], ((ti >> 1) & 1) ^ 1);    // the epilogue has drained this accumulator
+                    tc05::fence_after_sync();
+                    for (int kb = 0; kb < nbx; ++kb) {
+                        tc05::mbar_wait(&b_full[s], ph);
+                        tc05::fence_after_sync();
+                        const uint64_t a_desc = tc05::make_kmajor_sw128_desc(as_a + kb * kBoxA);
+                        const uint64_t b_desc = tc05::make_mnmajor_sw128_desc(bs_a + s * kStageB, 64 * kTileK * 2);
+#pragma unroll
+                        for (int kk = 0; kk < kTileK / 16; ++kk)
+                            tc05::mma_f16_ss(tmem_base + sb * kTileN, a_desc + 2u * kk, b_desc + 128u * kk, idesc, (kb | kk) ? 1u : 0u);
+                        tc05::mma_commit(&b_empty[s]);
+                        if (++s == stages) { s = 0; ph ^= 1; }
+                    }
+                    tc05::mma_commit(&t_full[sb]);
+                }
+                tc05::mma_commit(a_empty);
+            }
+        }
+    } else {
+        // ===================== epilogue: thread = accumulator row, 4 x 32 columns per block =====================
+        const int e = threadIdx.x - 64;
+        const int q = warp & 3;                 // TMEM lane quarter of this warp
+        const int r_in = q * 32 + lane;
+        int ti = 0;
+        for (int c = blockIdx.x; c < L.nchunks; c += gridDim.x) {
+            const Chunk k = decode_chunk(L, c);
+            for (int nb = k.b0; nb < k.b1; ++nb, ++ti) {
+                const int sb = ti & 1, n0 = nb * kTileN;
+                tc05::mbar_wait(&t_full[sb], (ti >> 1) & 1);
+                tc05::fence_after_sync();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t acc[kOutBoxes][32];
+#pragma unroll
+                    for (int cc = 0; cc < kOutBoxes; ++cc)
+                        tc05::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sb * kTileN + (half * kOutBoxes + cc) * 32,
+                                                 acc[cc]);
+                    tc05::tmem_ld_wait();
+                    if (half == 1) {            // every column of this accumulator is in registers: hand it back
+                        tc05::fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) tc05::mbar_arrive(&t_empty[sb]);
+                    }
+                    // the previous bulk stores must have read the staging boxes before they are overwritten
+                    if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(kSweepEpiThreads) : "memory");
+#pragma unroll
+                    for (int cc = 0; cc < kOutBoxes; ++cc) {
+                        uint8_t* box = os + cc * kOutBox + r_in * 128;
+#pragma unroll
+                        for (int k4 = 0; k4 < 8; ++k4)
+                            *reinterpret_cast<uint4*>(box + ((k4 ^ (r_in & 7)) * 16)) =
+                                make_uint4(acc[cc][4 * k4], acc[cc][4 * k4 + 1], acc[cc][4 * k4 + 2], acc[cc][4 * k4 + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(kSweepEpiThreads) : "memory");
+                    if (e == 0) {
+#pragma unroll
+                        for (int cc = 0; cc < kOutBoxes; ++cc) {
+                            const int col = n0 + (half * kOutBoxes + cc) * 32;
+                            if (col < L.k_shard) tc05::tma_store_3d(&L.tmo[k.job], os + cc * kOutBox, col, k.m0, 0);
+                        }
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+        }
+        if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc05::fence_after_sync();
+        tc05::tmem_dealloc(tmem_base, kSweepTmemCols);
+    }
+}
+
+// how many column ranges every unit is cut into: fill the SMs, few waves, chunks long enough to amortise the reload of
+// the resident rows (~2 block times)
+int pick_ranges(int units, int nblocks, int sms) {
+    int best = 1;
+    double best_cost = 1e30;
+    for (int r = 1; r <= std::min(nblocks, 1024); ++r) {
+        const double chunks = (double)units * r;
+        const double waves = std::ceil(chunks / sms);
+        const double cost = waves * ((double)nblocks / r + 2.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = r; }
+    }
+    return best;
+}
+
+
+// =====================================================================================================================
+// bank_dx_kernel: d_feat[rows, dim] (+)= G[rows, (hi, lo), K_b] · bankᵀ — the backward product of simmatch_model.py:281,
+// a LONG contraction (the bank axis) onto a small output.  One CTA per SM owns a 128-row block and a range of the
+// contraction and keeps the WHOLE [128 x dim] fp32 accumulator in tensor memory (dim <= 512 columns = all of TMEM), so a
+// G tile is fetched once for all dim output columns (the tiled GEMM re-fetched it per 128-column tile: 4x at dim 512)
+// and each stage carries [G hi | G lo | dim bank rows] x 64 contraction columns.  The partial tiles of the CTAs that
+// share a row block are added with 16-byte reductions into the zero-initialised output.
+constexpr int kDxEpiWarps = 4;
+constexpr int kDxThreads = 64 + 32 * kDxEpiWarps;
+constexpr int kDxMaxStages = 6;
+
+struct alignas(64) BankDxLaunch {
+    CUtensorMap tmg;      // G [rows, nseg, K_b] K-major, boxes 64 x 128
+    CUtensorMap tmb;      // bank [dim, K_b] K-major, boxes 64 x 128
+    float* out;           // [rows, ld_out] fp32, zero-initialised
+    const float* row_scale;   // optional upstream gradient per row
+    long long ld_out;
+    int rows, dim, nseg, nbn /*128-row bank boxes*/, kboxes, ksplit, stages;
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kDxThreads, 1) bank_dx_kernel(const __grid_constant__ BankDxLaunch L) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = tc05::smem_u32(smem_raw);
+    uint8_t* base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    const int stage_bytes = (L.nseg + L.nbn) * kBoxA;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + L.stages * stage_bytes);
+    uint64_t* full = bars;                       // [kDxMaxStages]
+    uint64_t* empty = bars + kDxMaxStages;       // [kDxMaxStages]
+    uint64_t* acc_full = empty + kDxMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ks = blockIdx.x % L.ksplit, tm = blockIdx.x / L.ksplit;
+    const int m0 = tm * kTileM;
+    const int kb0 = (int)(((long long)ks * L.kboxes) / L.ksplit), kb1 = (int)(((long long)(ks + 1) * L.kboxes) / L.ksplit);
+    if (warp == 0 && lane == 0) {
+        tc05::tma_prefetch_desc(&L.tmg);
+        tc05::tma_prefetch_desc(&L.tmb);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kDxMaxStages; ++s) {
+                tc05::mbar_init(&full[s], 1);
+                tc05::mbar_init(&empty[s], 1);
+            }
+            tc05::mbar_init(acc_full, 1);
+            tc05::fence_mbar_init();
+        }
+        __syncwarp();
+        tc05::tmem_alloc(tmem_slot, L.tmem_cols);
+        tc05::tmem_relinquish();
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                tc05::mbar_wait(&empty[s], ph ^ 1);
+                tc05::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                uint8_t* dst = base + s * stage_bytes;
+                for (int sg = 0; sg < L.nseg; ++sg) tc05::tma_load_3d(dst + sg * kBoxA, &L.tmg, &full[s], kb * kTileK, m0, sg);
+                for (int nb = 0; nb < L.nbn; ++nb)
+                    tc05::tma_load_3d(dst + (L.nseg + nb) * kBoxA, &L.tmb, &full[s], kb * kTileK, nb * kTileN, 0);
+                if (++s == L.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                tc05::mbar_wait(&full[s], ph);
+                tc05::fence_after_sync();
+                const uint32_t st_a = tc05::smem_u32(base + s * stage_bytes);
+                for (int sg = 0; sg < L.nseg; ++sg) {
+                    const uint64_t a_desc = tc05::make_kmajor_sw128_desc(st_a + sg * kBoxA);
+                    for (int n0 = 0; n0 < L.dim; n0 += 256) {      // up to 256 output columns per instruction
+                        const int nn = min(256, L.dim - n0);
+                        const uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, (uint32_t)nn);
+                        const uint64_t b_desc = tc05::make_kmajor_sw128_desc(st_a + (L.nseg + n0 / kTileN) * kBoxA);
+#pragma unroll
+                        for (int kk = 0; kk < kTileK / 16; ++kk)
+                            tc05::mma_f16_ss(tmem_base + n0, a_desc + 2u * kk, b_desc + 2u * kk, idesc, (kb > kb0 || sg || kk) ? 1u : 0u);
+                    }
+                }
+                tc05::mma_commit(&empty[s]);
+                if (++s == L.stages) { s = 0; ph ^= 1; }
+            }
+            if (kb1 > kb0) tc05::mma_commit(acc_full);
+            else tc05::mbar_arrive(acc_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < L.rows;
+        const float rs = (L.row_scale && row_ok) ? L.row_scale[row] : 1.f;
+        tc05::mbar_wait(acc_full, 0);
+        tc05::fence_after_sync();
+        if (kb1 > kb0) {
+            for (int c = 0; c < L.dim; c += 32) {
+                uint32_t acc[32];
+                tc05::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, acc);
+                tc05::tmem_ld_wait();
+                if (row_ok) {
+                    float* dst = L.out + (long long)row * L.ld_out + c;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(acc[j]) * rs),
+                                     "f"(__uint_as_float(acc[j + 1]) * rs), "f"(__uint_as_float(acc[j + 2]) * rs),
+                                     "f"(__uint_as_float(acc[j + 3]) * rs)
+                                     : "memory");
+                }
+            }
+        }
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc05::fence_after_sync();
+        tc05::tmem_dealloc(tmem_base, L.tmem_cols);
+    }
+}
+
+}  // namespace
+
+bool bank_logits_eligible(int dtype, int64_t rows, int64_t dim, int64_t k_shard, int64_t ldz) {
+    static const bool off = [] { const char* e = std::getenv("STIL_BANK_SWEEP"); return e && e[0] == '0'; }();
+    return !off && dtype == STIL_BF16 && rows >= 1 && dim >= 64 && dim % 64 == 0 && dim <= 512 && k_shard % 8 == 0 && ldz % 4 == 0;
+}
+
+int launch_bank_logits(const void* feat_ku, const void* feat_qu, int64_t rows, int64_t dim, int64_t ld, const void* bank,
+                       int64_t ld_bank, int64_t k_shard, float* zt, float* zs, int64_t ldz, cudaStream_t stream) {
+    BankSweepLaunch L;
+    std::memset(&L, 0, sizeof(L));
+    int rc;
+    if ((rc = make_operand_map(&L.tma[0], feat_ku, dim, rows, 1, ld, ld * rows, 128))) return rc;
+    if ((rc = make_operand_map(&L.tma[1], feat_qu, dim, rows, 1, ld, ld * rows, 128))) return rc;
+    if ((rc = make_operand_map(&L.tmb, bank, k_shard, dim, 1, ld_bank, ld_bank * dim, 64))) return rc;
+    STIL_REQUIRE(make_out_map(&L.tmo[0], zt, k_shard, rows, ldz, 1, 0) && make_out_map(&L.tmo[1], zs, k_shard, rows, ldz, 1, 0),
+                 STIL_E_ALIGN, "bank sweep: the logits buffers need a 16-byte aligned base and ld %% 4 == 0");
+    int dev = 0, sms = 148;
+    STIL_CUDA(cudaGetDevice(&dev));
+    STIL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    L.k_shard = (int)k_shard;
+    L.nbx = (int)(dim / kTileK);
+    L.tiles_m = (int)ceil_div(rows, kTileM);
+    L.nblocks = (int)ceil_div(k_shard, kTileN);
+    L.ranges = pick_ranges(2 * L.tiles_m, L.nblocks, sms);
+    L.nchunks = 2 * L.tiles_m * L.ranges;
+    const int fixed = 1024 + L.nbx * kBoxA + kOutBoxes * kOutBox + kSweepBarBytes;
+    L.stages = std::min(kMaxStagesB, (kSmemLimit - fixed) / kStageB);
+    STIL_REQUIRE(L.stages >= 2, STIL_E_SHAPE, "bank sweep: no room for the bank ring at dim %lld", (long long)dim);
+    const int smem = fixed + L.stages * kStageB;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(bank_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (attr_err == cudaSuccess) prefer_max_shared(bank_logits_kernel);
+    });
+    STIL_CUDA(attr_err);
+    bank_logits_kernel<<<std::min(sms, L.nchunks), kSweepThreads, smem, stream>>>(L);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+bool bank_dx_eligible(int dtype, int64_t rows, int64_t dim, int64_t k_shard, const float* out, int64_t ld_out) {
+    static const bool off = [] { const char* e = std::getenv("STIL_BANK_SWEEP"); return e && e[0] == '0'; }();
+    return !off && dtype == STIL_BF16 && rows >= 1 && dim >= 64 && dim % 64 == 0 && dim <= 512 && k_shard % 8 == 0 && ld_out % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+}
+
+int launch_bank_dx(const __nv_bfloat16* gop, int64_t ldg, int g_nseg, int64_t rows, const void* bank, int64_t ld_bank, int64_t dim,
+                   int64_t k_shard, const float* row_scale, float* out, int64_t ld_out, cudaStream_t stream) {
+    BankDxLaunch L;
+    std::memset(&L, 0, sizeof(L));
+    int rc;
+    if ((rc = make_operand_map(&L.tmg, gop, k_shard, rows, g_nseg, (int64_t)g_nseg * ldg, ldg, 128))) return rc;
+    if ((rc = make_operand_map(&L.tmb, bank, k_shard, dim, 1, ld_bank, ld_bank * dim, 128))) return rc;
+    int dev = 0, sms = 148;
+    STIL_CUDA(cudaGetDevice(&dev));
+    STIL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    L.out = out; L.row_scale = row_scale; L.ld_out = ld_out;
+    L.rows = (int)rows; L.dim = (int)dim; L.nseg = g_nseg;
+    L.nbn = (int)ceil_div(dim, kTileN);
+    L.kboxes = (int)ceil_div(k_shard, kTileK);
+    const int tiles_m = (int)ceil_div(rows, kTileM);
+    L.ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(L.kboxes, sms / tiles_m));
+    const int stage_bytes = (L.nseg + L.nbn) * kBoxA;
+    L.stages = std::min(kDxMaxStages, (kSmemLimit - 1024 - kSweepBarBytes) / stage_bytes);
+    STIL_REQUIRE(L.stages >= 2, STIL_E_SHAPE, "bank dX: no room for two stages at dim %lld", (long long)dim);
+    L.tmem_cols = 32;
+    while ((int64_t)L.tmem_cols < dim) L.tmem_cols <<= 1;
+    const int smem = 1024 + kSweepBarBytes + L.stages * stage_bytes;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(bank_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (attr_err == cudaSuccess) prefer_max_shared(bank_dx_kernel);
+    });
+    STIL_CUDA(attr_err);
+    // the partial tiles are ADDED: start from zero
+    STIL_CUDA(cudaMemset2DAsync(out, ld_out * sizeof(float), 0, dim * sizeof(float), rows, stream));
+    bank_dx_kernel<<<tiles_m * L.ksplit, kDxThreads, smem, stream>>>(L);
+    STIL_LAUNCH_CHECK();
+    return STIL_OK;
+}
+
+}  // namespace stil

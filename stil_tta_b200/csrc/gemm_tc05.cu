@@ -1157,7 +1157,7 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t r
 }
 
 // fp32 output map [cols, rows, slices]: 32 x 128 x 1 boxes (128 bytes wide), 128-byte swizzle; false = `out` not eligible
-static bool make_out_map(CUtensorMap* tm, float* base, int64_t cols, int64_t rows, int64_t ld, int64_t slices, int64_t slice_stride) {
+bool make_out_map(CUtensorMap* tm, float* base, int64_t cols, int64_t rows, int64_t ld, int64_t slices, int64_t slice_stride) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0 || (slices > 1 && (slice_stride & 3) != 0)) return false;
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)std::max<int64_t>(slices, 1)};

@@ -143,8 +143,18 @@ struct GemmLaunch {
 // Build the operand tensor map.  `base` bf16, logical [rows, nseg, inner]; strides in elements.
 int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t rows, int64_t nseg,
                      int64_t row_stride, int64_t seg_stride, int box_rows = 128);
+// fp32 output map [cols, rows, slices] for bulk tensor stores: 32 x 128 x 1 boxes, 128-byte swizzle; false = not eligible
+bool make_out_map(CUtensorMap* tm, float* base, int64_t cols, int64_t rows, int64_t ld, int64_t slices, int64_t slice_stride);
 void gemm_job_tiles(GemmLaunch& L);  // fills tiles_m/tiles_n/tile_begin/total_tiles
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream);
+// a7 bank sweep (bank_sweep.cu): zt = feat_ku · bank, zs = feat_qu · bank by the persistent resident-rows kernel
+bool bank_logits_eligible(int dtype, int64_t rows, int64_t dim, int64_t k_shard, int64_t ldz);
+int launch_bank_logits(const void* feat_ku, const void* feat_qu, int64_t rows, int64_t dim, int64_t ld, const void* bank,
+                       int64_t ld_bank, int64_t k_shard, float* zt, float* zs, int64_t ldz, cudaStream_t stream);
+// out[rows, dim] = row_scale * (G[rows, (hi, lo), k_shard] · bankᵀ): whole-accumulator-in-TMEM split contraction
+bool bank_dx_eligible(int dtype, int64_t rows, int64_t dim, int64_t k_shard, const float* out, int64_t ld_out);
+int launch_bank_dx(const __nv_bfloat16* gop, int64_t ldg, int g_nseg, int64_t rows, const void* bank, int64_t ld_bank, int64_t dim,
+                   int64_t k_shard, const float* row_scale, float* out, int64_t ld_out, cudaStream_t stream);
 // Turn a GEMM_GRAD job + the GEMM_STORE job that would consume its G into one GEMM_BWD job (false: shapes / shared memory
 // do not allow the fused kernel — launch the two separately)
 bool make_bwd_job(GemmJob& out, const GemmJob& grad, const GemmJob& store, int nsplit);

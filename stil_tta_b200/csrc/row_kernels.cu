@@ -1386,46 +1386,88 @@ __global__ void __launch_bounds__(kSimBlock) simmatch_rows_kernel(const float* _
 // hence z <= 1 and e = exp((z - 1)/T) lies in [e^{-2/T}, 1]: no overflow, and for the reference temperatures (0.1) no
 // underflow that matters (e^{-20} = 2e-9 against a row sum >= 1 entry of order 1... K_b entries of order e^{-10}).
 //   stats[row] = [ sum_j e_t | sum_j e_s | sum_j e_t p[y_j] z_s/st | A_c = sum_{j in c} e_t  (c < C) ]      one pass over j
-__device__ __forceinline__ float shifted_exp(float z, float inv_t) { return __expf(fminf((z - 1.f) * inv_t, 60.f)); }
+// c1 = log2(e)/T: e = 2^(z*c1 - c1), one FFMA + one clamp + one ex2.approx (relative error 2^-22, identical in the
+// statistics and the gradient pass)
+__device__ __forceinline__ float shifted_exp(float z, float c1) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fminf(fmaf(z, c1, -c1), 86.f)));
+    return y;
+}
+// The per-class sums A_c are accumulated in 36-bit FIXED POINT, as two native 32-bit shared-memory atomics per column
+// (hi = bits 18.., lo = bits 0..17 of e * 2^36).  A float atomicAdd on shared memory is a compare-and-swap loop
+// (ATOMS.CAST.SPIN): with 286 classes and 32 random labels per warp instruction it retried so often that the kernel ran at
+// 25 % of the HBM rate with half of its stall samples on the loop (profiles/r2_ncu_bank_before.txt).  Integer sums are
+// also order-independent: the statistics of a shard are bit-reproducible.  e <= 1 (+ bf16 rounding of unit vectors), at
+// most kSimFxCols columns per block: hi <= 2^18 * 8192 * 1.x < 2^32, lo < 2^18 * 8192 = 2^31.
+constexpr float kSimFxScale = 68719476736.f;   // 2^36: absolute resolution 1.5e-11 per column
+constexpr int kSimFxLoBits = 18;
+constexpr int kSimFxCols = 8192;
+// both logit rows and the int64 labels can be read 16 bytes at a time from any column that is a multiple of 4
+__device__ __forceinline__ bool sim_vec4(const float* zt, const float* zs, long long ldz, const long long* labels) {
+    return (ldz & 3) == 0 && ((reinterpret_cast<uintptr_t>(zt) | reinterpret_cast<uintptr_t>(zs) | reinterpret_cast<uintptr_t>(labels)) & 15) == 0;
+}
 
 __global__ void __launch_bounds__(kSimBlock) simmatch_shard_stats_kernel(const float* __restrict__ zt, const float* __restrict__ zs,
                                                                          long long ldz, const long long* __restrict__ labels,
                                                                          int k_shard, const float* __restrict__ p_all, int C,
                                                                          float inv_tt, float inv_st, float* __restrict__ stats,
                                                                          long long chunk_stride) {
-    extern __shared__ float sm[];   // p[C] | A[C] | red[8]
+    extern __shared__ float sm[];   // p[C] | A hi[C] | A lo[C] | red[8]
     float* sp = sm;
-    float* sA = sm + C;
-    float* red = sm + 2 * C;
+    unsigned int* sHi = reinterpret_cast<unsigned int*>(sm + C);
+    unsigned int* sLo = sHi + C;
+    float* red = sm + 3 * C;
     const int row = blockIdx.x;
     // a row is cut into gridDim.y column chunks (one block each) so that a few hundred rows still fill the chip; chunk c
     // writes its partial statistics to stats + c * chunk_stride, simmatch_shard_reduce_kernel adds the chunks in order
-    const int cw = (k_shard + gridDim.y - 1) / gridDim.y;
-    const int j0 = blockIdx.y * cw, j1 = min(k_shard, j0 + cw);
+    const int cw = ((k_shard + gridDim.y - 1) / gridDim.y + 3) & ~3;
+    const int j0 = min(k_shard, (int)blockIdx.y * cw), j1 = min(k_shard, j0 + cw);
     stats += (long long)blockIdx.y * chunk_stride;
     const float* rt = zt + (long long)row * ldz;
     const float* rs = zs + (long long)row * ldz;
     for (int c = threadIdx.x; c < C; c += kSimBlock) {
         sp[c] = p_all[(long long)row * C + c];
-        sA[c] = 0.f;
+        sHi[c] = 0u;
+        sLo[c] = 0u;
     }
     __syncthreads();
+    const float ct = inv_tt * 1.4426950408889634f, cs = inv_st * 1.4426950408889634f;
     float st_ = 0.f, ss_ = 0.f, num = 0.f;
-    for (int j = j0 + threadIdx.x; j < j1; j += kSimBlock) {
-        const float z_s = rs[j];
-        const float et = shifted_exp(rt[j], inv_tt);
-        const int y = (int)labels[j];
+    auto column = [&](float z_t, float z_s, int y) {
+        const float et = shifted_exp(z_t, ct);
         st_ += et;
-        ss_ += shifted_exp(z_s, inv_st);
-        num += et * sp[y] * (z_s * inv_st);
-        atomicAdd(&sA[y], et);
+        ss_ += shifted_exp(z_s, cs);
+        num = fmaf(et * sp[y], z_s, num);           // the 1/st of z_s/st is applied once, after the reduction
+        const unsigned long long v = __float2ull_rn(fminf(et, 1.5f) * kSimFxScale);
+        atomicAdd(&sHi[y], (unsigned int)(v >> kSimFxLoBits));
+        atomicAdd(&sLo[y], (unsigned int)v & ((1u << kSimFxLoBits) - 1u));
+    };
+    // four columns per thread per trip (16-byte loads of both logit rows and of the int64 labels, two trips in flight);
+    // chunk starts are multiples of 4 and rows are 16-byte aligned (ldz % 4 == 0)
+    int jv = j0;
+    if (sim_vec4(zt, zs, ldz, labels)) {
+        const int j4 = j0 + ((j1 - j0) & ~3);
+#pragma unroll 2
+        for (int j = j0 + 4 * threadIdx.x; j < j4; j += 4 * kSimBlock) {
+            const float4 a = *reinterpret_cast<const float4*>(rt + j), b = *reinterpret_cast<const float4*>(rs + j);
+            const longlong2 l0 = __ldg(reinterpret_cast<const longlong2*>(labels + j));
+            const longlong2 l1 = __ldg(reinterpret_cast<const longlong2*>(labels + j + 2));
+            column(a.x, b.x, (int)l0.x);
+            column(a.y, b.y, (int)l0.y);
+            column(a.z, b.z, (int)l1.x);
+            column(a.w, b.w, (int)l1.y);
+        }
+        jv = j4;
     }
+    for (int j = jv + threadIdx.x; j < j1; j += kSimBlock) column(rt[j], rs[j], (int)labels[j]);
+    num *= inv_st;
     st_ = block_reduce(st_, red, false);
     ss_ = block_reduce(ss_, red, false);
     num = block_reduce(num, red, false);
     float* out = stats + (long long)row * (3 + C);
     if (threadIdx.x == 0) { out[0] = st_; out[1] = ss_; out[2] = num; }
-    for (int c = threadIdx.x; c < C; c += kSimBlock) out[3 + c] = sA[c];
+    for (int c = threadIdx.x; c < C; c += kSimBlock)
+        out[3 + c] = __ull2float_rn(((unsigned long long)sHi[c] << kSimFxLoBits) + sLo[c]) * (1.f / kSimFxScale);
 }
 
 // stats[i] = sum over chunks, in chunk order (deterministic)
@@ -1478,10 +1520,35 @@ __global__ void __launch_bounds__(kSimBlock) simmatch_shard_grad_kernel(const fl
     const float* rs = zs + (long long)row * ldz;
     const float inv_sum_s = norms[2 * row], inv_den = norms[2 * row + 1];
     __nv_bfloat16* gh = gop + (long long)row * g_nseg * ld_g;
-    const int cw = (k_shard + gridDim.y - 1) / gridDim.y;
-    const int j0 = blockIdx.y * cw, j1 = min(k_shard, j0 + cw);
-    for (int j = j0 + threadIdx.x; j < j1; j += kSimBlock) {
-        const float g = (shifted_exp(rs[j], inv_st) * inv_sum_s - shifted_exp(rt[j], inv_tt) * sm[(int)labels[j]] * inv_den) * inv_st;
+    const int cw = ((k_shard + gridDim.y - 1) / gridDim.y + 3) & ~3;
+    const int j0 = min(k_shard, (int)blockIdx.y * cw), j1 = min(k_shard, j0 + cw);
+    const float ct = inv_tt * 1.4426950408889634f, cs = inv_st * 1.4426950408889634f;
+    const float ws = inv_sum_s * inv_st, wt = inv_den * inv_st;
+    auto column = [&](float z_t, float z_s, int y) { return shifted_exp(z_s, cs) * ws - shifted_exp(z_t, ct) * sm[y] * wt; };
+    int jv = j0;
+    if (sim_vec4(zt, zs, ldz, labels) && (ld_g & 3) == 0 && (reinterpret_cast<uintptr_t>(gop) & 7) == 0) {
+        const int j4 = j0 + ((j1 - j0) & ~3);
+#pragma unroll 2
+        for (int j = j0 + 4 * threadIdx.x; j < j4; j += 4 * kSimBlock) {
+            const float4 a = *reinterpret_cast<const float4*>(rt + j), b = *reinterpret_cast<const float4*>(rs + j);
+            const longlong2 l0 = __ldg(reinterpret_cast<const longlong2*>(labels + j));
+            const longlong2 l1 = __ldg(reinterpret_cast<const longlong2*>(labels + j + 2));
+            const float g[4] = {column(a.x, b.x, (int)l0.x), column(a.y, b.y, (int)l0.y), column(a.z, b.z, (int)l1.x),
+                                column(a.w, b.w, (int)l1.y)};
+            __align__(8) __nv_bfloat16 h[4];
+            __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                h[u] = __float2bfloat16_rn(g[u]);
+                l[u] = __float2bfloat16_rn(g[u] - __bfloat162float(h[u]));
+            }
+            *reinterpret_cast<uint2*>(gh + j) = *reinterpret_cast<const uint2*>(h);
+            if (g_nseg > 1) *reinterpret_cast<uint2*>(gh + ld_g + j) = *reinterpret_cast<const uint2*>(l);
+        }
+        jv = j4;
+    }
+    for (int j = jv + threadIdx.x; j < j1; j += kSimBlock) {
+        const float g = column(rt[j], rs[j], (int)labels[j]);
         const __nv_bfloat16 h = __float2bfloat16_rn(g);
         gh[j] = h;
         if (g_nseg > 1) gh[ld_g + j] = __float2bfloat16_rn(g - __bfloat162float(h));
@@ -1729,13 +1796,15 @@ int64_t masked_softce_blocks(int64_t rows, int64_t) {
 
 int simmatch_shard_chunks(int64_t rows, int64_t k_shard) {
     // ~2048 blocks in flight, at least 1024 columns per block
-    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div(2048, std::max<int64_t>(rows, 1)), 32), k_shard / 1024));
+    const int64_t fill = std::min<int64_t>(std::min<int64_t>(ceil_div(2048, std::max<int64_t>(rows, 1)), 32), k_shard / 1024);
+    // the fixed-point class sums of simmatch_shard_stats_kernel hold at most 8192 columns per block
+    return (int)std::max<int64_t>(std::max<int64_t>(1, fill), ceil_div(k_shard, 8192));
 }
 int launch_simmatch_shard_stats(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
                                 const float* p_all, int num_classes, float tt, float st, float* stats, float* chunk_scratch,
                                 cudaStream_t stream) {
     if (rows == 0) return STIL_OK;
-    const size_t smem = (2 * (size_t)num_classes + 8) * sizeof(float);
+    const size_t smem = (3 * (size_t)num_classes + 8) * sizeof(float);
     STIL_REQUIRE(smem <= 48 * 1024, STIL_E_SHAPE, "simmatch: too many classes (%d)", num_classes);
     const int nchunk = simmatch_shard_chunks(rows, k_shard);
     const long long n = (long long)rows * (3 + num_classes);
