@@ -321,17 +321,24 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                 }
             }
             __syncwarp();
-            if (lane == 0) {
+            {
+                // the whole (converged) warp walks the ring and ONE elected lane issues: the operands of the bulk-tensor
+                // instructions are then warp-uniform for the compiler (uniform registers); inside an `if (lane == 0)`
+                // branch every issue went through an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall
+                const bool leader = tc05::elect_one();
                 int s = 0;
                 uint32_t ph = 1;            // second pass over the ring waits for the first release of each slot
                 for (int kb = first; kb < nkb; ++kb) {
                     tc05::mbar_wait(&empty_bar[s], ph ^ 1);
-                    tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                    load_x(kb, s);
-                    load_y(kb, s);
+                    if (leader) {
+                        tc05::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                        load_x(kb, s);
+                        load_y(kb, s);
+                    }
+                    __syncwarp();
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
-                STIL_TRACE(2);
+                if (lane == 0) STIL_TRACE(2);
             }
         }
         if (clustered) {   // the two cluster barriers of the split-K reduction (every thread of the cluster takes part)
@@ -340,11 +347,20 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // Converged warp, one elected lane issues: descriptors and TMEM addresses stay in uniform registers and the four
+        // tcgen05.mma of a stage go out back to back.  Inside an `if (lane == 0)` branch the compiler wrapped every MMA in
+        // an ELECT / 4 x R2UR.BROADCAST / BRA.U.ANY waterfall: ~100 cycles of dependent issue per 64 cycles of tensor work
+        // (profiles/r2_bank_timeline.txt has the switch-off experiments that found it).
+        {
+            const bool leader = tc05::elect_one();
             const bool mn = MODE == GEMM_STORE && J.y_mn_major != 0;
             const bool xmn = MODE == GEMM_STORE && J.x_mn_major != 0;
             // bits 15 / 16: A / B given MN-major
             const uint32_t idesc = tc05::make_idesc_bf16_f32(kTileM, kTileN) | (mn ? (1u << 16) : 0u) | (xmn ? (1u << 15) : 0u);
+            // K-major: 16 bf16 = 32 B inside the swizzle atom (+2 in the >>4 address field);
+            // MN-major: 16 contraction rows = 2 KiB (+128)
+            const uint32_t a_step = xmn ? 128u : 2u;
+            const uint32_t b_step = mn ? 128u : 2u;
             int s = 0;
             uint32_t ph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -356,19 +372,21 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                                             : tc05::make_kmajor_sw128_desc(a_addr);
                 const uint64_t b_desc = mn ? tc05::make_mnmajor_sw128_desc(b_addr, 64 * kTileK * 2)
                                            : tc05::make_kmajor_sw128_desc(b_addr);
-                // K-major: 16 bf16 = 32 B inside the swizzle atom (+2 in the >>4 address field);
-                // MN-major: 16 contraction rows = 2 KiB (+128)
-                const uint32_t a_step = xmn ? 128u : 2u;
-                const uint32_t b_step = mn ? 128u : 2u;
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < kTileK / 16; ++k)
-                    tc05::mma_f16_ss(tmem_base, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) ? 1u : 0u);
-                tc05::mma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                    for (int k = 0; k < kTileK / 16; ++k)
+                        tc05::mma_f16_ss(tmem_base, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) ? 1u : 0u);
+                    tc05::mma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                }
+                __syncwarp();
                 if (++s == kStages) { s = 0; ph ^= 1; }
             }
-            if (nkb > 0) tc05::mma_commit(tmem_full_bar);
-            else tc05::mbar_arrive(tmem_full_bar);   // empty slice of a split contraction: nothing to wait for
-            STIL_TRACE(3);
+            if (leader) {
+                if (nkb > 0) tc05::mma_commit(tmem_full_bar);
+                else tc05::mbar_arrive(tmem_full_bar);   // empty slice of a split contraction: nothing to wait for
+            }
+            __syncwarp();
+            if (lane == 0) STIL_TRACE(3);
         }
         if (clustered) {
             tc05::cluster_arrive(); tc05::cluster_wait();
@@ -872,15 +890,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gemm_bwd_kernel(const __grid_c
     const uint32_t y_bytes = (uint32_t)(J.bw_ny * nbx * kBoxBytes);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (converged warp, one elected lane issues) =====================
+        const bool leader = tc05::elect_one();
+        {
             auto load_x = [&]() {
+                if (!leader) return;
                 tc05::mbar_arrive_expect_tx(x_full, (uint32_t)(J.bw_nx * nbx * kBoxBytes));
                 for (int sg = 0; sg < J.bw_nx; ++sg)
                     for (int b = 0; b < nbx; ++b)
                         tc05::tma_load_3d(xs + (sg * nbx + b) * kBoxBytes, &J.tmx, x_full, b * 64, m0, sg);
             };
             auto load_y = [&](int i) {
+                if (!leader) return;
                 const int yb = i % nbuf, n0 = (split + i * nsplit) * kTileN;
                 tc05::mbar_arrive_expect_tx(&y_full[yb], y_bytes);
                 for (int sg = 0; sg < J.bw_ny; ++sg)
@@ -897,20 +918,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gemm_bwd_kernel(const __grid_c
                 const int yb = i % nbuf;
                 tc05::mbar_wait(&y_empty[yb], ((i / nbuf) & 1) ^ 1);
                 load_y(i);
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+        const bool leader = tc05::elect_one();
+        {
             const uint32_t idesc1 = tc05::make_idesc_bf16_f32(kTileM, kTileN);
             const uint32_t idesc2 = tc05::make_idesc_bf16_f32(kTileM, J.D) | (1u << 16);   // B = Y tile, MN-major
             const uint32_t xs_a = tc05::smem_u32(xs), ys_a = tc05::smem_u32(ys), g_a = tc05::smem_u32(gsm);
+            // a completed phase stays complete: what ANY lane has seen holds for the warp (keeps the loop converged)
             auto mma1_ready = [&](int i) {
-                return tc05::mbar_test(&y_full[i % nbuf], (i / nbuf) & 1) && tc05::mbar_test(&s_empty[i & 1], ((i >> 1) & 1) ^ 1);
+                return __any_sync(0xffffffffu, tc05::mbar_test(&y_full[i % nbuf], (i / nbuf) & 1)) &&
+                       __any_sync(0xffffffffu, tc05::mbar_test(&s_empty[i & 1], ((i >> 1) & 1) ^ 1));
             };
             auto mma1 = [&](int i) {     // logits of tile i into TMEM buffer i & 1 (caller checked mma1_ready)
                 const int yb = i % nbuf, sb = i & 1;
                 tc05::fence_after_sync();
+                if (!leader) return;
                 uint32_t acc = 0;
                 for (int p = 0; p < J.npair; ++p)
                     for (int b = 0; b < nbx; ++b) {
@@ -928,6 +954,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gemm_bwd_kernel(const __grid_c
             auto mma2 = [&](int i) {     // dX += G(tile i) · Y(tile i): contraction over the tile's 128 columns
                 const int yb = i % nbuf;   // (caller saw g_full complete its phase i)
                 tc05::fence_after_sync();
+                if (!leader) return;
                 for (int p = 0; p < J.npair2; ++p) {
                     const uint64_t b_base = tc05::make_mnmajor_sw128_desc(
                         ys_a + yb * J.bw_y_stride + (J.yseg2[p] * nbx) * kBoxBytes, kBoxBytes);
@@ -951,11 +978,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gemm_bwd_kernel(const __grid_c
             int n1 = 0, n2 = 0;
             unsigned long long spins = 0;
             while (n2 < ntile) {
-                if (n1 < ntile && n1 < n2 + 2 && mma1_ready(n1)) { mma1(n1++); spins = 0; continue; }
-                if (n2 < n1 && tc05::mbar_test(g_full, n2 & 1)) { mma2(n2++); spins = 0; continue; }
+                if (n1 < ntile && n1 < n2 + 2 && mma1_ready(n1)) { mma1(n1++); __syncwarp(); spins = 0; continue; }
+                if (n2 < n1 && __any_sync(0xffffffffu, tc05::mbar_test(g_full, n2 & 1))) { mma2(n2++); __syncwarp(); spins = 0; continue; }
                 if (++spins > (1ull << 28)) __trap();
             }
-            if (ntile == 0) tc05::mbar_arrive(dx_full);
+            if (ntile == 0 && leader) tc05::mbar_arrive(dx_full);
+            __syncwarp();
         }
     } else {
         // ===================== epilogue: 16 warps, thread = row, one 32-column chunk per warp =====================
@@ -1136,7 +1164,7 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t rows, int64_t nseg,
-                     int64_t row_stride, int64_t seg_stride, int box_rows) {
+                     int64_t row_stride, int64_t seg_stride, int box_rows, int box_segs) {
     EncodeTiledFn enc = get_encode_fn();
     STIL_REQUIRE(enc != nullptr, STIL_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     STIL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, STIL_E_ALIGN, "operand base %p not 16-byte aligned", base);
@@ -1145,7 +1173,7 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t r
                  (long long)seg_stride);
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)nseg};
     cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)seg_stride * 2};
-    cuuint32_t box[3] = {kTileK, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {kTileK, (cuuint32_t)box_rows, (cuuint32_t)box_segs};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

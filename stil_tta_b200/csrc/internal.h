@@ -142,7 +142,7 @@ struct GemmLaunch {
 
 // Build the operand tensor map.  `base` bf16, logical [rows, nseg, inner]; strides in elements.
 int make_operand_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t rows, int64_t nseg,
-                     int64_t row_stride, int64_t seg_stride, int box_rows = 128);
+                     int64_t row_stride, int64_t seg_stride, int box_rows = 128, int box_segs = 1);
 // fp32 output map [cols, rows, slices] for bulk tensor stores: 32 x 128 x 1 boxes, 128-byte swizzle; false = not eligible
 bool make_out_map(CUtensorMap* tm, float* base, int64_t cols, int64_t rows, int64_t ld, int64_t slices, int64_t slice_stride);
 void gemm_job_tiles(GemmLaunch& L);  // fills tiles_m/tiles_n/tile_begin/total_tiles

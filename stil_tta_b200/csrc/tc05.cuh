@@ -83,10 +83,25 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
         : "memory");
 }
 
+// Pull a box into L2 ahead of the load that will want it (no shared memory, no barrier): hides the DRAM part of the
+// latency of a later tma_load_3d when the smem ring is too shallow to cover it.
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 // 3-D tiled store shared -> global (bulk async group); out-of-range parts of the box are clipped.
 __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+        ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// 3-D tiled REDUCTION shared -> global: global[box] += smem[box] element-wise (fp32 add done by the memory system, one
+// bulk operation per box instead of one 16-byte atomic per thread and four columns)
+__device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
         ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
