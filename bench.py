@@ -789,7 +789,7 @@ def run_bank_arm(args, rank, world, dev, dist_on):
     bk = synth.make_bank(kb, d, c)
     unit = torch.nn.functional.normalize
     shard = kb // world
-    sb = S.ShardedSimMatchBank(d, kb, c, dtype=torch.bfloat16, device=dev)
+    sb = S.ShardedSimMatchBank(d, kb, c, dtype=torch.bfloat16, device=dev, use_graph=not args.bank_eager)
     sb.load_shard(bk["bank"][rank * shard:(rank + 1) * shard], bk["labels"][rank * shard:(rank + 1) * shard])
     nb = 8
     gen = torch.Generator().manual_seed(100 + rank)
@@ -861,7 +861,9 @@ def run_bank_arm(args, rank, world, dev, dist_on):
             "dtype": "bf16 operands / f32 accumulate / f32 gradients", "data": "synthetic",
             "config": make_config(bank_workload(world), rows, world,
                                   "the bank shard (64 MiB / N) and the logits tiles stream from HBM every sweep; inputs rotate over 8 batches",
-                                  False, "NCCL all_gather(queries), all_reduce(per-row statistics)" if dist_on else "none (one GPU)", "n/a"),
+                                  not args.bank_eager,
+                                  "NCCL all_gather(queries), all_reduce(per-row statistics), reduce_scatter(dX partials)" if dist_on else "none (one GPU)",
+                                  "n/a"),
             "e2e": {"value": rows * world / (ms_step_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_step_e2e,
                     "h2d_bytes_per_step": 2 * rows * d * 2 + rows * c * 4, "d2h_bytes_per_step": rows * d * 2},
             "gpu_launches": sb.launches_per_step * steps, "parity_check": parity, "clocks": cs.summary(),
@@ -891,6 +893,7 @@ def main():
     ap.add_argument("--transport", default="fused", choices=["fused", "p2p", "nccl"],
                     help="N>1 exchange: fused peer-memory schedule, blocking peer-memory all-gathers, or NCCL")
     ap.add_argument("--nbuf", type=int, default=0, help="experiments: override the number of rotating batches")
+    ap.add_argument("--bank-eager", action="store_true", help="--config C5: eager launches instead of one CUDA graph per sweep")
     ap.add_argument("--no-graph", action="store_true", help="N>1 only: do not capture kernels+NCCL in a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

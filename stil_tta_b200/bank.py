@@ -87,7 +87,7 @@ def simmatch_bank(feat_ku: torch.Tensor, feat_qu: torch.Tensor, prob_ku_orig: to
 class _ShardedSimMatchFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat_ku, feat_qu, prob_ku_orig, owner, tt, st, c_smooth):
-        prob_ku, loss_in, jac = owner._sweep(feat_ku, feat_qu, prob_ku_orig, tt, st, c_smooth, ctx.needs_input_grad[1])
+        prob_ku, loss_in, jac = owner._run_sweep(feat_ku, feat_qu, prob_ku_orig, tt, st, c_smooth, ctx.needs_input_grad[1])
         ctx.jac = jac
         ctx.in_dtype = feat_qu.dtype
         ctx.mark_non_differentiable(prob_ku)
@@ -121,10 +121,17 @@ class ShardedSimMatchBank:
 
     ``emulate_shards=S`` (tests, one process): the bank is split into ``S`` shards swept one after the other on this GPU
     and the collectives become sums — the same kernels, offsets and additive statistics as ``S`` ranks.
+
+    ``use_graph=True``: the whole sweep (gathers, kernels, collectives) is captured into ONE CUDA graph per input signature
+    (shapes, dtype, temperatures, smoothing, gradient wanted) on first use and replayed afterwards — the eager sweep is ~15
+    launches and four extension calls, and on a B200 the host needs longer to enqueue them than the GPU to run them.  The
+    graph reads the bank and label buffers in place (``update`` / ``load`` stay visible); inputs are copied into the
+    graph's static buffers and the three small results are cloned out, so callers see ordinary tensors.  Every rank must
+    capture with the same signature sequence (the collectives are part of the graph).
     """
 
     def __init__(self, dim: int, k_bank: int, num_classes: int, dtype=torch.bfloat16, device="cuda", group=None,
-                 emulate_shards: int = 1) -> None:
+                 emulate_shards: int = 1, use_graph: bool = False) -> None:
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -143,6 +150,8 @@ class ShardedSimMatchBank:
         self.bank = [alloc_bank(dim, self.k_shard, dtype, self.dev) for _ in range(self.nshards)]
         self.labels = [torch.zeros(self.k_shard, dtype=torch.int64, device=self.dev) for _ in range(self.nshards)]
         self._ws = None
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
         # gather x2 (+p), GEMM, stats, all-reduce, finish, grad, memset, split-K GEMM, grad_finish, reduce-scatter
         self.launches_per_step = self.nshards * 7 + 1
 
@@ -254,6 +263,44 @@ class ShardedSimMatchBank:
 
     def _device_guard(self):
         return torch.cuda.device(self.dev)
+
+    # ------------------------------------------------------------------------------------------ CUDA graph
+    def _run_sweep(self, feat_ku, feat_qu, prob_ku_orig, tt, st, c_smooth, need_grad):
+        if not self.use_graph:
+            return self._sweep(feat_ku, feat_qu, prob_ku_orig, tt, st, c_smooth, need_grad)
+        key = (tuple(feat_ku.shape), feat_ku.dtype, feat_qu.dtype, tuple(prob_ku_orig.shape), prob_ku_orig.dtype,
+               float(tt), float(st), float(c_smooth), bool(need_grad))
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = self._capture(feat_ku, feat_qu, prob_ku_orig, tt, st, c_smooth, need_grad)
+        graph, s_in, s_out = ent
+        with self._device_guard():
+            s_in[0].copy_(feat_ku.detach())
+            s_in[1].copy_(feat_qu.detach())
+            s_in[2].copy_(prob_ku_orig.detach())
+            graph.replay()
+            return tuple(None if t is None else t.clone() for t in s_out)
+
+    def _capture(self, feat_ku, feat_qu, prob_ku_orig, tt, st, c_smooth, need_grad):
+        """Warm up on a side stream (workspace allocation, lazy kernel attributes, NCCL channels), then capture one sweep."""
+        with self._device_guard():
+            s_in = [feat_ku.detach().clone(), feat_qu.detach().clone(), prob_ku_orig.detach().clone()]
+            cur = torch.cuda.current_stream(self.dev)
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._sweep(s_in[0], s_in[1], s_in[2], tt, st, c_smooth, need_grad)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                s_out = self._sweep(s_in[0], s_in[1], s_in[2], tt, st, c_smooth, need_grad)
+        return graph, s_in, s_out
+
+    def drop_graphs(self) -> None:
+        """Forget the captured sweeps (after ``load`` replaced the bank tensors, or to release their memory)."""
+        self._graphs.clear()
 
     def __call__(self, feat_ku, feat_qu, prob_ku_orig, tt: float, st: float, c_smooth: float):
         """``(prob_ku, loss_in)`` of ``simmatch_model.py:268-286`` for this rank's rows against the WHOLE (sharded) bank."""

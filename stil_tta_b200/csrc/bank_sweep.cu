@@ -561,9 +561,11 @@ int launch_bank_dx(const __nv_bfloat16* gop, int64_t ldg, int g_nseg, int64_t ro
     if ((rc = make_operand_map(&L.tmg, gop, k_shard, rows, g_nseg, (int64_t)g_nseg * ldg, ldg, 128))) return rc;
     if ((rc = make_operand_map(&L.tmb, bank, k_shard, dim, 1, ld_bank, ld_bank * dim, 128))) return rc;
     STIL_REQUIRE(make_out_map(&L.tmo, out, dim, rows, ld_out, 1, 0), STIL_E_ALIGN, "bank dX: output needs a 16-byte aligned base and ld %% 4 == 0");
-    int dev = 0, sms = 148;
-    STIL_CUDA(cudaGetDevice(&dev));
-    STIL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static const int sms = [] {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+        return n;
+    }();
     L.out = out; L.row_scale = row_scale; L.ld_out = ld_out;
     L.rows = (int)rows; L.dim = (int)dim; L.nseg = g_nseg;
     L.nbn = (int)ceil_div(dim, kTileN);

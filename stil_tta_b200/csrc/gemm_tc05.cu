@@ -376,7 +376,10 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
 #pragma unroll
                     for (int k = 0; k < kTileK / 16; ++k)
                         tc05::mma_f16_ss(tmem_base, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) ? 1u : 0u);
-                    tc05::mma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                    // frees the smem stage when these MMAs retire — only if the producer will refill it: a tcgen05.commit
+                    // costs ~0.2 us of (serialised) completion tracking (bank_sweep.cu experiments), and behind a queue of
+                    // useless ones the tile's final commit reaches the epilogue late
+                    if (kb + kStages < nkb) tc05::mma_commit(&empty_bar[s]);
                 }
                 __syncwarp();
                 if (++s == kStages) { s = 0; ph ^= 1; }
@@ -967,8 +970,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gemm_bwd_kernel(const __grid_c
                                              (i | p | kb | k) ? 1u : 0u);
                     }
                 }
-                tc05::mma_commit(g_empty);           // G buffer free for the next tile
-                tc05::mma_commit(&y_empty[yb]);      // Y buffer free for the tile after next
+                // (only the releases somebody will wait for: every commit is ~0.2 us of serialised completion tracking)
+                if (i + 1 < ntile) tc05::mma_commit(g_empty);                // G buffer free for the next tile
+                if (i + nbuf < ntile) tc05::mma_commit(&y_empty[yb]);       // Y buffer free for the tile after next
                 if (i == ntile - 1) tc05::mma_commit(dx_full);
             };
             tc05::mbar_wait(x_full, 0);

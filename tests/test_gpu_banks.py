@@ -377,3 +377,42 @@ def test_sharded_simmatch_bank_matches_whole_bank_oracle(S, rows, kb, d, c, dtyp
     whole = torch.cat([b.float().cpu() for b in sb.bank], dim=1)
     assert float((whole[:, idx].t().norm(dim=1) - 1).abs().max()) < 1e-2
     assert not torch.equal(whole.t().to(dtype), bank_rows)
+
+
+@pytest.mark.parametrize("rows,kb,d,c", [(96, 1024, 128, 10), (448, 8192, 512, 286)])
+def test_sharded_simmatch_bank_cuda_graph_replays(S, rows, kb, d, c):
+    """use_graph=True: the captured sweep gives the eager sweep's results on NEW inputs, and sees bank updates made between
+    replays (the graph reads the bank and label buffers in place)."""
+    g = torch.Generator().manual_seed(7 * rows + kb)
+    unit = F.normalize
+    bank_rows = unit(torch.randn(kb, d, generator=g)).to(torch.bfloat16)
+    labels = torch.randint(0, c, (kb,), generator=g)
+    eager = S.ShardedSimMatchBank(d, kb, c, device="cuda")
+    graphed = S.ShardedSimMatchBank(d, kb, c, device="cuda", use_graph=True)
+    for sb in (eager, graphed):
+        sb.load(bank_rows, labels)
+    for it in range(3):
+        fk = dev(unit(torch.randn(rows, d, generator=g)).to(torch.bfloat16))
+        fq = unit(torch.randn(rows, d, generator=g)).to(torch.bfloat16)
+        p = dev(torch.softmax(torch.randn(rows, c, generator=g) * 3, 1))
+        outs = []
+        for sb in (eager, graphed):
+            fqc = dev(fq.float()).requires_grad_(True)      # fp32 leaf: the gradient comes back unrounded
+            prob_ku, loss_in = sb(fk, fqc, p, 0.1, 0.1, 0.9)
+            (gq,) = torch.autograd.grad(loss_in.mean(), fqc)
+            outs.append((prob_ku, loss_in, gq))
+        assert len(graphed._graphs) == 1
+        assert float((outs[0][0] - outs[1][0]).abs().max()) <= 1e-6
+        assert_rel(outs[1][1], outs[0][1].detach().cpu(), 1e-5, "loss_in (graph replay vs eager)")
+        # the dX partials are reduced in arrival order (bulk fp32 reductions): equal up to summation order
+        assert_rel(outs[1][2], outs[0][2].cpu(), 1e-4, "d_feat_qu (graph replay vs eager)")
+        idx = dev(torch.randperm(kb, generator=g)[:32])
+        k_new, y_new = dev(unit(torch.randn(32, d, generator=g))), dev(torch.randint(0, c, (32,), generator=g))
+        for sb in (eager, graphed):
+            sb.update(k_new, y_new, idx)
+    # without a gradient: a second signature, a second graph
+    with torch.no_grad():
+        pe, le = eager(fk, dev(fq), p, 0.1, 0.1, 0.9)
+        pg, lg = graphed(fk, dev(fq), p, 0.1, 0.1, 0.9)
+    assert len(graphed._graphs) == 2
+    assert_rel(lg, le.cpu(), 1e-5, "loss_in (no-grad graph vs eager)")

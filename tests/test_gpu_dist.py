@@ -107,6 +107,16 @@ def _bank_worker(rank, world, port):
         e1 = float((loss_in.cpu() - ref["loss_in"][loc].detach()).abs().max() / ref["loss_in"][loc].abs().max())
         e2 = float((gq.float().cpu() - g_ref[loc]).abs().max() / g_ref[loc].abs().max())
         assert e1 <= 1e-3 and e2 <= 4e-3, (e1, e2)       # gq is bf16 (input dtype): 2^-9 output rounding on top of 1e-3
+        # the same sweep captured into one CUDA graph per rank (collectives included), replayed on the same inputs
+        sg = S.ShardedSimMatchBank(d, kb, c, dtype=torch.bfloat16, device=f"cuda:{rank}", use_graph=True)
+        sg.load(bank_rows, labels)
+        for _ in range(2):
+            fq2 = fq_all[loc].cuda().requires_grad_(True)
+            prob_g, loss_g = sg(fk_all[loc].cuda(), fq2, p_all[loc].cuda(), 0.1, 0.1, 0.9)
+            (gq2,) = torch.autograd.grad(loss_g.mean(), fq2)
+            assert float((prob_g - prob_ku).abs().max()) <= 1e-6
+            assert float((loss_g - loss_in).abs().max() / loss_in.abs().max()) <= 1e-5
+            assert float((gq2.float() - gq.float()).abs().max() / gq.float().abs().max()) <= 1e-5
         ok = True
     except BaseException:
         import traceback
