@@ -109,11 +109,12 @@ class ShardedSimMatchBank:
     ``K/W`` columns for the gathered rows of all ranks — the same tensor work per GPU, 1/W of the bank bytes per GPU, and
     the bank grows with the node.  One step (``__call__``, the block ``simmatch_model.py:268-286``):
 
-      1. all-gather ``feat_ku``, ``feat_qu``, ``prob_ku_orig`` over ranks (rows of all ranks, rank-major)
+      1. ONE all-gather of the packed rows ``[feat_ku | feat_qu | prob_ku_orig]`` over ranks (rows of all ranks, rank-major)
       2. ``stil_simmatch_shard_stats``: logits against the local shard, per-row statistics with a FIXED shift
          (unit vectors: ``e = exp((z - 1)/T)``), so that they are ADDITIVE over shards
-      3. all-reduce(SUM) of the ``[W*rows, 3 + C]`` statistics
-      4. ``stil_simmatch_shard_finish``: ``prob_ku`` (``:280``), ``loss_in`` (``:286``) and the normalisers
+      3. reduce-scatter(SUM) of the ``[W*rows, 3 + C]`` statistics: every rank gets the totals of its own rows
+      4. ``stil_simmatch_shard_finish`` on those rows: ``prob_ku`` (``:280``), ``loss_in`` (``:286``) and the two normalisers
+         per row, which are all-gathered (``[W*rows, 2]``) for the gradient pass
       5. (when ``feat_qu`` needs a gradient) ``stil_simmatch_shard_grad``: ``G = (S - T')/st`` on the shard's columns and
          the partial ``G · bank_shardᵀ``; reduce-scatter(SUM) gives every rank ``d loss_in / d feat_qu`` of its own rows.
          It is computed in the forward, while the bank still holds what the forward saw (the reference overwrites bank
@@ -201,7 +202,9 @@ class ShardedSimMatchBank:
     def _k_stats(self, s, fk, fq, p, tt, st, out):
         lib, bank = _lib.load(), self.bank[s]
         rows_all, d = fq.shape
-        check(lib.stil_simmatch_shard_stats(ptr(fk), ptr(fq), dtype_code(fq), rows_all, d, d, ptr(bank), bank.stride(0),
+        if fk.stride(0) != fq.stride(0) or fk.stride(1) != 1 or fq.stride(1) != 1:
+            raise ValueError("feat_ku / feat_qu must share one row stride")
+        check(lib.stil_simmatch_shard_stats(ptr(fk), ptr(fq), dtype_code(fq), rows_all, d, fq.stride(0), ptr(bank), bank.stride(0),
                                             ptr(self.labels[s]), self.k_shard, ptr(p), p.shape[1], float(tt), float(st), ptr(out),
                                             ptr(self._ws[s]), self._ws[s].numel(), _lib.stream_ptr(self.dev)))
 
@@ -223,9 +226,23 @@ class ShardedSimMatchBank:
 
     def _sweep(self, feat_ku, feat_qu, prob_ku_orig, tt, st, c_smooth, need_grad):
         dev, W = self.dev, self.world
-        fk = self._gather(feat_ku.detach().to(self.dtype).contiguous())
-        fq = self._gather(feat_qu.detach().to(self.dtype).contiguous())
-        p = self._gather(prob_ku_orig.detach().to(torch.float32).contiguous())
+        fk = feat_ku.detach().to(self.dtype).contiguous()
+        fq = feat_qu.detach().to(self.dtype).contiguous()
+        p = prob_ku_orig.detach().to(torch.float32).contiguous()
+        if W > 1:
+            # ONE all-gather instead of three (each is ~12 us of latency at these sizes): a row of the packed buffer is
+            # [feat_ku | feat_qu | prob_ku_orig | pad to 16 bytes]; the kernels read the features in place through the row
+            # stride, the probabilities are copied out (the kernels want them contiguous)
+            u8 = torch.uint8
+            parts = [fk.view(u8), fq.view(u8), p.view(u8)]
+            nbytes = sum(t.shape[1] for t in parts)
+            if nbytes % 16:
+                parts.append(torch.zeros(fk.shape[0], 16 - nbytes % 16, dtype=u8, device=fk.device))
+            packed = self._gather(torch.cat(parts, dim=1))
+            o1, o2 = parts[0].shape[1], parts[0].shape[1] + parts[1].shape[1]
+            fk = packed[:, :o1].view(self.dtype)
+            fq = packed[:, o1:o2].view(self.dtype)
+            p = packed[:, o2:o2 + parts[2].shape[1]].view(torch.float32).contiguous()
         rows_all, d = fq.shape
         rows = rows_all // W
         c = p.shape[1]
@@ -240,10 +257,18 @@ class ShardedSimMatchBank:
                 self._k_stats(s, fk, fq, p, tt, st, part)
                 if self.nshards > 1:
                     stats += part
+            lo = self.rank * rows
             if W > 1:
-                self.dist.all_reduce(stats, group=self.group)
-            prob_all, loss_all, norms = torch.empty(rows_all, c, **f32), torch.empty(rows_all, **f32), torch.empty(rows_all, 2, **f32)
-            self._k_finish(stats, p, st, c_smooth, prob_all, loss_all, norms)
+                # every rank finishes ITS rows: reduce-scatter of the statistics (instead of an all-reduce of all W*rows rows),
+                # then only the two normalisers per row travel back to everybody for the gradient pass
+                mine = torch.empty(rows, 3 + c, **f32)
+                self.dist.reduce_scatter_tensor(mine, stats, group=self.group)
+                prob_ku, loss_in, norms_mine = torch.empty(rows, c, **f32), torch.empty(rows, **f32), torch.empty(rows, 2, **f32)
+                self._k_finish(mine, p[lo:lo + rows], st, c_smooth, prob_ku, loss_in, norms_mine)
+                norms = self._gather(norms_mine) if need_grad else None
+            else:
+                prob_ku, loss_in, norms = torch.empty(rows_all, c, **f32), torch.empty(rows_all, **f32), torch.empty(rows_all, 2, **f32)
+                self._k_finish(stats, p, st, c_smooth, prob_ku, loss_in, norms)
             jac = None
             if need_grad:
                 jall = torch.zeros(rows_all, d, **f32) if self.nshards > 1 else None
@@ -258,8 +283,7 @@ class ShardedSimMatchBank:
                     self.dist.reduce_scatter_tensor(jac, jall, group=self.group)
                 else:
                     jac = jall
-        lo = self.rank * rows
-        return prob_all[lo:lo + rows], loss_all[lo:lo + rows], jac
+        return prob_ku, loss_in, jac
 
     def _device_guard(self):
         return torch.cuda.device(self.dev)

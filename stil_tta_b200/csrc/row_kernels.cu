@@ -1447,15 +1447,33 @@ __global__ void __launch_bounds__(kSimBlock) simmatch_shard_stats_kernel(const f
     int jv = j0;
     if (sim_vec4(zt, zs, ldz, labels)) {
         const int j4 = j0 + ((j1 - j0) & ~3);
-#pragma unroll 2
-        for (int j = j0 + 4 * threadIdx.x; j < j4; j += 4 * kSimBlock) {
-            const float4 a = *reinterpret_cast<const float4*>(rt + j), b = *reinterpret_cast<const float4*>(rs + j);
-            const longlong2 l0 = __ldg(reinterpret_cast<const longlong2*>(labels + j));
-            const longlong2 l1 = __ldg(reinterpret_cast<const longlong2*>(labels + j + 2));
+        // software pipeline: the next trip's 64 bytes are requested before this trip's columns are processed (the shared
+        // atomics keep the compiler from hoisting the loads itself; ncu had half of the stall samples on the first use
+        // of loaded data at 39 % of the HBM rate)
+        int j = j0 + 4 * threadIdx.x;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        longlong2 l0 = make_longlong2(0, 0), l1 = l0;
+        if (j < j4) {
+            a = *reinterpret_cast<const float4*>(rt + j);
+            b = *reinterpret_cast<const float4*>(rs + j);
+            l0 = __ldg(reinterpret_cast<const longlong2*>(labels + j));
+            l1 = __ldg(reinterpret_cast<const longlong2*>(labels + j + 2));
+        }
+        for (; j < j4; j += 4 * kSimBlock) {
+            const int jn = j + 4 * kSimBlock;
+            float4 an = a, bn = b;
+            longlong2 l0n = l0, l1n = l1;
+            if (jn < j4) {
+                an = *reinterpret_cast<const float4*>(rt + jn);
+                bn = *reinterpret_cast<const float4*>(rs + jn);
+                l0n = __ldg(reinterpret_cast<const longlong2*>(labels + jn));
+                l1n = __ldg(reinterpret_cast<const longlong2*>(labels + jn + 2));
+            }
             column(a.x, b.x, (int)l0.x);
             column(a.y, b.y, (int)l0.y);
             column(a.z, b.z, (int)l1.x);
             column(a.w, b.w, (int)l1.y);
+            a = an; b = bn; l0 = l0n; l1 = l1n;
         }
         jv = j4;
     }
