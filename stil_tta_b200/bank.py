@@ -153,8 +153,9 @@ class ShardedSimMatchBank:
         self._ws = None
         self.use_graph = bool(use_graph)
         self._graphs = {}
-        # gather x2 (+p), GEMM, stats, all-reduce, finish, grad, memset, split-K GEMM, grad_finish, reduce-scatter
-        self.launches_per_step = self.nshards * 7 + 1
+        # this library's kernels per sweep and shard: logits, statistics, chunk reduce, G, dX (+ one finish per sweep); the
+        # collectives, the packing cat / copies and the memset are not counted
+        self.launches_per_step = self.nshards * 5 + 1
 
     def _check_device(self) -> None:
         if self.dev.type != "cuda":

@@ -535,13 +535,8 @@ int launch_bank_logits(const void* feat_ku, const void* feat_qu, int64_t rows, i
     const int fixed = 1024 + kOutBoxes * kOutBox + kSweepBarBytes;
     L.stages = std::min(kMaxStagesB, (kSmemLimit - fixed) / kStageB);
     const int smem = fixed + L.stages * kStageB;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(bank_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        if (attr_err == cudaSuccess) prefer_max_shared(bank_logits_kernel);
-    });
-    STIL_CUDA(attr_err);
+    static std::atomic<unsigned long long> smem_set{0};
+    STIL_CUDA(ensure_dynamic_smem(smem_set, reinterpret_cast<const void*>(&bank_logits_kernel), kSmemLimit));
     bank_logits_kernel<<<std::min(sms, L.nchunks), kSweepThreads, smem, stream>>>(L);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
@@ -580,13 +575,8 @@ int launch_bank_dx(const __nv_bfloat16* gop, int64_t ldg, int g_nseg, int64_t ro
     L.tmem_cols = 32;
     while ((int64_t)L.tmem_cols < dim) L.tmem_cols <<= 1;
     const int smem = 1024 + kSweepBarBytes + L.stages * stage_bytes;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(bank_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        if (attr_err == cudaSuccess) prefer_max_shared(bank_dx_kernel);
-    });
-    STIL_CUDA(attr_err);
+    static std::atomic<unsigned long long> smem_set{0};
+    STIL_CUDA(ensure_dynamic_smem(smem_set, reinterpret_cast<const void*>(&bank_dx_kernel), kSmemLimit));
     // the partial tiles are ADDED: start from zero
     STIL_CUDA(cudaMemset2DAsync(out, ld_out * sizeof(float), 0, dim * sizeof(float), rows, stream));
     bank_dx_kernel<<<tiles_m * L.ksplit, kDxThreads, smem, stream>>>(L);

@@ -1,5 +1,6 @@
 // Shared host/device helpers for the STiL head kernels (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -60,6 +61,21 @@ struct Workspace {
 template <class K>
 inline void prefer_max_shared(K kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+// cudaFuncSetAttribute acts on the CURRENT device: opt a kernel into its dynamic shared memory (and the max-shared carve-out)
+// once per device.  `mask` is a function-local static of the call site (one per kernel instantiation), bit = device ordinal.
+inline cudaError_t ensure_dynamic_smem(std::atomic<unsigned long long>& mask, const void* kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    mask.fetch_or(bit, std::memory_order_release);
+    return cudaSuccess;
 }
 
 bool pdl_enabled();            // api.cu (stil_debug_pdl)

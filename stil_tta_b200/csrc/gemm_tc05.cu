@@ -677,6 +677,17 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                         for (int j = 0; j < 32; ++j) l[j] = fsx * (l[j] - fsx * xrow[kCPW - 1][j] * fin_dot);
                     }
                 }
+                if (J.out_tma) {
+                    // fp32 dX: swizzled box in the idle operand ring, one bulk tensor store per box after the loop.  Thread =
+                    // row stores straight to global are 32 scattered 16-byte pieces per instruction: ~2 us of LSU time per
+                    // tile, on the last kernel of the step's critical chain (profiles/r2_gemm_timeline_c2.txt: epilogue 5 us)
+                    const int r_in = q * 32 + lane;
+                    uint8_t* box = tiles + c * (kTileM * 128) + r_in * 128;
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4)
+                        *reinterpret_cast<float4*>(box + ((k4 ^ (r_in & 7)) * 16)) = make_float4(l[4 * k4], l[4 * k4 + 1], l[4 * k4 + 2], l[4 * k4 + 3]);
+                    continue;
+                }
                 if (row_ok) store32_from_float(J.fin_dx, J.fin_dx_dtype, (long long)row * J.fin_ld_dx + n0 + c * 32, nv, l);
             } else if (MODE == GEMM_STORE && ksplit > 1 && J.slice_stride == 0 && !clustered) {
                 // split contraction: add this CTA's partial tile (an empty slice adds nothing)
@@ -703,7 +714,7 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                 if (J.out_tma) {
                     // fp32 tile -> 128-byte-swizzled [128 rows x 32 floats] boxes in the (idle) operand ring -> ONE bulk tensor
                     // store per box after the loop: the per-lane path below needed 32 store instructions per 32 x 32 block and
-                    // made the epilogue the long pole of the bank logits (202 us for 2 x 448 x 65536, profiles/r2_c5_kernels.txt)
+                    // made the epilogue the long pole of the bank logits (202 us for 2 x 448 x 65536, profiles/r2_bank_timeline.txt)
                     const bool empty = MODE == GEMM_STORE && ksplit > 1 && nkb == 0 && !clustered;
                     const int r_in = q * 32 + lane;
                     uint8_t* box = tiles + c * (kTileM * 128) + r_in * 128;
@@ -775,8 +786,8 @@ __global__ void __launch_bounds__(threads_for(OCC), OCC) gemm_tc05_kernel(const 
                 }
             }
         }
-        if ((MODE == GEMM_STATS || MODE == GEMM_STORE) && J.out && J.out_tma && !cluster_follower &&
-            !(MODE == GEMM_STORE && J.fin_dx != nullptr)) {
+        if ((MODE == GEMM_STATS || MODE == GEMM_STORE) && J.out_tma && !cluster_follower &&
+            (J.out != nullptr || (MODE == GEMM_STORE && J.fin_dx != nullptr))) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy (TMA)
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             if (e == 0) {
@@ -1221,13 +1232,8 @@ int gemm_set_trace(void* buf) {
 template <int MODE, int OCC>
 static int launch_gemm_mode(const GemmLaunch& L, cudaStream_t stream) {
     constexpr int smem = smem_bytes_for(OCC == 1 ? kMaxStages : 3);
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_tc05_kernel<MODE, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (attr_err == cudaSuccess) prefer_max_shared(gemm_tc05_kernel<MODE, OCC>);
-    });
-    STIL_CUDA(attr_err);
+    static std::atomic<unsigned long long> smem_set{0};
+    STIL_CUDA(ensure_dynamic_smem(smem_set, reinterpret_cast<const void*>(&gemm_tc05_kernel<MODE, OCC>), smem));
     if (MODE == GEMM_STORE && L.cluster_k > 1) {
         STIL_CUDA(launch_pdl_cluster(gemm_tc05_kernel<MODE, OCC>, dim3(L.total_tiles), dim3(threads_for(OCC)), smem, stream,
                                      L.cluster_k, L));
@@ -1292,13 +1298,8 @@ bool make_bwd_job(GemmJob& out, const GemmJob& grad, const GemmJob& store, int n
 static int launch_gemm_bwd(const GemmLaunch& L, cudaStream_t stream) {
     int smem = 0;
     for (int j = 0; j < L.njobs; ++j) smem = std::max(smem, L.job[j].bw_misc_off + kBwdMiscBytes + 1024);
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (attr_err == cudaSuccess) prefer_max_shared(gemm_bwd_kernel);
-    });
-    STIL_CUDA(attr_err);
+    static std::atomic<unsigned long long> smem_set{0};
+    STIL_CUDA(ensure_dynamic_smem(smem_set, reinterpret_cast<const void*>(&gemm_bwd_kernel), 227 * 1024));
     STIL_CUDA(launch_pdl(gemm_bwd_kernel, dim3(L.total_tiles), dim3(kBwdThreads), (size_t)smem, stream, L));
     return STIL_OK;
 }
@@ -1337,6 +1338,11 @@ int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
             const bool accum = mode == GEMM_STORE && J.ksplit > 1 && J.slice_stride == 0 && L.cluster_k <= 1;
             // N % 4: a bulk tensor store clips out-of-range columns in 16-byte granules — with N = 130 it overwrote columns
             // 130-131, which belong to the neighbouring block of the CoMatch graphs (found by tests/test_gpu_banks.py)
+            if (!no_tma_out && mode == GEMM_STORE && J.fin_dx && J.fin_dx_dtype == STIL_F32 && (J.N & 3) == 0) {
+                // fused normalise-backward epilogue with an fp32 dX: the map is over the final gradient
+                if (make_out_map(&J.tmg, static_cast<float*>(J.fin_dx), J.N, J.M, J.fin_ld_dx, 1, 0)) J.out_tma = 1;
+                continue;
+            }
             if (no_tma_out || !J.out || J.fin_dx || accum || J.fwd_norm || (J.N & 3) != 0) continue;
             if (make_out_map(&J.tmg, J.out, J.N, J.M, J.ld_out, sliced ? J.ksplit : 1, J.slice_stride)) J.out_tma = 1;
         }

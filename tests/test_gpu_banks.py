@@ -344,6 +344,11 @@ def test_comatch_backward_after_queue_enqueue(S, BO):
 @pytest.mark.parametrize("rows,kb,d,c,dtype,shards", [
     (96, 1024, 128, 10, torch.bfloat16, 1), (96, 1024, 128, 10, torch.bfloat16, 4), (64, 640, 64, 10, torch.float32, 2),
     (448, 4096, 128, 286, torch.bfloat16, 8), (448, 65536, 512, 286, torch.bfloat16, 8),      # the last one is BASELINE config C5
+    # ragged shapes of the persistent sweep kernels (csrc/bank_sweep.cu): partial row blocks, shard widths that are not a
+    # multiple of 64 / 128 columns (two-box TMA path, clipped bulk stores), every supported dim, several chunks per CTA
+    (130, 1000, 256, 7, torch.bfloat16, 1), (64, 200, 384, 5, torch.bfloat16, 1), (300, 2112, 512, 10, torch.bfloat16, 2),
+    (1, 136, 128, 3, torch.bfloat16, 1), (2100, 1024, 128, 10, torch.bfloat16, 1),
+    (96, 1024, 192, 10, torch.bfloat16, 1),                                                   # dim % 128 != 0: tiled-GEMM path
 ])
 def test_sharded_simmatch_bank_matches_whole_bank_oracle(S, rows, kb, d, c, dtype, shards):
     """The column-sharded sweep (fixed-shift additive statistics; `shards` emulated one after the other on this GPU — the same
