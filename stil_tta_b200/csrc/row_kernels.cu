@@ -33,16 +33,10 @@ constexpr int kPrepRows = kRowBlock / 32;  // one warp per row
 // chain start its prologue now, and wait for the previous one's results before touching global memory.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// exp(x) for x <= 0 as ONE multiply and ONE special-function instruction (ex2.approx: relative error <= 2^-22; the rounding
+// exp(x - m), m * log2(e) formed once per row, as ONE fused multiply-add and ONE special-function instruction (ex2.approx: relative error <= 2^-22; the rounding
 // of x * log2(e) adds |x| * 2^-24).  libdevice expf costs ~14 instructions per call and made the row kernels
-// instruction-bound (ncu, profiles/r2_ncu_rows.txt: 65 % issue-slot utilisation at 38 % of the HBM peak); the softmax
+// instruction-bound (ncu, profiles/r2_ncu_rows_before.txt: 65 % issue-slot utilisation at 38 % of the HBM peak); the softmax
 // probabilities differ from torch's by <= 2e-6, far inside the 1e-5 ambiguity band of DESIGN.md §2.
-__device__ __forceinline__ float exp_fast(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
-    return y;
-}
-// exp(x - m) with m * log2(e) formed once per row: one FFMA + one ex2 per element
 __device__ __forceinline__ float exp_fast_shift(float x, float m_log2e) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaf(x, 1.4426950408889634f, -m_log2e)));
@@ -1396,7 +1390,8 @@ __device__ __forceinline__ float shifted_exp(float z, float c1) {
 // The per-class sums A_c are accumulated in 36-bit FIXED POINT, as two native 32-bit shared-memory atomics per column
 // (hi = bits 18.., lo = bits 0..17 of e * 2^36).  A float atomicAdd on shared memory is a compare-and-swap loop
 // (ATOMS.CAST.SPIN): with 286 classes and 32 random labels per warp instruction it retried so often that the kernel ran at
-// 25 % of the HBM rate with half of its stall samples on the loop (profiles/r2_ncu_bank_before.txt).  Integer sums are
+// 25 % of the HBM rate with half of its stall samples on the loop (profiles/r2_ncu_bank_before.txt; replicating the accumulators 4-8x per block to spread the
+// remaining bank conflicts was tried and bought nothing: the pass is latency-bound).  Integer sums are
 // also order-independent: the statistics of a shard are bit-reproducible.  e <= 1 (+ bf16 rounding of unit vectors), at
 // most kSimFxCols columns per block: hi <= 2^18 * 8192 * 1.x < 2^32, lo < 2^18 * 8192 = 2^31.
 constexpr float kSimFxScale = 68719476736.f;   // 2^36: absolute resolution 1.5e-11 per column
@@ -1815,8 +1810,8 @@ int64_t masked_softce_blocks(int64_t rows, int64_t) {
 int simmatch_shard_chunks(int64_t rows, int64_t k_shard) {
     // ~2048 blocks in flight, at least 1024 columns per block
     const int64_t fill = std::min<int64_t>(std::min<int64_t>(ceil_div(2048, std::max<int64_t>(rows, 1)), 32), k_shard / 1024);
-    // the fixed-point class sums of simmatch_shard_stats_kernel hold at most 8192 columns per block
-    return (int)std::max<int64_t>(std::max<int64_t>(1, fill), ceil_div(k_shard, 8192));
+    // the fixed-point class sums of simmatch_shard_stats_kernel hold at most kSimFxCols columns per block
+    return (int)std::max<int64_t>(std::max<int64_t>(1, fill), ceil_div(k_shard, kSimFxCols));
 }
 int launch_simmatch_shard_stats(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
                                 const float* p_all, int num_classes, float tt, float st, float* stats, float* chunk_scratch,
