@@ -338,6 +338,41 @@ STIL_API int stil_club_bwd(const void* mu, const void* y, int dtype, int64_t row
                            const float* g_bound, const float* g_est, float* d_mu, float* d_y, int64_t ld_grad, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Pseudo-label thresholds of the remaining baselines.
+ *
+ * FreeMatch self-adaptive threshold — replaces FreeMatchModel.update + .masking,
+ * models/MatchModel/FreeMatchFolder/freematch_model.py:128-165.  Two calls so that a data-parallel caller can add the
+ * statistics of all ranks in between (the reference all-gathers the probabilities, :129-130; the sums are the same thing):
+ *   stil_freematch_stats        probabilities (softmax when is_logits, :153-157), row max / first arg max (:132,:161),
+ *                               stats [2*C + 2] f32 = [ column sums | arg-max histogram | sum of row maxima | rows ]
+ *   stil_freematch_update_mask  EMA update of the DEVICE-resident state time_p [1], p_model [C], label_hist [C] (:137-144,
+ *                               clip_thresh != 0 clips time_p to [0, 0.95]) and mask [rows] f32 0/1 =
+ *                               max_probs >= time_p * p_model[max_idx] / max(p_model) (:162-164)
+ * max_probs / max_idx / probs_out may be NULL in stil_freematch_stats (kept in the workspace; pass the SAME workspace and
+ * NULL again to stil_freematch_update_mask).
+ *
+ * stil_threshold_rows — CoTraining cross pseudo labels, models/SemiMultimodal/CoTraining.py:141-146: probs = softmax(logits),
+ * max_probs / max_idx (may be NULL), mask = max_probs >= threshold (f32 0/1).
+ *
+ * FreeMatch fairness loss — replaces entropy_loss, FreeMatchFolder/freematch_utils.py:17-45 (rows with mask != 0 are
+ * selected): loss [1], hist_mean [1] (= hist_s.mean()); bwd writes d loss / d logits_s * grad_loss[0] (NULL = 1) for every
+ * row (zero for unselected rows) from what fwd left in the workspace. */
+STIL_API int64_t stil_threshold_workspace_bytes(int64_t rows, int64_t num_classes);
+STIL_API int stil_freematch_stats(const float* probs_or_logits, int64_t ld, int64_t rows, int64_t num_classes, int is_logits, float* stats,
+                                  float* max_probs, int64_t* max_idx, float* probs_out, int64_t ld_probs, void* workspace,
+                                  int64_t workspace_bytes, void* stream);
+STIL_API int stil_freematch_update_mask(const float* stats_total, int64_t rows, int64_t num_classes, float momentum, float clip_thresh,
+                                        float* time_p, float* p_model, float* label_hist, const float* max_probs, const int64_t* max_idx,
+                                        float* mask, void* workspace, int64_t workspace_bytes, void* stream);
+STIL_API int stil_threshold_rows(const float* logits, int64_t ld, int64_t rows, int64_t num_classes, float threshold, float* probs,
+                                 int64_t ld_probs, float* max_probs, int64_t* max_idx, float* mask, void* stream);
+STIL_API int stil_freematch_entropy_fwd(const float* mask, const float* logits_s, int64_t ld, int64_t rows, int64_t num_classes,
+                                        const float* p_model, const float* label_hist, float* loss, float* hist_mean, void* workspace,
+                                        int64_t workspace_bytes, void* stream);
+STIL_API int stil_freematch_entropy_bwd(int64_t rows, int64_t num_classes, const float* grad_loss, float* d_logits_s, int64_t ld_grad,
+                                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * f-1 — masked soft-target CE of the three student heads on the unlabelled rows, forward and
  * gradient in one pass.  Replaces STiLModel.py:301-303.
  *   losses[3]  = (loss_m_u, loss_i_u, loss_t_u), each a mean over `rows`

@@ -38,6 +38,7 @@ from __future__ import annotations
 from typing import Dict, Optional, Tuple
 
 import torch
+import torch.nn.functional as F
 
 Tensor = torch.Tensor
 
@@ -319,3 +320,58 @@ def momentum_update_ema(main_state: Dict[str, Tensor], ema_state: Dict[str, Tens
                 v_ema.mul_(momentum).add_((1.0 - momentum) * v_main)                  # :166
         elif param_names is None or k in param_names:
             v_ema.mul_(momentum).add_((1.0 - momentum) * v_main)                      # :168
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FreeMatch self-adaptive threshold / fairness loss, CoTraining cross pseudo labels
+# ------------------------------------------------------------------------------------------------------------------
+def freematch_masking(state: Dict[str, Tensor], logits_x_ulb: Tensor, m: float = 0.999, clip_thresh: float = 0.0,
+                      softmax_x_ulb: bool = True) -> Dict[str, Tensor]:
+    """``FreeMatchModel.masking`` incl. its ``update`` — models/MatchModel/FreeMatchFolder/freematch_model.py:128-165.
+    ``state`` = {time_p, p_model, label_hist} is updated IN PLACE like the reference's attributes."""
+    probs = torch.softmax(logits_x_ulb.detach(), dim=-1) if softmax_x_ulb else logits_x_ulb.detach()      # :153-157
+    max_probs, max_idx = torch.max(probs, dim=-1, keepdim=True)                                           # :132
+    state["time_p"] = state["time_p"] * m + (1 - m) * max_probs.mean()                                    # :137
+    if clip_thresh:
+        state["time_p"] = torch.clip(state["time_p"], 0.0, 0.95)                                          # :139-140
+    state["p_model"] = state["p_model"] * m + (1 - m) * probs.mean(dim=0)                                 # :142
+    hist = torch.bincount(max_idx.reshape(-1), minlength=state["p_model"].shape[0]).to(state["p_model"].dtype)
+    state["label_hist"] = state["label_hist"] * m + (1 - m) * (hist / hist.sum())                         # :143-144
+    max_probs, max_idx = probs.max(dim=-1)                                                                # :161
+    mod = state["p_model"] / torch.max(state["p_model"], dim=-1)[0]                                       # :162
+    thr = state["time_p"] * mod[max_idx]
+    return {"mask": max_probs.ge(thr).to(max_probs.dtype), "max_probs": max_probs, "max_idx": max_idx, "thr": thr, "probs": probs}
+
+
+def freematch_entropy_loss(mask: Tensor, logits_s: Tensor, prob_model: Tensor, label_hist: Tensor) -> Tuple[Tensor, Tensor]:
+    """``entropy_loss`` — FreeMatchFolder/freematch_utils.py:17-45."""
+    def inf_to_zero(v):                                                                                   # :12-14
+        v = v.clone()
+        v[v == float("inf")] = 0.0
+        return v
+    logits_s = logits_s[mask.bool()]                                                                      # :18-21
+    prob_s = logits_s.softmax(dim=-1)
+    _, pred = torch.max(prob_s, dim=-1)
+    hist_s = torch.bincount(pred, minlength=logits_s.shape[1]).to(logits_s.dtype)
+    hist_s = hist_s / hist_s.sum()                                                                        # :26-27
+    mod_prob_model = prob_model.reshape(1, -1) * inf_to_zero(1 / label_hist.reshape(1, -1)).detach()     # :30-34
+    mod_prob_model = mod_prob_model / mod_prob_model.sum(dim=-1, keepdim=True)
+    mod_mean = prob_s.mean(dim=0, keepdim=True) * inf_to_zero(1 / hist_s).detach()                        # :38-41
+    mod_mean = mod_mean / mod_mean.sum(dim=-1, keepdim=True)
+    loss = (mod_prob_model * torch.log(mod_mean + 1e-12)).sum(dim=1)                                      # :43-44
+    return loss.mean(), hist_s.mean()
+
+
+def cotraining_unsup(y_hat_i_u: Tensor, y_hat_t_u: Tensor, y_hat_i_e_u: Tensor, y_hat_t_e_u: Tensor, threshold: float
+                     ) -> Dict[str, Tensor]:
+    """The unsupervised part of ``CoTraining.training_step`` — models/SemiMultimodal/CoTraining.py:141-149 (arguments are the
+    unlabelled rows ``[B_l:]`` of the student and teacher logits)."""
+    pl_i = torch.softmax(y_hat_i_e_u.detach(), dim=1)                                                     # :141
+    pl_t = torch.softmax(y_hat_t_e_u.detach(), dim=1)                                                     # :142
+    max_i, _ = torch.max(pl_i, dim=1)
+    max_t, _ = torch.max(pl_t, dim=1)
+    mask_i, mask_t = max_i.ge(threshold), max_t.ge(threshold)                                             # :145-146
+    loss_i_u = (F.cross_entropy(y_hat_i_u, pl_t, reduction="none") * mask_t).mean()                       # :148
+    loss_t_u = (F.cross_entropy(y_hat_t_u, pl_i, reduction="none") * mask_i).mean()                       # :149
+    return {"pseudo_label_i": pl_i, "pseudo_label_t": pl_t, "mask_i": mask_i, "mask_t": mask_t, "max_prob_i": max_i,
+            "max_prob_t": max_t, "loss_i_u": loss_i_u, "loss_t_u": loss_t_u}

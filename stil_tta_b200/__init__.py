@@ -19,6 +19,8 @@ _LAZY = {
     "SmoothedLabels": "bank_blocks",
     "Linear": "linear", "linear": "linear",
     "EmaTeacher": "ema", "momentum_update_ema": "ema",
+    "FreeMatchThreshold": "thresholds", "entropy_loss": "thresholds", "threshold_rows": "thresholds",
+    "cotraining_pseudo_labels": "thresholds",
     "CLUBMean": "club", "club_bound": "club", "club_learning_loss": "club", "club_both": "club", "STiLHead": "head", "DistributedSTiLHead": "head", "GlobalBatch": "distributed", "P2PBuffer": "distributed", "all_reduce_prototype_partials": "distributed",
 }
 

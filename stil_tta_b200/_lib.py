@@ -105,6 +105,12 @@ SIGNATURES = {
                                         vp, i32, i64, vp, i64, vp]),
     "stil_softmax_rows": (i32, [vp, i32, i64, i64, i64, vp, i64, vp]),
     "stil_da_batch_mean": (i32, [vp, i64, i64, i64, vp, vp]),
+    "stil_threshold_workspace_bytes": (i64, [i64, i64]),
+    "stil_freematch_stats": (i32, [vp, i64, i64, i64, i32, vp, vp, vp, vp, i64, vp, i64, vp]),
+    "stil_freematch_update_mask": (i32, [vp, i64, i64, f32, f32, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "stil_threshold_rows": (i32, [vp, i64, i64, i64, f32, vp, i64, vp, vp, vp, vp]),
+    "stil_freematch_entropy_fwd": (i32, [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, i64, vp]),
+    "stil_freematch_entropy_bwd": (i32, [i64, i64, vp, vp, i64, vp, i64, vp]),
     "stil_da_apply": (i32, [vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp]),
     "stil_simmatch_workspace_bytes": (i64, [i64, i64, i64, i32]),
     "stil_simmatch_fwd": (i32, [vp, vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, f32, f32, f32, vp, vp, i32, vp,

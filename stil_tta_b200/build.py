@@ -12,7 +12,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT_DIR = PKG / "_C"
 LIB = OUT_DIR / "libstil_head.so"
-SOURCES = ["api.cu", "gemm_tc05.cu", "row_kernels.cu", "bank_kernels.cu", "bank_sweep.cu", "p2p.cu"]
+SOURCES = ["api.cu", "gemm_tc05.cu", "row_kernels.cu", "bank_kernels.cu", "bank_sweep.cu", "threshold_kernels.cu", "p2p.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

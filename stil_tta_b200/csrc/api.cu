@@ -1368,6 +1368,49 @@ STIL_API int stil_simmatch_shard_grad(int dtype, int64_t rows, int64_t dim, cons
                              workspace, workspace_bytes, stream);
 }
 
+// =============================================================================== FreeMatch / CoTraining thresholds
+STIL_API int64_t stil_threshold_workspace_bytes(int64_t rows, int64_t num_classes) { return threshold_workspace_bytes(rows, num_classes); }
+
+STIL_API int stil_freematch_stats(const float* probs_or_logits, int64_t ld, int64_t rows, int64_t num_classes, int is_logits, float* stats,
+                                  float* max_probs, int64_t* max_idx, float* probs_out, int64_t ld_probs, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+    STIL_REQUIRE(probs_or_logits && stats && rows >= 1 && num_classes >= 1 && ld >= num_classes && (!probs_out || ld_probs >= num_classes),
+                 STIL_E_ARG, "freematch_stats: bad arguments");
+    return launch_freematch_stats(probs_or_logits, ld, rows, num_classes, is_logits, stats, max_probs, max_idx, probs_out, ld_probs,
+                                  workspace, workspace_bytes, S(stream));
+}
+
+STIL_API int stil_freematch_update_mask(const float* stats_total, int64_t rows, int64_t num_classes, float momentum, float clip_thresh,
+                                        float* time_p, float* p_model, float* label_hist, const float* max_probs, const int64_t* max_idx,
+                                        float* mask, void* workspace, int64_t workspace_bytes, void* stream) {
+    STIL_REQUIRE(stats_total && time_p && p_model && label_hist && num_classes >= 1 && (rows == 0 || mask), STIL_E_ARG,
+                 "freematch_update_mask: bad arguments");
+    return launch_freematch_update_mask(stats_total, rows, num_classes, momentum, clip_thresh, time_p, p_model, label_hist, max_probs,
+                                        max_idx, mask, workspace, workspace_bytes, S(stream));
+}
+
+STIL_API int stil_threshold_rows(const float* logits, int64_t ld, int64_t rows, int64_t num_classes, float threshold, float* probs,
+                                 int64_t ld_probs, float* max_probs, int64_t* max_idx, float* mask, void* stream) {
+    STIL_REQUIRE(rows == 0 || (logits && probs && max_probs && mask && num_classes >= 1 && ld >= num_classes && ld_probs >= num_classes),
+                 STIL_E_ARG, "threshold_rows: bad arguments");
+    return launch_threshold_rows(logits, ld, rows, num_classes, threshold, probs, ld_probs, max_probs, max_idx, mask, S(stream));
+}
+
+STIL_API int stil_freematch_entropy_fwd(const float* mask, const float* logits_s, int64_t ld, int64_t rows, int64_t num_classes,
+                                        const float* p_model, const float* label_hist, float* loss, float* hist_mean, void* workspace,
+                                        int64_t workspace_bytes, void* stream) {
+    STIL_REQUIRE(mask && logits_s && p_model && label_hist && loss && hist_mean && rows >= 1 && num_classes >= 1 && ld >= num_classes,
+                 STIL_E_ARG, "freematch_entropy_fwd: bad arguments");
+    return launch_freematch_entropy_fwd(mask, logits_s, ld, rows, num_classes, p_model, label_hist, loss, hist_mean, workspace,
+                                        workspace_bytes, S(stream));
+}
+
+STIL_API int stil_freematch_entropy_bwd(int64_t rows, int64_t num_classes, const float* grad_loss, float* d_logits_s, int64_t ld_grad,
+                                        void* workspace, int64_t workspace_bytes, void* stream) {
+    STIL_REQUIRE(d_logits_s && rows >= 1 && num_classes >= 1 && ld_grad >= num_classes, STIL_E_ARG, "freematch_entropy_bwd: bad arguments");
+    return launch_freematch_entropy_bwd(rows, num_classes, grad_loss, d_logits_s, ld_grad, workspace, workspace_bytes, S(stream));
+}
+
 // =============================================================================================== f-1
 STIL_API int64_t stil_masked_softce_workspace_bytes(int64_t rows) {
     Workspace W(nullptr, 0);

@@ -339,6 +339,21 @@ int launch_club_fwd(const void* mu, const void* y, int dtype, int64_t ld, int64_
                     float* est, cudaStream_t stream);
 int launch_club_bwd(const void* mu, const void* y, int dtype, int64_t ld, int64_t rows, int64_t dim, const float* stats,
                     const float* g_bound, const float* g_est, float* d_mu, float* d_y, int64_t ld_g, cudaStream_t stream);
+// FreeMatch / CoTraining thresholds (threshold_kernels.cu)
+int64_t threshold_workspace_bytes(int64_t rows, int64_t C);
+int launch_freematch_stats(const float* x, int64_t ld, int64_t rows, int64_t C, int is_logits, float* stats, float* max_p,
+                           int64_t* max_i, float* probs_out, int64_t ld_probs, void* workspace, int64_t workspace_bytes,
+                           cudaStream_t stream);
+int launch_freematch_update_mask(const float* stats_total, int64_t rows, int64_t C, float momentum, float clip_thresh, float* time_p,
+                                 float* p_model, float* label_hist, const float* max_p, const int64_t* max_i, float* mask,
+                                 void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int launch_threshold_rows(const float* logits, int64_t ld, int64_t rows, int64_t C, float threshold, float* probs, int64_t ld_probs,
+                          float* max_p, int64_t* max_i, float* mask, cudaStream_t stream);
+int launch_freematch_entropy_fwd(const float* mask, const float* logits_s, int64_t ld, int64_t rows, int64_t C, const float* p_model,
+                                 const float* label_hist, float* loss, float* hist_mean, void* workspace, int64_t workspace_bytes,
+                                 cudaStream_t stream);
+int launch_freematch_entropy_bwd(int64_t rows, int64_t C, const float* grad_loss, float* d_logits, int64_t ld_g, void* workspace,
+                                 int64_t workspace_bytes, cudaStream_t stream);
 // probs / qmean with rows renormalised (the second half of launch_da_apply)
 int launch_da_rows(const float* probs, int64_t ld, int64_t rows, int64_t k, const float* qmean, float* out, int64_t ld_out,
                    cudaStream_t stream);
