@@ -251,7 +251,8 @@ class ShardedSimMatchBank:
             raise ValueError("feature / probability shapes do not match the bank")
         self._alloc_ws(rows_all, d, dtype_code(fq))
         f32 = dict(dtype=torch.float32, device=dev)
-        stats = torch.zeros(rows_all, 3 + c, **f32)
+        # one shard: the statistics kernels write every entry; several emulated shards: summed into a cleared buffer
+        stats = torch.zeros(rows_all, 3 + c, **f32) if self.nshards > 1 else torch.empty(rows_all, 3 + c, **f32)
         part = torch.empty(rows_all, 3 + c, **f32) if self.nshards > 1 else stats
         with self._device_guard():
             for s in range(self.nshards):

@@ -1361,9 +1361,14 @@ STIL_API int stil_simmatch_shard_grad(int dtype, int64_t rows, int64_t dim, cons
     STIL_REQUIRE(workspace && P.bytes <= workspace_bytes, STIL_E_WORKSPACE, "simmatch workspace too small");
     if (rows == 0) return STIL_OK;
     // G (bf16 hi+lo) from the logits the statistics pass left in the workspace, then dX_partial = G · bank_shardᵀ
+    // when the persistent dX kernel follows (it ADDS partial tiles) and the output is one contiguous block, the G pass clears it
+    const bool fold_zero = ld_grad == dim && (rows * dim) % 4 == 0 && bank_dx_eligible(dtype, rows, dim, k_shard, d_feat_partial, ld_grad);
     if ((rc = launch_simmatch_shard_grad(P.zt, P.zs, P.ldz, reinterpret_cast<const long long*>(labels), (int)rows, (int)k_shard,
-                                         prob_ku_orig, (int)num_classes, tt, st, norms, P.gop, P.ldg, 2, S(stream))))
+                                         prob_ku_orig, (int)num_classes, tt, st, norms, P.gop, P.ldg, 2,
+                                         fold_zero ? d_feat_partial : nullptr, rows * dim, S(stream))))
         return rc;
+    if (fold_zero)
+        return launch_bank_dx(P.gop, P.ldg, 2, rows, bank, ld_bank, dim, k_shard, nullptr, d_feat_partial, ld_grad, S(stream), true);
     return stil_simmatch_bwd(nullptr, dtype, rows, dim, bank, ld_bank, k_shard, nullptr, d_feat_partial, STIL_F32, ld_grad,
                              workspace, workspace_bytes, stream);
 }

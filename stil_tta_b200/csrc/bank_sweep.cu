@@ -549,7 +549,7 @@ bool bank_dx_eligible(int dtype, int64_t rows, int64_t dim, int64_t k_shard, con
 }
 
 int launch_bank_dx(const __nv_bfloat16* gop, int64_t ldg, int g_nseg, int64_t rows, const void* bank, int64_t ld_bank, int64_t dim,
-                   int64_t k_shard, const float* row_scale, float* out, int64_t ld_out, cudaStream_t stream) {
+                   int64_t k_shard, const float* row_scale, float* out, int64_t ld_out, cudaStream_t stream, bool out_is_zero) {
     BankDxLaunch L;
     std::memset(&L, 0, sizeof(L));
     int rc;
@@ -578,7 +578,7 @@ int launch_bank_dx(const __nv_bfloat16* gop, int64_t ldg, int g_nseg, int64_t ro
     static std::atomic<unsigned long long> smem_set{0};
     STIL_CUDA(ensure_dynamic_smem(smem_set, reinterpret_cast<const void*>(&bank_dx_kernel), kSmemLimit));
     // the partial tiles are ADDED: start from zero
-    STIL_CUDA(cudaMemset2DAsync(out, ld_out * sizeof(float), 0, dim * sizeof(float), rows, stream));
+    if (!out_is_zero) STIL_CUDA(cudaMemset2DAsync(out, ld_out * sizeof(float), 0, dim * sizeof(float), rows, stream));
     bank_dx_kernel<<<tiles_m * L.ksplit, kDxThreads, smem, stream>>>(L);
     STIL_LAUNCH_CHECK();
     return STIL_OK;

@@ -154,7 +154,7 @@ int launch_bank_logits(const void* feat_ku, const void* feat_qu, int64_t rows, i
 // out[rows, dim] = row_scale * (G[rows, (hi, lo), k_shard] · bankᵀ): whole-accumulator-in-TMEM split contraction
 bool bank_dx_eligible(int dtype, int64_t rows, int64_t dim, int64_t k_shard, const float* out, int64_t ld_out);
 int launch_bank_dx(const __nv_bfloat16* gop, int64_t ldg, int g_nseg, int64_t rows, const void* bank, int64_t ld_bank, int64_t dim,
-                   int64_t k_shard, const float* row_scale, float* out, int64_t ld_out, cudaStream_t stream);
+                   int64_t k_shard, const float* row_scale, float* out, int64_t ld_out, cudaStream_t stream, bool out_is_zero = false);
 // Turn a GEMM_GRAD job + the GEMM_STORE job that would consume its G into one GEMM_BWD job (false: shapes / shared memory
 // do not allow the fused kernel — launch the two separately)
 bool make_bwd_job(GemmJob& out, const GemmJob& grad, const GemmJob& store, int nsplit);
@@ -303,7 +303,7 @@ int launch_simmatch_shard_finish(const float* stats, const float* p_all, int row
                                  float* p_out, float* loss_in, float* norms, cudaStream_t stream);
 int launch_simmatch_shard_grad(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
                                const float* p_all, int num_classes, float tt, float st, const float* norms, __nv_bfloat16* gop,
-                               long long ld_g, int g_nseg, cudaStream_t stream);
+                               long long ld_g, int g_nseg, float* zero_out, long long zero_n, cudaStream_t stream);
 int launch_softmax_rows(const void* y, int dtype, int64_t ld, int64_t rows, int64_t k, float* out, int64_t ld_out,
                         cudaStream_t stream);
 int launch_col_sum(const float* x, int64_t ld, int64_t rows, int64_t k, float* out, cudaStream_t stream);

@@ -1524,8 +1524,14 @@ __global__ void __launch_bounds__(kSimBlock) simmatch_shard_grad_kernel(const fl
                                                                         long long ldz, const long long* __restrict__ labels,
                                                                         int k_shard, const float* __restrict__ p_all, int C,
                                                                         float inv_tt, float inv_st, const float* __restrict__ norms,
-                                                                        __nv_bfloat16* gop, long long ld_g, int g_nseg) {
+                                                                        __nv_bfloat16* gop, long long ld_g, int g_nseg,
+                                                                        float4* __restrict__ zero_out, long long zero_n4) {
     extern __shared__ float sm[];   // p[C]
+    // the dX product that follows ADDS its partial tiles into its output: clear it from here (one memset node and one
+    // launch gap less per sweep)
+    for (long long i = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * kSimBlock + threadIdx.x; i < zero_n4;
+         i += (long long)gridDim.x * gridDim.y * kSimBlock)
+        zero_out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int row = blockIdx.x;
     for (int c = threadIdx.x; c < C; c += kSimBlock) sm[c] = p_all[(long long)row * C + c];
     __syncthreads();
@@ -1842,11 +1848,12 @@ int launch_simmatch_shard_finish(const float* stats, const float* p_all, int row
 }
 int launch_simmatch_shard_grad(const float* zt, const float* zs, long long ldz, const long long* labels, int rows, int k_shard,
                                const float* p_all, int num_classes, float tt, float st, const float* norms, __nv_bfloat16* gop,
-                               long long ld_g, int g_nseg, cudaStream_t stream) {
+                               long long ld_g, int g_nseg, float* zero_out, long long zero_n, cudaStream_t stream) {
     if (rows == 0) return STIL_OK;
     const size_t smem = (size_t)num_classes * sizeof(float);
     simmatch_shard_grad_kernel<<<dim3(rows, simmatch_shard_chunks(rows, k_shard)), kSimBlock, smem, stream>>>(
-        zt, zs, ldz, labels, k_shard, p_all, num_classes, 1.f / tt, 1.f / st, norms, gop, ld_g, g_nseg);
+        zt, zs, ldz, labels, k_shard, p_all, num_classes, 1.f / tt, 1.f / st, norms, gop, ld_g, g_nseg,
+        reinterpret_cast<float4*>(zero_out), zero_out ? zero_n / 4 : 0);
     STIL_LAUNCH_CHECK();
     return STIL_OK;
 }
