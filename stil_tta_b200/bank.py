@@ -167,6 +167,7 @@ class ShardedSimMatchBank:
     # ------------------------------------------------------------------------------------------
     def load_shard(self, bank_rows: torch.Tensor, labels: torch.Tensor, shard: int = 0) -> None:
         """Fill local shard ``shard`` from ``bank_rows [k_shard, dim]`` (row-major, unit rows) and its labels."""
+        self._check_labels(labels)
         self.bank[shard].copy_(bank_rows.to(self.dev).t())
         self.labels[shard].copy_(labels.to(self.dev))
 
@@ -179,6 +180,7 @@ class ShardedSimMatchBank:
     def update(self, k: torch.Tensor, y: torch.Tensor, index: torch.Tensor) -> None:
         """``_update_bank`` (``simmatch_model.py:141-147``) with GLOBAL column indices: ``k``/``y``/``index`` are gathered
         over ranks like the reference does, then every rank writes the columns it owns."""
+        self._check_labels(y)
         if self.world > 1:
             k, y, index = self._gather(k.contiguous()), self._gather(y.contiguous()), self._gather(index.contiguous())
         for s in range(self.nshards):
@@ -186,6 +188,12 @@ class ShardedSimMatchBank:
             mine = (index >= g) & (index < g + self.k_shard)
             if bool(mine.any()):
                 self._k_update(s, k[mine], y[mine], index[mine] - g)
+
+    def _check_labels(self, y: torch.Tensor) -> None:
+        """The sweep kernels index per-class accumulators with the stored labels (the reference's ``gather`` / ``scatter_add``
+        raise on a bad class, ``simmatch_model.py:274-279``): refuse them where they enter the bank."""
+        if y.numel() and (int(y.min()) < 0 or int(y.max()) >= self.num_classes):
+            raise ValueError(f"bank labels must lie in [0, {self.num_classes})")
 
     def _k_update(self, s, k, y, index_local) -> None:
         from .bank_blocks import update_bank

@@ -415,6 +415,8 @@ def test_sharded_simmatch_bank_cuda_graph_replays(S, rows, kb, d, c):
         k_new, y_new = dev(unit(torch.randn(32, d, generator=g))), dev(torch.randint(0, c, (32,), generator=g))
         for sb in (eager, graphed):
             sb.update(k_new, y_new, idx)
+    with pytest.raises(ValueError):                 # a class id outside [0, C) is refused where it enters the bank
+        eager.update(k_new, torch.full_like(y_new, c), idx)
     # without a gradient: a second signature, a second graph
     with torch.no_grad():
         pe, le = eager(fk, dev(fq), p, 0.1, 0.1, 0.9)
