@@ -49,6 +49,33 @@ def test_oracle_cotraining_fixture_is_self_consistent():
         assert torch.allclose(out["loss_i_u"].reshape(1), _t(z, f"{name}_loss_i_u"), rtol=1e-6)
 
 
+def test_freematch_batch_statistics_are_additive_over_ranks():
+    """The CUDA drop-in all-reduces ``[column sums | arg-max histogram | sum of row maxima | rows]`` instead of gathering the
+    probabilities of all ranks (``freematch_model.py:129-130``): the update computed from the summed statistics of two half
+    batches equals the reference update on the concatenated batch."""
+    from oracle import stil_head_oracle as O
+    g = torch.Generator().manual_seed(5)
+    c, m = 7, 0.999
+    logits = torch.randn(64, c, generator=g) * 3
+    state = {"p_model": torch.rand(c, generator=g), "label_hist": torch.rand(c, generator=g), "time_p": torch.tensor(0.4)}
+    ref = {k: v.clone() for k, v in state.items()}
+    O.freematch_masking(ref, logits, m=m)
+    stats = torch.zeros(2 * c + 2, dtype=torch.float64)
+    for part in (logits[:40], logits[40:]):                       # two "ranks"
+        p = torch.softmax(part, -1)
+        mp, mi = p.max(-1)
+        stats[:c] += p.sum(0).double()
+        stats[c:2 * c] += torch.bincount(mi, minlength=c).double()
+        stats[2 * c] += mp.sum().double()
+        stats[2 * c + 1] += part.shape[0]
+    n = stats[2 * c + 1]
+    time_p = state["time_p"] * m + (1 - m) * (stats[2 * c] / n).float()
+    p_model = state["p_model"] * m + (1 - m) * (stats[:c] / n).float()
+    label_hist = state["label_hist"] * m + (1 - m) * (stats[c:2 * c] / n).float()
+    assert torch.allclose(time_p, ref["time_p"], rtol=1e-6) and torch.allclose(p_model, ref["p_model"], rtol=1e-6)
+    assert torch.allclose(label_hist, ref["label_hist"], rtol=1e-6)
+
+
 def test_threshold_dropins_refuse_cpu_tensors():
     import stil_tta_b200 as S
     with pytest.raises((RuntimeError, ValueError)):
