@@ -11,10 +11,10 @@
 // bank_logits_kernel: one CTA per SM.  A CTA owns a UNIT (teacher or student rows of one 128-row block) and walks over a
 // range of 128-column bank blocks:
 //   * the unit's rows live in TENSOR MEMORY (tcgen05.mma with the A operand from TMEM: 128 lanes x dim/2 columns of packed
-//     bf16 pairs, written once per chunk with tcgen05.st), so shared memory belongs to the bank ring.  A stage of the ring
-//     is only 0.13 us of tensor work and a stage round trip (TMA latency + MMA completion + two mbarrier hops) measured
-//     0.8-1.2 us: with the rows in shared memory (128 KiB) the ring had 4 stages and the kernel ran at 1/3 of the MMA rate
-//     whatever else was switched off (the STIL_SWEEP_DEBUG experiments in profiles/r2_bank_timeline.txt);
+//     bf16 pairs, written once per chunk with tcgen05.st), so shared memory belongs to the bank ring and the output
+//     staging (rows in shared memory cost 128 KiB and left a 4-stage ring of 16 KiB stages).  A ring stage is 128 contraction
+//     rows (32 KiB, 8 MMAs): a tcgen05.commit costs ~0.2 us of completion tracking, a 64-row stage is 0.13 us of tensor work
+//     (the STIL_SWEEP_DEBUG switch-off experiments in profiles/r2_bank_timeline.txt);
 //   * warp 0 streams bank blocks through the ring (TMA, the bank read in place as an MN-major operand), warp 1 issues the
 //     MMAs into one of TWO 128-column TMEM accumulators, two groups of 4 warps drain the other one (tcgen05.ld ->
 //     128-byte-swizzled fp32 boxes in shared memory -> bulk tensor stores; each group owns 64 of the 128 columns), so the
